@@ -1,0 +1,167 @@
+/*
+ * tagrec_b200.h — C ABI of libtagrec_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the graph-embedding train + full-sort evaluation hot path of
+ * chenzheng5555/tag-aware-recommendation.  The reference has NO FFI of its own (it is 100 % Python); each entry
+ * point below names the reference call site(s) (file:line, relative to the reference root) whose device work it
+ * replaces.  The reference-side binding is the ctypes stub in INTEGRATION.md / tag-aware-recommendation_b200/_lib.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative TAGREC_E* code otherwise; tagrec_last_error() gives text
+ *     (thread-local);
+ *   - the CALLER owns every buffer (torch allocates); the library never frees or keeps a pointer after the call;
+ *   - all pointers are DEVICE pointers on the current device unless the parameter is documented "host";
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); launches are
+ *     asynchronous and never synchronise, except the functions documented "synchronises";
+ *   - tables are row-major float32 [n_rows, dim]; rows must be 16-byte aligned (dim % 4 == 0);
+ *   - CSR: rowptr int64 [n+1], col int32 [nnz] ascending inside a row, val float32 [nnz].
+ */
+#ifndef TAGREC_B200_H
+#define TAGREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAGREC_OK 0
+#define TAGREC_EINVAL (-1)   /* bad argument (null pointer, unsupported dim, ...) */
+#define TAGREC_ECUDA (-2)    /* a CUDA runtime call / launch failed */
+#define TAGREC_ENOMEM (-3)   /* caller-provided workspace or output capacity too small */
+
+int tagrec_version(void);
+const char* tagrec_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's "gpu_launches"). */
+uint64_t tagrec_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K0  adjacency -> CSR            replaces model/help/adj.py:7-35 (create_ui_adj / create_uit_adj, lil_matrix
+ *                                 block assembly), adj.py:90-110 (bi_norm / si_norm value computation) and
+ *                                 adj.py:144-150 (sp2tensor).
+ * The degree power d = np.power(rowsum, p) stays on the HOST in numpy (adj.py:93,105): numpy's float32 pow is not
+ * reproducible on device, and bit-exact values need that very function.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Bytes of workspace tagrec_csr_build_structure needs for `n_directed` = 2*(e_ui+e_ut+e_it) (+ n if self loops). */
+size_t tagrec_csr_workspace_bytes(int64_t n_directed);
+
+/* Block adjacency [[0,R],[R^T,0]] (or the 3x3 user/item/tag block matrix when e_ut+e_it > 0), duplicates summed,
+ * rows ascending, columns ascending inside a row.
+ *   ui_row/ui_col (e_ui), ut_row/ut_col (e_ut), it_row/it_col (e_it): int64 block-local indices (device).
+ *   self_loops: 0 none | 1 add I BEFORE the degree is taken (adj.py:81 'si_norm_self')
+ *                      | 2 add I with weight 1 that is NOT part of the degree (adj.py:83 'ngcf').
+ * Outputs: rowptr[n+1]; col[cap], weight[cap] (integer multiplicities as float, adj.py data before normalising);
+ *   degree[n] = float32 weighted row sum (adj.py:92,103); *nnz_host (HOST) = entries written.
+ * Synchronises `stream` (it has to return nnz). */
+int tagrec_csr_build_structure(const int64_t* ui_row, const int64_t* ui_col, int64_t e_ui,
+                               const int64_t* ut_row, const int64_t* ut_col, int64_t e_ut,
+                               const int64_t* it_row, const int64_t* it_col, int64_t e_it,
+                               int64_t n_user, int64_t n_item, int64_t n_tag, int self_loops,
+                               void* workspace, size_t workspace_bytes,
+                               int64_t* rowptr, int32_t* col, float* weight, int64_t cap,
+                               float* degree, int64_t* nnz_host, void* stream);
+
+/* val[j] = (dpow[row]*w[j])*dpow[col]   mode 0  bi_norm   (adj.py:97, two roundings, left to right)
+ *        =  dpow[row]*w[j]              mode 1  si_norm / si_norm_self / ngcf (diagonal of 'ngcf' stays 1)
+ *        =  w[j]*dpow[col]              mode 2  transpose of mode 1 (values of A^T for the backward SpMM)
+ *        =  w[j]                        mode 3  'plain'
+ * self_loops as above (mode 1/2 with self_loops==2 keep the diagonal at exactly 1). */
+int tagrec_csr_normalise(const int64_t* rowptr, const int32_t* col, const float* weight, const float* dpow,
+                         int64_t n, int mode, int self_loops, float* val, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K1  CSR SpMM with fused epilogues      replaces model/help/adj.py:158-167 (split_mm = torch.sparse.mm) and
+ *                                        its autograd transpose, plus model/lightgcn.py:54-60.
+ * Long rows (> TAGREC_LONG_ROW nnz) are split into chunks whose partial sums meet in `long_scratch`
+ * (n_long x dim floats, zero on entry, left zero on exit) guarded by `long_counter` (n_long ints, zero/zero).
+ * long_rows[n_long] = row ids; item_slot/item_begin/item_end[n_items] = chunk -> (slot in long_rows, nnz range).
+ * All five may be NULL when n_long == 0.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define TAGREC_LONG_ROW 4096
+#define TAGREC_LONG_CHUNK 2048
+
+typedef struct {
+    const int64_t* rowptr;
+    const int32_t* col;
+    const float* val;
+    int64_t n_rows;
+    const int32_t* long_rows;
+    const int32_t* item_slot;
+    const int64_t* item_begin;
+    const int64_t* item_end;
+    int64_t n_long;
+    int64_t n_items;
+    float* long_scratch;
+    int32_t* long_counter;
+} tagrec_csr_t;
+
+/* y = A x (+ beta*y)                        adj.py:162,166; also A^T g when given the transposed values. */
+int tagrec_spmm(const tagrec_csr_t* a, const float* x, float* y, int dim, float beta, void* stream);
+
+/* One LightGCN layer, lightgcn.py:55-60:   y = A x   (raw, propagates)
+ *   acc = (first ? x : acc) + y / max(||y||_2, 1e-12);  if (last) acc *= final_scale   [final_scale = 1/(L+1)] */
+int tagrec_lightgcn_fwd_layer(const tagrec_csr_t* a, const float* x, float* y, float* acc, int dim, int first,
+                              int last, float final_scale, void* stream);
+
+/* One backward layer of the same (closed form of autograd through lightgcn.py:55-60):
+ *   gy = g_final * (upstream ? upstream[0] : 1) * inv_layers
+ *   e_k != NULL :  g_out = nb(gy, e_k) + (g_next ? A g_next : 0)
+ *                  nb(g,e) = (g - y (y.g)) / ||e||,  y = e/||e||   (g / 1e-12 when ||e|| < 1e-12)
+ *   e_k == NULL :  g_out = gy + A g_next + (reg_grad ? (upstream ? upstream[1] : 1) * reg_grad : 0)
+ * `a` must hold the values of A^T (== A for bi_norm).  g_out may alias reg_grad. */
+int tagrec_lightgcn_bwd_layer(const tagrec_csr_t* a, const float* g_next, const float* e_k, const float* g_final,
+                              const float* reg_grad, const float* upstream, float inv_layers, float* g_out,
+                              int dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K2  fused BPR step            replaces model/lightgcn.py:68-82 / model/ngcf.py:95-105 (3 gathers, mul_loss,
+ *                               l2reg_loss: model/help/loss.py:4-12,27-32) and their index_put_ backward.
+ *   triples: int64 [b,3] row-major (u, i+, i-) — train_data/bpr_training_data.py:44; items index the table at
+ *   row item_offset + i.  loss_kind 0 softplus, 1 logsigmoid (loss.py:8-11).
+ *   loss_out[0] = mean loss, loss_out[1] = reg * 1/2 sum ||rows of reg_src||^2 / b  (overwritten)
+ *   g_final += d loss / d final;  g_reg += d loss_out[1] / d reg_src (skipped when reg == 0 or g_reg NULL).
+ * ---------------------------------------------------------------------------------------------------------- */
+int tagrec_bpr_fwd_bwd(const int64_t* triples, int64_t b, int64_t item_offset, const float* final_table,
+                       const float* reg_src, int dim, float reg, int loss_kind, float* g_final, float* g_reg,
+                       float* loss_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K3  full-sort evaluation      replaces model/lightgcn.py:84-89 (predict_rating), training/basic_test.py:40-48
+ *                               (mask train items with -1024, torch.topk) and training/utils.py:7-35 (metrics).
+ *   users int64 [nu]; user_table [*,dim], item_table [n_item,dim];
+ *   train_ptr int64 [n_user+1] / train_items int32 (ascending per user): items to mask;
+ *   topk_ids int32 [nu,k] / topk_scores float32 [nu,k]: best k by (-score, item id), score = sigmoid(dot) as the
+ *   reference ranks it (masked items rank as -1024).
+ * ---------------------------------------------------------------------------------------------------------- */
+int tagrec_eval_topk(const int64_t* users, int64_t nu, const float* user_table, const float* item_table,
+                     int64_t n_item, int dim, const int64_t* train_ptr, const int32_t* train_items, int k,
+                     int32_t* topk_ids, float* topk_scores, void* workspace, size_t workspace_bytes, void* stream);
+size_t tagrec_eval_workspace_bytes(int64_t nu, int64_t n_item, int k);
+
+/* metric sums over users (training/utils.py:15-35): out[4*nk] = recall|precision|hr|ndcg per k (double, +=). */
+int tagrec_eval_metrics(const int64_t* users, int64_t nu, const int32_t* topk_ids, int kmax,
+                        const int64_t* test_ptr, const int32_t* test_items, const int32_t* ks, int nk,
+                        double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * BPR negative sampler          replaces train_data/bpr_training_data.py:29-45 + train_data/utils.py:19-28,52-55.
+ * Host version: bit-exact numpy-legacy MT19937 stream for cpu_core == 1 (parity mode).  All pointers HOST.
+ *   state: 625 uint32 (624 words + position), advanced exactly as the parent's RandomState is (shuffle only).
+ * Device version: Philox counter RNG, rejection against the user's ascending train row (throughput mode).
+ * ---------------------------------------------------------------------------------------------------------- */
+void tagrec_mt19937_seed(uint32_t seed, uint32_t* state);
+int tagrec_sample_bpr_host(uint32_t* state, const int64_t* edges /*[e,2]*/, int64_t e, const int64_t* train_ptr,
+                           const int64_t* train_items_sorted, int64_t num_item, int64_t* triples_out /*[e,3]*/);
+int tagrec_sample_bpr_device(const int64_t* edges, int64_t e, const int64_t* train_ptr, const int32_t* train_items,
+                             int64_t num_item, uint64_t seed, uint64_t epoch, int64_t* triples_out, void* stream);
+
+/* Fused dense Adam (torch.optim.Adam semantics, com.py:25): one pass over param/grad/m/v. */
+int tagrec_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAGREC_B200_H */

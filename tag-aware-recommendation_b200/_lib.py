@@ -1,0 +1,97 @@
+"""ctypes binding of libtagrec_b200.so (the C ABI declared in include/tagrec_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.  The product never routes
+through the CPU oracle or through torch ops for the kernels it declares.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtagrec_b200.so")
+
+LONG_ROW = 4096       # TAGREC_LONG_ROW
+LONG_CHUNK = 2048     # TAGREC_LONG_CHUNK
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int
+_f32 = C.c_float
+_sz = C.c_size_t
+_u64 = C.c_uint64
+_u32 = C.c_uint32
+
+
+class CsrDesc(C.Structure):
+    """tagrec_csr_t"""
+    _fields_ = [("rowptr", _p), ("col", _p), ("val", _p), ("n_rows", _i64), ("long_rows", _p), ("item_slot", _p),
+                ("item_begin", _p), ("item_end", _p), ("n_long", _i64), ("n_items", _i64), ("long_scratch", _p),
+                ("long_counter", _p)]
+
+
+# name -> (restype, argtypes); must list every symbol of include/tagrec_b200.h (tests/test_abi.py checks that)
+PROTOTYPES = {
+    "tagrec_version": (_i32, []),
+    "tagrec_last_error": (C.c_char_p, []),
+    "tagrec_launch_count": (_u64, []),
+    "tagrec_csr_workspace_bytes": (_sz, [_i64]),
+    "tagrec_csr_build_structure": (_i32, [_p, _p, _i64, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i32, _p, _sz,
+                                          _p, _p, _p, _i64, _p, C.POINTER(_i64), _p]),
+    "tagrec_csr_normalise": (_i32, [_p, _p, _p, _p, _i64, _i32, _i32, _p, _p]),
+    "tagrec_spmm": (_i32, [C.POINTER(CsrDesc), _p, _p, _i32, _f32, _p]),
+    "tagrec_lightgcn_fwd_layer": (_i32, [C.POINTER(CsrDesc), _p, _p, _p, _i32, _i32, _i32, _f32, _p]),
+    "tagrec_lightgcn_bwd_layer": (_i32, [C.POINTER(CsrDesc), _p, _p, _p, _p, _p, _f32, _p, _i32, _p]),
+    "tagrec_bpr_fwd_bwd": (_i32, [_p, _i64, _i64, _p, _p, _i32, _f32, _i32, _p, _p, _p, _p]),
+    "tagrec_eval_topk": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p]),
+    "tagrec_eval_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "tagrec_eval_metrics": (_i32, [_p, _i64, _p, _i32, _p, _p, _p, _i32, _p, _p]),
+    "tagrec_mt19937_seed": (None, [_u32, _p]),
+    "tagrec_sample_bpr_host": (_i32, [_p, _p, _i64, _p, _p, _i64, _p]),
+    "tagrec_sample_bpr_device": (_i32, [_p, _i64, _p, _p, _i64, _u64, _u64, _p, _p]),
+    "tagrec_adam_step": (_i32, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _p]),
+}
+
+_lib = None
+
+
+class TagrecError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TagrecError(f"{LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              f"(nvcc -gencode arch=compute_100a,code=sm_100a); there is no CPU fallback")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().tagrec_last_error()
+        raise TagrecError(f"{what} failed with code {code}: {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / numpy array, None -> NULL."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def stream_ptr(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count():
+    return int(lib().tagrec_launch_count())

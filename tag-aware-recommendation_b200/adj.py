@@ -1,0 +1,200 @@
+"""Adjacency build -> device CSR + the SpMM primitive (drop-in for model/help/adj.py).
+
+``creat_adj(data, use_tag, norm_type, split_adj_k, device)`` keeps the reference's signature (adj.py:38-46) but
+returns a :class:`CsrGraph` (rowptr int64 / col int32 / val fp32 resident in HBM, built by K0 on the device)
+instead of an un-coalesced torch COO that is re-sorted on every multiply.  ``split_mm(graph, E)`` (adj.py:158-167)
+is the K1 SpMM kernel.  The only host arithmetic is ``np.power(degree, p)`` — numpy's float32 pow, the very call
+the reference makes (adj.py:93,105), needed for bit-exact values.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CsrDesc, LONG_CHUNK, LONG_ROW, check, lib, ptr, stream_ptr
+
+_NORM = {"bi_norm": (0, 0, -0.5), "si_norm": (1, 0, -1), "si_norm_self": (1, 1, -1), "ngcf": (1, 2, -1)}
+
+
+class CsrGraph:
+    """Normalised N x N adjacency in CSR on one device, plus the long-row plan K1 needs."""
+
+    def __init__(self, n, rowptr, col, val, val_t, weight, norm_type, num_list):
+        self.n = int(n)
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self.val_t = val_t if val_t is not None else val       # values of A^T (same tensor when A is symmetric)
+        self.weight = weight
+        self.norm_type = norm_type
+        self.num_list = list(num_list)
+        self.shape = (self.n, self.n)
+        self.device = rowptr.device
+        self._build_plan()
+
+    # --- torch-sparse-like accessors the reference's models use (dgcf.py:50, disengcn.py:27) ---
+    def _nnz(self):
+        return int(self.col.numel())
+
+    def row_ids(self):
+        deg = self.rowptr[1:] - self.rowptr[:-1]
+        return torch.repeat_interleave(torch.arange(self.n, device=self.device), deg)
+
+    def _indices(self):
+        return torch.stack([self.row_ids(), self.col.long()])
+
+    def _values(self):
+        return self.val
+
+    def _build_plan(self):
+        """Rows above TAGREC_LONG_ROW nnz are cut into TAGREC_LONG_CHUNK pieces (see csrc/spmm.cu)."""
+        dev = self.device
+        deg = self.rowptr[1:] - self.rowptr[:-1]
+        long_rows = torch.nonzero(deg > LONG_ROW).flatten()
+        self.n_long = int(long_rows.numel())
+        if self.n_long == 0:
+            self.long_rows = self.item_slot = self.item_begin = self.item_end = None
+            self.n_items = 0
+            self._scratch = {}
+            return
+        nchunks = (deg[long_rows] + LONG_CHUNK - 1) // LONG_CHUNK
+        slot = torch.repeat_interleave(torch.arange(self.n_long, device=dev), nchunks)
+        first = torch.cumsum(nchunks, 0) - nchunks
+        k = torch.arange(slot.numel(), device=dev) - first[slot]
+        begin = self.rowptr[long_rows][slot] + k * LONG_CHUNK
+        end = torch.minimum(begin + LONG_CHUNK, self.rowptr[long_rows + 1][slot])
+        self.long_rows = long_rows.to(torch.int32)
+        self.item_slot = slot.to(torch.int32)
+        self.item_begin, self.item_end = begin.contiguous(), end.contiguous()
+        self.n_items = int(slot.numel())
+        self._scratch = {}
+
+    def desc(self, dim, transposed=False):
+        """tagrec_csr_t for a launch at feature width ``dim`` (scratch rows are dim floats wide)."""
+        d = CsrDesc()
+        d.rowptr, d.col = ptr(self.rowptr), ptr(self.col)
+        d.val = ptr(self.val_t if transposed else self.val)
+        d.n_rows = self.n
+        d.n_long, d.n_items = self.n_long, self.n_items
+        if self.n_long:
+            if dim not in self._scratch:
+                self._scratch[dim] = (torch.zeros(self.n_long, dim, dtype=torch.float32, device=self.device),
+                                      torch.zeros(self.n_long, dtype=torch.int32, device=self.device))
+            scr, cnt = self._scratch[dim]
+            d.long_rows, d.item_slot = ptr(self.long_rows), ptr(self.item_slot)
+            d.item_begin, d.item_end = ptr(self.item_begin), ptr(self.item_end)
+            d.long_scratch, d.long_counter = ptr(scr), ptr(cnt)
+        return d
+
+    def row_slabs(self, k):
+        """adj.py:114-130 split_sp_mat row folds (kept for API parity; K1 always runs on the whole CSR)."""
+        f = self.n // k
+        return [(i * f, self.n if i == k - 1 else (i + 1) * f) for i in range(k)]
+
+
+def _as_dev_i64(x, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.int64), device=device)
+
+
+def build_csr(n_user, n_item, ui, norm_type, device, n_tag=0, ut=None, it=None):
+    """K0.  ``ui``/``ut``/``it`` = (row_idx, col_idx) pairs (numpy or torch), block-local ids, one entry per listed
+    pair (duplicates are summed like the reference's COO->LIL conversion, data/utils.py:50-53)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.TagrecError("tagrec_b200 builds and multiplies the adjacency on a CUDA device only (no CPU fallback)")
+    L = lib()
+    with torch.cuda.device(device):
+        st = stream_ptr(device)
+        mode, self_loops, power = _NORM.get(norm_type, (3, 0, None))
+        blocks = [(_as_dev_i64(ui[0], device), _as_dev_i64(ui[1], device))]
+        use_tag = ut is not None
+        if use_tag:
+            blocks += [(_as_dev_i64(ut[0], device), _as_dev_i64(ut[1], device)),
+                       (_as_dev_i64(it[0], device), _as_dev_i64(it[1], device))]
+        else:
+            blocks += [(None, None), (None, None)]
+        counts = [0 if r is None else int(r.numel()) for r, _ in blocks]
+        n = n_user + n_item + (n_tag if use_tag else 0)
+        m = 2 * sum(counts) + (n if self_loops else 0)
+        ws = torch.empty(int(L.tagrec_csr_workspace_bytes(m)), dtype=torch.uint8, device=device)
+        rowptr = torch.empty(n + 1, dtype=torch.int64, device=device)
+        col = torch.empty(max(m, 1), dtype=torch.int32, device=device)
+        weight = torch.empty(max(m, 1), dtype=torch.float32, device=device)
+        degree = torch.empty(n, dtype=torch.float32, device=device)
+        nnz = C.c_int64(0)
+        check(L.tagrec_csr_build_structure(ptr(blocks[0][0]), ptr(blocks[0][1]), counts[0],
+                                           ptr(blocks[1][0]), ptr(blocks[1][1]), counts[1],
+                                           ptr(blocks[2][0]), ptr(blocks[2][1]), counts[2],
+                                           n_user, n_item, n_tag if use_tag else 0, self_loops,
+                                           ptr(ws), ws.numel(), ptr(rowptr), ptr(col), ptr(weight), col.numel(),
+                                           ptr(degree), C.byref(nnz), st), "tagrec_csr_build_structure")
+        del ws
+        nnz = nnz.value
+        col = col[:nnz].clone() if nnz < col.numel() else col
+        weight = weight[:nnz].clone() if nnz < weight.numel() else weight
+        val_t = None
+        if mode == 3:
+            val = weight
+        else:
+            # adj.py:93-94 / 105-106 — numpy's float32 pow on the host, inf -> 0
+            with np.errstate(divide="ignore"):
+                dpow = np.power(degree.cpu().numpy(), power).astype(np.float32)
+            dpow[np.isinf(dpow)] = 0.0
+            dpow = torch.from_numpy(dpow).to(device)
+            val = torch.empty(nnz, dtype=torch.float32, device=device)
+            check(L.tagrec_csr_normalise(ptr(rowptr), ptr(col), ptr(weight), ptr(dpow), n, mode, self_loops,
+                                         ptr(val), st), "tagrec_csr_normalise")
+            if mode == 1:   # D^-1 A is not symmetric: backward needs the values of A^T = A D^-1
+                val_t = torch.empty(nnz, dtype=torch.float32, device=device)
+                check(L.tagrec_csr_normalise(ptr(rowptr), ptr(col), ptr(weight), ptr(dpow), n, 2, self_loops,
+                                             ptr(val_t), st), "tagrec_csr_normalise")
+        nums = [n_user, n_item] + ([n_tag] if use_tag else [])
+        return CsrGraph(n, rowptr, col, val, val_t, weight if mode != 3 else None, norm_type, nums)
+
+
+def creat_adj(data, use_tag, norm_type, split_adj_k, device):
+    """adj.py:38-46.  ``data.ui_adj`` / ``ut_adj`` / ``it_adj`` are scipy COO matrices (data/cf_load.py:24,
+    data/tgcn_load.py:21-22).  ``split_adj_k`` is accepted and ignored (one CSR)."""
+    ui = (data.ui_adj.row, data.ui_adj.col)
+    n_user, n_item = data.ui_adj.shape
+    if use_tag:
+        return build_csr(n_user, n_item, ui, norm_type, device, data.ut_adj.shape[1],
+                         (data.ut_adj.row, data.ut_adj.col), (data.it_adj.row, data.it_adj.col))
+    return build_csr(n_user, n_item, ui, norm_type, device)
+
+
+def spmm_raw(graph, x, out=None, transposed=False, beta=0.0):
+    """y = A x (or A^T x) through K1, no autograd."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    d = graph.desc(x.shape[1], transposed)
+    check(lib().tagrec_spmm(C.byref(d), ptr(x), ptr(out), x.shape[1], float(beta), stream_ptr(x.device)),
+          "tagrec_spmm")
+    return out
+
+
+class _SpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, graph, x):
+        ctx.graph = graph
+        return spmm_raw(graph, x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, spmm_raw(ctx.graph, g.contiguous(), transposed=True)
+
+
+def split_mm(norm_adj, all_embed):
+    """adj.py:158-167 — differentiable A @ E."""
+    return _SpMM.apply(norm_adj, all_embed)
+
+
+def node_drop(graph, keep_prob, training=False):
+    """adj.py:170-191.  Identity at the default p == 0 / eval; edge dropout with p > 0 is not implemented on the
+    CSR path (statistical parity only)."""
+    assert 0 <= keep_prob < 1
+    if keep_prob == 0 or not training:
+        return graph
+    raise NotImplementedError("node_drop > 0 is not supported by the CSR path")

@@ -1,0 +1,158 @@
+"""Full-sort evaluation loop — drop-in for training/basic_test.py:12-111 (+ training/utils.py).
+
+``Basic_test(data, args).run(model, istest=False, group_k=0)`` returns the same dict
+``{'recall': [per k], 'precision': [...], 'hr': [...], 'ndcg': [...], 'auc': [x]}`` (or a dict of such dicts keyed
+``inter<{n}-{count}`` when ``group_k > 1``).  Per user batch the model's ``eval_topk`` (K3) produces the masked
+top-K directly; metric sums stay on the device until the end.  Models without ``eval_topk`` go through
+``predict_rating`` + ``torch.topk`` exactly like the reference.
+
+Documented deviations: (i) ties are ordered by item id (the reference's torch.topk order is arbitrary);
+(ii) no crash when ``len(users) % test_batch == 0`` (the reference yields an empty batch and raises IndexError,
+training/utils.py:48-54).
+"""
+import time
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from . import config
+from .bpr_training_data import user_items_to_csr
+from .eval_ops import metric_sums
+
+
+def minibatch(data, batch_size):
+    """training/utils.py:48-54 without the trailing empty batch."""
+    for i in range(0, len(data), batch_size):
+        yield data[i:i + batch_size]
+
+
+def user_group_split(test_ui, train_ui, k, method="interaction"):
+    """training/utils.py:62-109 (method 'interaction': equal shares of the total interaction count)."""
+    num_inter = defaultdict(list)
+    tot_inter = 0
+    for u in test_ui.keys():
+        n_inter = len(test_ui[u]) + (len(train_ui[u]) if u in train_ui else 0)
+        num_inter[n_inter].append(u)
+        tot_inter += n_inter
+    step = tot_inter // k
+    end = list(range(step, tot_inter + 1, step))
+    end[-1] = tot_inter
+    groups, count, i, temp = dict(), 0, 0, []
+    for n in sorted(num_inter):
+        temp += num_inter[n]
+        count += n * len(num_inter[n])
+        if count >= end[i]:
+            groups[n] = temp
+            temp = []
+            i += 1
+            print(f"interaction < {n} has {len(groups[n])} user")
+    return groups
+
+
+def auc_rank_sum(scores_row, test_items):
+    """training/utils.py:37-45 for one user on the host (used only by the predict_rating fallback)."""
+    from sklearn.metrics import roc_auc_score
+    r_all = np.zeros((len(scores_row),))
+    r_all[test_items] = 1
+    keep = scores_row >= 0
+    return roc_auc_score(r_all[keep], scores_row[keep])
+
+
+class Basic_test():
+    def __init__(self, data, args=None):
+        cfg = config.current()
+        self.args = args
+        self.pos_ui = data.user_items['train']
+        self.true_ui = dict()
+        if cfg['has_val'] == True:
+            self.true_ui['val'] = data.user_items['val']
+        self.true_ui['test'] = data.user_items['test']
+        self.num_user = int(data.num['user'])
+        self._dev_csr = {}
+        print("Basic_test got ready!")
+
+    def _csr(self, name, dic, device):
+        key = (name, str(device))
+        if key not in self._dev_csr:
+            p, items = user_items_to_csr(dic, self.num_user)
+            self._dev_csr[key] = (torch.as_tensor(p, device=device), torch.as_tensor(items, device=device).to(torch.int32))
+        return self._dev_csr[key]
+
+    def epoch_test(self, model, true_name, true_ui, all_users=None):
+        cfg = config.current()
+        if all_users is None:
+            all_users = list(true_ui.keys())
+        topks = list(cfg['topks'])
+        max_k = max(topks)
+        device = cfg['device']
+        n = len(all_users)
+        if hasattr(model, "eval_topk"):
+            train_ptr, train_items = self._csr("train", self.pos_ui, device)
+            test_ptr, test_items = self._csr(true_name, true_ui, device)
+            sums = torch.zeros((4, len(topks)), dtype=torch.float64, device=device)
+            auc_sum = torch.zeros((), dtype=torch.float64, device=device)
+            want_auc = cfg.get('eval_auc', True) and hasattr(model, "eval_auc")
+            users_t = torch.as_tensor(np.asarray(all_users, dtype=np.int64), device=device)
+            for s in range(0, n, cfg['test_batch']):
+                ub = users_t[s:s + cfg['test_batch']]
+                ids, _ = model.eval_topk(ub, max_k, train_ptr, train_items)
+                metric_sums(ub, ids, test_ptr, test_items, topks, out=sums)
+                if want_auc:
+                    auc_sum += model.eval_auc(ub, train_ptr, train_items, test_ptr, test_items)
+            sums = (sums / n).cpu().numpy()
+            ret = {'recall': list(sums[0]), 'precision': [np.float32(x) for x in sums[1]], 'hr': list(sums[2]),
+                   'ndcg': list(sums[3])}
+            if want_auc:
+                ret['auc'] = [float(auc_sum.item()) / n]
+            return ret
+        return self._epoch_test_dense(model, true_ui, all_users, topks)
+
+    def _epoch_test_dense(self, model, true_ui, all_users, topks):
+        """The reference's own procedure (basic_test.py:30-80) for models that only offer predict_rating."""
+        cfg = config.current()
+        max_k, n = max(topks), len(all_users)
+        tot = {k: np.zeros(len(topks)) for k in ('recall', 'precision', 'hr', 'ndcg')}
+        auc = 0.0
+        with torch.no_grad():
+            for user in minibatch(all_users, cfg['test_batch']):
+                rating = model.predict_rating(torch.tensor(user, dtype=torch.long, device=cfg['device']))
+                rows, cols = [], []
+                for i, u in enumerate(user):
+                    its = self.pos_ui.get(u, [])
+                    rows.extend([i] * len(its))
+                    cols.extend(its)
+                rating[rows, cols] = -(1 << 10)
+                _, top = torch.topk(rating, k=max_k)
+                top = top.cpu().numpy()
+                rating_h = rating.cpu().numpy()
+                for i, u in enumerate(user):
+                    truth = true_ui[u]
+                    label = np.isin(top[i], truth).astype(np.float64)
+                    auc += auc_rank_sum(rating_h[i], truth)
+                    for q, k in enumerate(topks):
+                        right = label[:k].sum()
+                        tot['precision'][q] += right / k
+                        tot['recall'][q] += right / len(truth)
+                        tot['hr'][q] += right > 0
+                        disc = 1.0 / np.log2(np.arange(2, k + 2))
+                        idcg = disc[:min(k, len(truth))].sum() or 1.0
+                        tot['ndcg'][q] += (label[:k] * disc).sum() / idcg
+        ret = {k: list(v / n) for k, v in tot.items()}
+        ret['auc'] = [auc / n]
+        return ret
+
+    def run(self, model, istest=False, group_k=0):
+        cfg = config.current()
+        model.eval()
+        if istest == False and cfg['has_val']:
+            name = 'val'
+        else:
+            name = 'test'
+        true_ui = self.true_ui[name]
+        if group_k > 1:
+            all_result = dict()
+            for key, all_user in user_group_split(true_ui, self.pos_ui, group_k).items():
+                all_result[f"inter<{key}-{len(all_user)}"] = self.epoch_test(model, name, true_ui, all_user)
+            return all_result
+        return self.epoch_test(model, name, true_ui)

@@ -1,0 +1,189 @@
+// BPR negative sampler.  Replaces train_data/bpr_training_data.py:29-45 + train_data/utils.py:19-28,52-55
+// (a Python loop per edge inside forked workers, list-scan membership, np.vstack, np.random.shuffle, H2D).
+//
+// Two modes:
+//  * tagrec_sample_bpr_host   — parity mode, HOST code: the numpy-legacy MT19937 stream restated in C++
+//    (init_genrand seeding, one 32-bit output per masked-rejection attempt of randint, descending Fisher-Yates
+//    shuffle with the same bounded draw).  Bit-exact with the reference for cpu_core == 1: the
+//    negatives are drawn from a COPY of the generator (the forked worker), the caller's state is advanced only by
+//    the shuffle.
+//  * tagrec_sample_bpr_device — throughput mode, sm_100a kernel: Philox4x32-10 counter RNG keyed by
+//    (seed, epoch, edge, attempt), the same masked rejection for an unbiased item, membership by binary search in
+//    the user's ascending train row, and the epoch shuffle as an on-the-fly Feistel permutation of the edge index
+//    (no sort, no second pass).  Statistically equivalent to the reference, not the same stream.
+#include <vector>
+
+#include "common.cuh"
+
+namespace tagrec {
+
+// ------------------------------------------------------------------------------------------------ MT19937 (host)
+struct Mt {
+    uint32_t* mt;   // 624 words
+    uint32_t* pos;  // index of the next word, 624 == needs a twist
+    void twist() {
+        for (int k = 0; k < 624; ++k) {
+            const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+            mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        *pos = 0;
+    }
+    uint32_t next() {
+        if (*pos >= 624) twist();
+        uint32_t y = mt[(*pos)++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    // numpy random_interval / buffered_bounded_masked_uint32: uniform in [0, mx], mx < 2^32
+    uint32_t bounded(uint32_t mx) {
+        if (mx == 0) return 0;
+        uint32_t mask = mx;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+        uint32_t v;
+        while ((v = next() & mask) > mx) {}
+        return v;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ Philox (device)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x, uint32_t k) {
+    x ^= k;
+    x *= 0x9E3779B1u; x ^= x >> 15;
+    x *= 0x85EBCA77u; x ^= x >> 13;
+    x *= 0xC2B2AE3Du; x ^= x >> 16;
+    return x;
+}
+
+// Bijection on [0, n): 4-round Feistel network on 2*h bits with cycle walking.
+__device__ __forceinline__ uint64_t feistel_perm(uint64_t i, uint64_t n, int h, uint64_t key) {
+    const uint64_t half_mask = (1ull << h) - 1ull;
+    do {
+        uint64_t l = i >> h, r = i & half_mask;
+#pragma unroll
+        for (int round = 0; round < 4; ++round) {
+            const uint64_t f = mix32((uint32_t)r ^ (uint32_t)(r >> 32), (uint32_t)(key >> (8 * round)) + 0x632BE5ABu * round);
+            const uint64_t nl = r, nr = (l ^ f) & half_mask;
+            l = nl; r = nr;
+        }
+        i = (l << h) | r;
+    } while (i >= n);
+    return i;
+}
+
+__global__ void __launch_bounds__(256)
+sample_bpr_kernel(const int64_t* __restrict__ edges, int64_t e, const int64_t* __restrict__ train_ptr,
+                  const int32_t* __restrict__ train_items, uint32_t num_item, uint64_t seed, uint64_t epoch, int h,
+                  int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    const uint64_t src = feistel_perm((uint64_t)i, (uint64_t)e, h, seed * 0x9E3779B97F4A7C15ull + epoch);
+    const int64_t u = edges[2 * src], pos = edges[2 * src + 1];
+    const int64_t lo0 = train_ptr[u], hi0 = train_ptr[u + 1];
+    const uint32_t mx = num_item - 1;
+    uint32_t mask = mx;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    int64_t neg = -1;
+    for (uint32_t blk = 0; neg < 0; ++blk) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)src, (uint32_t)(src >> 32), (uint32_t)epoch, blk), key);
+        const uint32_t draws[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const uint32_t cand = draws[d] & mask;
+            if (neg >= 0 || cand > mx) continue;
+            int64_t lo = lo0, hi = hi0;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if ((uint32_t)__ldg(train_items + mid) < cand) lo = mid + 1; else hi = mid;
+            }
+            if (!(lo < hi0 && (uint32_t)__ldg(train_items + lo) == cand)) neg = cand;
+        }
+        if (blk > (1u << 20)) neg = 0;   // a user that interacted with every item: cannot happen in valid data
+    }
+    out[3 * i] = u;
+    out[3 * i + 1] = pos;
+    out[3 * i + 2] = neg;
+}
+
+}  // namespace tagrec
+
+using namespace tagrec;
+
+extern "C" void tagrec_mt19937_seed(uint32_t seed, uint32_t* state) {
+    // init_genrand — what np.random.seed(int) does
+    state[0] = seed;
+    for (uint32_t i = 1; i < 624; ++i) state[i] = 1812433253u * (state[i - 1] ^ (state[i - 1] >> 30)) + i;
+    state[624] = 624;
+}
+
+extern "C" int tagrec_sample_bpr_host(uint32_t* state, const int64_t* edges, int64_t e, const int64_t* train_ptr,
+                                      const int64_t* train_items_sorted, int64_t num_item, int64_t* triples_out) {
+    TAGREC_REQUIRE(state && edges && train_ptr && train_items_sorted && triples_out, "null pointer");
+    TAGREC_REQUIRE(num_item > 0 && num_item <= 0xffffffffll, "num_item out of range");
+    // the forked worker: a copy of the generator (bpr_training_data.py:37-39 with cpu_core == 1)
+    std::vector<uint32_t> wstate(state, state + 625);
+    Mt worker{wstate.data(), wstate.data() + 624};
+    std::vector<int64_t> tmp((size_t)e * 3);
+    for (int64_t k = 0; k < e; ++k) {
+        const int64_t u = edges[2 * k];
+        const int64_t* lo = train_items_sorted + train_ptr[u];
+        const int64_t* hi = train_items_sorted + train_ptr[u + 1];
+        int64_t neg;
+        for (;;) {                                               // train_data/utils.py:22-26
+            neg = (int64_t)worker.bounded((uint32_t)(num_item - 1));
+            const int64_t *a = lo, *b = hi;
+            while (a < b) {
+                const int64_t* mid = a + (b - a) / 2;
+                if (*mid < neg) a = mid + 1; else b = mid;
+            }
+            if (!(a < hi && *a == neg)) break;
+        }
+        tmp[3 * k] = u;
+        tmp[3 * k + 1] = edges[2 * k + 1];
+        tmp[3 * k + 2] = neg;
+    }
+    // the parent: np.random.shuffle(arange(e)) then data[index] (train_data/utils.py:52-55)
+    Mt parent{state, state + 624};
+    std::vector<int64_t> idx((size_t)e);
+    for (int64_t k = 0; k < e; ++k) idx[k] = k;
+    for (int64_t i = e - 1; i >= 1; --i) {
+        const int64_t j = (int64_t)parent.bounded((uint32_t)i);
+        std::swap(idx[i], idx[j]);
+    }
+    for (int64_t k = 0; k < e; ++k) {
+        triples_out[3 * k] = tmp[3 * idx[k]];
+        triples_out[3 * k + 1] = tmp[3 * idx[k] + 1];
+        triples_out[3 * k + 2] = tmp[3 * idx[k] + 2];
+    }
+    return TAGREC_OK;
+}
+
+extern "C" int tagrec_sample_bpr_device(const int64_t* edges, int64_t e, const int64_t* train_ptr,
+                                        const int32_t* train_items, int64_t num_item, uint64_t seed, uint64_t epoch,
+                                        int64_t* triples_out, void* stream) {
+    TAGREC_REQUIRE(edges && train_ptr && train_items && triples_out, "null pointer");
+    TAGREC_REQUIRE(num_item > 0 && num_item <= 0x7fffffffll, "num_item out of range");
+    if (e == 0) return TAGREC_OK;
+    int bits = 1;
+    while ((1ll << bits) < e) ++bits;
+    const int h = (bits + 1) / 2;
+    TAGREC_LAUNCH(sample_bpr_kernel, (unsigned)((e + 255) / 256), 256, 0, stream, edges, e, train_ptr, train_items,
+                  (uint32_t)num_item, seed, epoch, h, triples_out);
+    return TAGREC_OK;
+}

@@ -1,0 +1,159 @@
+"""Data containers the hot path consumes + deterministic synthetic graphs of the BASELINE shapes.
+
+The reference's loaders (data/cf_load.py, data/tgcn_load.py — out of scope, host I/O) hand the models an object with
+``num`` (dict user/item/tag/weight), ``ui_adj`` / ``ut_adj`` / ``it_adj`` (scipy COO float32), ``user_items``
+(dict split -> dict u -> list) and ``edge_index`` (dict split -> E x 2 ndarray).  :class:`Dataset` is that contract;
+``load_text`` reads the reference's file formats (train.txt / test.txt: ``u i1 i2 ...``; user_item_tag.txt:
+``u i t``; data/utils.py:9-46) and the ``synth_*`` functions generate graphs of the named shapes (SURVEY §8 d):
+user activity ~ lognormal, item popularity ~ Zipf(s), duplicates removed per user, 80/20 split per user.
+"""
+import os
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+
+class Dataset:
+    def __init__(self):
+        self.num, self.user_items, self.edge_index = {}, {}, {}
+        self.ui_adj = self.ut_adj = self.it_adj = None
+        self.uit_data = None
+
+
+def _coo(rows, cols, shape):
+    # data/utils.py:50-53 to_sparse_adj
+    return sp.coo_matrix((np.ones_like(rows), (rows, cols)), dtype=np.float32, shape=shape)
+
+
+def dict_edges(d):
+    """data/utils.py:121-129 dict_info: (E,2) in dict / list order."""
+    u = np.concatenate([np.full(len(v), k, dtype=np.int64) for k, v in d.items()]) if d else np.zeros(0, np.int64)
+    i = np.concatenate([np.asarray(v, dtype=np.int64) for v in d.values()]) if d else np.zeros(0, np.int64)
+    return np.stack([u, i], 1)
+
+
+def finish(ds, n_user, n_item, uit=None, n_tag=0):
+    ds.edge_index = {k: dict_edges(v) for k, v in ds.user_items.items()}
+    ds.num = {"user": int(n_user), "item": int(n_item)}
+    e = ds.edge_index["train"]
+    ds.ui_adj = _coo(e[:, 0], e[:, 1], (n_user, n_item))
+    if uit is not None:
+        ds.uit_data = np.unique(np.asarray(uit, dtype=np.int32), axis=0)           # data/utils.py:11-13
+        ds.num["tag"] = int(n_tag)
+        ds.ut_adj = _coo(ds.uit_data[:, 0], ds.uit_data[:, 2], (n_user, n_tag))
+        ds.it_adj = _coo(ds.uit_data[:, 1], ds.uit_data[:, 2], (n_item, n_tag))
+        ds.num["weight"] = int(max(ds.ui_adj.max(), ds.ut_adj.tocsr().max(), ds.it_adj.tocsr().max()))
+    return ds
+
+
+def load_text(file_dir, has_val=False):
+    """data/cf_load.py:8-28 + data/tgcn_load.py:11-25 on the reference's own file formats."""
+    def read(name):
+        out = {}
+        with open(os.path.join(file_dir, name)) as f:
+            for line in f:
+                x = [int(t) for t in line.strip().split(' ') if t]
+                if len(x) > 1:
+                    out[x[0]] = list(set(out.get(x[0], []) + x[1:]))
+        return out
+    ds = Dataset()
+    ds.user_items["train"] = read("train.txt")
+    if has_val:
+        ds.user_items["val"] = read("val.txt")
+    ds.user_items["test"] = read("test.txt")
+    mx_u = max(max(d) for d in ds.user_items.values())
+    mx_i = max(max(max(v) for v in d.values()) for d in ds.user_items.values())
+    uit_path = os.path.join(file_dir, "user_item_tag.txt")
+    uit = np.loadtxt(uit_path, dtype=np.int32).reshape(-1, 3) if os.path.exists(uit_path) else None
+    return finish(ds, mx_u + 1, mx_i + 1, uit, int(uit[:, 2].max()) + 1 if uit is not None else 0)
+
+
+def write_text(ds, file_dir):
+    os.makedirs(file_dir, exist_ok=True)
+    for part, d in ds.user_items.items():
+        with open(os.path.join(file_dir, f"{part}.txt"), "w") as f:
+            for u, its in d.items():
+                f.write(" ".join(str(x) for x in [u] + list(its)) + "\n")
+    if ds.uit_data is not None:
+        np.savetxt(os.path.join(file_dir, "user_item_tag.txt"), ds.uit_data, fmt="%d")
+
+
+def synth_bipartite(n_user, n_item, n_edge, seed=2020, zipf=0.9, sigma=1.0, test_frac=0.2, n_tag=0, tags_per_edge=1.5):
+    """Host (numpy) generator for the small/medium shapes (C1-C4).  ``n_edge`` counts train+test interactions."""
+    rng = np.random.RandomState(seed)
+    act = rng.lognormal(0.0, sigma, n_user)
+    pop = 1.0 / np.arange(1, n_item + 1) ** zipf
+    cdf = np.cumsum(pop / pop.sum())
+    perm = rng.permutation(n_item)                    # popularity is not correlated with the item id
+    want = float(n_edge)
+    for _ in range(6):                                # duplicates are dropped; re-draw until the count is close
+        deg = np.maximum(1, np.round(act / act.sum() * want)).astype(np.int64)
+        deg = np.minimum(deg, n_item // 2)
+        users = np.repeat(np.arange(n_user), deg)
+        items = perm[np.minimum(np.searchsorted(cdf, rng.rand(len(users))), n_item - 1)]
+        key = np.unique(users.astype(np.int64) * n_item + items)
+        if abs(len(key) - n_edge) <= 0.01 * n_edge:
+            break
+        want *= n_edge / len(key)
+    users, items = key // n_item, key % n_item
+    is_test = rng.rand(len(users)) < test_frac
+    # every user keeps at least one train item
+    first = np.r_[True, users[1:] != users[:-1]]
+    is_test[first] = False
+    ds = Dataset()
+    order = rng.permutation(len(users))               # list order inside a user is arbitrary in the files
+    users, items, is_test = users[order], items[order], is_test[order]
+    srt = np.argsort(users, kind="stable")
+    users, items, is_test = users[srt], items[srt], is_test[srt]
+    for part, m in (("train", ~is_test), ("test", is_test)):
+        u, i = users[m], items[m]
+        cut = np.flatnonzero(np.r_[True, u[1:] != u[:-1]])
+        ds.user_items[part] = {int(u[a]): i[a:b].tolist() for a, b in zip(cut, np.r_[cut[1:], len(u)])}
+    uit = None
+    if n_tag:
+        tu, ti = users[~is_test], items[~is_test]
+        k = rng.poisson(tags_per_edge, len(tu)).clip(0, 4)
+        ru, ri = np.repeat(tu, k), np.repeat(ti, k)
+        tp = 1.0 / np.arange(1, n_tag + 1) ** 0.8
+        tags = np.minimum(np.searchsorted(np.cumsum(tp / tp.sum()), rng.rand(len(ru))), n_tag - 1)
+        uit = np.stack([ru, ri, tags], 1)
+    return finish(ds, n_user, n_item, uit, n_tag)
+
+
+SHAPES = {
+    # BASELINE.json configs: total interactions; ~80 % land in train
+    "lastfm": dict(n_user=1892, n_item=17632, n_edge=92834),
+    "delicious_tags": dict(n_user=1867, n_item=69223, n_edge=104799, n_tag=40897),
+    "gowalla": dict(n_user=29858, n_item=40981, n_edge=1027370),
+    "amazon_book": dict(n_user=52643, n_item=91599, n_edge=2984108),
+}
+
+
+def synth_named(name, seed=2020):
+    return synth_bipartite(seed=seed, **SHAPES[name])
+
+
+def synth_bipartite_device(n_user, n_item, n_edge, device, seed=2020, zipf=0.9, sigma=1.0):
+    """Device (torch) generator for the 1 B-edge shape (C5): returns unique, (u, i)-sorted train pairs as int64
+    device tensors.  Counter-style: one pass, no host arrays, no global np.unique (SURVEY §8 d)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    act = torch.exp(torch.randn(n_user, generator=g, device=device, dtype=torch.float64) * sigma)
+    deg = torch.clamp((act / act.sum() * n_edge).round().to(torch.int64), 1, n_item // 2)
+    users = torch.repeat_interleave(torch.arange(n_user, device=device), deg)
+    m = users.numel()
+    # inverse CDF of a truncated power law p(k) ~ k^-s on [1, n_item]
+    a = 1.0 - zipf
+    r = torch.rand(m, generator=g, device=device, dtype=torch.float64)
+    rank = torch.pow(r * (float(n_item) ** a - 1.0) + 1.0, 1.0 / a).to(torch.int64).clamp_(1, n_item) - 1
+    del r
+    # scatter popularity over the id space with an affine bijection (multiplier coprime with n_item)
+    mult = 2654435761 % n_item
+    while np.gcd(mult, n_item) != 1:
+        mult += 1
+    items = (rank * mult + 12345) % n_item
+    del rank
+    key = torch.unique(users * n_item + items)        # sorted, duplicates removed
+    del users, items
+    return torch.div(key, n_item, rounding_mode="floor"), key % n_item

@@ -1,0 +1,12 @@
+"""Import alias: ``import tagrec_b200`` loads the package that lives in ``tag-aware-recommendation_b200/``
+(the directory name the project layout prescribes is not a valid Python identifier)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tag-aware-recommendation_b200")
+_spec = importlib.util.spec_from_file_location("tagrec_b200", os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["tagrec_b200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,83 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/tagrec_b200.h declares (no GPU calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+import tagrec_b200 as T
+from helpers import nums, user_lists
+from tagrec_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "tagrec_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tagrec_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = declared_symbols()
+    assert len(names) >= 15
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in tagrec_b200.h but not exported"
+        assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype in _lib.py"
+    assert sorted(_lib.PROTOTYPES) == names
+
+
+def test_version_and_error_text():
+    L = _lib.lib()
+    assert L.tagrec_version() >= 100
+    # argument validation needs no GPU: a null output pointer is rejected with text
+    rc = L.tagrec_spmm(None, None, None, 64, 0.0, None)
+    assert rc == -1 and b"null" in L.tagrec_last_error()
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libtagrec_b200.so")
+    try:
+        _lib.lib()
+        raise AssertionError("expected TagrecError")
+    except _lib.TagrecError as e:
+        assert "no CPU fallback" in str(e)
+
+
+def test_host_sampler_bit_exact_vs_reference(tiny, medium):
+    """tagrec_sample_bpr_host (C++, host) == the reference's BPR_training_data with cpu_core=1, two epochs."""
+    L = _lib.lib()
+    for g in (tiny, medium):
+        U, I, _, _ = nums(g)
+        ptr_, items = T.bpr_training_data.user_items_to_csr(user_lists(g, "train"), U)
+        state = np.empty(625, dtype=np.uint32)
+        L.tagrec_mt19937_seed(2020, _lib.ptr(state))
+        edges = np.ascontiguousarray(g["edge_index_train"], dtype=np.int64)
+        for want in (g["sampler_first"], g["sampler_second"]):
+            out = np.empty((len(edges), 3), dtype=np.int64)
+            rc = L.tagrec_sample_bpr_host(_lib.ptr(state), _lib.ptr(edges), len(edges), _lib.ptr(ptr_),
+                                          _lib.ptr(items), I, _lib.ptr(out))
+            assert rc == 0
+            assert np.array_equal(out, want)
+
+
+def test_sampler_class_mt19937_mode_uses_numpy_global_state(tiny):
+    """Drop-in class in parity mode: seeds come from np.random like the reference (init_seed -> np.random.seed)."""
+    import torch
+    U, I, _, _ = nums(tiny)
+    T.set_config("lightgcn", train_batch=64, cpu_core=1, sampler="mt19937", device=torch.device("cpu"))
+
+    class D:
+        pass
+    d = D()
+    d.num = {"user": U, "item": I}
+    d.user_items = {"train": user_lists(tiny, "train")}
+    d.edge_index = {"train": tiny["edge_index_train"]}
+    np.random.seed(2020)
+    s = T.BPR_training_data(d, None)
+    assert np.array_equal(s.all_train_data.numpy(), tiny["sampler_first"])
+    s.reset()
+    assert np.array_equal(s.all_train_data.numpy(), tiny["sampler_second"])
+    assert [len(b) for b in s.mini_batch()] == list(tiny["sampler_batch_sizes"])
