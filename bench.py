@@ -237,6 +237,9 @@ def run_ours(args):
     timer = Fn.KernelTimer()
     launches0 = T.launch_count()
     barrier()
+    profiling = os.environ.get("TAGREC_PROFILE") == "1"      # ncu --profile-from-start off captures region A only
+    if profiling:
+        torch.cuda.profiler.start()
     with ClockSampler(local) as clocks:
         Fn.KERNEL_TIMER = timer
         if small:
@@ -257,6 +260,8 @@ def run_ours(args):
             barrier()
             ms = a.elapsed_time(b)
         Fn.KERNEL_TIMER = None
+    if profiling:
+        torch.cuda.profiler.stop()
     launches = T.launch_count() - launches0
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -284,6 +289,13 @@ def run_ours(args):
     e2e = {"value": BATCH * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 8, "d2h_bytes_per_step": 8,
            "last_loss": last}
 
+    per_rank = None
+    if world > 1:
+        mine = {"rank": rank, "fwd_ms": timer.mean_ms("spmm_fwd"), "bwd_ms": timer.mean_ms("spmm_bwd"),
+                "all_gather_ms": timer.mean_ms("all_gather"), "all_gathers_per_step": timer.count("all_gather") // K,
+                "nnz": info["nnz"], "rows": info["n"]}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -312,6 +324,8 @@ def run_ours(args):
                                                 nnz=info["nnz"], nodes=info["n"], long_rows=info["n_long_rows"]),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline,
             "setup_s": round(setup_s, 1)}
+    if per_rank:
+        line["per_rank"] = per_rank
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_reference(sample_shape(shape), 3, 1, info["nnz"])
         line["cpu_baseline"] = cb

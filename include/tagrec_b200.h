@@ -83,11 +83,13 @@ int tagrec_csr_normalise(const int64_t* rowptr, const int32_t* col, const float*
 #define TAGREC_LONG_CHUNK 2048
 
 typedef struct {
-    const int64_t* rowptr;
-    const int32_t* col;
+    const int64_t* rowptr;      /* n_rows + 1 entries, local (rowptr[0] == 0 for a row block) */
+    const int32_t* col;         /* GLOBAL column ids: rows of the gathered table */
     const float* val;
-    int64_t n_rows;
-    const int32_t* long_rows;
+    int64_t n_rows;             /* rows of this block */
+    int64_t row_offset;         /* global id of local row 0: every epilogue table (y, acc, e_k, g_final, ...) is a
+                                   full-size table indexed by row_offset + r; 0 on a single GPU */
+    const int32_t* long_rows;   /* LOCAL row ids */
     const int32_t* item_slot;
     const int64_t* item_begin;
     const int64_t* item_end;

@@ -18,4 +18,5 @@ from .bpr_training_data import Abstract_training_data, BPR_training_data        
 from .basic_train import Basic_train, epoch_training           # noqa: F401
 from .basic_test import Basic_test                             # noqa: F401
 from .early_stop import Early_stop                             # noqa: F401
-from . import data                                             # noqa: F401
+from .optim import FusedAdam                                   # noqa: F401
+from . import data, distributed                                # noqa: F401

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtagrec_b200.so")
+LIB_PATH = os.environ.get("TAGREC_LIB") or os.path.join(_HERE, "libtagrec_b200.so")   # TAGREC_LIB: tuning builds
 
 LONG_ROW = 4096       # TAGREC_LONG_ROW
 LONG_CHUNK = 2048     # TAGREC_LONG_CHUNK
@@ -23,7 +23,7 @@ _u32 = C.c_uint32
 
 class CsrDesc(C.Structure):
     """tagrec_csr_t"""
-    _fields_ = [("rowptr", _p), ("col", _p), ("val", _p), ("n_rows", _i64), ("long_rows", _p), ("item_slot", _p),
+    _fields_ = [("rowptr", _p), ("col", _p), ("val", _p), ("n_rows", _i64), ("row_offset", _i64), ("long_rows", _p), ("item_slot", _p),
                 ("item_begin", _p), ("item_end", _p), ("n_long", _i64), ("n_items", _i64), ("long_scratch", _p),
                 ("long_counter", _p)]
 

@@ -20,8 +20,11 @@ _NORM = {"bi_norm": (0, 0, -0.5), "si_norm": (1, 0, -1), "si_norm_self": (1, 1, 
 class CsrGraph:
     """Normalised N x N adjacency in CSR on one device, plus the long-row plan K1 needs."""
 
-    def __init__(self, n, rowptr, col, val, val_t, weight, norm_type, num_list):
-        self.n = int(n)
+    def __init__(self, n, rowptr, col, val, val_t, weight, norm_type, num_list, row_offset=0, comm=None):
+        self.n = int(n)                                    # rows of the tables it multiplies (global node count)
+        self.n_rows = int(rowptr.numel()) - 1              # rows stored here (== n unless this is a rank's row block)
+        self.row_offset = int(row_offset)
+        self.comm = comm                                   # distributed.RowComm when the rows are sharded
         self.rowptr, self.col, self.val = rowptr, col, val
         self.val_t = val_t if val_t is not None else val       # values of A^T (same tensor when A is symmetric)
         self.weight = weight
@@ -37,7 +40,7 @@ class CsrGraph:
 
     def row_ids(self):
         deg = self.rowptr[1:] - self.rowptr[:-1]
-        return torch.repeat_interleave(torch.arange(self.n, device=self.device), deg)
+        return torch.repeat_interleave(torch.arange(self.n_rows, device=self.device) + self.row_offset, deg)
 
     def _indices(self):
         return torch.stack([self.row_ids(), self.col.long()])
@@ -73,7 +76,8 @@ class CsrGraph:
         d = CsrDesc()
         d.rowptr, d.col = ptr(self.rowptr), ptr(self.col)
         d.val = ptr(self.val_t if transposed else self.val)
-        d.n_rows = self.n
+        d.n_rows = self.n_rows
+        d.row_offset = self.row_offset
         d.n_long, d.n_items = self.n_long, self.n_items
         if self.n_long:
             if dim not in self._scratch:

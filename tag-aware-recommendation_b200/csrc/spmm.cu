@@ -41,42 +41,59 @@ __device__ __forceinline__ float sub_sum(float v, unsigned mask) {
     return v;
 }
 
+// Tuning knobs (compile-time; defaults = the configuration measured best on B200, see profiles/):
+//   SPMM_U     gathers issued back to back per lane before the first FMA (rows in flight per sub-warp)
+//   SPMM_WPB   warps per block (small blocks: a block retires as soon as its few rows are done)
+//   SPMM_MINB  __launch_bounds__ min blocks per SM (caps registers so that SPMM_WPB*SPMM_MINB warps are resident)
+#ifndef SPMM_U
+#define SPMM_U 8
+#endif
+#ifndef SPMM_WPB
+#define SPMM_WPB 2
+#endif
+#ifndef SPMM_MINB
+#define SPMM_MINB 16
+#endif
+
 // acc = sum_{j in [begin,end), chunk(j) == part (mod nparts)} val[j] * x[col[j]]   for this lane's float4 slice.
 template <int LPR>
 __device__ __forceinline__ float4 gather_rows(const int32_t* __restrict__ col, const float* __restrict__ val,
                                               const float4* __restrict__ x4, int64_t begin, int64_t end, int part,
                                               int nparts, int sl, unsigned mask) {
+    constexpr int U = SPMM_U < LPR ? SPMM_U : LPR;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int64_t base = begin + (int64_t)part * LPR;
-    const int64_t step = (int64_t)nparts * LPR;
+    const int32_t* __restrict__ colp = col + begin;
+    const float* __restrict__ valp = val + begin;
+    const int len = (int)(end - begin);          // a row (or chunk) never exceeds 2^31 entries
+    const int step = nparts * LPR;
+    int base = part * LPR;
     int c = 0;
     float v = 0.f;
-    if (base + sl < end) {
-        c = __ldcs(col + base + sl);
-        v = __ldcs(val + base + sl);
+    if (base + sl < len) {
+        c = __ldcs(colp + base + sl);
+        v = __ldcs(valp + base + sl);
     }
-    while (base < end) {
-        const int64_t nbase = base + step;
+    const float4* __restrict__ xs = x4 + sl;
+    while (base < len) {
+        const int nbase = base + step;
         int cn = 0;
         float vn = 0.f;
-        if (nbase + sl < end) {  // prefetch the next index chunk while this chunk's rows are in flight
-            cn = __ldcs(col + nbase + sl);
-            vn = __ldcs(val + nbase + sl);
+        if (nbase + sl < len) {  // prefetch the next index chunk while this chunk's rows are in flight
+            cn = __ldcs(colp + nbase + sl);
+            vn = __ldcs(valp + nbase + sl);
         }
-        const int cnt = (int)min((int64_t)LPR, end - base);
+        const int cnt = min(LPR, len - base);
 #pragma unroll
-        for (int j0 = 0; j0 < LPR; j0 += 8) {
+        for (int j0 = 0; j0 < LPR; j0 += U) {
             if (j0 < cnt) {
-                float4 xv[8];
-                float vv[8];
+                float4 xv[U];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < U; ++j) {
                     const int cj = __shfl_sync(mask, c, j0 + j, LPR);
-                    vv[j] = __shfl_sync(mask, v, j0 + j, LPR);
-                    xv[j] = (j0 + j < cnt) ? ldg4(x4 + (int64_t)cj * LPR + sl) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xv[j] = (j0 + j < cnt) ? ldg4(xs + (int64_t)cj * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) fma4(acc, vv[j], xv[j]);
+                for (int j = 0; j < U; ++j) fma4(acc, __shfl_sync(mask, v, j0 + j, LPR), xv[j]);
             }
         }
         c = cn;
@@ -174,10 +191,10 @@ __device__ __forceinline__ float4 combine_subs(float4 p) {
     return p;
 }
 
-constexpr int kWarpsPerBlock = 8;
+constexpr int kWarpsPerBlock = SPMM_WPB;
 
 template <int LPR, int EPI>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, SPMM_MINB)
 spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_blocks, int gather) {
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31;
@@ -210,7 +227,7 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
             const float4 tot = __ldcg(scr);
             __stcg(scr, make_float4(0.f, 0.f, 0.f, 0.f));
             if (lane == 0) a.long_counter[slot] = 0;
-            epilogue<LPR, EPI>(ep, r, tot, sl, mask);
+            epilogue<LPR, EPI>(ep, r + a.row_offset, tot, sl, mask);
         }
         return;
     }
@@ -255,7 +272,7 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
             }
         }
     }
-    if (valid && !is_long) epilogue<LPR, EPI>(ep, r, acc, sl, mask);
+    if (valid && !is_long) epilogue<LPR, EPI>(ep, r + a.row_offset, acc, sl, mask);
 }
 
 template <int EPI>

@@ -62,6 +62,10 @@ def lightgcn_forward_layers(graph, e0, n_layer, raw, final):
         if t:
             t.stop("spmm_fwd")
         x = raw[k]
+        if graph.comm is not None and k < n_layer - 1:
+            graph.comm.all_gather_rows(x)                 # the next layer gathers rows of every rank
+    if graph.comm is not None:
+        graph.comm.all_gather_rows(final)
     return final
 
 
@@ -83,12 +87,16 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
         if t:
             t.stop(name)
         g_next = out
+        if graph.comm is not None:
+            graph.comm.all_gather_rows(g_next)
     if t:
         t.start("spmm_bwd")
     check(L.tagrec_lightgcn_bwd_layer(C.byref(d), ptr(g_next), None, ptr(g_final), ptr(reg_grad), ptr(upstream), inv,
                                       ptr(g_out), dim, st), "tagrec_lightgcn_bwd_layer")
     if t:
         t.stop("spmm_bwd")
+    if graph.comm is not None:
+        graph.comm.all_gather_rows(g_out)
     return g_out
 
 

@@ -345,3 +345,19 @@ def test_fused_adam_vs_torch():
         check(lib().tagrec_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), 0.01, 0.9, 0.999, 1e-8, 0.0, step,
                                      stream_ptr()), "adam")
     assert relerr(p.cpu().numpy(), ref.detach().cpu().numpy()) < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------------- multi-GPU
+def test_multi_gpu_sharded_step_matches_single():
+    """Only on boxes with >= 2 GPUs (gpurun --gpus 2): torchrun tests/multi_gpu_check.py."""
+    import os
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
