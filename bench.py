@@ -154,7 +154,8 @@ def run_reference(args):
 
 
 def config_of(args, shape):
-    return {"workload": f"LightGCN {LAYERS}-layer dim-{DIM} BPR batch {BATCH}, synthetic {shape['n_user']} users x "
+    return {"optimizer": "tagrec_b200.FusedAdam" if getattr(args, "optimizer", "fused") == "fused" else "torch.optim.Adam",
+            "workload": f"LightGCN {LAYERS}-layer dim-{DIM} BPR batch {BATCH}, synthetic {shape['n_user']} users x "
                         f"{shape['n_item']} items, ~{shape['n_edge']} interactions ({args.workload}); full-graph "
                         f"propagation fwd+bwd + Adam every step (reference semantics)",
             "batch": BATCH, "dim": DIM, "layers": LAYERS, "l2": "inputs larger than L2 (tables >> 126 MB)"
@@ -211,7 +212,9 @@ def run_ours(args):
                                                            T._lib.ptr(triples), T._lib.stream_ptr(dev)), "sampler")
         del edges, train_items
         info = {"nnz": graph._nnz(), "n": graph.n, "n_long_rows": graph.n_long, "parallelism": "single"}
-    opt = torch.optim.Adam(model.parameters(), lr=0.001)
+    # com.py:25 composes optim.Adam(model.parameters(), lr); FusedAdam is this package's drop-in for it (same update
+    # rule, one kernel per tensor).  --optimizer torch runs the reference's own choice.
+    opt = (T.FusedAdam if args.optimizer == "fused" else torch.optim.Adam)(model.parameters(), lr=0.001)
     model.train()
     torch.cuda.synchronize()
     setup_s = time.time() - t0
@@ -293,6 +296,7 @@ def run_ours(args):
     if world > 1:
         mine = {"rank": rank, "fwd_ms": timer.mean_ms("spmm_fwd"), "bwd_ms": timer.mean_ms("spmm_bwd"),
                 "all_gather_ms": timer.mean_ms("all_gather"), "all_gathers_per_step": timer.count("all_gather") // K,
+                "barrier_ms": timer.mean_ms("barrier"),
                 "nnz": info["nnz"], "rows": info["n"]}
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
@@ -308,7 +312,7 @@ def run_ours(args):
     achieved = bytes_per_launch / (fwd_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         try:
             traffic = json.load(open(tp)).get(args.workload)
         except Exception:
@@ -326,6 +330,7 @@ def run_ours(args):
             "setup_s": round(setup_s, 1)}
     if per_rank:
         line["per_rank"] = per_rank
+        line["partition"] = {k: info.get(k) for k in ("bounds", "type_weight_s_per_nnz", "balance_feedback")}
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_reference(sample_shape(shape), 3, 1, info["nnz"])
         line["cpu_baseline"] = cb
@@ -374,6 +379,7 @@ def main():
     ap.add_argument("--workload", default="lightgcn_1b", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-users", type=int, default=16384)
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

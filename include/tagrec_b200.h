@@ -99,6 +99,19 @@ typedef struct {
     int32_t* long_counter;
 } tagrec_csr_t;
 
+/* Fused compute + collective (multi-GPU, no reference equivalent — the reference is single-device): where an
+ * output row of K1 is stored.  n == 0 / NULL: the local table only.  n >= 1: the same [N, dim] table on n ranks of
+ * one NVSwitch domain; base[r] = rank r's copy mapped into this process (CUDA peer / symmetric memory), base[self]
+ * included.  A single NVLS multicast address is expressed as n == 1.  The row block's all-gather then happens
+ * inside the SpMM epilogue (stores over NVLink 5 overlap the gathers from HBM); the caller places a cross-rank
+ * barrier between this launch and the first launch that reads the table. */
+#define TAGREC_MAX_PEERS 8
+typedef struct {
+    int32_t n;
+    int32_t self;
+    void* base[TAGREC_MAX_PEERS];
+} tagrec_mirror_t;
+
 /* y = A x (+ beta*y)                        adj.py:162,166; also A^T g when given the transposed values. */
 int tagrec_spmm(const tagrec_csr_t* a, const float* x, float* y, int dim, float beta, void* stream);
 
@@ -106,6 +119,10 @@ int tagrec_spmm(const tagrec_csr_t* a, const float* x, float* y, int dim, float 
  *   acc = (first ? x : acc) + y / max(||y||_2, 1e-12);  if (last) acc *= final_scale   [final_scale = 1/(L+1)] */
 int tagrec_lightgcn_fwd_layer(const tagrec_csr_t* a, const float* x, float* y, float* acc, int dim, int first,
                               int last, float final_scale, void* stream);
+
+int tagrec_lightgcn_fwd_layer_p2p(const tagrec_csr_t* a, const float* x, float* y, float* acc, int dim, int first,
+                                  int last, float final_scale, const tagrec_mirror_t* y_mirror,
+                                  const tagrec_mirror_t* acc_mirror, void* stream);
 
 /* One backward layer of the same (closed form of autograd through lightgcn.py:55-60):
  *   gy = g_final * (upstream ? upstream[0] : 1) * inv_layers
@@ -116,6 +133,10 @@ int tagrec_lightgcn_fwd_layer(const tagrec_csr_t* a, const float* x, float* y, f
 int tagrec_lightgcn_bwd_layer(const tagrec_csr_t* a, const float* g_next, const float* e_k, const float* g_final,
                               const float* reg_grad, const float* upstream, float inv_layers, float* g_out,
                               int dim, void* stream);
+
+int tagrec_lightgcn_bwd_layer_p2p(const tagrec_csr_t* a, const float* g_next, const float* e_k, const float* g_final,
+                                  const float* reg_grad, const float* upstream, float inv_layers, float* g_out,
+                                  int dim, const tagrec_mirror_t* out_mirror, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K2  fused BPR step            replaces model/lightgcn.py:68-82 / model/ngcf.py:95-105 (3 gathers, mul_loss,

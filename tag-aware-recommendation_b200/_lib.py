@@ -28,6 +28,11 @@ class CsrDesc(C.Structure):
                 ("long_counter", _p)]
 
 
+class MirrorDesc(C.Structure):
+    """tagrec_mirror_t"""
+    _fields_ = [("n", C.c_int32), ("self", C.c_int32), ("base", _p * 8)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/tagrec_b200.h (tests/test_abi.py checks that)
 PROTOTYPES = {
     "tagrec_version": (_i32, []),
@@ -40,6 +45,10 @@ PROTOTYPES = {
     "tagrec_spmm": (_i32, [C.POINTER(CsrDesc), _p, _p, _i32, _f32, _p]),
     "tagrec_lightgcn_fwd_layer": (_i32, [C.POINTER(CsrDesc), _p, _p, _p, _i32, _i32, _i32, _f32, _p]),
     "tagrec_lightgcn_bwd_layer": (_i32, [C.POINTER(CsrDesc), _p, _p, _p, _p, _p, _f32, _p, _i32, _p]),
+    "tagrec_lightgcn_fwd_layer_p2p": (_i32, [C.POINTER(CsrDesc), _p, _p, _p, _i32, _i32, _i32, _f32,
+                                             C.POINTER(MirrorDesc), C.POINTER(MirrorDesc), _p]),
+    "tagrec_lightgcn_bwd_layer_p2p": (_i32, [C.POINTER(CsrDesc), _p, _p, _p, _p, _p, _f32, _p, _i32,
+                                             C.POINTER(MirrorDesc), _p]),
     "tagrec_bpr_fwd_bwd": (_i32, [_p, _i64, _i64, _p, _p, _i32, _f32, _i32, _p, _p, _p, _p]),
     "tagrec_eval_topk": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "tagrec_eval_workspace_bytes": (_sz, [_i64, _i64, _i32]),

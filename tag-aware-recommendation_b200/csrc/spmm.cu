@@ -22,7 +22,27 @@ namespace tagrec {
 
 enum { EPI_PLAIN = 0, EPI_FWD = 1, EPI_BWD = 2, EPI_BWD0 = 3 };
 
+// Where an output row is stored.  n == 0: the local table only.  n >= 1: the same table on n ranks of one NVSwitch
+// domain — base[r] is rank r's copy mapped into this process (peer memory over NVLink 5), or a single NVLS
+// multicast address (n == 1) that the switch replicates to every rank.  This is the all-gather of the sharded path,
+// fused into the SpMM epilogue: rows cross NVLink while the next rows are still being gathered from HBM.
+struct Mirror {
+    int n;
+    float* base[TAGREC_MAX_PEERS];
+};
+
+__device__ __forceinline__ void store_row(float* local, const Mirror& m, int64_t o, const float4& v) {
+    if (m.n == 0) {
+        reinterpret_cast<float4*>(local)[o] = v;
+        return;
+    }
+#pragma unroll
+    for (int p = 0; p < TAGREC_MAX_PEERS; ++p)
+        if (p < m.n) reinterpret_cast<float4*>(m.base[p])[o] = v;
+}
+
 struct Epi {
+    Mirror my, macc;        // mirrors of y / acc (n == 0: local only)
     float* y;               // output rows (plain / fwd: raw layer, bwd: g_out)
     const float* x0;        // fwd, first layer: source of the accumulator (E0)
     float* acc;             // fwd: running sum
@@ -120,7 +140,7 @@ __device__ __forceinline__ void epilogue(const Epi& ep, int64_t r, float4 acc, i
         // lightgcn.py:55-60: raw layer propagates, normalised copy joins the mean
         const float ss = sub_sum<LPR>(dot4(acc, acc), mask);
         const float nrm = fmaxf(sqrtf(ss), 1e-12f);
-        reinterpret_cast<float4*>(ep.y)[o] = acc;
+        store_row(ep.y, ep.my, o, acc);
         float4* a4 = reinterpret_cast<float4*>(ep.acc);
         float4 a = ep.first ? __ldg(reinterpret_cast<const float4*>(ep.x0) + o) : a4[o];
         a.x += acc.x / nrm;
@@ -133,7 +153,7 @@ __device__ __forceinline__ void epilogue(const Epi& ep, int64_t r, float4 acc, i
             a.z *= ep.scale;
             a.w *= ep.scale;
         }
-        a4[o] = a;
+        store_row(ep.acc, ep.macc, o, a);
     } else {
         const float up0 = ep.upstream ? __ldg(ep.upstream) : 1.f;
         const float s = ep.scale * up0;
@@ -175,7 +195,7 @@ __device__ __forceinline__ void epilogue(const Epi& ep, int64_t r, float4 acc, i
                 out.w = fmaf(up1, rg.w, out.w);
             }
         }
-        reinterpret_cast<float4*>(ep.y)[o] = out;
+        store_row(ep.y, ep.my, o, out);
     }
 }
 
@@ -316,10 +336,30 @@ extern "C" int tagrec_spmm(const tagrec_csr_t* a, const float* x, float* y, int 
     return launch<EPI_PLAIN>(a, x, ep, dim, 1, stream);
 }
 
+static int set_mirror(Mirror& m, const tagrec_mirror_t* src) {
+    m.n = 0;
+    if (!src || src->n == 0) return TAGREC_OK;
+    TAGREC_REQUIRE(src->n >= 1 && src->n <= TAGREC_MAX_PEERS, "mirror: bad rank count");
+    m.n = src->n;
+    for (int p = 0; p < src->n; ++p) {
+        TAGREC_REQUIRE(src->base[p], "mirror: null base pointer");
+        m.base[p] = static_cast<float*>(src->base[p]);
+    }
+    return TAGREC_OK;
+}
+
 extern "C" int tagrec_lightgcn_fwd_layer(const tagrec_csr_t* a, const float* x, float* y, float* acc, int dim,
                                          int first, int last, float final_scale, void* stream) {
+    return tagrec_lightgcn_fwd_layer_p2p(a, x, y, acc, dim, first, last, final_scale, nullptr, nullptr, stream);
+}
+
+extern "C" int tagrec_lightgcn_fwd_layer_p2p(const tagrec_csr_t* a, const float* x, float* y, float* acc, int dim,
+                                             int first, int last, float final_scale, const tagrec_mirror_t* y_mirror,
+                                             const tagrec_mirror_t* acc_mirror, void* stream) {
     TAGREC_REQUIRE(y && acc, "y/acc is null");
     Epi ep{};
+    if (int rc = set_mirror(ep.my, y_mirror)) return rc;
+    if (int rc = set_mirror(ep.macc, acc_mirror)) return rc;
     ep.y = y;
     ep.x0 = x;
     ep.acc = acc;
@@ -332,8 +372,17 @@ extern "C" int tagrec_lightgcn_fwd_layer(const tagrec_csr_t* a, const float* x, 
 extern "C" int tagrec_lightgcn_bwd_layer(const tagrec_csr_t* a, const float* g_next, const float* e_k,
                                          const float* g_final, const float* reg_grad, const float* upstream,
                                          float inv_layers, float* g_out, int dim, void* stream) {
+    return tagrec_lightgcn_bwd_layer_p2p(a, g_next, e_k, g_final, reg_grad, upstream, inv_layers, g_out, dim, nullptr,
+                                         stream);
+}
+
+extern "C" int tagrec_lightgcn_bwd_layer_p2p(const tagrec_csr_t* a, const float* g_next, const float* e_k,
+                                             const float* g_final, const float* reg_grad, const float* upstream,
+                                             float inv_layers, float* g_out, int dim,
+                                             const tagrec_mirror_t* out_mirror, void* stream) {
     TAGREC_REQUIRE(g_final && g_out, "g_final/g_out is null");
     Epi ep{};
+    if (int rc = set_mirror(ep.my, out_mirror)) return rc;
     ep.y = g_out;
     ep.e_k = e_k;
     ep.g_final = g_final;

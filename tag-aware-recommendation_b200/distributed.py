@@ -13,6 +13,8 @@ per layer, forward and backward (A is symmetric for bi_norm, so the backward use
 Parameters and optimizer state stay replicated (state_dict / external optim.Adam unchanged, SURVEY §8 e): every row
 of the gradient is computed by exactly one rank and broadcast, so the replicas stay bit-identical.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -20,8 +22,10 @@ import torch.distributed as dist
 from .adj import CsrGraph
 
 
-def partition_rows(rowptr, world, type_bounds=None, type_weight=None, row_cost=3.0):
+def partition_rows(rowptr, world, type_bounds=None, type_weight=None, row_cost=3.0, range_scale=None):
     """Contiguous row ranges with (almost) equal COST.  cost(row) = w[type(row)] * nnz(row) + row_cost * min(w):
+    ``range_scale`` = (bounds, factors): multiply the modelled cost of the rows of each old range by a measured
+    correction (one feedback step on the real fused kernel, see build_sharded_lightgcn).
     ``type_bounds`` = cumulative node counts [0, n_user, n_user+n_item, ...] and ``type_weight`` = measured seconds
     per nnz of each node type (rows of popular-column blocks hit L2 and are cheaper than rows whose neighbours are
     spread over a table far larger than L2); both None -> plain nnz balance.  The per-row term stands for the
@@ -35,7 +39,11 @@ def partition_rows(rowptr, world, type_bounds=None, type_weight=None, row_cost=3
             w[type_bounds[t]:type_bounds[t + 1]] = float(wt)
         cost = deg * w + row_cost * float(min(type_weight))
     else:
-        cost = deg
+        cost = deg + row_cost
+    if range_scale is not None:                          # feedback: (old_bounds, measured/predicted factor per range)
+        old, fac = range_scale
+        for p in range(len(fac)):
+            cost[old[p]:old[p + 1]] *= float(fac[p])
     cum = torch.cat([torch.zeros(1, dtype=torch.float64, device=rp.device), torch.cumsum(cost, 0)])
     total = float(cum[-1])
     targets = torch.tensor([total * p / world for p in range(1, world)], dtype=torch.float64, device=rp.device)
@@ -81,12 +89,60 @@ def slice_csr(rowptr, col, val, lo, hi):
     return (rowptr[lo:hi + 1] - rowptr[lo]).clone(), col[a:b].clone(), (val[a:b].clone() if val is not None else None)
 
 
+class PeerTables:
+    """Full-size tables in symmetric memory (torch.distributed._symmetric_memory: cuMem allocations mapped into every
+    rank of the NVSwitch domain).  A table allocated here can be the target of K1's fused epilogue stores
+    (tagrec_mirror_t): every rank writes its row block straight into every rank's copy — through the NVLS multicast
+    address when the fabric offers one, else through the per-peer mappings — and ``barrier()`` (a device-side
+    signal exchange on the current stream) separates producers from the next kernel that gathers from the table."""
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem, self.group, self.device = symm_mem, group or dist.group.WORLD, device
+        self.tables = {}
+        self.use_multicast = os.environ.get("TAGREC_MULTICAST", "1") != "0"
+        self.kind = None
+
+    def table(self, name, shape):
+        """(tensor, MirrorDesc) — allocated and rendezvoused once (collective: all ranks must ask in the same order)."""
+        from ._lib import MirrorDesc
+        ent = self.tables.get(name)
+        if ent is None or tuple(ent[0].shape) != tuple(shape):
+            t = self.symm_mem.empty(*shape, dtype=torch.float32, device=self.device)
+            hdl = self.symm_mem.rendezvous(t, self.group)
+            m = MirrorDesc()
+            m.self = hdl.rank
+            mc = int(hdl.multicast_ptr or 0) if self.use_multicast else 0
+            if mc:
+                m.n = 1
+                m.base[0] = mc
+                self.kind = "nvls-multicast"
+            else:
+                m.n = hdl.world_size
+                for r in range(hdl.world_size):
+                    m.base[r] = int(hdl.buffer_ptrs[r])
+                self.kind = "peer-stores"
+            ent = (t, hdl, m)
+            self.tables[name] = ent
+        return ent[0], ent[2]
+
+    def barrier(self, name):
+        self.tables[name][1].barrier(channel=0)
+
+
 class RowComm:
-    """In-place all-gather of row blocks of a full-size [N, dim] table."""
+    """Reassembles row blocks of a full-size [N, dim] table: NCCL all-gather (in place), or — ``peer`` set — the
+    fused peer-store path where the all-gather has already happened inside the producing kernel."""
 
     def __init__(self, bounds, rank, world, group=None):
         self.bounds, self.rank, self.world, self.group = list(bounds), rank, world, group
         self.bytes_moved = 0
+        self.peer = None
+
+    def enable_p2p(self, device):
+        """Switch to the fused path; raises if symmetric memory cannot be set up (caller decides about NCCL)."""
+        self.peer = PeerTables(self.group, device)
+        return self.peer
 
     @property
     def lo(self):
@@ -118,16 +174,20 @@ class RowComm:
         return table
 
 
-def shard_graph(full: CsrGraph, rank, world, group=None, calibrate=True):
+def shard_graph(full: CsrGraph, rank, world, group=None, calibrate=True, weights=None, range_scale=None, peer=None):
     """Row block of ``full`` for this rank (plus the communicator that reassembles tables).  With ``calibrate`` the
     cut points equalise MEASURED cost (see partition_rows), otherwise nnz."""
-    if calibrate and world > 1 and full.device.type == "cuda":
+    if weights is not None:
+        tb, tw = weights
+        bounds = partition_rows(full.rowptr, world, tb, tw, range_scale=range_scale)
+    elif calibrate and world > 1 and full.device.type == "cuda":
         tb, tw = calibrate_type_weights(full, group=group)
         bounds = partition_rows(full.rowptr, world, tb, tw)
     else:
         tb, tw = None, None
         bounds = partition_rows(full.rowptr, world)
     comm = RowComm(bounds, rank, world, group)
+    comm.peer = peer
     lo, hi = comm.lo, comm.hi
     rp, col, val = slice_csr(full.rowptr, full.col, full.val, lo, hi)
     val_t = None
@@ -136,7 +196,58 @@ def shard_graph(full: CsrGraph, rank, world, group=None, calibrate=True):
         val_t = full.val_t[a:b].clone()
     g = CsrGraph(full.n, rp, col, val, val_t, None, full.norm_type, full.num_list, row_offset=lo, comm=comm)
     g.type_weight = tw
+    g.type_bounds = tb
     return g
+
+
+def rebalance_by_measurement(full, graph, rank, world, dim=64, n_layer=3):
+    """One feedback step: time the REAL fused forward layer (mirrored epilogue stores included) on the current row
+    blocks, scale each block's modelled cost by measured/mean, and cut again.  Collective."""
+    from .functional import lightgcn_forward_layers
+    dev = full.device
+    n = full.n
+    comm = graph.comm
+    names = [f"raw{k}" for k in range(n_layer - 1)] + ["final"]
+    mirrors = None
+    tabs = {}
+    if comm.peer is not None:
+        mirrors = {}
+        for nm in names:
+            t, m = comm.peer.table(nm, (n, dim))
+            tabs[nm] = t
+            mirrors[id(t)] = m
+            mirrors["name", id(t)] = nm
+    else:
+        for nm in names:
+            tabs[nm] = torch.empty((n, dim), device=dev)
+    raw = [tabs[f"raw{k}"] for k in range(n_layer - 1)] + [torch.empty((n, dim), device=dev)]
+    e0 = torch.randn(n, dim, device=dev) * 0.1
+    d = graph.desc(dim)
+    from ._lib import check, lib, ptr, stream_ptr
+    import ctypes as C
+    times = []
+    for it in range(3):
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        m = mirrors.get(id(raw[0])) if mirrors else None
+        check(lib().tagrec_lightgcn_fwd_layer_p2p(C.byref(d), ptr(e0), ptr(raw[0]), ptr(tabs["final"]), dim, 1, 0, 0.25,
+                                                  C.byref(m) if m is not None else None, None, stream_ptr(dev)),
+              "calibration layer")
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    mine = torch.tensor([min(times[1:])], dtype=torch.float64, device=dev)
+    allt = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allt, mine)
+    tms = [float(x.item()) for x in allt]
+    mean = sum(tms) / world
+    fac = [tm / mean for tm in tms]
+    new = shard_graph(full, rank, world, comm.group, weights=(graph.type_bounds, graph.type_weight),
+                      range_scale=(comm.bounds, fac), peer=comm.peer)
+    new.balance_feedback = {"ms_before": tms}
+    return new
 
 
 def build_sharded_lightgcn(shape, dev, rank, world, n_triples, seed=2020):
@@ -160,6 +271,17 @@ def build_sharded_lightgcn(shape, dev, rank, world, n_triples, seed=2020):
                                                        T._lib.ptr(triples), T._lib.stream_ptr(dev)), "sampler")
     del edges, train_items, train_ptr
     graph = shard_graph(full, rank, world)
+    mode = "nccl all-gather per layer"
+    if os.environ.get("TAGREC_P2P", "1") != "0":
+        try:
+            graph.comm.enable_p2p(dev).table("probe", (8, 64))
+            mode = f"all-gather fused into the K1 epilogue ({graph.comm.peer.kind} over NVLink)"
+        except Exception as e:                       # loud, not silent: the JSON line names the path that ran
+            print(f"[tagrec_b200] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-gather",
+                  flush=True)
+            graph.comm.peer = None
+    if os.environ.get("TAGREC_REBALANCE", "1") != "0":
+        graph = rebalance_by_measurement(full, graph, rank, world)
     nnz_full, n_long_full = full._nnz(), full.n_long
     del full
     torch.cuda.empty_cache()
@@ -170,6 +292,7 @@ def build_sharded_lightgcn(shape, dev, rank, world, n_triples, seed=2020):
     torch.manual_seed(seed)
     model = T.LightGCN(Data)
     info = {"nnz": graph._nnz(), "n": graph.n_rows, "n_long_rows": graph.n_long, "nnz_global": nnz_full,
-            "parallelism": f"node-range row blocks x{world} (all-gather per layer, replicated parameters)",
-            "rows_local": graph.n_rows, "bounds": graph.comm.bounds, "type_weight_s_per_nnz": graph.type_weight}
+            "parallelism": f"node-range row blocks x{world}, {mode}, replicated parameters",
+            "rows_local": graph.n_rows, "bounds": graph.comm.bounds, "type_weight_s_per_nnz": graph.type_weight,
+            "balance_feedback": getattr(graph, "balance_feedback", None)}
     return model, triples, info

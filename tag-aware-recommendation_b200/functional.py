@@ -47,56 +47,97 @@ def _buf(ws, name, shape, device, dtype=torch.float32):
     return t
 
 
-def lightgcn_forward_layers(graph, e0, n_layer, raw, final):
+def _mref(m):
+    return C.byref(m) if m is not None else None
+
+
+def lightgcn_forward_layers(graph, e0, n_layer, raw, final, mirrors=None):
     """lightgcn.py:52-60 — L launches of K1 with the fused normalise + running-mean epilogue.
-    raw[k] receives the un-normalised E^{k+1}; ``final`` the mean table."""
+    raw[k] receives the un-normalised E^{k+1}; ``final`` the mean table.
+    Sharded graphs: ``mirrors`` (dict id(tensor) -> MirrorDesc, tables in symmetric memory) selects the fused
+    peer-store all-gather + barrier; without it the row blocks are all-gathered with NCCL after each launch."""
     L, st, dim = lib(), stream_ptr(e0.device), e0.shape[1]
     d = graph.desc(dim)
+    comm = graph.comm
     x = e0
     t = KERNEL_TIMER
     for k in range(n_layer):
+        last = k == n_layer - 1
+        my = mirrors.get(id(raw[k])) if (mirrors and not last) else None
+        ma = mirrors.get(id(final)) if (mirrors and last) else None
         if t:
             t.start("spmm_fwd")
-        check(L.tagrec_lightgcn_fwd_layer(C.byref(d), ptr(x), ptr(raw[k]), ptr(final), dim, int(k == 0),
-                                          int(k == n_layer - 1), 1.0 / (n_layer + 1), st), "tagrec_lightgcn_fwd_layer")
+        check(L.tagrec_lightgcn_fwd_layer_p2p(C.byref(d), ptr(x), ptr(raw[k]), ptr(final), dim, int(k == 0), int(last),
+                                              1.0 / (n_layer + 1), _mref(my), _mref(ma), st),
+              "tagrec_lightgcn_fwd_layer")
         if t:
             t.stop("spmm_fwd")
         x = raw[k]
-        if graph.comm is not None and k < n_layer - 1:
-            graph.comm.all_gather_rows(x)                 # the next layer gathers rows of every rank
-    if graph.comm is not None:
-        graph.comm.all_gather_rows(final)
+        if comm is not None:
+            if mirrors:
+                if t:
+                    t.start("barrier")
+                comm.peer.barrier(mirrors["name", id(final if last else x)])
+                if t:
+                    t.stop("barrier")
+            else:
+                if not last:
+                    comm.all_gather_rows(x)                 # the next layer gathers rows of every rank
+                else:
+                    comm.all_gather_rows(final)
     return final
 
 
-def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad=None, upstream=None):
+def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad=None, upstream=None, mirrors=None,
+                             sparse_rows=None, g_first=None):
     """Closed-form backward of the above: one elementwise launch (layer L) + L launches of K1 on
-    A^T with the normalise-Jacobian epilogue.  ``bufs`` = two scratch tables, ``g_out`` receives dL/dE0."""
+    A^T with the normalise-Jacobian epilogue.  ``bufs`` = two scratch tables, ``g_out`` receives dL/dE0.
+    Sharded + ``mirrors``: outputs are stored to every rank by the kernels; the first table G_L is non-zero only on
+    ``sparse_rows`` (the batch's nodes), so only those rows are exchanged (``g_first``: a table that is zero outside
+    this rank's block and outside ``sparse_rows``)."""
     L, st, dim = lib(), stream_ptr(g_final.device), g_final.shape[1]
     d = graph.desc(dim, transposed=True)
+    comm = graph.comm
     inv = 1.0 / (n_layer + 1)
     g_next = None
     t = KERNEL_TIMER
     for k in range(n_layer, 0, -1):
-        out = bufs[k % 2]
-        name = "spmm_bwd" if g_next is not None else "bwd_elementwise"
+        first = g_next is None
+        sparse = first and mirrors is not None and sparse_rows is not None and g_first is not None
+        out = g_first if sparse else bufs[k % 2]
+        m = mirrors.get(id(out)) if (mirrors and not sparse) else None
+        name = "bwd_elementwise" if first else "spmm_bwd"
         if t:
             t.start(name)
-        check(L.tagrec_lightgcn_bwd_layer(C.byref(d), ptr(g_next), ptr(raw[k - 1]), ptr(g_final), None, ptr(upstream),
-                                          inv, ptr(out), dim, st), "tagrec_lightgcn_bwd_layer")
+        check(L.tagrec_lightgcn_bwd_layer_p2p(C.byref(d), ptr(g_next), ptr(raw[k - 1]), ptr(g_final), None,
+                                              ptr(upstream), inv, ptr(out), dim, _mref(m), st),
+              "tagrec_lightgcn_bwd_layer")
         if t:
             t.stop(name)
         g_next = out
-        if graph.comm is not None:
-            graph.comm.all_gather_rows(g_next)
+        if comm is not None:
+            if sparse:
+                rows = out.index_select(0, sparse_rows)          # zero where another rank owns the node
+                torch.distributed.all_reduce(rows, group=comm.group)
+                out.index_copy_(0, sparse_rows, rows)
+            elif mirrors:
+                comm.peer.barrier(mirrors["name", id(out)])
+            else:
+                comm.all_gather_rows(g_next)
+    m = mirrors.get(id(g_out)) if mirrors else None
     if t:
         t.start("spmm_bwd")
-    check(L.tagrec_lightgcn_bwd_layer(C.byref(d), ptr(g_next), None, ptr(g_final), ptr(reg_grad), ptr(upstream), inv,
-                                      ptr(g_out), dim, st), "tagrec_lightgcn_bwd_layer")
+    check(L.tagrec_lightgcn_bwd_layer_p2p(C.byref(d), ptr(g_next), None, ptr(g_final), ptr(reg_grad), ptr(upstream), inv,
+                                          ptr(g_out), dim, _mref(m), st), "tagrec_lightgcn_bwd_layer")
     if t:
         t.stop("spmm_bwd")
-    if graph.comm is not None:
-        graph.comm.all_gather_rows(g_out)
+    if comm is not None:
+        if mirrors:
+            comm.peer.barrier(mirrors["name", id(g_out)])
+        else:
+            comm.all_gather_rows(g_out)
+    if comm is not None and mirrors is not None and sparse_rows is not None and g_first is not None:
+        g_first.index_fill_(0, sparse_rows, 0.0)                # keep the invariant for the next step
     return g_out
 
 
@@ -114,6 +155,23 @@ def bpr_fwd_bwd(batch, item_offset, final, reg_src, reg, loss_kind, g_final, g_r
         t.stop("bpr")
 
 
+def _tables(model, names, n, dim, dev):
+    """Persistent [n, dim] work tables of a model.  On a sharded graph with the peer path enabled, the tables that
+    other ranks write into live in symmetric memory and come with their MirrorDesc."""
+    ws, comm = model._ws, model.norm_adj.comm
+    peer = comm.peer if comm is not None else None
+    out, mirrors = {}, ({} if peer is not None else None)
+    for name, shared in names:
+        if peer is not None and shared:
+            tns, m = peer.table(name, (n, dim))
+            mirrors[id(tns)] = m
+            mirrors["name", id(tns)] = name
+        else:
+            tns = _buf(ws, name, (n, dim), dev)
+        out[name] = tns
+    return out, mirrors
+
+
 class LightGCNLossFn(torch.autograd.Function):
     """model.loss(batch) of LightGCN (lightgcn.py:68-82) as ONE autograd node: L fused SpMM launches, one fused BPR
     launch in forward; 1 + L launches in backward."""
@@ -123,20 +181,29 @@ class LightGCNLossFn(torch.autograd.Function):
         ws, graph, nl = model._ws, model.norm_adj, model.num_layer
         dev = embeds[0].device
         n, dim = graph.n, embeds[0].shape[1]
-        e0 = _buf(ws, "e0", (n, dim), dev)
-        torch.cat([e.detach() for e in embeds], dim=0, out=e0)
-        raw = [_buf(ws, f"raw{k}", (n, dim), dev) for k in range(nl)]
-        final = _buf(ws, "final", (n, dim), dev)
-        lightgcn_forward_layers(graph, e0, nl, raw, final)
-        g_final = _buf(ws, "g_final", (n, dim), dev)
-        g_final.zero_()
-        g_reg = None
-        if model.reg != 0:
-            g_reg = _buf(ws, "g_reg", (n, dim), dev)
-            g_reg.zero_()
+        e0 = model._flat_params()                                   # [n, dim] storage the parameters are views of
+        names = [(f"raw{k}", k < nl - 1) for k in range(nl)] + [("final", True)]
+        tabs, mirrors = _tables(model, names, n, dim, dev)
+        raw, final = [tabs[f"raw{k}"] for k in range(nl)], tabs["final"]
+        ws["raw_list"] = raw
+        lightgcn_forward_layers(graph, e0, nl, raw, final, mirrors)
+        batch = batch.contiguous()
+        nodes = torch.cat([batch[:, 0], batch[:, 1] + model.num_list[0], batch[:, 2] + model.num_list[0]])
+        # gradient tables are zero outside the rows the previous batch touched: re-zero just those rows
+        for name in ("g_final", "g_reg"):
+            if name == "g_reg" and model.reg == 0:
+                continue
+            tns = ws.get(name)
+            if tns is None or tns.shape != (n, dim) or tns.device != dev:
+                ws[name] = torch.zeros((n, dim), dtype=torch.float32, device=dev)
+            elif ws.get(name + "_dirty") is not None:
+                tns.index_fill_(0, ws[name + "_dirty"], 0.0)
+            ws[name + "_dirty"] = nodes
+        g_final = ws["g_final"]
+        g_reg = ws["g_reg"] if model.reg != 0 else None
         loss_out = torch.empty(2, dtype=torch.float32, device=dev)
         bpr_fwd_bwd(batch, model.num_list[0], final, e0, model.reg, model.loss_func, g_final, g_reg, loss_out)
-        ctx.model, ctx.has_reg = model, g_reg is not None
+        ctx.model, ctx.has_reg, ctx.nodes = model, g_reg is not None, nodes
         ctx.sizes = [e.shape[0] for e in embeds]
         return loss_out[0], loss_out[1]
 
@@ -147,10 +214,19 @@ class LightGCNLossFn(torch.autograd.Function):
         g_final = ws["g_final"]
         dev, (n, dim) = g_final.device, g_final.shape
         upstream = torch.stack([g_loss.reshape(()), g_regterm.reshape(())]).to(torch.float32)
-        raw = [ws[f"raw{k}"] for k in range(nl)]
-        bufs = [_buf(ws, "gbuf0", (n, dim), dev), _buf(ws, "gbuf1", (n, dim), dev)]
-        g_e0 = torch.empty((n, dim), dtype=torch.float32, device=dev)
-        lightgcn_backward_layers(graph, raw, g_final, nl, bufs, g_e0, ws["g_reg"] if ctx.has_reg else None, upstream)
+        raw = ws["raw_list"]
+        p2p = graph.comm is not None and graph.comm.peer is not None
+        tabs, mirrors = _tables(model, [("gbuf0", True), ("gbuf1", True)] + ([("g_e0", True)] if p2p else []), n, dim,
+                                dev)
+        g_e0 = tabs["g_e0"] if p2p else torch.empty((n, dim), dtype=torch.float32, device=dev)
+        g_first = None
+        if p2p:
+            g_first = ws.get("g_first")
+            if g_first is None or g_first.shape != (n, dim):
+                g_first = ws["g_first"] = torch.zeros((n, dim), dtype=torch.float32, device=dev)
+        lightgcn_backward_layers(graph, raw, g_final, nl, [tabs["gbuf0"], tabs["gbuf1"]], g_e0,
+                                 ws["g_reg"] if ctx.has_reg else None, upstream, mirrors,
+                                 ctx.nodes if p2p else None, g_first)
         return (None, None) + tuple(torch.split(g_e0, ctx.sizes, dim=0))
 
 

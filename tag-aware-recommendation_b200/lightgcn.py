@@ -48,6 +48,25 @@ class LightGCN(nn.Module):
             nn.init.xavier_uniform_(p)
 
     # ------------------------------------------------------------------------------------------------
+    def _flat_params(self):
+        """One [N, dim] table whose row blocks ARE the parameters (``embed[k].data`` are views of it), so the
+        kernels read E0 in place instead of torch.cat-ing the ParameterList every step (lightgcn.py:52).  Rebuilt
+        whenever the parameters were re-allocated behind our back (``.to()``, ``load_state_dict(assign=True)``)."""
+        flat = self._ws.get("flat")
+        off, ok = 0, flat is not None
+        if ok:
+            for p in self.embed:
+                ok = ok and p.device == flat.device and p.data_ptr() == flat[off:off + p.shape[0]].data_ptr()
+                off += p.shape[0]
+        if not ok:
+            flat = torch.cat([p.detach() for p in self.embed], dim=0)
+            off = 0
+            for p in self.embed:
+                p.data = flat[off:off + p.shape[0]]
+                off += p.shape[0]
+            self._ws["flat"] = flat
+        return flat
+
     def _dropout_active(self):
         return self.training and (self.node_drop > 0 or any(p > 0 for p in self.message_drop_list[:self.num_layer]))
 
