@@ -342,9 +342,11 @@ def run_ours(args):
 
 
 def eval_leg(T, model, shape, dev, n_users):
-    """Secondary metric of BASELINE.json: full-rank eval users/s (K3: scoring + mask + top-20 + metric sums)."""
+    """Secondary metric of BASELINE.json: full-rank eval users/s (K3: scoring + mask + top-20 + metric sums).
+    Both scoring paths are timed: the tcgen05 TF32-filter path (default for dim 64) and the exact-fp32 CUDA-core
+    path; they return identical lists (checked here on the benchmark inputs)."""
     import torch
-    from tagrec_b200.eval_ops import metric_sums
+    from tagrec_b200.eval_ops import metric_sums, topk_scores
     graph = model.norm_adj
     U = shape["n_user"]
     n_users = min(n_users, U)
@@ -355,19 +357,31 @@ def eval_leg(T, model, shape, dev, n_users):
     # synthetic ground truth: each user's "test item" is its first train neighbour (exercises the metric kernel)
     test_ptr = torch.arange(0, U + 1, device=dev)
     test_items = train_items[train_ptr[:-1].clamp(max=train_items.numel() - 1)].contiguous()
-    for _ in range(2):
-        ids, _ = model.eval_topk(users, 20, train_ptr, train_items)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    ids, _ = model.eval_topk(users, 20, train_ptr, train_items)
-    sums = metric_sums(users, ids, test_ptr, test_items, [20])
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b)
+    with torch.no_grad():
+        all_users, all_items = model.forward()[:2]
+    all_users, all_items = all_users.contiguous(), all_items.contiguous()
     flops = 2.0 * n_users * shape["n_item"] * DIM
-    return {"users_per_s": n_users / (ms / 1e3), "users": n_users, "ms": ms, "tflops": flops / (ms * 1e-3) / 1e12,
-            "kernel": "eval_topk_kernel (fp32 CUDA-core path)"}
+    out, ids_by_path = {}, {}
+    for path in ("tf32", "fp32"):
+        for _ in range(2):
+            ids, _ = topk_scores(users, all_users, all_items, train_ptr, train_items, 20, path=path)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ids, _ = topk_scores(users, all_users, all_items, train_ptr, train_items, 20, path=path)
+        metric_sums(users, ids, test_ptr, test_items, [20])
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        ids_by_path[path] = ids
+        out[path] = {"users_per_s": n_users / (ms / 1e3), "ms": ms, "tflops": flops / (ms * 1e-3) / 1e12}
+    same = bool(torch.equal(ids_by_path["tf32"], ids_by_path["fp32"]))
+    tf32_peak = 1100.0      # nominal dense TF32 TFLOP/s (B200_PROFILING.md); no measured TF32 figure in MEASURED_PEAKS
+    return {"users_per_s": out["tf32"]["users_per_s"], "users": n_users, "items": shape["n_item"], "k": 20,
+            "ms": out["tf32"]["ms"], "tflops": out["tf32"]["tflops"],
+            "tensor_frac_of_nominal_tf32": out["tf32"]["tflops"] / tf32_peak,
+            "kernel": "eval_tc_kernel (tcgen05.mma kind::tf32 filter + exact fp32 re-score)",
+            "fp32_cuda_core_path": out["fp32"], "paths_identical": same}
 
 
 def main():

@@ -163,6 +163,20 @@ int tagrec_eval_topk(const int64_t* users, int64_t nu, const float* user_table, 
                      int32_t* topk_ids, float* topk_scores, void* workspace, size_t workspace_bytes, void* stream);
 size_t tagrec_eval_workspace_bytes(int64_t nu, int64_t n_item, int k);
 
+/* Same, with the scoring path chosen by the caller.  Both paths return the same top-K (by (-score, id) of the exact
+ * fp32 dot product, sequential fmaf over the feature index):
+ *   TAGREC_EVAL_FP32  CUDA-core fp32 tiles (any dim % 32 == 0);
+ *   TAGREC_EVAL_TF32  dim == 64: tcgen05.mma kind::tf32 (accumulators in TMEM, item tiles by TMA) as a filter with a
+ *                     proven error margin, every candidate re-scored in exact fp32 (csrc/eval_tc.cu);
+ *   TAGREC_EVAL_AUTO  TF32 when dim == 64, else FP32 (what tagrec_eval_topk does). */
+#define TAGREC_EVAL_AUTO 0
+#define TAGREC_EVAL_FP32 1
+#define TAGREC_EVAL_TF32 2
+int tagrec_eval_topk_ex(const int64_t* users, int64_t nu, const float* user_table, const float* item_table,
+                        int64_t n_item, int dim, const int64_t* train_ptr, const int32_t* train_items, int k,
+                        int32_t* topk_ids, float* topk_scores, void* workspace, size_t workspace_bytes, int path,
+                        void* stream);
+
 /* metric sums over users (training/utils.py:15-35): out[4*nk] = recall|precision|hr|ndcg per k (double, +=). */
 int tagrec_eval_metrics(const int64_t* users, int64_t nu, const int32_t* topk_ids, int kmax,
                         const int64_t* test_ptr, const int32_t* test_items, const int32_t* ks, int nk,

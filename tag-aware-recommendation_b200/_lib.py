@@ -52,6 +52,7 @@ PROTOTYPES = {
     "tagrec_bpr_fwd_bwd": (_i32, [_p, _i64, _i64, _p, _p, _i32, _f32, _i32, _p, _p, _p, _p]),
     "tagrec_eval_topk": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "tagrec_eval_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "tagrec_eval_topk_ex": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _sz, _i32, _p]),
     "tagrec_eval_metrics": (_i32, [_p, _i64, _p, _i32, _p, _p, _p, _i32, _p, _p]),
     "tagrec_mt19937_seed": (None, [_u32, _p]),
     "tagrec_sample_bpr_host": (_i32, [_p, _p, _i64, _p, _p, _i64, _p]),

@@ -142,6 +142,90 @@ bpr_kernel(const int64_t* __restrict__ triples, int64_t b, int64_t item_offset, 
     }
 }
 
+// Wide rows (dim > 128: NGCF's 256-d concat, ngcf.py:89; TGCN's 192-d, tgcn.py:227-229): one WARP per triple, each
+// lane owns the float4 chunks sl, sl+32, ... of a row (NC = ceil(dim/128) chunks in registers).  Same arithmetic.
+template <int NC>
+__global__ void __launch_bounds__(256)
+bpr_wide_kernel(const int64_t* __restrict__ triples, int64_t b, int64_t item_offset, const float4* __restrict__ f4,
+                const float4* __restrict__ r4, int c4, float reg, int loss_kind, float4* __restrict__ gf4,
+                float4* __restrict__ gr4, float* __restrict__ loss_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const float inv_b = 1.f / (float)b;
+    float loss_t = 0.f, reg_t = 0.f;
+    if (t < b) {
+        const int64_t u = __ldg(triples + 3 * t);
+        const int64_t p = __ldg(triples + 3 * t + 1) + item_offset;
+        const int64_t q = __ldg(triples + 3 * t + 2) + item_offset;
+        float4 fu[NC], fp[NC], fq[NC];
+        float pos = 0.f, neg = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int j = lane + 32 * c;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            fu[c] = j < c4 ? __ldg(f4 + u * c4 + j) : z;
+            fp[c] = j < c4 ? __ldg(f4 + p * c4 + j) : z;
+            fq[c] = j < c4 ? __ldg(f4 + q * c4 + j) : z;
+            pos += dot4(fu[c], fp[c]);
+            neg += dot4(fu[c], fq[c]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            pos += __shfl_xor_sync(0xffffffffu, pos, o);
+            neg += __shfl_xor_sync(0xffffffffu, neg, o);
+        }
+        const float x = neg - pos;
+        loss_t = loss_kind == 1 ? neg_logsigmoid_neg(x) : softplus_torch(x);
+        const float s = inv_b / (1.f + expf(-x));
+        const bool same = r4 == f4;
+        const float cr = reg * inv_b;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int j = lane + 32 * c;
+            if (j >= c4) continue;
+            float4 gu = make_float4(s * (fq[c].x - fp[c].x), s * (fq[c].y - fp[c].y), s * (fq[c].z - fp[c].z),
+                                    s * (fq[c].w - fp[c].w));
+            float4 gp = make_float4(-s * fu[c].x, -s * fu[c].y, -s * fu[c].z, -s * fu[c].w);
+            float4 gq = make_float4(s * fu[c].x, s * fu[c].y, s * fu[c].z, s * fu[c].w);
+            if (reg != 0.f) {
+                const float4 ru = same ? fu[c] : __ldg(r4 + u * c4 + j);
+                const float4 rp = same ? fp[c] : __ldg(r4 + p * c4 + j);
+                const float4 rq = same ? fq[c] : __ldg(r4 + q * c4 + j);
+                reg_t += dot4(ru, ru) + dot4(rp, rp) + dot4(rq, rq);
+                if (gr4 == gf4) {   // the L2 term reads the table the scores read: one reduction per row
+                    fma4(gu, cr, ru);
+                    fma4(gp, cr, rp);
+                    fma4(gq, cr, rq);
+                } else if (gr4) {
+                    red_add4(gr4 + u * c4 + j, make_float4(cr * ru.x, cr * ru.y, cr * ru.z, cr * ru.w));
+                    red_add4(gr4 + p * c4 + j, make_float4(cr * rp.x, cr * rp.y, cr * rp.z, cr * rp.w));
+                    red_add4(gr4 + q * c4 + j, make_float4(cr * rq.x, cr * rq.y, cr * rq.z, cr * rq.w));
+                }
+            }
+            red_add4(gf4 + u * c4 + j, gu);
+            red_add4(gf4 + p * c4 + j, gp);
+            red_add4(gf4 + q * c4 + j, gq);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) reg_t += __shfl_xor_sync(0xffffffffu, reg_t, o);
+    }
+    __shared__ float s_loss[8], s_reg[8];
+    if (lane == 0) {
+        s_loss[threadIdx.x >> 5] = loss_t;
+        s_reg[threadIdx.x >> 5] = reg_t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tl = 0.f, tr = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            tl += s_loss[w];
+            tr += s_reg[w];
+        }
+        atomicAdd(loss_out, tl * inv_b);
+        if (reg != 0.f) atomicAdd(loss_out + 1, 0.5f * reg * tr * inv_b);
+    }
+}
+
 }  // namespace tagrec
 
 using namespace tagrec;
@@ -151,9 +235,25 @@ extern "C" int tagrec_bpr_fwd_bwd(const int64_t* triples, int64_t b, int64_t ite
                                   float* g_reg, float* loss_out, void* stream) {
     TAGREC_REQUIRE(triples && final_table && g_final && loss_out, "null pointer");
     TAGREC_REQUIRE(b > 0, "empty batch");
-    TAGREC_REQUIRE(dim == 32 || dim == 64 || dim == 128, "dim must be 32, 64 or 128");
+    TAGREC_REQUIRE(dim >= 4 && dim % 4 == 0 && dim <= 1024, "dim must be a multiple of 4, at most 1024");
     TAGREC_REQUIRE(reg == 0.f || reg_src, "reg != 0 needs reg_src");
     TAGREC_CUDA(cudaMemsetAsync(loss_out, 0, 2 * sizeof(float), (cudaStream_t)stream));
+    if (!(dim == 32 || dim == 64 || dim == 128)) {
+        const int c4 = dim / 4, nc = (c4 + 31) / 32;
+        const unsigned wgrid = (unsigned)((b + 7) / 8);
+        const float4* wf4 = reinterpret_cast<const float4*>(final_table);
+        const float4* wr4 = reinterpret_cast<const float4*>(reg_src);
+        float4* wgf4 = reinterpret_cast<float4*>(g_final);
+        float4* wgr4 = reinterpret_cast<float4*>(g_reg);
+#define TAGREC_BPR_WIDE(NC) TAGREC_LAUNCH((bpr_wide_kernel<NC>), wgrid, 256, 0, stream, triples, b, item_offset, wf4, \
+                                          wr4, c4, reg, loss_kind, wgf4, wgr4, loss_out)
+        if (nc <= 1) TAGREC_BPR_WIDE(1);
+        else if (nc <= 2) TAGREC_BPR_WIDE(2);
+        else if (nc <= 4) TAGREC_BPR_WIDE(4);
+        else TAGREC_BPR_WIDE(8);
+#undef TAGREC_BPR_WIDE
+        return TAGREC_OK;
+    }
     const int lpr = dim / 4, rpw = 32 / lpr;
     const int64_t warps = (b + rpw - 1) / rpw;
     const unsigned grid = (unsigned)((warps + 7) / 8);

@@ -1,0 +1,524 @@
+// K3-TC — full-sort evaluation on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+// Replaces model/lightgcn.py:84-89 (predict_rating: sigmoid(U_b @ I^T), a materialised B x n_item matrix),
+// training/basic_test.py:42-48 (mask train items with -1024, torch.topk) for dim_latent == 64 tables.
+//
+// The only dense contraction of the path: scores[u, i] = <U[u, :], I[i, :]>, K = 64.  One CTA owns 128*NH users
+// (NH "halves" of 128 rows) and a contiguous range of items ("split"); it streams 128-item tiles:
+//
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d of the item tile [128 x 64] fp32 (two 128B-swizzled boxes
+//                              of 32 floats) into a ring of B stages, mbarrier complete_tx
+//   warp 1      MMA issuer     one lane: 8*NH tcgen05.mma.kind::tf32 (M128 x N128 x K8) per tile, A = user tile
+//                              resident in smem (K-major, SW128), B = item tile, D = fp32 accumulator in TMEM
+//                              (2 accumulator stages x NH halves x 128 columns); tcgen05.commit -> mbarrier
+//   warps 2..   epilogue       thread = user row: tcgen05.ld 32 columns at a time, max-tree, compare with the row's
+//                              running threshold (a register).  Scores never leave the SM.
+//
+// Exactness.  TF32 inputs carry 10 mantissa bits, so the tensor-core score is only a FILTER: a score is a candidate
+// when  s_tf32 > thr_exact - margin,  margin = 2.2e-3 * ||u||_2 * max_i ||i||_2  >=  the worst-case TF32 error
+// (2 * 2^-10 * sum_k |u_k i_k|  <=  2^-9 ||u|| ||i||, plus accumulation slack).  Every candidate is re-scored in
+// exact fp32 (sequential fmaf over k = 0..63 — the same canonical order as the CUDA-core path in eval_topk.cu)
+// straight from the smem copies of the two rows, and only exact scores enter the row's sorted K-list and its
+// threshold.  The result is therefore identical to the fp32 path: top-K by (-score, item id).
+//
+// Train-item masking costs no memory traffic in the common case: a per-row cursor over the user's ascending train
+// row keeps the next masked item id in a register (items are visited in ascending id order).  Masked items are never
+// candidates; if a user has fewer than K un-masked items the merge kernel appends the first masked ids with score
+// -1024, which is exactly the (-score, id) order the reference's -1024 fill produces (basic_test.py:47).
+#include <cuda.h>
+#include <float.h>
+
+#include "common.cuh"
+#include "eval_tc.cuh"
+
+namespace tagrec {
+
+constexpr int TC_M = 128;                 // user rows per accumulator half (UMMA M)
+constexpr int TC_N = 128;                 // items per tile (UMMA N)
+constexpr int TC_D = 64;                  // feature dim == GEMM K
+constexpr int TC_KH_BYTES = TC_N * 128;   // one 128B-swizzled k-half of a tile: 128 rows x 32 floats = 16 KB
+constexpr int TC_TILE_BYTES = 2 * TC_KH_BYTES;   // 32 KB (A half or B stage)
+constexpr int TC_MAX_STAGES = 4;
+constexpr float TC_MARGIN = 2.2e-3f;
+
+struct TcArgs {
+    const int64_t* users;
+    int64_t nu;
+    const float* user_table;
+    const float* item_table;
+    int64_t n_item;
+    const int64_t* train_ptr;
+    const int32_t* train_items;
+    const float* item_maxnorm;   // device scalar: max_i ||I_i||_2
+    int k;
+    int splits;
+    int stages;
+    int64_t items_per_split;     // multiple of TC_N
+    float* part_scores;          // [nu, splits, k]  raw exact dot products, -inf when absent
+    int32_t* part_ids;           // [nu, splits, k]  -1 when absent
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) {
+            printf("tagrec eval_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+                   threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);     // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset = 1024  bits [32,46)
+    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: D = f32, A = B = tf32, both K-major, N = 128, M = 128.
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
+                              ((uint32_t)(TC_M >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Byte offset of 16-byte chunk c16 (0..15) of row `row` inside a [128 x 64] fp32 tile stored as two SW128 k-halves.
+__device__ __forceinline__ uint32_t sw128_off(int row, int c16) {
+    return (uint32_t)((c16 >> 3) * TC_KH_BYTES + row * 128 + (((c16 & 7) ^ (row & 7)) << 4));
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+template <int NH>
+__global__ void __launch_bounds__(64 + 128 * NH, 1)
+eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
+    constexpr int ROWS = TC_M * NH;
+    constexpr int EPI_WARPS = 4 * NH;
+    constexpr int TMEM_COLS = 2 * NH * TC_N;      // 256 or 512: a power of two >= 32
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int S = a.stages, K = a.k;
+    unsigned char* As = base;                                         // NH x 32 KB
+    unsigned char* Bs = As + NH * TC_TILE_BYTES;                      // S  x 32 KB
+    float* ls = reinterpret_cast<float*>(Bs + S * TC_TILE_BYTES);     // [K][ROWS] scores, descending per row
+    int32_t* li = reinterpret_cast<int32_t*>(ls + (size_t)K * ROWS);  // [K][ROWS] item ids
+    uint64_t* bars = reinterpret_cast<uint64_t*>(li + (size_t)K * ROWS);
+    uint64_t* full = bars;                        // [S]  TMA -> MMA
+    uint64_t* bfree = bars + TC_MAX_STAGES;       // [S]  epilogue -> TMA
+    uint64_t* accfull = bars + 2 * TC_MAX_STAGES; // [2]  MMA -> epilogue
+    uint64_t* accfree = accfull + 2;              // [2]  epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfree + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t u0 = (int64_t)blockIdx.x * ROWS;
+    const int split = blockIdx.y;
+    const int64_t i_begin = (int64_t)split * a.items_per_split;
+    const int64_t i_end = min(a.n_item, i_begin + a.items_per_split);
+    const int n_tiles = (int)((i_end - i_begin + TC_N - 1) / TC_N);
+
+    // ---- prologue: barriers, TMEM, user tile -> smem (generic proxy, swizzled like the TMA would) ----
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(smem_u32(full + s), 1);
+            mbar_init(smem_u32(bfree + s), EPI_WARPS);
+        }
+        for (int x = 0; x < 2; ++x) {
+            mbar_init(smem_u32(accfull + x), 1);
+            mbar_init(smem_u32(accfree + x), EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int idx = tid; idx < ROWS * 16; idx += blockDim.x) {
+        const int row = idx >> 4, c16 = idx & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (u0 + row < a.nu) {
+            const int64_t u = __ldg(a.users + u0 + row);
+            v = __ldg(reinterpret_cast<const float4*>(a.user_table + u * TC_D) + c16);
+        }
+        *reinterpret_cast<float4*>(As + (row >> 7) * TC_TILE_BYTES + sw128_off(row & 127, c16)) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // smem writes -> visible to tcgen05.mma
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t % S;
+                mbar_wait(smem_u32(bfree + s), ((t / S) & 1) ^ 1);
+                const uint32_t bar = smem_u32(full + s);
+                mbar_expect_tx(bar, TC_TILE_BYTES);
+                const uint32_t dst = smem_u32(Bs + s * TC_TILE_BYTES);
+                const int row0 = (int)(i_begin + (int64_t)t * TC_N);
+                tma_load_2d(dst, &item_map, bar, 0, row0);
+                tma_load_2d(dst + TC_KH_BYTES, &item_map, bar, 32, row0);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t % S, acc = t & 1;
+                mbar_wait(smem_u32(accfree + acc), ((t >> 1) & 1) ^ 1);
+                mbar_wait(smem_u32(full + s), (t / S) & 1);
+                tc_fence_after();
+                const uint32_t b0 = smem_u32(Bs + s * TC_TILE_BYTES);
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const uint32_t a0 = smem_u32(As + h * TC_TILE_BYTES);
+                    const uint32_t d = tmem_base + (uint32_t)((acc * NH + h) * TC_N);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {     // K = 8 per instruction: 4 per 128-byte swizzle row, 2 k-halves
+                        const uint32_t off = (uint32_t)((kk >> 2) * TC_KH_BYTES + (kk & 3) * 32);
+                        umma_tf32(d, umma_desc_sw128(a0 + off), umma_desc_sw128(b0 + off), kk > 0);
+                    }
+                }
+                umma_commit(smem_u32(accfull + acc));    // arrives when every MMA above has completed
+            }
+        }
+    } else {
+        // ================= epilogue: thread = user row =================
+        const int e = warp - 2;                 // 0 .. 4*NH-1
+        const int h = e >> 2;
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = h * TC_M + q * 32 + lane;
+        const bool valid = u0 + row < a.nu;
+        const unsigned char* arow = As + h * TC_TILE_BYTES;
+        const int arow_l = q * 32 + lane;
+        float thr = -INFINITY, thr_lo = valid ? -INFINITY : INFINITY, margin = 0.f;
+        int cnt = 0;
+        int64_t tc = 0, te = 0;
+        int32_t nxt = INT32_MAX;                // smallest train item of this user not yet passed
+        if (valid) {
+            const int64_t u = __ldg(a.users + u0 + row);
+            float ss = 0.f;
+            for (int c16 = 0; c16 < 16; ++c16) {
+                const float4 v = *reinterpret_cast<const float4*>(arow + sw128_off(arow_l, c16));
+                ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+            }
+            margin = TC_MARGIN * sqrtf(ss) * __ldg(a.item_maxnorm) + FLT_MIN;
+            tc = __ldg(a.train_ptr + u);
+            te = __ldg(a.train_ptr + u + 1);
+            // first train item inside this split
+            int64_t lo = tc, hi = te;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if ((int64_t)__ldg(a.train_items + mid) < i_begin) lo = mid + 1; else hi = mid;
+            }
+            tc = lo;
+            nxt = tc < te ? __ldg(a.train_items + tc) : INT32_MAX;
+        }
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s = t % S, acc = t & 1;
+            const int64_t it0 = i_begin + (int64_t)t * TC_N;
+            const unsigned char* brow = Bs + s * TC_TILE_BYTES;
+            mbar_wait(smem_u32(accfull + acc), (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * NH + h) * TC_N);
+#pragma unroll 1
+            for (int c = 0; c < TC_N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c * 32, v);
+                tmem_ld_wait();
+                float m = __uint_as_float(v[0]);
+#pragma unroll
+                for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+                if (m > thr_lo) {
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr_lo) ? (1u << j) : 0u;
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int il = c * 32 + j;
+                        const int64_t item = it0 + il;
+                        if (item >= i_end) break;                 // zero-filled rows past the split / table end
+                        // train-item cursor: nxt = smallest train item >= item (galloping, then bisection)
+                        if ((int64_t)nxt < item) {
+                            int64_t step = 1, lo = tc + 1;
+                            while (lo + step < te && (int64_t)__ldg(a.train_items + lo + step) < item) {
+                                lo += step;
+                                step <<= 1;
+                            }
+                            int64_t hi = min(te, lo + step + 1);
+                            while (lo < hi) {
+                                const int64_t mid = (lo + hi) >> 1;
+                                if ((int64_t)__ldg(a.train_items + mid) < item) lo = mid + 1; else hi = mid;
+                            }
+                            tc = lo;
+                            nxt = tc < te ? __ldg(a.train_items + tc) : INT32_MAX;
+                        }
+                        if ((int64_t)nxt == item) continue;       // masked (basic_test.py:47)
+                        // exact fp32 score, canonical sequential order
+                        float ex = 0.f;
+#pragma unroll
+                        for (int c16 = 0; c16 < 16; ++c16) {
+                            const float4 uu = *reinterpret_cast<const float4*>(arow + sw128_off(arow_l, c16));
+                            const float4 ii = *reinterpret_cast<const float4*>(brow + sw128_off(il, c16));
+                            ex = fmaf(uu.x, ii.x, ex);
+                            ex = fmaf(uu.y, ii.y, ex);
+                            ex = fmaf(uu.z, ii.z, ex);
+                            ex = fmaf(uu.w, ii.w, ex);
+                        }
+                        if (cnt < K || ex > thr) {
+                            int pos = cnt < K ? cnt : K - 1;
+                            while (pos > 0 && ls[(size_t)(pos - 1) * ROWS + row] < ex) {
+                                ls[(size_t)pos * ROWS + row] = ls[(size_t)(pos - 1) * ROWS + row];
+                                li[(size_t)pos * ROWS + row] = li[(size_t)(pos - 1) * ROWS + row];
+                                --pos;
+                            }
+                            ls[(size_t)pos * ROWS + row] = ex;
+                            li[(size_t)pos * ROWS + row] = (int32_t)item;
+                            if (cnt < K) ++cnt;
+                            if (cnt == K) {
+                                thr = ls[(size_t)(K - 1) * ROWS + row];
+                                thr_lo = thr - margin;
+                            }
+                        }
+                    }
+                }
+            }
+            // this warp is done with accumulator `acc` and with B stage `s`
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(accfree + acc));
+                mbar_arrive(smem_u32(bfree + s));
+            }
+        }
+        if (valid) {
+            const size_t o = ((size_t)(u0 + row) * a.splits + split) * K;
+            for (int j = 0; j < K; ++j) {
+                a.part_scores[o + j] = j < cnt ? ls[(size_t)j * ROWS + row] : -INFINITY;
+                a.part_ids[o + j] = j < cnt ? li[(size_t)j * ROWS + row] : -1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// max_i ||I_i||_2 (for the TF32 error margin).  16 lanes per 64-float row, coalesced.
+__global__ void __launch_bounds__(256) item_maxnorm_kernel(const float4* __restrict__ it, int64_t n_item, float* out) {
+    const int lane = threadIdx.x & 31, sub = lane >> 4, sl = lane & 15;
+    const unsigned mask = 0xffffu << (sub * 16);
+    float best = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 4);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); r < n_item; r += stride) {
+        const float4 v = __ldg(it + r * 16 + sl);
+        best = fmaxf(best, half_sum(dot4(v, v), mask));
+    }
+    best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 16));
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(best) * 1.0001f));   // non-negative floats order as ints
+}
+
+// Merge the per-split K-best lists of one user (one warp per user); emit sigmoid scores.  If fewer than k un-masked
+// items exist, the tail is the user's first train items with score -1024 (== (-score, id) order of the reference).
+__global__ void __launch_bounds__(256)
+eval_tc_merge_kernel(const float* __restrict__ ps, const int32_t* __restrict__ pi, const int64_t* __restrict__ users,
+                     int64_t nu, int splits, int k, const int64_t* __restrict__ train_ptr,
+                     const int32_t* __restrict__ train_items, int32_t* __restrict__ out_ids,
+                     float* __restrict__ out_scores) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= nu) return;
+    const int n = splits * k;
+    const float* s = ps + (size_t)w * n;
+    const int32_t* id = pi + (size_t)w * n;
+    int valid = 0;
+    for (int i = lane; i < n; i += 32) {
+        const float si = s[i];
+        const int32_t ii = id[i];
+        if (ii < 0) continue;
+        ++valid;
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const float sj = s[j];
+            const int32_t ij = id[j];
+            rank += (ij >= 0) && ((sj > si) || (sj == si && ij < ii));
+        }
+        if (rank < k) {
+            out_ids[(size_t)w * k + rank] = ii;
+            out_scores[(size_t)w * k + rank] = 1.f / (1.f + expf(-si));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    if (valid < k) {
+        const int64_t u = users[w];
+        const int64_t tb = train_ptr[u], te = train_ptr[u + 1];
+        for (int j = valid + lane; j < k; j += 32) {
+            const int64_t src = tb + (j - valid);
+            out_ids[(size_t)w * k + j] = src < te ? train_items[src] : -1;
+            out_scores[(size_t)w * k + j] = src < te ? -1024.f : -INFINITY;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static size_t tc_smem(int nh, int stages, int k) {
+    return 1024 + (size_t)nh * TC_TILE_BYTES + (size_t)stages * TC_TILE_BYTES + (size_t)2 * k * TC_M * nh * 4 + 256;
+}
+
+TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
+    TcPlan p{};
+    p.ok = false;
+    if (dim != TC_D || k < 1 || k > 128 || nu < 1 || n_item < 1) return p;
+    const size_t budget = 227 * 1024;
+    // two halves per CTA halve the L2 traffic of the item stream; use them when there are enough users
+    p.nh = nu > TC_M ? 2 : 1;
+    for (;; p.nh = 1) {
+        p.stages = TC_MAX_STAGES;
+        while (p.stages >= 2 && tc_smem(p.nh, p.stages, k) > budget) --p.stages;
+        if (p.stages >= (p.nh == 2 ? 3 : 2)) break;
+        if (p.nh == 1) return p;
+    }
+    const int64_t user_tiles = (nu + TC_M * p.nh - 1) / (TC_M * p.nh);
+    const int64_t item_tiles = (n_item + TC_N - 1) / TC_N;
+    // item splits: fill the 148 SMs in as few, as full waves as possible; every split restarts its thresholds, so
+    // keep at least 8 tiles per split
+    int64_t best_s = 1;
+    double best_eff = 0.0;
+    const int64_t max_s = max((int64_t)1, min((int64_t)1024, item_tiles / 8));
+    for (int64_t s = 1; s <= max_s; ++s) {
+        const int64_t ctas = user_tiles * s;
+        const int64_t waves = (ctas + kSMs - 1) / kSMs;
+        if (waves > 4 && s > 1) break;
+        const double eff = (double)ctas / (double)(waves * kSMs);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_s = s; }
+    }
+    p.splits = (int)best_s;
+    p.items_per_split = ((item_tiles + p.splits - 1) / p.splits) * TC_N;
+    p.splits = (int)((n_item + p.items_per_split - 1) / p.items_per_split);
+    p.smem = tc_smem(p.nh, p.stages, k);
+    p.ok = true;
+    return p;
+}
+
+int eval_topk_tc(const int64_t* users, int64_t nu, const float* user_table, const float* item_table, int64_t n_item,
+                 const int64_t* train_ptr, const int32_t* train_items, int k, int32_t* topk_ids, float* topk_scores,
+                 void* workspace, size_t workspace_bytes, void* stream, const TcPlan& p) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(TAGREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver", __FILE__, __LINE__);
+    TAGREC_REQUIRE((reinterpret_cast<uintptr_t>(item_table) & 15) == 0, "item table must be 16-byte aligned");
+    const size_t need = 256 + (size_t)nu * p.splits * k * 8;
+    if (!workspace || workspace_bytes < need) return fail(TAGREC_ENOMEM, "eval workspace too small", __FILE__, __LINE__);
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)TC_D, (cuuint64_t)n_item};
+    const cuuint64_t gstride[1] = {(cuuint64_t)TC_D * 4};
+    const cuuint32_t box[2] = {32, (cuuint32_t)TC_N};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(item_table), gdim, gstride, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TAGREC_ECUDA, "cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+
+    TcArgs a{};
+    a.users = users; a.nu = nu; a.user_table = user_table; a.item_table = item_table; a.n_item = n_item;
+    a.train_ptr = train_ptr; a.train_items = train_items; a.k = k; a.splits = p.splits; a.stages = p.stages;
+    a.items_per_split = p.items_per_split;
+    float* maxnorm = reinterpret_cast<float*>(workspace);
+    a.item_maxnorm = maxnorm;
+    a.part_scores = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+    a.part_ids = reinterpret_cast<int32_t*>(a.part_scores + (size_t)nu * p.splits * k);
+    cudaStream_t st = (cudaStream_t)stream;
+    TAGREC_CUDA(cudaMemsetAsync(maxnorm, 0, 4, st));
+    const int64_t nb = min((int64_t)kSMs * 8, (n_item + 15) / 16);
+    TAGREC_LAUNCH(item_maxnorm_kernel, (unsigned)nb, 256, 0, stream, reinterpret_cast<const float4*>(item_table), n_item,
+                  maxnorm);
+    const dim3 grid((unsigned)((nu + TC_M * p.nh - 1) / (TC_M * p.nh)), (unsigned)p.splits);
+    if (p.nh == 2) {
+        TAGREC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        TAGREC_LAUNCH(eval_tc_kernel<2>, grid, 64 + 256, p.smem, stream, map, a);
+    } else {
+        TAGREC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        TAGREC_LAUNCH(eval_tc_kernel<1>, grid, 64 + 128, p.smem, stream, map, a);
+    }
+    TAGREC_LAUNCH(eval_tc_merge_kernel, (unsigned)((nu + 7) / 8), 256, 0, stream, a.part_scores, a.part_ids, users, nu,
+                  p.splits, k, train_ptr, train_items, topk_ids, topk_scores);
+    return TAGREC_OK;
+}
+
+size_t eval_tc_workspace_bytes(int64_t nu, const TcPlan& p, int k) { return 256 + (size_t)nu * p.splits * k * 8; }
+
+}  // namespace tagrec

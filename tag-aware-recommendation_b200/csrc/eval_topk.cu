@@ -15,8 +15,10 @@
 // Ranking key: the raw dot product (sigmoid is monotone; the reference ranks sigmoid(dot), lightgcn.py:88).  Masked
 // (train) items rank below every un-masked item, in id order — as the reference's -1024 does (basic_test.py:47).
 #include <float.h>
+#include <algorithm>
 
 #include "common.cuh"
+#include "eval_tc.cuh"
 
 namespace tagrec {
 
@@ -293,16 +295,37 @@ static int pick_splits(int64_t nu, int64_t n_item) {
 using namespace tagrec;
 
 extern "C" size_t tagrec_eval_workspace_bytes(int64_t nu, int64_t n_item, int k) {
+    // large enough for either path (the tensor-core plan depends on dim only through dim == 64)
     const int s = pick_splits(nu, n_item);
-    return (size_t)nu * s * k * 8 + 256;
+    size_t need = (size_t)nu * s * k * 8 + 256;
+    const TcPlan p = tc_plan(nu, n_item, 64, k);
+    if (p.ok) need = std::max(need, eval_tc_workspace_bytes(nu, p, k));
+    return need;
 }
 
 extern "C" int tagrec_eval_topk(const int64_t* users, int64_t nu, const float* user_table, const float* item_table,
                                 int64_t n_item, int dim, const int64_t* train_ptr, const int32_t* train_items, int k,
                                 int32_t* topk_ids, float* topk_scores, void* workspace, size_t workspace_bytes,
                                 void* stream) {
+    return tagrec_eval_topk_ex(users, nu, user_table, item_table, n_item, dim, train_ptr, train_items, k, topk_ids,
+                               topk_scores, workspace, workspace_bytes, TAGREC_EVAL_AUTO, stream);
+}
+
+extern "C" int tagrec_eval_topk_ex(const int64_t* users, int64_t nu, const float* user_table, const float* item_table,
+                                   int64_t n_item, int dim, const int64_t* train_ptr, const int32_t* train_items,
+                                   int k, int32_t* topk_ids, float* topk_scores, void* workspace,
+                                   size_t workspace_bytes, int path, void* stream) {
     TAGREC_REQUIRE(users && user_table && item_table && train_ptr && topk_ids && topk_scores, "null pointer");
     TAGREC_REQUIRE(k >= 1 && k <= KMAX, "k must be in 1..128");
+    TAGREC_REQUIRE(path == TAGREC_EVAL_AUTO || path == TAGREC_EVAL_FP32 || path == TAGREC_EVAL_TF32, "bad path");
+    TAGREC_REQUIRE(n_item > 0 && n_item < (1ll << 31), "n_item out of range");
+    if (path != TAGREC_EVAL_FP32) {
+        const TcPlan p = tc_plan(nu, n_item, dim, k);
+        if (p.ok)
+            return eval_topk_tc(users, nu, user_table, item_table, n_item, train_ptr, train_items, k, topk_ids,
+                                topk_scores, workspace, workspace_bytes, stream, p);
+        TAGREC_REQUIRE(path == TAGREC_EVAL_AUTO, "tensor-core path needs dim == 64 and k <= 128");
+    }
     TAGREC_REQUIRE(dim >= 4 && dim % KC == 0, "dim must be a multiple of 32");
     TAGREC_REQUIRE(n_item > 0 && n_item < (1ll << 31), "n_item out of range");
     if (nu == 0) return TAGREC_OK;

@@ -4,9 +4,14 @@ import torch
 from ._lib import check, lib, ptr, stream_ptr
 
 
-def topk_scores(users, user_table, item_table, train_ptr, train_items, k):
+PATHS = {"auto": 0, "fp32": 1, "tf32": 2}     # TAGREC_EVAL_*
+
+
+def topk_scores(users, user_table, item_table, train_ptr, train_items, k, path="auto"):
     """users int64 [nu] (rows of user_table); returns (ids int32 [nu,k], scores fp32 [nu,k]) ordered by
-    (-score, item id); train items of each user rank below everything else with score -1024."""
+    (-score, item id); train items of each user rank below everything else with score -1024.
+    ``path``: "auto" (tcgen05 TF32 filter + exact fp32 re-score when dim == 64, else the fp32 CUDA-core tiles),
+    "fp32" or "tf32" — all return the same lists."""
     L = lib()
     dev = user_table.device
     users = users.to(device=dev, dtype=torch.int64).contiguous()
@@ -15,8 +20,9 @@ def topk_scores(users, user_table, item_table, train_ptr, train_items, k):
     ids = torch.empty((nu, k), dtype=torch.int32, device=dev)
     scores = torch.empty((nu, k), dtype=torch.float32, device=dev)
     ws = torch.empty(int(L.tagrec_eval_workspace_bytes(nu, n_item, k)), dtype=torch.uint8, device=dev)
-    check(L.tagrec_eval_topk(ptr(users), nu, ptr(ut), ptr(it), n_item, dim, ptr(train_ptr), ptr(train_items), k,
-                             ptr(ids), ptr(scores), ptr(ws), ws.numel(), stream_ptr(dev)), "tagrec_eval_topk")
+    check(L.tagrec_eval_topk_ex(ptr(users), nu, ptr(ut), ptr(it), n_item, dim, ptr(train_ptr), ptr(train_items), k,
+                                ptr(ids), ptr(scores), ptr(ws), ws.numel(), PATHS[path], stream_ptr(dev)),
+          "tagrec_eval_topk")
     return ids, scores
 
 

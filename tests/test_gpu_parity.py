@@ -311,6 +311,75 @@ def test_k3_shapes_vs_oracle(nu, n_item, dim, k):
         assert near_tie_ok(ms[r], ids[r], ref[r], k), f"row {r}"
 
 
+def _random_eval_case(nu, n_item, k, seed, scale=1.0, heavy=False, n_tables=None):
+    g = torch.Generator().manual_seed(seed)
+    n_tab = n_tables or (nu + 5)
+    ut = torch.randn(n_tab, 64, generator=g) * scale
+    it = torch.randn(n_item, 64, generator=g) * scale
+    rng = np.random.RandomState(seed)
+    users = rng.permutation(n_tab)[:nu]
+    train = {}
+    for u in range(n_tab):
+        hi = max(1, min(n_item - k, (n_item // 2) if (heavy and u % 7 == 0) else 40))
+        train[u] = sorted(rng.choice(n_item, rng.randint(0, hi), replace=False).tolist())
+    ptr_, items = T.bpr_training_data.user_items_to_csr(train, n_tab)
+    return (torch.tensor(users, device=dev()), ut.to(dev()), it.to(dev()), torch.tensor(ptr_, device=dev()),
+            torch.tensor(items, device=dev()).int())
+
+
+@pytest.mark.parametrize("nu,n_item,k,scale,heavy", [
+    (1, 50, 20, 1.0, False), (64, 129, 5, 1.0, False), (130, 5000, 20, 1.0, True), (300, 40000, 20, 0.1, True),
+    (129, 1025, 64, 1.0, False), (257, 3000, 100, 1.0, False), (700, 20000, 10, 3.0, False)])
+def test_k3_tensor_core_path_equals_fp32_path(nu, n_item, k, scale, heavy):
+    """tcgen05 TF32 filter + exact fp32 re-score (csrc/eval_tc.cu) returns the SAME ids and scores as the exact
+    fp32 CUDA-core path — bit-exact, including item-id tie-breaks, partial tiles, several item splits, users with
+    very long train rows and both CTA shapes (1 / 2 user halves)."""
+    from tagrec_b200.eval_ops import topk_scores
+    users, ut, it, ptr_, items = _random_eval_case(nu, n_item, k, 1000 + nu + n_item, scale, heavy)
+    ids_a, sc_a = topk_scores(users, ut, it, ptr_, items, k, path="fp32")
+    ids_b, sc_b = topk_scores(users, ut, it, ptr_, items, k, path="tf32")
+    torch.cuda.synchronize()
+    assert torch.equal(ids_a, ids_b)
+    assert torch.equal(sc_a, sc_b)
+
+
+def test_k3_tensor_core_ties_and_masked_tail():
+    """Duplicate item rows (exact score ties -> lower id first) and a user with fewer than k un-masked items."""
+    from tagrec_b200.eval_ops import topk_scores
+    I = 1000
+    g = torch.Generator().manual_seed(5)
+    it = torch.randn(I, 64, generator=g) * 0.1
+    it[500:1000] = it[0:500]                                   # every item has an exact twin 500 ids later
+    ut = torch.randn(3, 64, generator=g) * 0.1
+    free = [3, 503, 777]
+    train0 = [i for i in range(I) if i not in free]
+    ptr_ = torch.tensor([0, len(train0), len(train0), len(train0)], device=dev())
+    items = torch.tensor(train0, device=dev(), dtype=torch.int32)
+    users = torch.tensor([0, 1, 2], device=dev())
+    ids, sc = topk_scores(users, ut.to(dev()), it.to(dev()), ptr_, items, 8, path="tf32")
+    ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+    dense = (ut.double() @ it.double().T).numpy()
+    assert set(ids[0, :3]) == set(free) and list(ids[0, 3:]) == [0, 1, 2, 4, 5]
+    assert np.all(sc[0, 3:] == -1024.0)
+    for r in (1, 2):
+        want = np.lexsort((np.arange(I), -dense[r]))[:8]
+        assert list(ids[r]) == list(want)
+        assert all(ids[r, j] + 500 == ids[r, j + 1] for j in range(0, 8, 2))      # twins adjacent, lower id first
+
+
+def test_k3_tensor_core_large_vs_torch():
+    """16 K-item / 2 K-user case against torch fp64 scores: sets equal up to near-ties."""
+    from tagrec_b200.eval_ops import topk_scores
+    users, ut, it, ptr_, items = _random_eval_case(2000, 16000, 20, 77, 0.3, True, n_tables=2100)
+    ids, _ = topk_scores(users, ut, it, ptr_, items, 20, path="tf32")
+    scores = (ut[users].double() @ it.double().T).cpu().numpy()
+    ms = OM.mask_train(scores, users.cpu().numpy(), ptr_.cpu().numpy(), items.cpu().numpy())
+    ref = OM.topk_ids(ms, 20)
+    ids = ids.cpu().numpy()
+    for r in range(len(users)):
+        assert near_tie_ok(ms[r], ids[r], ref[r], 20), f"row {r}"
+
+
 # ------------------------------------------------------------------------------------------------------- sampler
 def test_device_sampler_properties(medium):
     U, I, _, _ = nums(medium)
