@@ -183,6 +183,75 @@ int tagrec_eval_metrics(const int64_t* users, int64_t nu, const int32_t* topk_id
                         double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * K6  NGCF dense half-layer (64 -> 64)     replaces model/ngcf.py:77-86 and its autograd: two products against
+ *                                          (W + b) — bias added to the WEIGHT matrix —, LeakyReLU(0.2), sum,
+ *                                          F.normalize.  All tables [n, 64] row-major; w* [64, 64], b* [64].
+ *   fwd: out = lrelu((nei+e)(w1+b1)) + lrelu((nei*e)(w2+b2)); nrm = out / max(||out||, 1e-12);
+ *        s_act / t_act = the two activations (saved for backward).
+ *   bwd: g = g_out (may be NULL) + J_normalize(out)^T g_nrm (rows g_nrm_ld floats apart: a column slice of the
+ *        concatenated gradient); gs = g*lrelu'(s), gt = g*lrelu'(t) (outputs: the caller forms dW = x^T gs with a
+ *        library GEMM); g_nei = gs(w1+b1)^T + (gt(w2+b2)^T)*e;  g_e = gs(w1+b1)^T + (gt(w2+b2)^T)*nei.
+ * ---------------------------------------------------------------------------------------------------------- */
+int tagrec_ngcf_dense_fwd(const float* nei, const float* e, const float* w1, const float* b1, const float* w2,
+                          const float* b2, int64_t n, int dim, float* out, float* nrm, float* s_act, float* t_act,
+                          void* stream);
+int tagrec_ngcf_dense_bwd(const float* g_out, const float* g_nrm, int64_t g_nrm_ld, const float* out,
+                          const float* s_act, const float* t_act, const float* nei, const float* e, const float* w1,
+                          const float* b1, const float* w2, const float* b2, int64_t n, int dim, float* g_nei,
+                          float* g_e, float* gs, float* gt, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K5  disentangled routing (DGCF / DisenGCN)     replaces model/dgcf.py:68-110 (iterate_update, factor_update) and
+ *                                                model/disengcn.py:29-43 (neighbour routing inside Layer.forward).
+ * Structure = rowptr int64 [n+1] / col int32 [nnz] of the 'plain' adjacency (values ignored, dgcf.py:90,
+ * disengcn.py:27).  Factor count is 4, rows are 64-d = 4 chunks of 16; per-edge quantities are [nnz, 4] float
+ * (one float4 per edge, factor-minor).  Node tables are [n, 64] row-major, dinv is [n, 4].
+ * ---------------------------------------------------------------------------------------------------------- */
+/* w[e,:] = softmax_k(logit[e,:]) (dgcf.py:74); dinv[h,k] = 1/sqrt(sum_{e in row h} w[e,k]), 0 for empty rows
+ * (dgcf.py:95-97). */
+int tagrec_edge_softmax_rowsum(const int64_t* rowptr, int64_t n_rows, const float* logit, float* w, float* dinv,
+                               void* stream);
+/* val[e,k] = dinv[h,k] * w[e,k] * dinv[t,k]: the per-factor operator D A_k D of dgcf.py:98-101 as edge values. */
+int tagrec_edge_scale(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const float* w, const float* dinv,
+                      float* val, void* stream);
+/* y[h, chunk k] = (res ? res[h] : 0) + sum_{e=(h,t)} val[perm ? perm[e] : e, k] * x[t, chunk k]
+ *   y_raw  (optional) the sum;  y_norm (optional) each 16-d chunk L2-normalised (dgcf.py:79, disengcn.py:41);
+ *   mean_acc (optional) running mean of the normalised layers: (first ? mean_x0 : mean_acc) + y_norm, times
+ *   mean_scale when last (dgcf.py:59-61).  perm = reverse-edge permutation => multiplies by the TRANSPOSED operator. */
+int tagrec_spmm4(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const float* val, const int32_t* perm,
+                 const float* x, const float* res, float* y_raw, float* y_norm, float* mean_acc, const float* mean_x0,
+                 int mean_first, int mean_last, float mean_scale, void* stream);
+/* d[e,k] = <a[h, chunk k], b[t, chunk k]>;  mode 0: out[e,:] += d (dgcf.py:103-109, A_values += A_score)
+ *                                           mode 1: out[e,:] = softmax_k(d) (disengcn.py:31-34). */
+int tagrec_edge_dot4(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const float* a, const float* b,
+                     float* out, int mode, void* stream);
+/* y = x / max(||x||_2 per 16-d chunk, 1e-12), optionally tanh(y) (dgcf.py:106-108). */
+int tagrec_chunk_normalize(const float* x, int64_t n_rows, int apply_tanh, float* y, void* stream);
+/* out = J^T g for y = chunk_normalize(x). */
+int tagrec_chunk_normalize_bwd(const float* g, const float* x, int64_t n_rows, float* out, void* stream);
+/* rev[e(h,t)] = e(t,h); *missing (device int) counts edges without a reverse (0 for a symmetric structure). */
+int tagrec_csr_reverse_perm(const int64_t* rowptr, const int32_t* col, int64_t n_rows, int32_t* rev, int32_t* missing,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K4  TGCN neighbour attention      replaces model/tgcn.py:20-37 (Attention1.forward: [N,k,64] gathers, repeat,
+ *                                   two matmuls, softmax over k, weighted sum) and its index_put_ backward.
+ * The caller supplies the three dense projections (plain GEMMs):
+ *     pv [n, 32] = e_v W1[:64] + b,   ww [n_w, 32] = e_w W1[64:],   pj [n_j, 32] = e_j W2
+ * nbr / nbw: int64 [n, ld] neighbour tables (data/utils.py:87-106): entry = id + 1, 0 = padding (zero row, still a
+ * softmax slot, tgcn.py:21-24); the first k columns are used (tgcn.py:199).  v [32] = attention vector.
+ *   fwd: att[n,k] = softmax_k(relu(pv + ww[w-1] + pj[j-1]) . v);  out[n,64] = sum_k att * ej[j-1]
+ *   bwd: g_pv (written), g_ww / g_pj / g_ej / g_v (ACCUMULATED: caller zeroes them).
+ * ---------------------------------------------------------------------------------------------------------- */
+int tagrec_nbr_attention_fwd(const float* pv, const float* ww, const float* pj, const float* ej, const float* v,
+                             const int64_t* nbr, const int64_t* nbw, int64_t n, int k, int64_t ld, int dim,
+                             int dim_atten, float* out, float* att, void* stream);
+int tagrec_nbr_attention_bwd(const float* g_out, const float* att, const float* pv, const float* ww, const float* pj,
+                             const float* ej, const float* v, const int64_t* nbr, const int64_t* nbw, int64_t n, int k,
+                             int64_t ld, int n_w, int dim, int dim_atten, float* g_pv, float* g_ww, float* g_pj,
+                             float* g_ej, float* g_v, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * BPR negative sampler          replaces train_data/bpr_training_data.py:29-45 + train_data/utils.py:19-28,52-55.
  * Host version: bit-exact numpy-legacy MT19937 stream for cpu_core == 1 (parity mode).  All pointers HOST.
  *   state: 625 uint32 (624 words + position), advanced exactly as the parent's RandomState is (shuffle only).

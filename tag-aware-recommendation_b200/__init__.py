@@ -14,7 +14,12 @@ from . import _lib                                             # noqa: F401
 from ._lib import TagrecError, launch_count                    # noqa: F401
 from .adj import CsrGraph, build_csr, creat_adj, split_mm, spmm_raw, node_drop   # noqa: F401
 from .lightgcn import LightGCN                                 # noqa: F401
-from .bpr_training_data import Abstract_training_data, BPR_training_data         # noqa: F401
+from .ngcf import NGCF                                         # noqa: F401
+from .dgcf import DGCF                                         # noqa: F401
+from .disengcn import DisenGCN                                 # noqa: F401
+from .tgcn import TGCN                                         # noqa: F401
+from . import routing                                          # noqa: F401
+from .bpr_training_data import Abstract_training_data, BPR_training_data, DGCF_training_data   # noqa: F401
 from .basic_train import Basic_train, epoch_training           # noqa: F401
 from .basic_test import Basic_test                             # noqa: F401
 from .early_stop import Early_stop                             # noqa: F401

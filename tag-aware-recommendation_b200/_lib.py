@@ -54,6 +54,18 @@ PROTOTYPES = {
     "tagrec_eval_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "tagrec_eval_topk_ex": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _sz, _i32, _p]),
     "tagrec_eval_metrics": (_i32, [_p, _i64, _p, _i32, _p, _p, _p, _i32, _p, _p]),
+    "tagrec_ngcf_dense_fwd": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
+    "tagrec_ngcf_dense_bwd": (_i32, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
+    "tagrec_edge_softmax_rowsum": (_i32, [_p, _i64, _p, _p, _p, _p]),
+    "tagrec_edge_scale": (_i32, [_p, _p, _i64, _p, _p, _p, _p]),
+    "tagrec_spmm4": (_i32, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f32, _p]),
+    "tagrec_edge_dot4": (_i32, [_p, _p, _i64, _p, _p, _p, _i32, _p]),
+    "tagrec_chunk_normalize": (_i32, [_p, _i64, _i32, _p, _p]),
+    "tagrec_chunk_normalize_bwd": (_i32, [_p, _p, _i64, _p, _p]),
+    "tagrec_csr_reverse_perm": (_i32, [_p, _p, _i64, _p, _p, _p]),
+    "tagrec_nbr_attention_fwd": (_i32, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i64, _i32, _i32, _p, _p, _p]),
+    "tagrec_nbr_attention_bwd": (_i32, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i64, _i32, _i32, _i32,
+                                        _p, _p, _p, _p, _p, _p]),
     "tagrec_mt19937_seed": (None, [_u32, _p]),
     "tagrec_sample_bpr_host": (_i32, [_p, _p, _i64, _p, _p, _i64, _p]),
     "tagrec_sample_bpr_device": (_i32, [_p, _i64, _p, _p, _i64, _u64, _u64, _p, _p]),

@@ -100,3 +100,97 @@ class BPR_training_data(Abstract_training_data):
               "tagrec_sample_bpr_device")
         self.epoch += 1
         return out
+
+
+class DGCF_training_data(Abstract_training_data):
+    """Drop-in for train_data/bpr_training_data.py:47-84 (the NGCF-style sampler DGCF / DisenGCN / DisenHAN use,
+    com.py:35,46,57): every batch = ``train_batch`` sampled users with one positive and one negative item each, plus
+    the (unused) ``cor`` index sample; ``tot_inter = E // B + 1`` batches per epoch; ``reset()`` is a no-op;
+    ``mini_batch()`` yields ``(data, cor)`` tuples (models unpack them, dgcf.py:116).
+
+    CFG['sampler'] == 'mt19937' restates the reference's host procedure call for call — ``random.sample`` for the
+    users and the ``cor`` indices, ``np.random.choice`` for the positive, ``np.random.randint`` rejection for the
+    negative (train_data/utils.py:58-78) — so seeding ``random`` and ``np.random`` reproduces its stream bit for
+    bit.  'device' (default) draws users/positives with torch's CUDA generator and the negatives with the Philox
+    rejection kernel (``tagrec_sample_bpr_device``)."""
+
+    def __init__(self, data, args=None):
+        super().__init__(args)
+        cfg = config.current()
+        self.batch_size = cfg['train_batch']
+        self.cor_batch = cfg.get('cor_batch', 100)
+        self.use_tag = cfg['use_tag']
+        self.mode = cfg.get('sampler', 'device')
+        self.seed = int(cfg.get('seed', 2020))
+        self.num_item = int(data.num['item'])
+        self.num_user = int(data.num['user'])
+        self.num_tag = int(data.num.get('tag', 0)) if isinstance(data.num, dict) else int(data.num['tag'])
+        self.train_ui = data.user_items['train']
+        self.pos_inter = data.edge_index['train']
+        self.tot_inter = self.pos_inter.shape[0] // self.batch_size + 1
+        self.calls = 0
+        if self.mode == "device":
+            dev = self.device
+            ptr_h, items_h = user_items_to_csr(self.train_ui, self.num_user)
+            self._ptr_d = torch.as_tensor(ptr_h, device=dev)
+            self._items_d = torch.as_tensor(items_h, device=dev).to(torch.int32)
+            self._users_d = torch.as_tensor(np.fromiter(self.train_ui.keys(), dtype=np.int64), device=dev)
+            self._gen = torch.Generator(device=dev)
+            self._gen.manual_seed(self.seed)
+        start = time.time()
+        self.mini_sample()
+        print(f"DGCF_training_data producer,tot_inter:{self.tot_inter},cor_batch:{self.cor_batch},"
+              f"[mini_sample time:{time.time()-start}]")
+
+    def _host_sample(self):
+        import random
+        all_user = list(self.train_ui.keys())
+        if len(all_user) > self.batch_size:
+            sample_user = random.sample(all_user, self.batch_size)
+        else:
+            sample_user = np.random.choice(all_user, self.batch_size)
+        rows = []
+        for u in sample_user:
+            pos_list = self.train_ui[u]
+            pos_i = np.random.choice(pos_list)
+            while True:
+                neg_i = np.random.randint(0, self.num_item)
+                if neg_i not in pos_list:
+                    break
+            rows.append([u, pos_i, neg_i])
+        data = torch.tensor(np.array(rows), dtype=torch.long, device=self.device)
+        cor = [random.sample(list(range(self.num_user)), self.cor_batch),
+               random.sample(list(range(self.num_item)), self.cor_batch)]
+        if self.use_tag:
+            cor.append(random.sample(list(range(self.num_tag)), self.cor_batch))
+        return data, torch.tensor(np.stack(cor), dtype=torch.long, device=self.device)
+
+    def _device_sample(self):
+        dev, b, g = self.device, self.batch_size, self._gen
+        nu = self._users_d.numel()
+        if nu > b:
+            users = self._users_d[torch.randperm(nu, device=dev, generator=g)[:b]]
+        else:
+            users = self._users_d[torch.randint(0, nu, (b,), device=dev, generator=g)]
+        deg = self._ptr_d[users + 1] - self._ptr_d[users]
+        off = torch.minimum((torch.rand(b, device=dev, generator=g, dtype=torch.float64) * deg).long(), deg - 1)
+        pos = self._items_d[self._ptr_d[users] + off].long()
+        edges = torch.stack([users, pos], 1).contiguous()
+        out = torch.empty((b, 3), dtype=torch.int64, device=dev)
+        check(lib().tagrec_sample_bpr_device(ptr(edges), b, ptr(self._ptr_d), ptr(self._items_d), self.num_item,
+                                             self.seed, self.calls, ptr(out), stream_ptr(dev)),
+              "tagrec_sample_bpr_device")
+        sizes = [self.num_user, self.num_item] + ([self.num_tag] if self.use_tag else [])
+        cor = torch.stack([torch.randperm(n, device=dev, generator=g)[:self.cor_batch] for n in sizes])
+        return out, cor
+
+    def mini_sample(self):
+        self.calls += 1
+        return self._host_sample() if self.mode != "device" else self._device_sample()
+
+    def reset(self):
+        pass
+
+    def mini_batch(self):
+        for _ in range(0, self.tot_inter):
+            yield self.mini_sample()

@@ -28,6 +28,8 @@
 #include <cuda.h>
 #include <float.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "eval_tc.cuh"
 
@@ -38,7 +40,7 @@ constexpr int TC_N = 128;                 // items per tile (UMMA N)
 constexpr int TC_D = 64;                  // feature dim == GEMM K
 constexpr int TC_KH_BYTES = TC_N * 128;   // one 128B-swizzled k-half of a tile: 128 rows x 32 floats = 16 KB
 constexpr int TC_TILE_BYTES = 2 * TC_KH_BYTES;   // 32 KB (A half or B stage)
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_STAGES = 6;
 constexpr float TC_MARGIN = 2.2e-3f;
 
 struct TcArgs {
@@ -141,25 +143,61 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int c16) {
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
+// TC_TS == 1 (default): the A operand (user rows) lives in TENSOR MEMORY (tcgen05.mma "TS" form): every epilogue
+// thread stores its own 64-float user row into its TMEM lane once (tcgen05.st).  An SS-form M128 x N128 x K8 TF32
+// MMA reads 4 KB of A + 4 KB of B from shared memory per 64 cycles = 128 B/clk, i.e. ALL of an SM's shared-memory
+// bandwidth, leaving nothing for the TMA writes of the next item tile; with A in TMEM the MMA reads 64 B/clk and
+// the 64 KB of smem the user tile occupied become two more item-tile stages.
+// TC_TS == 0: A in shared memory (SS form), kept for comparison.
+#ifndef TC_TS
+#define TC_TS 1
+#endif
+#ifndef TC_EXPERIMENT
+#define TC_EXPERIMENT 0      // 1 / 2: timing experiments (wrong results), see tools/tune_eval.sh
+#endif
+constexpr int TC_NACC = 3;        // accumulator ring (128 columns each)
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 template <int NH>
 __global__ void __launch_bounds__(64 + 128 * NH, 1)
 eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
     constexpr int ROWS = TC_M * NH;
-    constexpr int EPI_WARPS = 4 * NH;
-    constexpr int TMEM_COLS = 2 * NH * TC_N;      // 256 or 512: a power of two >= 32
+    constexpr bool kTS = TC_TS != 0;
+    constexpr int A_COLS = kTS ? 64 * NH : 0;                 // TMEM columns holding the user rows (one fp32 per column)
+    constexpr int TMEM_COLS = 512;                            // A_COLS + TC_NACC * 128 <= 512, power of two
+    constexpr int A_SMEM = kTS ? 0 : NH * TC_TILE_BYTES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int S = a.stages, K = a.k;
-    unsigned char* As = base;                                         // NH x 32 KB
-    unsigned char* Bs = As + NH * TC_TILE_BYTES;                      // S  x 32 KB
-    float* ls = reinterpret_cast<float*>(Bs + S * TC_TILE_BYTES);     // [K][ROWS] scores, descending per row
+    unsigned char* As = base;                                         // SS form only: NH x 32 KB
+    unsigned char* Bs = base + A_SMEM;                                // S x 32 KB
+    float* ls = reinterpret_cast<float*>(Bs + S * TC_TILE_BYTES);     // [K][ROWS] scores (unsorted K-lists)
     int32_t* li = reinterpret_cast<int32_t*>(ls + (size_t)K * ROWS);  // [K][ROWS] item ids
     uint64_t* bars = reinterpret_cast<uint64_t*>(li + (size_t)K * ROWS);
-    uint64_t* full = bars;                        // [S]  TMA -> MMA
-    uint64_t* bfree = bars + TC_MAX_STAGES;       // [S]  epilogue -> TMA
-    uint64_t* accfull = bars + 2 * TC_MAX_STAGES; // [2]  MMA -> epilogue
-    uint64_t* accfree = accfull + 2;              // [2]  epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfree + 2);
+    uint64_t* full = bars;                                    // [S]     TMA -> MMA
+    uint64_t* bfree = bars + TC_MAX_STAGES;                   // [S]     epilogue -> TMA
+    uint64_t* accfull = bars + 2 * TC_MAX_STAGES;             // [NACC]  MMA -> epilogue
+    uint64_t* accfree = accfull + TC_NACC;                    // [NACC]  epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfree + TC_NACC);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t u0 = (int64_t)blockIdx.x * ROWS;
@@ -168,15 +206,20 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
     const int64_t i_end = min(a.n_item, i_begin + a.items_per_split);
     const int n_tiles = (int)((i_end - i_begin + TC_N - 1) / TC_N);
 
-    // ---- prologue: barriers, TMEM, user tile -> smem (generic proxy, swizzled like the TMA would) ----
+#if TC_EXPERIMENT != 0
+    long long dbg_c0 = clock64();
+    unsigned long long dbg_t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+#endif
+    // ---- prologue: barriers, TMEM allocation ----
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(smem_u32(full + s), 1);
-            mbar_init(smem_u32(bfree + s), EPI_WARPS);
+            mbar_init(smem_u32(bfree + s), 4 * NH);           // every epilogue warp releases the stage
         }
-        for (int x = 0; x < 2; ++x) {
+        for (int x = 0; x < TC_NACC; ++x) {
             mbar_init(smem_u32(accfull + x), 1);
-            mbar_init(smem_u32(accfree + x), EPI_WARPS);
+            mbar_init(smem_u32(accfree + x), 4);              // the 4 warps of ONE half drain an accumulator
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -185,20 +228,56 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
                      ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int idx = tid; idx < ROWS * 16; idx += blockDim.x) {
-        const int row = idx >> 4, c16 = idx & 15;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (u0 + row < a.nu) {
-            const int64_t u = __ldg(a.users + u0 + row);
-            v = __ldg(reinterpret_cast<const float4*>(a.user_table + u * TC_D) + c16);
+    if constexpr (!kTS) {     // user tile -> smem (generic proxy), swizzled exactly like a TMA SWIZZLE_128B box
+        for (int idx = tid; idx < ROWS * 16; idx += blockDim.x) {
+            const int row = idx >> 4, c16 = idx & 15;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (u0 + row < a.nu) {
+                const int64_t u = __ldg(a.users + u0 + row);
+                v = __ldg(reinterpret_cast<const float4*>(a.user_table + u * TC_D) + c16);
+            }
+            *reinterpret_cast<float4*>(As + (row >> 7) * TC_TILE_BYTES + sw128_off(row & 127, c16)) = v;
         }
-        *reinterpret_cast<float4*>(As + (row >> 7) * TC_TILE_BYTES + sw128_off(row & 127, c16)) = v;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // smem writes -> visible to tcgen05.mma
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // smem writes -> visible to tcgen05.mma
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_base = tmem_base + (uint32_t)A_COLS;
+
+    // epilogue-thread identity (computed by every thread; only warps >= 2 use it)
+    const int e = warp - 2;                     // 0 .. 4*NH-1
+    const int h = e >> 2;
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int row = h * TC_M + q * 32 + lane;
+    const bool is_epi = warp >= 2;
+    const bool valid = is_epi && (u0 + row < a.nu);
+    const float4* urow = nullptr;               // this thread's user row in global memory (exact re-scores)
+    float unorm2 = 0.f;
+    if (is_epi) {
+        if (valid) urow = reinterpret_cast<const float4*>(a.user_table + __ldg(a.users + u0 + row) * TC_D);
+        // row -> registers (two halves of 32 floats) -> this thread's TMEM lane, columns h*64 .. h*64+63
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) v = __ldg(urow + half * 8 + c);
+                unorm2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, unorm2))));
+                r[4 * c + 0] = __float_as_uint(v.x);
+                r[4 * c + 1] = __float_as_uint(v.y);
+                r[4 * c + 2] = __float_as_uint(v.z);
+                r[4 * c + 3] = __float_as_uint(v.w);
+            }
+            if constexpr (kTS) tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 64 + half * 32), r);
+        }
+        if constexpr (kTS) tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();                            // user rows are in TMEM before the first MMA reads them
+    tc_fence_after();
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -206,6 +285,9 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % S;
                 mbar_wait(smem_u32(bfree + s), ((t / S) & 1) ^ 1);
+#if TC_EXPERIMENT >= 4
+                if (t >= S) continue;                         // timing experiment: no item-tile traffic (pure MMA rate)
+#endif
                 const uint32_t bar = smem_u32(full + s);
                 mbar_expect_tx(bar, TC_TILE_BYTES);
                 const uint32_t dst = smem_u32(Bs + s * TC_TILE_BYTES);
@@ -218,49 +300,60 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
         // ================= MMA issuer =================
         if (lane == 0) {
             for (int t = 0; t < n_tiles; ++t) {
-                const int s = t % S, acc = t & 1;
-                mbar_wait(smem_u32(accfree + acc), ((t >> 1) & 1) ^ 1);
+                const int s = t % S;
+#if TC_EXPERIMENT >= 4
+                if (t < S)
+#endif
                 mbar_wait(smem_u32(full + s), (t / S) & 1);
-                tc_fence_after();
                 const uint32_t b0 = smem_u32(Bs + s * TC_TILE_BYTES);
 #pragma unroll
-                for (int h = 0; h < NH; ++h) {
-                    const uint32_t a0 = smem_u32(As + h * TC_TILE_BYTES);
-                    const uint32_t d = tmem_base + (uint32_t)((acc * NH + h) * TC_N);
+                for (int hh = 0; hh < NH; ++hh) {
+                    const int n = t * NH + hh, r = n % TC_NACC;
+                    mbar_wait(smem_u32(accfree + r), ((n / TC_NACC) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = acc_base + (uint32_t)(r * TC_N);
+#if TC_EXPERIMENT == 5      // timing experiment: half as many MMA instructions, each N = 256 (same flops, wrong results)
+                    if (hh == 0) {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const uint32_t off = (uint32_t)((kk >> 2) * TC_KH_BYTES + (kk & 3) * 32);
+                            const uint32_t idesc256 = (TC_IDESC & ~(0x3Fu << 17)) | ((256u >> 3) << 17);
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                                ::"r"(acc_base), "r"(tmem_base + (uint32_t)(kk * 8)), "l"(umma_desc_sw128(b0 + off)),
+                                  "r"(idesc256), "r"((uint32_t)(kk > 0)) : "memory");
+                        }
+                    }
+                    umma_commit(smem_u32(accfull + r));
+                    continue;
+#endif
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {     // K = 8 per instruction: 4 per 128-byte swizzle row, 2 k-halves
                         const uint32_t off = (uint32_t)((kk >> 2) * TC_KH_BYTES + (kk & 3) * 32);
-                        umma_tf32(d, umma_desc_sw128(a0 + off), umma_desc_sw128(b0 + off), kk > 0);
+                        if constexpr (kTS)
+                            umma_tf32_ts(d, tmem_base + (uint32_t)(hh * 64 + kk * 8), umma_desc_sw128(b0 + off), kk > 0);
+                        else
+                            umma_tf32(d, umma_desc_sw128(smem_u32(As + hh * TC_TILE_BYTES) + off),
+                                      umma_desc_sw128(b0 + off), kk > 0);
                     }
+                    umma_commit(smem_u32(accfull + r));  // arrives when every MMA issued so far has completed
                 }
-                umma_commit(smem_u32(accfull + acc));    // arrives when every MMA above has completed
             }
         }
     } else {
         // ================= epilogue: thread = user row =================
-        const int e = warp - 2;                 // 0 .. 4*NH-1
-        const int h = e >> 2;
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int row = h * TC_M + q * 32 + lane;
-        const bool valid = u0 + row < a.nu;
-        const unsigned char* arow = As + h * TC_TILE_BYTES;
-        const int arow_l = q * 32 + lane;
         float thr = -INFINITY, thr_lo = valid ? -INFINITY : INFINITY, margin = 0.f;
-        int cnt = 0;
+        int cnt = 0, minpos = 0;                // the K-list is UNSORTED; minpos = entry to evict ((score, -id) minimum)
         int64_t tc = 0, te = 0;
         int32_t nxt = INT32_MAX;                // smallest train item of this user not yet passed
         if (valid) {
             const int64_t u = __ldg(a.users + u0 + row);
-            float ss = 0.f;
-            for (int c16 = 0; c16 < 16; ++c16) {
-                const float4 v = *reinterpret_cast<const float4*>(arow + sw128_off(arow_l, c16));
-                ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
-            }
-            margin = TC_MARGIN * sqrtf(ss) * __ldg(a.item_maxnorm) + FLT_MIN;
+            margin = TC_MARGIN * sqrtf(unorm2) * __ldg(a.item_maxnorm) + FLT_MIN;
             tc = __ldg(a.train_ptr + u);
             te = __ldg(a.train_ptr + u + 1);
-            // first train item inside this split
-            int64_t lo = tc, hi = te;
+            int64_t lo = tc, hi = te;           // first train item inside this split
             while (lo < hi) {
                 const int64_t mid = (lo + hi) >> 1;
                 if ((int64_t)__ldg(a.train_items + mid) < i_begin) lo = mid + 1; else hi = mid;
@@ -269,82 +362,111 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
             nxt = tc < te ? __ldg(a.train_items + tc) : INT32_MAX;
         }
         for (int t = 0; t < n_tiles; ++t) {
-            const int s = t % S, acc = t & 1;
+            const int s = t % S;
+            const int n = t * NH + h, r = n % TC_NACC;
             const int64_t it0 = i_begin + (int64_t)t * TC_N;
             const unsigned char* brow = Bs + s * TC_TILE_BYTES;
-            mbar_wait(smem_u32(accfull + acc), (t >> 1) & 1);
+            mbar_wait(smem_u32(accfull + r), (n / TC_NACC) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * NH + h) * TC_N);
-#pragma unroll 1
+            const uint32_t taddr = acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * TC_N);
+            // ---- fast path: 128 TF32 scores of this row -> a 128-bit candidate mask (usually empty) ----
+            uint32_t cm[TC_N / 32];
+#if TC_EXPERIMENT == 1
+            if (t == 8) thr_lo = INFINITY;                    // timing experiment: no candidate work after warm-up
+#endif
+#pragma unroll
             for (int c = 0; c < TC_N / 32; ++c) {
                 uint32_t v[32];
+#if TC_EXPERIMENT == 2
+                if (c >= 2) { cm[c] = 0; continue; }          // timing experiment: drain only half of the accumulator
+#elif TC_EXPERIMENT >= 3
+                if (t > 0) { cm[c] = 0; continue; }           // timing experiment: no drain at all (MMA + TMA floor)
+#endif
                 tmem_ld32(taddr + c * 32, v);
                 tmem_ld_wait();
                 float m = __uint_as_float(v[0]);
 #pragma unroll
                 for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+                uint32_t mask = 0;
                 if (m > thr_lo) {
-                    uint32_t mask = 0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr_lo) ? (1u << j) : 0u;
-                    while (mask) {
-                        const int j = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const int il = c * 32 + j;
-                        const int64_t item = it0 + il;
-                        if (item >= i_end) break;                 // zero-filled rows past the split / table end
-                        // train-item cursor: nxt = smallest train item >= item (galloping, then bisection)
-                        if ((int64_t)nxt < item) {
-                            int64_t step = 1, lo = tc + 1;
-                            while (lo + step < te && (int64_t)__ldg(a.train_items + lo + step) < item) {
-                                lo += step;
-                                step <<= 1;
-                            }
-                            int64_t hi = min(te, lo + step + 1);
-                            while (lo < hi) {
-                                const int64_t mid = (lo + hi) >> 1;
-                                if ((int64_t)__ldg(a.train_items + mid) < item) lo = mid + 1; else hi = mid;
-                            }
-                            tc = lo;
-                            nxt = tc < te ? __ldg(a.train_items + tc) : INT32_MAX;
-                        }
-                        if ((int64_t)nxt == item) continue;       // masked (basic_test.py:47)
-                        // exact fp32 score, canonical sequential order
-                        float ex = 0.f;
+                }
+                cm[c] = mask;
+            }
+            // the accumulator is drained: hand it back to the MMA warp before the (rare, slow) candidate work
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(accfree + r));
+            // ---- slow path: all lanes' candidates of this tile in lockstep ----
+            uint64_t lo64 = (uint64_t)cm[0] | ((uint64_t)cm[1] << 32), hi64 = (uint64_t)cm[2] | ((uint64_t)cm[3] << 32);
+            while (lo64 | hi64) {
+                int il;
+                if (lo64) {
+                    il = __ffsll((long long)lo64) - 1;
+                    lo64 &= lo64 - 1;
+                } else {
+                    il = 64 + __ffsll((long long)hi64) - 1;
+                    hi64 &= hi64 - 1;
+                }
+                const int64_t item = it0 + il;
+                if (item >= i_end) break;                     // zero-filled rows past the split / table end
+                // train-item cursor: nxt = smallest train item >= item (galloping, then bisection)
+                if ((int64_t)nxt < item) {
+                    int64_t step = 1, lo = tc + 1;
+                    while (lo + step < te && (int64_t)__ldg(a.train_items + lo + step) < item) {
+                        lo += step;
+                        step <<= 1;
+                    }
+                    int64_t hi = min(te, lo + step + 1);
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if ((int64_t)__ldg(a.train_items + mid) < item) lo = mid + 1; else hi = mid;
+                    }
+                    tc = lo;
+                    nxt = tc < te ? __ldg(a.train_items + tc) : INT32_MAX;
+                }
+                if ((int64_t)nxt == item) continue;           // masked (basic_test.py:47)
+                // exact fp32 score, canonical sequential order; item row from the smem stage, user row from L1/L2
+                float ex = 0.f;
 #pragma unroll
-                        for (int c16 = 0; c16 < 16; ++c16) {
-                            const float4 uu = *reinterpret_cast<const float4*>(arow + sw128_off(arow_l, c16));
-                            const float4 ii = *reinterpret_cast<const float4*>(brow + sw128_off(il, c16));
-                            ex = fmaf(uu.x, ii.x, ex);
-                            ex = fmaf(uu.y, ii.y, ex);
-                            ex = fmaf(uu.z, ii.z, ex);
-                            ex = fmaf(uu.w, ii.w, ex);
-                        }
-                        if (cnt < K || ex > thr) {
-                            int pos = cnt < K ? cnt : K - 1;
-                            while (pos > 0 && ls[(size_t)(pos - 1) * ROWS + row] < ex) {
-                                ls[(size_t)pos * ROWS + row] = ls[(size_t)(pos - 1) * ROWS + row];
-                                li[(size_t)pos * ROWS + row] = li[(size_t)(pos - 1) * ROWS + row];
-                                --pos;
+                for (int c16 = 0; c16 < 16; ++c16) {
+                    const float4 uu = __ldg(urow + c16);
+                    const float4 ii = *reinterpret_cast<const float4*>(brow + sw128_off(il, c16));
+                    ex = fmaf(uu.x, ii.x, ex);
+                    ex = fmaf(uu.y, ii.y, ex);
+                    ex = fmaf(uu.z, ii.z, ex);
+                    ex = fmaf(uu.w, ii.w, ex);
+                }
+                // items arrive in ascending id order, so on a score tie the incumbent (smaller id) stays: strict >
+                if (cnt < K || ex > thr) {
+                    const int pos = cnt < K ? cnt : minpos;
+                    ls[(size_t)pos * ROWS + row] = ex;
+                    li[(size_t)pos * ROWS + row] = (int32_t)item;
+                    if (cnt < K) ++cnt;
+                    if (cnt == K) {     // new evictee: lowest score, largest id among equals
+                        float best = INFINITY;
+                        int32_t besti = -1;
+                        int bp = 0;
+#pragma unroll 4
+                        for (int j = 0; j < K; ++j) {
+                            const float sj = ls[(size_t)j * ROWS + row];
+                            const int32_t ij = li[(size_t)j * ROWS + row];
+                            if (sj < best || (sj == best && ij > besti)) {
+                                best = sj;
+                                besti = ij;
+                                bp = j;
                             }
-                            ls[(size_t)pos * ROWS + row] = ex;
-                            li[(size_t)pos * ROWS + row] = (int32_t)item;
-                            if (cnt < K) ++cnt;
-                            if (cnt == K) {
-                                thr = ls[(size_t)(K - 1) * ROWS + row];
-                                thr_lo = thr - margin;
-                            }
                         }
+                        thr = best;
+                        minpos = bp;
+                        thr_lo = thr - margin;
                     }
                 }
             }
-            // this warp is done with accumulator `acc` and with B stage `s`
-            tc_fence_before();
+            // this warp no longer reads B stage `s`
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(smem_u32(accfree + acc));
-                mbar_arrive(smem_u32(bfree + s));
-            }
+            if (lane == 0) mbar_arrive(smem_u32(bfree + s));
         }
         if (valid) {
             const size_t o = ((size_t)(u0 + row) * a.splits + split) * K;
@@ -356,6 +478,15 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
     }
     tc_fence_before();
     __syncthreads();
+#if TC_EXPERIMENT != 0
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+        unsigned long long dbg_t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t1));
+        const long long dc = clock64() - dbg_c0;
+        printf("eval_tc experiment: %lld SM cycles in %llu ns => %.0f MHz, %d tiles, %.1f cycles/tile\n", dc,
+               dbg_t1 - dbg_t0, 1e3 * (double)dc / (double)(dbg_t1 - dbg_t0), n_tiles, (double)dc / n_tiles);
+    }
+#endif
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
@@ -437,7 +568,8 @@ static EncodeTiledFn encode_tiled() {
 }
 
 static size_t tc_smem(int nh, int stages, int k) {
-    return 1024 + (size_t)nh * TC_TILE_BYTES + (size_t)stages * TC_TILE_BYTES + (size_t)2 * k * TC_M * nh * 4 + 256;
+    const size_t a_smem = TC_TS ? 0 : (size_t)nh * TC_TILE_BYTES;
+    return 1024 + a_smem + (size_t)stages * TC_TILE_BYTES + (size_t)2 * k * TC_M * nh * 4 + 256;
 }
 
 TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
@@ -455,18 +587,10 @@ TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
     }
     const int64_t user_tiles = (nu + TC_M * p.nh - 1) / (TC_M * p.nh);
     const int64_t item_tiles = (n_item + TC_N - 1) / TC_N;
-    // item splits: fill the 148 SMs in as few, as full waves as possible; every split restarts its thresholds, so
-    // keep at least 8 tiles per split
-    int64_t best_s = 1;
-    double best_eff = 0.0;
-    const int64_t max_s = max((int64_t)1, min((int64_t)1024, item_tiles / 8));
-    for (int64_t s = 1; s <= max_s; ++s) {
-        const int64_t ctas = user_tiles * s;
-        const int64_t waves = (ctas + kSMs - 1) / kSMs;
-        if (waves > 4 && s > 1) break;
-        const double eff = (double)ctas / (double)(waves * kSMs);
-        if (eff > best_eff + 1e-9) { best_eff = eff; best_s = s; }
-    }
+    // item splits: every split restarts its thresholds (K * ln(items/K) slow-path candidates per row and split), so
+    // use as few as fill ONE wave of the 148 SMs, with at least 8 tiles per split
+    int64_t best_s = user_tiles >= kSMs ? 1 : kSMs / user_tiles;
+    best_s = std::max<int64_t>(1, std::min<int64_t>(best_s, item_tiles / 8));
     p.splits = (int)best_s;
     p.items_per_split = ((item_tiles + p.splits - 1) / p.splits) * TC_N;
     p.splits = (int)((n_item + p.items_per_split - 1) / p.items_per_split);

@@ -281,3 +281,41 @@ class BprLossFn(torch.autograd.Function):
         gf = g_final * g_loss
         gr = None if (g_reg is None or ctx.same) else g_reg * g_regterm
         return None, None, None, None, gf, gr
+
+
+class NgcfDenseFn(torch.autograd.Function):
+    """K6: the dense half of one NGCF layer (ngcf.py:77-86) as one autograd node — one fused forward launch, one
+    fused backward launch + the two weight-gradient GEMMs (x^T g, plain cuBLAS through torch)."""
+
+    @staticmethod
+    def forward(ctx, nei, e, w1, b1, w2, b2):
+        nei_c, e_c = nei.detach().contiguous(), e.detach().contiguous()
+        w1c, b1c, w2c, b2c = (t.detach().contiguous() for t in (w1, b1, w2, b2))
+        out, nrm = torch.empty_like(e_c), torch.empty_like(e_c)
+        s_act, t_act = torch.empty_like(e_c), torch.empty_like(e_c)
+        n, dim = e_c.shape
+        check(lib().tagrec_ngcf_dense_fwd(ptr(nei_c), ptr(e_c), ptr(w1c), ptr(b1c), ptr(w2c), ptr(b2c), n, dim, ptr(out),
+                                          ptr(nrm), ptr(s_act), ptr(t_act), stream_ptr(e_c.device)),
+              "tagrec_ngcf_dense_fwd")
+        ctx.save_for_backward(nei_c, e_c, w1c, b1c, w2c, b2c, out, s_act, t_act)
+        return out, nrm
+
+    @staticmethod
+    def backward(ctx, g_out, g_nrm):
+        nei, e, w1, b1, w2, b2, out, s_act, t_act = ctx.saved_tensors
+        n, dim = e.shape
+        if g_nrm is None:
+            g_nrm = torch.zeros_like(e)
+        if g_nrm.stride(1) != 1 or g_nrm.stride(0) % 4 != 0 or g_nrm.data_ptr() % 16 != 0:
+            g_nrm = g_nrm.contiguous()
+        if g_out is not None:
+            g_out = g_out.contiguous()
+        g_nei, g_e = torch.empty_like(e), torch.empty_like(e)
+        gs, gt = torch.empty_like(e), torch.empty_like(e)
+        check(lib().tagrec_ngcf_dense_bwd(ptr(g_out), ptr(g_nrm), g_nrm.stride(0), ptr(out), ptr(s_act), ptr(t_act),
+                                          ptr(nei), ptr(e), ptr(w1), ptr(b1), ptr(w2), ptr(b2), n, dim, ptr(g_nei),
+                                          ptr(g_e), ptr(gs), ptr(gt), stream_ptr(e.device)), "tagrec_ngcf_dense_bwd")
+        gw1 = torch.mm((nei + e).t(), gs)          # d/d(W1 + b1)
+        gw2 = torch.mm((nei * e).t(), gt)
+        # the bias is broadcast over the ROWS of W (ngcf.py:78): its gradient is the column sum of dW
+        return g_nei, g_e, gw1, gw1.sum(0, keepdim=True), gw2, gw2.sum(0, keepdim=True)

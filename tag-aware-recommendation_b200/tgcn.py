@@ -1,0 +1,255 @@
+"""TGCN — drop-in for model/tgcn.py: same classes (``Attention1``, ``BasicLayer``, ``TGCN``), parameter names, shapes
+and creation order (state_dict keys ``embed.user|item|tag|weight``, ``layer.<k>.U|q|p|Wf|bf``,
+``layer.<k>.atten1.<type>.W_1|W_2|b|v``, ``layer.<k>.conv.bit_level.weight``, ``layer.<k>.conv.vec_level.conv_<j>
+.weight``), ``forward`` / ``loss`` / ``transtag_loss`` / ``predict_rating`` / ``get_ego_embed``.
+
+Neighbour attention (tgcn.py:11-37) — the gather/scatter family that is 45 % of the reference's step — runs on K4
+(csrc/nbr_attention.cu) through :class:`NbrAttentionFn`; its three dense projections, the type-level attention
+(tgcn.py:78-84), the bit-/vector-level Conv2d (tgcn.py:86-101, evaluated as fp32 matmuls) and the fusion layer
+(tgcn.py:103-106) are dense library ops (cuBLAS through torch).  The BPR loss runs on K2 over the 64*(L+1)-d concat
+rows (L2 term on the propagated rows, tgcn.py:247), evaluation on K3.
+"""
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import config
+from ._lib import check, lib, ptr, stream_ptr
+from .eval_ops import topk_scores
+from .functional import BprLossFn
+
+
+class NbrAttentionFn(torch.autograd.Function):
+    """out[v] = sum_k softmax_k(relu(pv[v] + ww[w_vk] + pj[j_vk]) . vvec) * ej[j_vk]   (index 0 = padding)."""
+
+    @staticmethod
+    def forward(ctx, pv, ww, pj, ej, vvec, nbr, nbw, k):
+        pv, ww, pj, ej, vvec = (t.detach().contiguous() for t in (pv, ww, pj, ej, vvec))
+        n = pv.shape[0]
+        out = torch.empty((n, ej.shape[1]), dtype=torch.float32, device=pv.device)
+        att = torch.empty((n, k), dtype=torch.float32, device=pv.device)
+        check(lib().tagrec_nbr_attention_fwd(ptr(pv), ptr(ww), ptr(pj), ptr(ej), ptr(vvec), ptr(nbr), ptr(nbw), n, k,
+                                             nbr.stride(0), ej.shape[1], pv.shape[1], ptr(out), ptr(att),
+                                             stream_ptr(pv.device)), "tagrec_nbr_attention_fwd")
+        ctx.save_for_backward(pv, ww, pj, ej, vvec, nbr, nbw, att)
+        ctx.k = k
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        pv, ww, pj, ej, vvec, nbr, nbw, att = ctx.saved_tensors
+        g_out = g_out.contiguous()
+        g_pv = torch.empty_like(pv)
+        g_ww, g_pj, g_ej, g_v = (torch.zeros_like(t) for t in (ww, pj, ej, vvec))
+        check(lib().tagrec_nbr_attention_bwd(ptr(g_out), ptr(att), ptr(pv), ptr(ww), ptr(pj), ptr(ej), ptr(vvec), ptr(nbr),
+                                             ptr(nbw), pv.shape[0], ctx.k, nbr.stride(0), ww.shape[0], ej.shape[1],
+                                             pv.shape[1], ptr(g_pv), ptr(g_ww), ptr(g_pj), ptr(g_ej), ptr(g_v),
+                                             stream_ptr(pv.device)), "tagrec_nbr_attention_bwd")
+        return g_pv, g_ww, g_pj, g_ej, g_v, None, None, None
+
+
+class Attention1(nn.Module):
+    def __init__(self, in_features: int, atten_dim: int, dim_w: int):
+        super().__init__()
+        self.in_features = in_features
+        self.W_1 = nn.Parameter(torch.empty(in_features + dim_w, atten_dim))
+        self.W_2 = nn.Parameter(torch.empty(in_features, atten_dim))
+        self.b = nn.Parameter(torch.empty(1, atten_dim))
+        self.v = nn.Parameter(torch.empty(1, atten_dim))
+
+    def forward(self, ev, ej, ew, v_jw, pj=None):
+        """tgcn.py:20-37.  ``pj`` = ej @ W_2 may be passed in when two calls share the neighbour type."""
+        v_j, v_w = v_jw
+        d = self.in_features
+        pv = torch.addmm(self.b, ev, self.W_1[:d])             # [e_v | e_w] W1 + b, split by rows of W1
+        ww = torch.matmul(ew, self.W_1[d:])
+        if pj is None:
+            pj = torch.matmul(ej, self.W_2)
+        return NbrAttentionFn.apply(pv, ww, pj, ej, self.v.reshape(-1), v_j, v_w, v_j.shape[1])
+
+
+class BasicLayer(nn.Module):
+    def __init__(self, in_features, out_features, atten_dim, weight_dim, num_bit_conv, num_vector_conv):
+        super().__init__()
+        self._in_dim = in_features
+        self._num_vector_conv = num_vector_conv
+        self._num_bit_conv = num_bit_conv
+        self.atten1 = nn.ModuleDict()
+        for name in ("user", "item", "tag"):
+            self.atten1.update({name: Attention1(in_features, atten_dim, weight_dim)})
+        self.U = nn.Parameter(torch.empty(in_features, atten_dim))
+        self.q = nn.Parameter(torch.empty(1, atten_dim))
+        self.p = nn.Parameter(torch.empty(1, atten_dim))
+        self.conv = self._conv_layer()
+        in_k = self._num_bit_conv * in_features + self._num_vector_conv * (3 + 2 + 1)
+        self.Wf = nn.Parameter(torch.empty(in_k, out_features))
+        self.bf = nn.Parameter(torch.empty(1, out_features))
+
+    def _conv_layer(self):
+        vector_dict = nn.ModuleDict()
+        for j in range(1, 4):
+            vector_dict.update({f"conv_{j}": nn.Conv2d(1, self._num_vector_conv, kernel_size=(j, self._in_dim), bias=False)})
+        return nn.ModuleDict({
+            "bit_level": nn.Conv2d(1, self._num_bit_conv, kernel_size=(3, 1), bias=False),
+            "vec_level": vector_dict,
+        })
+
+    def _atten2(self, u, i, t):
+        uit = torch.stack([u, i, t], dim=1)
+        x = torch.matmul(uit, self.U) + self.q
+        x = torch.matmul(F.relu(x), self.p.T)
+        return torch.softmax(x, dim=1) * uit
+
+    def _conv(self, eN):
+        """tgcn.py:86-101.  The four Conv2d are tiny contractions over a [N, 3, 64] stack; they are evaluated as fp32
+        matmuls on the modules' own weights (same values as F.conv2d) — cuDNN is free to run convolutions, forward
+        AND backward, in TF32 under torch's defaults, which would break fp32 parity of every upstream gradient."""
+        n = eN.shape[0]
+        wb = self.conv["bit_level"].weight[:, 0, :, 0]                       # [32, 3]
+        bit_e = F.relu(torch.einsum('cr,nrd->ncd', wb, eN)).reshape(n, -1)   # [N, 32*64], channel-major
+        vec_e = []
+        for j, model in enumerate(self.conv["vec_level"].values(), start=1):
+            w = model.weight.reshape(model.weight.shape[0], -1)              # [8, j*64]
+            pos = [torch.matmul(eN[:, p:p + j, :].reshape(n, -1), w.t()) for p in range(4 - j)]
+            vec_e.append(F.relu(torch.stack(pos, dim=2)).reshape(n, -1))     # [N, 8*(4-j)], channel-major
+        return torch.cat([bit_e, torch.cat(vec_e, dim=-1)], dim=1)
+
+    def _fusion(self, x):
+        return F.relu(torch.addmm(self.bf, x, self.Wf))
+
+    def forward(self, eu, ei, et, ew, u_iw, u_tw, i_uw, i_tw, t_uw, t_iw):
+        a_u, a_i, a_t = self.atten1["user"], self.atten1["item"], self.atten1["tag"]
+        pj_u, pj_i, pj_t = torch.matmul(eu, a_u.W_2), torch.matmul(ei, a_i.W_2), torch.matmul(et, a_t.W_2)
+        eu_iN = a_i.forward(eu, ei, ew, u_iw, pj_i)
+        eu_tN = a_t.forward(eu, et, ew, u_tw, pj_t)
+        ei_uN = a_u.forward(ei, eu, ew, i_uw, pj_u)
+        ei_tN = a_t.forward(ei, et, ew, i_tw, pj_t)
+        et_uN = a_u.forward(et, eu, ew, t_uw, pj_u)
+        et_iN = a_i.forward(et, ei, ew, t_iw, pj_i)
+        euN = self._atten2(eu, eu_iN, eu_tN)
+        eiN = self._atten2(ei_uN, ei, ei_tN)
+        etN = self._atten2(et_uN, et_iN, et)
+        return self._fusion(self._conv(euN)), self._fusion(self._conv(eiN)), self._fusion(self._conv(etN))
+
+
+class TGCN(nn.Module):
+    def __init__(self, data):
+        super().__init__()
+        self._config(config.current())
+        self.num_user = data.num['user']
+        self.num_item = data.num['item']
+        self.num_tag = data.num['tag']
+        self.num_weight = data.num['weight']
+        self._init_weight()
+        self.data = data
+        start = time.time()
+        self.all_sample = data.get_all_neighbor()
+        self._nbr_dev = None
+        self._cache = None
+        print(f"TGCN got ready! [neighbor sample time {time.time()-start}]")
+
+    def _config(self, cfg):
+        self.dim_latent = cfg['dim_latent']
+        self.dim_weight = cfg['dim_weight']
+        self.num_layer = len(cfg['dim_layer_list'])
+        self.dim_layer_list = [self.dim_latent] + list(cfg['dim_layer_list'])
+        self.dim_atten = cfg['dim_atten']
+        self.num_bit_conv = cfg['num_bit_conv']
+        self.num_vec_conv = cfg['num_vec_conv']
+        self.message_drop_list = cfg['message_drop_list']
+        self.device = cfg['device']
+        self.neighbor_k = cfg['neighbor_k']
+        self.reg = cfg['reg']
+        self.transtag_reg = cfg['transtag_reg']
+        self.loss_func = cfg['mul_loss_func']
+        self.margin = cfg['margin']
+        if any(d != 64 for d in self.dim_layer_list) or self.dim_atten != 32 or self.neighbor_k > 32:
+            raise NotImplementedError("K4 is built for 64-d layers, dim_atten 32 and neighbor_k <= 32 "
+                                      "(utility/config.py:41-51 defaults: 64 / 32 / 25)")
+
+    def _init_weight(self):
+        self.embed = nn.ParameterDict({
+            "user": nn.Parameter(torch.empty(self.num_user, self.dim_latent)),
+            "item": nn.Parameter(torch.empty(self.num_item, self.dim_latent)),
+            "tag": nn.Parameter(torch.empty(self.num_tag, self.dim_latent)),
+            "weight": nn.Parameter(torch.empty(self.num_weight, self.dim_weight)),
+        })
+        self.layer = nn.ModuleDict()
+        for k in range(self.num_layer):
+            self.layer.update({f'{k}': BasicLayer(self.dim_layer_list[k], self.dim_layer_list[k + 1], self.dim_atten,
+                                                  self.dim_weight, self.num_bit_conv, self.num_vec_conv)})
+        # tgcn.py:187-192: Xavier-uniform on every parameter (incl. biases and the Conv2d weights), creation order
+        for param in self.parameters():
+            nn.init.xavier_uniform_(param)
+
+    def sample(self):
+        """tgcn.py:194-202.  The reference shuffles an index vector it never uses (dead code) and takes the FIRST
+        ``neighbor_k`` columns; the shuffle still advances numpy's global generator once per relation, which the
+        parity-mode samplers read — so the draw is reproduced, the tables are uploaded once."""
+        for adj_w in self.all_sample:
+            np.random.shuffle(np.arange(np.asarray(adj_w[0]).shape[1]))
+        if self._nbr_dev is None or self._nbr_dev[0][0].device != self.embed["user"].device:
+            dev = self.embed["user"].device
+            self._nbr_dev = [tuple(torch.as_tensor(np.ascontiguousarray(np.asarray(x)[:, :self.neighbor_k]),
+                                                   dtype=torch.long, device=dev) for x in adj_w)
+                             for adj_w in self.all_sample]
+        return self._nbr_dev
+
+    def _propagate(self):
+        eu, ei = self.embed['user'], self.embed['item']
+        et, ew = self.embed['tag'], self.embed['weight']
+        embs_u, embs_i, embs_t = [eu], [ei], [et]
+        for i, layer in enumerate(self.layer.values()):
+            u_iw, u_tw, i_uw, i_tw, t_uw, t_iw = self.sample()
+            eu, ei, et = layer(eu, ei, et, ew, u_iw, u_tw, i_uw, i_tw, t_uw, t_iw)
+            eu = F.dropout(eu, p=self.message_drop_list[i], training=self.training)
+            ei = F.dropout(ei, p=self.message_drop_list[i], training=self.training)
+            et = F.dropout(et, p=self.message_drop_list[i], training=self.training)
+            embs_u.append(F.normalize(eu, p=2, dim=1))
+            embs_i.append(F.normalize(ei, p=2, dim=1))
+            embs_t.append(F.normalize(et, p=2, dim=1))
+        return torch.cat(embs_u, dim=1), torch.cat(embs_i, dim=1), torch.cat(embs_t, dim=1)
+
+    def forward(self):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._propagate()
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._cache is None or self._cache[0] != key:
+            with torch.no_grad():
+                self._cache = (key, self._propagate())
+        return self._cache[1]
+
+    def get_ego_embed(self):
+        return self.embed['user'], self.embed['item'], self.embed['tag']
+
+    def loss(self, batch_data):
+        all_users, all_items = self.forward()[:2]
+        final = torch.cat([all_users, all_items], dim=0)
+        return BprLossFn.apply(batch_data, self.num_user, self.reg, self.loss_func, final, final)
+
+    def transtag_loss(self, batch_data):
+        """tgcn.py:251-261 + model/help/loss.py:35-41 — ego rows only, tiny; plain torch ops."""
+        user, tag, pos_item, neg_item = batch_data.T
+        all_users, all_items, all_tags = self.get_ego_embed()
+        tag_emb, user_emb = all_tags[tag.long()], all_users[user.long()]
+        pos_i_emb, neg_i_emb = all_items[pos_item.long()], all_items[neg_item.long()]
+        pos_score = torch.norm(user_emb + tag_emb - pos_i_emb, p=2, dim=1)
+        neg_score = torch.norm(user_emb + tag_emb - neg_i_emb, p=2, dim=1)
+        loss = torch.mean(torch.relu(self.margin + pos_score - neg_score))
+        reg = 0
+        for emb in (user_emb, tag_emb, pos_i_emb, neg_i_emb):
+            reg = reg + emb.norm(2).pow(2)
+        reg_loss = 0.5 * reg / float(user_emb.shape[0])
+        return loss, self.transtag_reg * reg_loss
+
+    def predict_rating(self, users):
+        all_users, all_items = self.forward()[:2]
+        return torch.sigmoid(torch.matmul(all_users[users], all_items.t()))
+
+    def eval_topk(self, users, k, train_ptr, train_items):
+        with torch.no_grad():
+            all_users, all_items = self.forward()[:2]
+            return topk_scores(users, all_users.contiguous(), all_items.contiguous(), train_ptr, train_items, k)

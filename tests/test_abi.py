@@ -81,3 +81,35 @@ def test_sampler_class_mt19937_mode_uses_numpy_global_state(tiny):
     s.reset()
     assert np.array_equal(s.all_train_data.numpy(), tiny["sampler_second"])
     assert [len(b) for b in s.mini_batch()] == list(tiny["sampler_batch_sizes"])
+
+
+def test_dgcf_sampler_host_mode_bit_exact_vs_reference(tiny):
+    """T.DGCF_training_data in parity mode == the reference's class (train_data/bpr_training_data.py:47-84) after the
+    same random.seed / np.random.seed: sampled users, positives, rejection-sampled negatives and the cor indices."""
+    import random
+    import torch
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "dgcf_sampler.npz")))
+    U, I, Tg, _ = nums(tiny)
+
+    class D:
+        pass
+    d = D()
+    d.num = {"user": U, "item": I, "tag": Tg}
+    d.user_items = {"train": user_lists(tiny, "train")}
+    d.edge_index = {"train": tiny["edge_index_train"]}
+    for use_tag in (False, True):
+        tag = "tag" if use_tag else "notag"
+        T.set_config("dgcf", train_batch=16, use_tag=use_tag, cor_batch=10, sampler="mt19937", device=torch.device("cpu"))
+        random.seed(5)
+        np.random.seed(5)
+        s = T.DGCF_training_data(d, None)
+        s.reset()
+        batches = list(s.mini_batch())
+        assert len(batches) == len(tiny["edge_index_train"]) // 16 + 1
+        assert np.array_equal(np.stack([b[0].numpy() for b in batches]), gold[f"{tag}_data"])
+        assert np.array_equal(np.stack([b[1].numpy() for b in batches]), gold[f"{tag}_cor"])
+        T.set_config("dgcf", train_batch=64, use_tag=use_tag, cor_batch=10, sampler="mt19937", device=torch.device("cpu"))
+        random.seed(6)
+        np.random.seed(6)
+        s = T.DGCF_training_data(d, None)
+        assert np.array_equal(np.stack([b[0].numpy() for b in s.mini_batch()]), gold[f"{tag}_small_data"])

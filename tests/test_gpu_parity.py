@@ -3,6 +3,8 @@
 Tolerances (north_star): bit-exact CSR / top-K ids; <= 1e-5 relative (to the tensor's max magnitude) for fp32
 embeddings, loss and gradients; <= 1e-4 for Recall/NDCG.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -378,6 +380,322 @@ def test_k3_tensor_core_large_vs_torch():
     ids = ids.cpu().numpy()
     for r in range(len(users)):
         assert near_tie_ok(ms[r], ids[r], ref[r], 20), f"row {r}"
+
+
+# ---------------------------------------------------------------------------------------------------------- NGCF
+def _load_state(model, g, tag):
+    sd = model.state_dict()
+    with torch.no_grad():
+        for k in sd:
+            sd[k].copy_(torch.tensor(g[f"{tag}_param_{k}"]))
+    return list(sd.keys())
+
+
+@pytest.mark.parametrize("tag,use_tag", [("ngcf", False), ("ngcf_tag", True)])
+def test_ngcf_forward_loss_grad_vs_reference(tiny, tag, use_tag):
+    """T.NGCF (K1 SpMM on D^-1 A + I, fused dense half-layer K6, wide-row K2) == model/ngcf.py on identical inputs:
+    forward (N x 256 concat), loss tuple, every parameter gradient (embeddings, W and the bias-on-the-weight b)."""
+    T.set_config("ngcf", use_tag=use_tag, reg=1e-3, dim_layer_list=[64, 64, 64], device=dev())
+    model = T.NGCF(make_data(tiny)).to(dev())
+    keys = _load_state(model, tiny, tag)
+    ne = 3 if use_tag else 2
+    assert keys == [f"embed.{k}" for k in range(ne)] + [f"mat.{w}{j}_{k}" for k in range(3) for j in (1, 2) for w in "Wb"]
+    model.train()
+    fw = model.forward()
+    for k in range(ne):
+        assert fw[k].shape[1] == 256
+        assert relerr(fw[k].detach().cpu().numpy(), tiny[f"{tag}_fwd_{k}"]) < TOL
+    lossx = model.loss(torch.tensor(tiny[f"{tag}_batch"], device=dev()))
+    assert isinstance(lossx, tuple) and len(lossx) == 2
+    for j in range(2):
+        assert abs(lossx[j].item() - tiny[f"{tag}_loss"][j]) < TOL * abs(tiny[f"{tag}_loss"][j])
+    sum(lossx).backward()
+    for name, p in model.named_parameters():
+        want = tiny[f"{tag}_grad_{name}"]
+        assert relerr(p.grad.cpu().numpy(), want) < 2 * TOL, name
+    model.eval()
+    with torch.no_grad():
+        r = model.predict_rating(torch.tensor(tiny[f"{tag}_pred_users"], device=dev()))
+    assert relerr(r.cpu().numpy(), tiny[f"{tag}_pred"]) < TOL
+    # K3 on the 256-d table == (-score, id) order of the reference's own predict_rating rows
+    U = model.num_list[0]
+    d = make_data(tiny)
+    ptr_, items = T.bpr_training_data.user_items_to_csr(d.user_items["train"], U)
+    users = tiny[f"{tag}_pred_users"]
+    ids, _ = model.eval_topk(torch.tensor(users, device=dev()), 10, torch.tensor(ptr_, device=dev()),
+                             torch.tensor(items, device=dev()).int())
+    ms = OM.mask_train(tiny[f"{tag}_pred"].astype(np.float64), users, ptr_, items)
+    ref = OM.topk_ids(ms, 10)
+    for r_ in range(len(users)):
+        assert near_tie_ok(ms[r_], ids[r_].cpu().numpy(), ref[r_], 10)
+
+
+def test_ngcf_dense_kernel_vs_torch():
+    """K6 forward/backward against the same maths in torch fp64 (ragged row count, non-contiguous g_nrm slice)."""
+    from tagrec_b200.functional import NgcfDenseFn
+    g = torch.Generator().manual_seed(3)
+    n = 64 * 5 + 37
+    mk = lambda *s: torch.randn(*s, generator=g)
+    nei, e = mk(n, 64), mk(n, 64)
+    e[5] = 0.0
+    nei[5] = 0.0                                                # an all-zero row: normalise hits its eps branch
+    w1, b1, w2, b2 = mk(64, 64) * 0.2, mk(1, 64) * 0.2, mk(64, 64) * 0.2, mk(1, 64) * 0.2
+    up = mk(n, 256)
+    leaves = [t.clone().to(dev()).requires_grad_(True) for t in (nei, e, w1, b1, w2, b2)]
+    out, nrm = NgcfDenseFn.apply(*leaves)
+    big = torch.cat([out, nrm, out * 0, nrm * 0], dim=1)
+    (big * up.to(dev())).sum().backward()
+    ref = [t.clone().double().requires_grad_(True) for t in (nei, e, w1, b1, w2, b2)]
+    rn, re_, rw1, rb1, rw2, rb2 = ref
+    ro = torch.nn.functional.leaky_relu((rn + re_) @ (rw1 + rb1), 0.2) + \
+        torch.nn.functional.leaky_relu((rn * re_) @ (rw2 + rb2), 0.2)
+    rnrm = torch.nn.functional.normalize(ro, p=2, dim=1)
+    (torch.cat([ro, rnrm, ro * 0, rnrm * 0], dim=1) * up.double()).sum().backward()
+    assert relerr(out.detach().cpu().numpy(), ro.detach().numpy()) < TOL
+    assert relerr(nrm.detach().cpu().numpy(), rnrm.detach().numpy()) < TOL
+    for a, b in zip(leaves, ref):
+        assert relerr(a.grad.cpu().numpy(), b.grad.numpy()) < TOL
+
+
+@pytest.mark.parametrize("dim", [192, 256, 320])
+def test_k2_wide_rows_vs_oracle(dim):
+    """K2's warp-per-triple variant (NGCF 256-d / TGCN 192-d rows), L2 term on the propagated table itself."""
+    from tagrec_b200.functional import BprLossFn
+    g = torch.Generator().manual_seed(dim)
+    U, I, B = 30, 50, 97
+    final = torch.randn(U + I, dim, generator=g) * 0.3
+    rng = np.random.RandomState(dim)
+    batch = np.stack([rng.randint(0, U, B), rng.randint(0, I, B), rng.randint(0, I, B)], 1).astype(np.int64)
+    batch[1] = batch[0]                                         # duplicate triple: scatter collisions
+    f = final.clone().to(dev()).requires_grad_(True)
+    lossx = BprLossFn.apply(torch.tensor(batch, device=dev()), U, 1e-2, "logsigmoid", f, f)
+    sum(lossx).backward()
+    loss, reg_term, gf, ge = OP.bpr_forward_backward(final.double(), final.double(), batch, U, 1e-2, "logsigmoid",
+                                                     reg_on_final=True)
+    assert abs(lossx[0].item() - loss.item()) < TOL * abs(loss.item())
+    assert abs(lossx[1].item() - reg_term.item()) < TOL * abs(reg_term.item())
+    assert relerr(f.grad.cpu().numpy(), (gf + ge).numpy()) < TOL
+
+
+# ------------------------------------------------------------------------------------------ DGCF / DisenGCN (K5)
+def test_dgcf_forward_loss_grad_vs_reference(tiny):
+    """T.DGCF (4-intent routing on the K5 kernels) == model/dgcf.py: mean table, loss tuple, embedding gradients,
+    predict_rating.  The (data, cor) tuple convention of DGCF_training_data is kept (dgcf.py:116)."""
+    T.set_config("dgcf", use_tag=False, reg=1e-3, dim_layer_list=[64, 64, 64], device=dev())
+    model = T.DGCF(make_data(tiny)).to(dev())
+    assert _load_state(model, tiny, "dgcf") == ["embed.0", "embed.1"]
+    model.train()
+    fw = model.forward()
+    for k in range(2):
+        assert relerr(fw[k].detach().cpu().numpy(), tiny[f"dgcf_fwd_{k}"]) < TOL
+    lossx = model.loss((torch.tensor(tiny["dgcf_batch"], device=dev()), None))
+    for j in range(2):
+        assert abs(lossx[j].item() - tiny["dgcf_loss"][j]) < TOL * abs(tiny["dgcf_loss"][j])
+    sum(lossx).backward()
+    for k in range(2):
+        assert relerr(model.embed[k].grad.cpu().numpy(), tiny[f"dgcf_grad_embed.{k}"]) < 2 * TOL
+    model.eval()
+    with torch.no_grad():
+        r = model.predict_rating(torch.tensor(tiny["dgcf_pred_users"], device=dev()))
+    assert relerr(r.cpu().numpy(), tiny["dgcf_pred"]) < TOL
+
+
+def test_disengcn_forward_loss_grad_vs_reference(tiny):
+    """T.DisenGCN (projection GEMM + K5 neighbour routing) == model/disengcn.py on the tripartite graph: last-layer
+    table, loss tuple (L2 on the propagated rows), gradients of the embeddings and of every layer's W / b."""
+    T.set_config("disengcn", use_tag=True, reg=1e-3, dim_layer_list=[64, 64, 64], device=dev())
+    model = T.DisenGCN(make_data(tiny)).to(dev())
+    keys = _load_state(model, tiny, "disengcn")
+    assert keys == ["embed.0", "embed.1", "embed.2"] + [f"layer.{k}.{w}" for k in range(3) for w in "Wb"]
+    model.train()
+    fw = model.forward()
+    for k in range(3):
+        assert relerr(fw[k].detach().cpu().numpy(), tiny[f"disengcn_fwd_{k}"]) < TOL
+    lossx = model.loss((torch.tensor(tiny["disengcn_batch"], device=dev()), None))
+    for j in range(2):
+        assert abs(lossx[j].item() - tiny["disengcn_loss"][j]) < TOL * abs(tiny["disengcn_loss"][j])
+    sum(lossx).backward()
+    # DisenGCN's gradients are O(1e-6) sums of cancelling terms behind three normalisations: the reference's OWN
+    # float32 result is 3e-5 .. 5e-3 away from the float64 run of the same class (tests/golden/make_golden_fp64.py).
+    # Bar: the same order of accuracy against the float64 truth as the reference's own float32 run (within 4x).
+    truth = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "routing_fp64.npz")))
+    for name, p in model.named_parameters():
+        t64 = truth[f"disengcn_grad64_{name}"]
+        err_ref = relerr(tiny[f"disengcn_grad_{name}"], t64)
+        err_ours = relerr(p.grad.cpu().numpy(), t64)
+        assert err_ours <= max(2 * TOL, 4 * err_ref), (name, err_ours, err_ref)
+    for k in range(3):
+        assert relerr(fw[k].detach().cpu().numpy(), truth[f"disengcn_fwd64_{k}"]) < TOL
+    model.eval()
+    with torch.no_grad():
+        r = model.predict_rating(torch.tensor(tiny["disengcn_pred_users"], device=dev()))
+    assert relerr(r.cpu().numpy(), tiny["disengcn_pred"]) < TOL
+
+
+def test_k5_routing_kernels_vs_torch():
+    """Each K5 kernel against a dense torch fp64 restatement on a ragged random symmetric structure (isolated
+    nodes, a hub row longer than one 16-edge chunk, odd row count)."""
+    from tagrec_b200 import routing as R
+    rng = np.random.RandomState(4)
+    U, I = 37, 54
+    e_u = np.r_[rng.randint(0, U - 2, 300), np.zeros(40, dtype=np.int64)]       # user U-1, U-2 isolated; user 0 = hub
+    e_i = np.r_[rng.randint(0, I - 1, 300), np.arange(40)]
+    g = T.build_csr(U, I, (e_u, e_i), "plain", dev())
+    n, nnz = g.n, g._nnz()
+    rows = g.row_ids().cpu().numpy()
+    cols = g.col.cpu().numpy().astype(np.int64)
+    gen = torch.Generator().manual_seed(1)
+    logit = torch.randn(nnz, 4, generator=gen)
+    x = torch.randn(n, 64, generator=gen)
+    y = torch.randn(n, 64, generator=gen)
+    x[3] = 0.0
+    # R7 reverse permutation
+    rev = R.reverse_perm(g).cpu().numpy()
+    assert np.array_equal(rows[rev], cols) and np.array_equal(cols[rev], rows)
+    # R1 + R2
+    w = torch.empty(nnz, 4, device=dev())
+    dinv = torch.empty(n, 4, device=dev())
+    val = torch.empty(nnz, 4, device=dev())
+    R.edge_softmax_rowsum(g, logit.to(dev()), w, dinv)
+    R.edge_scale(g, w, dinv, val)
+    w_ref = torch.softmax(logit.double(), dim=1)
+    s_ref = torch.zeros(n, 4, dtype=torch.float64).index_add_(0, torch.tensor(rows), w_ref)
+    d_ref = torch.where(s_ref > 0, 1 / torch.sqrt(s_ref), torch.zeros_like(s_ref))
+    val_ref = d_ref[rows] * w_ref * d_ref[cols]
+    assert relerr(w.cpu().numpy(), w_ref.numpy()) < TOL and relerr(dinv.cpu().numpy(), d_ref.numpy()) < TOL
+    assert relerr(val.cpu().numpy(), val_ref.numpy()) < TOL
+    # R3 (plain, transposed through the permutation, residual, chunk-normalised, running mean)
+    xd = x.to(dev())
+    dense = torch.zeros(4, n, n, dtype=torch.float64)
+    dense[:, rows, cols] = val_ref.T
+    def mm(mats, t):
+        return torch.cat([mats[k] @ t[:, 16 * k:16 * k + 16].double() for k in range(4)], dim=1)
+    def cnorm(t):
+        v = t.reshape(t.shape[0], 4, 16)
+        return (v / v.norm(dim=2, keepdim=True).clamp_min(1e-12)).reshape(t.shape[0], 64)
+    raw, nrm, mean = (torch.empty(n, 64, device=dev()) for _ in range(3))
+    R.spmm4(g, val, xd, y_raw=raw, y_norm=nrm, mean_acc=mean, mean_x0=y.to(dev()), mean_first=True, mean_last=True,
+            mean_scale=0.25)
+    ref = mm(dense, x)
+    assert relerr(raw.cpu().numpy(), ref.numpy()) < TOL and relerr(nrm.cpu().numpy(), cnorm(ref).numpy()) < TOL
+    assert relerr(mean.cpu().numpy(), ((y.double() + cnorm(ref)) * 0.25).numpy()) < TOL
+    R.spmm4(g, val, xd, perm=R.reverse_perm(g), res=y.to(dev()), y_raw=raw)
+    assert relerr(raw.cpu().numpy(), (y.double() + mm(dense.transpose(1, 2), x)).numpy()) < TOL
+    # R4 both modes
+    acc = logit.clone().to(dev())
+    R.edge_dot4(g, xd, y.to(dev()), acc, softmax=False)
+    d4 = (x.double()[rows].reshape(nnz, 4, 16) * y.double()[cols].reshape(nnz, 4, 16)).sum(2)
+    assert relerr(acc.cpu().numpy(), (logit.double() + d4).numpy()) < TOL
+    R.edge_dot4(g, xd, y.to(dev()), acc, softmax=True)
+    assert relerr(acc.cpu().numpy(), torch.softmax(d4, dim=1).numpy()) < TOL
+    # R5 / R6
+    assert relerr(R.chunk_normalize(xd).cpu().numpy(), cnorm(x.double()).numpy()) < TOL
+    assert relerr(R.chunk_normalize(xd, tanh=True).cpu().numpy(), torch.tanh(cnorm(x.double())).numpy()) < TOL
+    xr = x.double().clone().requires_grad_(True)
+    (cnorm(xr) * y.double()).sum().backward()
+    got = R.chunk_normalize_bwd(y.to(dev()), xd).cpu().numpy()
+    keep = np.arange(n) != 3                       # the all-zero row: the reference's gradient there is g / eps
+    assert relerr(got[keep], xr.grad.numpy()[keep]) < TOL
+
+
+def test_dgcf_device_sampler_properties(tiny):
+    """Throughput-mode DGCF_training_data: (data, cor) shapes, positives are train items, negatives are not."""
+    T.set_config("dgcf", train_batch=16, use_tag=True, cor_batch=10, sampler="device", device=dev())
+    d = make_data(tiny)
+    s = T.DGCF_training_data(d, None)
+    batches = list(s.mini_batch())
+    assert len(batches) == len(tiny["edge_index_train"]) // 16 + 1
+    train = d.user_items["train"]
+    for data, cor in batches:
+        assert data.shape == (16, 3) and cor.shape == (3, 10) and data.dtype == torch.int64
+        for u, p, q in data.cpu().numpy():
+            assert p in train[int(u)] and q not in train[int(u)] and 0 <= q < d.num["item"]
+        assert len(set(data[:, 0].tolist())) == 16           # users sampled without replacement (random.sample)
+    assert not torch.equal(batches[0][0], batches[1][0])
+
+
+# ---------------------------------------------------------------------------------------------------- TGCN (K4)
+def _tgcn_model(tiny, tiny_tgcn):
+    T.set_config("tgcn", use_tag=True, reg=1e-3, dim_layer_list=[64, 64], neighbor_k=5, device=dev())
+    d = make_data(tiny, tags=True)
+    names = ["ui", "ut", "iu", "it", "tu", "ti"]
+    d.get_all_neighbor = lambda: [(tiny_tgcn[f"tgcn_nbr_{n}"], tiny_tgcn[f"tgcn_nbw_{n}"]) for n in names]
+    model = T.TGCN(d).to(dev())
+    sd = model.state_dict()
+    want = [k[len("tgcn_param_"):] for k in tiny_tgcn if k.startswith("tgcn_param_")]
+    assert sorted(sd.keys()) == sorted(want)
+    with torch.no_grad():
+        for k in sd:
+            sd[k].copy_(torch.tensor(tiny_tgcn[f"tgcn_param_{k}"]))
+    return model
+
+
+def test_tgcn_forward_loss_grad_vs_reference(tiny, tiny_tgcn):
+    """T.TGCN (neighbour attention on K4, dense parts on cuBLAS/cuDNN, K2 on 192-d rows) == model/tgcn.py with the
+    reference's own neighbour tables: concat outputs, loss tuple, the gradient of EVERY parameter."""
+    model = _tgcn_model(tiny, tiny_tgcn)
+    model.train()
+    fw = model.forward()
+    for k in range(3):
+        assert fw[k].shape[1] == 192
+        assert relerr(fw[k].detach().cpu().numpy(), tiny_tgcn[f"tgcn_fwd_{k}"]) < TOL
+    lossx = model.loss(torch.tensor(tiny_tgcn["tgcn_batch"], device=dev()))
+    for j in range(2):
+        assert abs(lossx[j].item() - tiny_tgcn["tgcn_loss"][j]) < TOL * abs(tiny_tgcn["tgcn_loss"][j])
+    sum(lossx).backward()
+    # Bar per tensor: within 1e-5 of the reference, or — for the O(1e-9) second-layer attention gradients, where the
+    # reference's own float32 run is up to 9e-5 away from its float64 run (tests/golden/make_golden_fp64.py) —
+    # within 4x of the reference's own float32 error against that float64 truth.
+    truth = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "routing_fp64.npz")))
+    bad = []
+    for name, p in model.named_parameters():
+        want = tiny_tgcn[f"tgcn_grad_{name}"]
+        got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(want)
+        t64 = truth[f"tgcn_grad64_{name}"]
+        err, err_ref = relerr(got, t64), relerr(want, t64)
+        if err > max(TOL, 4 * err_ref):
+            bad.append((name, err, err_ref))
+    assert not bad, bad
+
+
+def test_k4_neighbour_attention_vs_torch():
+    """K4 forward/backward against the reference formulation (tgcn.py:20-37) in torch fp64: padding slots (index 0)
+    take part in the softmax, duplicate neighbours and shared weight ids collide in the scatter."""
+    from tagrec_b200.tgcn import Attention1
+    g = torch.Generator().manual_seed(9)
+    nv, nj, nw, k = 77, 41, 4, 7
+    att = Attention1(64, 32, 10).to(dev())
+    with torch.no_grad():
+        for p in att.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+    ev, ej, ew = torch.randn(nv, 64, generator=g), torch.randn(nj, 64, generator=g), torch.randn(nw, 10, generator=g)
+    rng = np.random.RandomState(2)
+    v_j = rng.randint(0, nj + 1, (nv, 11))
+    v_w = rng.randint(1, nw + 1, (nv, 11)) * (v_j > 0)
+    v_j[5] = 0
+    v_w[5] = 0                                                   # a node without neighbours: all padding
+    up = torch.randn(nv, 64, generator=g)
+    leaves = [t.clone().to(dev()).requires_grad_(True) for t in (ev, ej, ew)]
+    tj = torch.tensor(v_j, device=dev())[:, :k]                  # a column slice: row stride 11 != k
+    tw = torch.tensor(v_w, device=dev())[:, :k]
+    out = att(leaves[0], leaves[1], leaves[2], (tj, tw))
+    (out * up.to(dev())).sum().backward()
+    # reference formulation, float64
+    P = {n: p.detach().cpu().double().requires_grad_(True) for n, p in att.named_parameters()}
+    r_ev, r_ej, r_ew = (t.clone().double().requires_grad_(True) for t in (ev, ej, ew))
+    ejp = torch.cat([torch.zeros(1, 64, dtype=torch.float64), r_ej])
+    ewp = torch.cat([torch.zeros(1, 10, dtype=torch.float64), r_ew])
+    eNj, eNw = ejp[torch.tensor(v_j[:, :k])], ewp[torch.tensor(v_w[:, :k])]
+    eNv = r_ev.unsqueeze(1).repeat(1, k, 1)
+    av = torch.cat([eNv, eNw], dim=-1) @ P["W_1"] + eNj @ P["W_2"] + P["b"]
+    a = torch.softmax(torch.relu(av) @ P["v"].T, dim=1)
+    ref = (a * eNj).sum(1)
+    (ref * up.double()).sum().backward()
+    assert relerr(out.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+    for got, want in zip(leaves, (r_ev, r_ej, r_ew)):
+        assert relerr(got.grad.cpu().numpy(), want.grad.numpy()) < TOL
+    for n, p in att.named_parameters():
+        assert relerr(p.grad.cpu().numpy(), P[n].grad.numpy()) < TOL, n
 
 
 # ------------------------------------------------------------------------------------------------------- sampler
