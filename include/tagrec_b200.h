@@ -177,6 +177,16 @@ int tagrec_eval_topk_ex(const int64_t* users, int64_t nu, const float* user_tabl
                         int32_t* topk_ids, float* topk_scores, void* workspace, size_t workspace_bytes, int path,
                         void* stream);
 
+/* Per-user AUC (training/utils.py:37-45 roc_auc_score over the un-masked items of one user, basic_test.py:52-53),
+ * summed over `users`: out[0] += sum of AUC_u, out[1] += number of users that have both classes (the reference raises
+ * for the others).  Positives = test items of u that are not train items; ties get half credit; ranking quantity =
+ * exact fp32 dot (see csrc/eval_auc.cu).  test_items int32 ascending per user; n_test_total = test_ptr[n_user]. */
+size_t tagrec_eval_auc_workspace_bytes(int64_t nu, int64_t n_test_total);
+int tagrec_eval_auc(const int64_t* users, int64_t nu, const float* user_table, const float* item_table, int64_t n_item,
+                    int dim, const int64_t* train_ptr, const int32_t* train_items, const int64_t* test_ptr,
+                    const int32_t* test_items, int64_t n_test_total, void* workspace, size_t workspace_bytes, double* out,
+                    void* stream);
+
 /* metric sums over users (training/utils.py:15-35): out[4*nk] = recall|precision|hr|ndcg per k (double, +=). */
 int tagrec_eval_metrics(const int64_t* users, int64_t nu, const int32_t* topk_ids, int kmax,
                         const int64_t* test_ptr, const int32_t* test_items, const int32_t* ks, int nk,
@@ -207,23 +217,26 @@ int tagrec_ngcf_dense_bwd(const float* g_out, const float* g_nrm, int64_t g_nrm_
  * disengcn.py:27).  Factor count is 4, rows are 64-d = 4 chunks of 16; per-edge quantities are [nnz, 4] float
  * (one float4 per edge, factor-minor).  Node tables are [n, 64] row-major, dinv is [n, 4].
  * ---------------------------------------------------------------------------------------------------------- */
-/* w[e,:] = softmax_k(logit[e,:]) (dgcf.py:74); dinv[h,k] = 1/sqrt(sum_{e in row h} w[e,k]), 0 for empty rows
+/* edge_row int32 [nnz] = row id of every CSR entry (the edge-parallel kernels are immune to hub rows).
+ * w[e,:] = softmax_k(logit[e,:]) (dgcf.py:74); dinv[h,k] = 1/sqrt(sum_{e in row h} w[e,k]), 0 for empty rows
  * (dgcf.py:95-97). */
-int tagrec_edge_softmax_rowsum(const int64_t* rowptr, int64_t n_rows, const float* logit, float* w, float* dinv,
-                               void* stream);
+int tagrec_edge_softmax_rowsum(const int32_t* edge_row, int64_t nnz, int64_t n_rows, const float* logit, float* w,
+                               float* dinv, void* stream);
 /* val[e,k] = dinv[h,k] * w[e,k] * dinv[t,k]: the per-factor operator D A_k D of dgcf.py:98-101 as edge values. */
-int tagrec_edge_scale(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const float* w, const float* dinv,
+int tagrec_edge_scale(const int32_t* edge_row, const int32_t* col, int64_t nnz, const float* w, const float* dinv,
                       float* val, void* stream);
 /* y[h, chunk k] = (res ? res[h] : 0) + sum_{e=(h,t)} val[perm ? perm[e] : e, k] * x[t, chunk k]
  *   y_raw  (optional) the sum;  y_norm (optional) each 16-d chunk L2-normalised (dgcf.py:79, disengcn.py:41);
  *   mean_acc (optional) running mean of the normalised layers: (first ? mean_x0 : mean_acc) + y_norm, times
- *   mean_scale when last (dgcf.py:59-61).  perm = reverse-edge permutation => multiplies by the TRANSPOSED operator. */
-int tagrec_spmm4(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const float* val, const int32_t* perm,
-                 const float* x, const float* res, float* y_raw, float* y_norm, float* mean_acc, const float* mean_x0,
-                 int mean_first, int mean_last, float mean_scale, void* stream);
+ *   mean_scale when last (dgcf.py:59-61).  perm = reverse-edge permutation => multiplies by the TRANSPOSED operator.
+ *   long_rows int32 [n_long] = ids of the rows with more than tagrec_spmm4_long_threshold() entries (one block each). */
+int tagrec_spmm4(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const int32_t* long_rows, int64_t n_long,
+                 const float* val, const int32_t* perm, const float* x, const float* res, float* y_raw, float* y_norm,
+                 float* mean_acc, const float* mean_x0, int mean_first, int mean_last, float mean_scale, void* stream);
+int tagrec_spmm4_long_threshold(void);
 /* d[e,k] = <a[h, chunk k], b[t, chunk k]>;  mode 0: out[e,:] += d (dgcf.py:103-109, A_values += A_score)
  *                                           mode 1: out[e,:] = softmax_k(d) (disengcn.py:31-34). */
-int tagrec_edge_dot4(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const float* a, const float* b,
+int tagrec_edge_dot4(const int32_t* edge_row, const int32_t* col, int64_t nnz, const float* a, const float* b,
                      float* out, int mode, void* stream);
 /* y = x / max(||x||_2 per 16-d chunk, 1e-12), optionally tanh(y) (dgcf.py:106-108). */
 int tagrec_chunk_normalize(const float* x, int64_t n_rows, int apply_tanh, float* y, void* stream);

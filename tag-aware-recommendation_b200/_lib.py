@@ -53,12 +53,15 @@ PROTOTYPES = {
     "tagrec_eval_topk": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "tagrec_eval_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "tagrec_eval_topk_ex": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _sz, _i32, _p]),
+    "tagrec_eval_auc_workspace_bytes": (_sz, [_i64, _i64]),
+    "tagrec_eval_auc": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _sz, _p, _p]),
     "tagrec_eval_metrics": (_i32, [_p, _i64, _p, _i32, _p, _p, _p, _i32, _p, _p]),
     "tagrec_ngcf_dense_fwd": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "tagrec_ngcf_dense_bwd": (_i32, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
-    "tagrec_edge_softmax_rowsum": (_i32, [_p, _i64, _p, _p, _p, _p]),
+    "tagrec_edge_softmax_rowsum": (_i32, [_p, _i64, _i64, _p, _p, _p, _p]),
     "tagrec_edge_scale": (_i32, [_p, _p, _i64, _p, _p, _p, _p]),
-    "tagrec_spmm4": (_i32, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f32, _p]),
+    "tagrec_spmm4": (_i32, [_p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f32, _p]),
+    "tagrec_spmm4_long_threshold": (_i32, []),
     "tagrec_edge_dot4": (_i32, [_p, _p, _i64, _p, _p, _p, _i32, _p]),
     "tagrec_chunk_normalize": (_i32, [_p, _i64, _i32, _p, _p]),
     "tagrec_chunk_normalize_bwd": (_i32, [_p, _p, _i64, _p, _p]),

@@ -2,9 +2,10 @@
 
 ``Basic_test(data, args).run(model, istest=False, group_k=0)`` returns the same dict
 ``{'recall': [per k], 'precision': [...], 'hr': [...], 'ndcg': [...], 'auc': [x]}`` (or a dict of such dicts keyed
-``inter<{n}-{count}`` when ``group_k > 1``).  Per user batch the model's ``eval_topk`` (K3) produces the masked
-top-K directly; metric sums stay on the device until the end.  Models without ``eval_topk`` go through
-``predict_rating`` + ``torch.topk`` exactly like the reference.
+``inter<{n}-{count}`` when ``group_k > 1``).  Per user chunk the model's ``eval_topk`` (K3: tcgen05 scoring + mask +
+top-K) produces the masked top-K directly, ``eval_auc`` (K3b) the per-user AUC sums; everything stays on the device
+until the end.  Models without ``eval_topk`` go through ``predict_rating`` + ``torch.topk`` exactly like the reference.
+Multi-GPU (new): users are sharded over the ranks of the default process group, sums are all-reduced.
 
 Documented deviations: (i) ties are ordered by item id (the reference's torch.topk order is arbitrary);
 (ii) no crash when ``len(users) % test_batch == 0`` (the reference yields an empty batch and raises IndexError,
@@ -79,43 +80,70 @@ class Basic_test():
             self._dev_csr[key] = (torch.as_tensor(p, device=device), torch.as_tensor(items, device=device).to(torch.int32))
         return self._dev_csr[key]
 
+    @staticmethod
+    def _world():
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
     def epoch_test(self, model, true_name, true_ui, all_users=None):
+        """basic_test.py:30-80.  With torch.distributed initialised (one process per GPU) the users are sharded
+        round-robin over the ranks and the metric sums are all-reduced — every rank returns the full result."""
         cfg = config.current()
         if all_users is None:
             all_users = list(true_ui.keys())
         topks = list(cfg['topks'])
-        max_k = max(topks)
-        device = cfg['device']
         n = len(all_users)
+        rank, world = self._world()
+        mine = all_users[rank::world] if (world > 1 and cfg.get('eval_shard', True)) else all_users
+        sharded = world > 1 and cfg.get('eval_shard', True)
         if hasattr(model, "eval_topk"):
-            train_ptr, train_items = self._csr("train", self.pos_ui, device)
-            test_ptr, test_items = self._csr(true_name, true_ui, device)
-            sums = torch.zeros((4, len(topks)), dtype=torch.float64, device=device)
-            auc_sum = torch.zeros((), dtype=torch.float64, device=device)
-            want_auc = cfg.get('eval_auc', True) and hasattr(model, "eval_auc")
-            users_t = torch.as_tensor(np.asarray(all_users, dtype=np.int64), device=device)
-            for s in range(0, n, cfg['test_batch']):
-                ub = users_t[s:s + cfg['test_batch']]
-                ids, _ = model.eval_topk(ub, max_k, train_ptr, train_items)
-                metric_sums(ub, ids, test_ptr, test_items, topks, out=sums)
-                if want_auc:
-                    auc_sum += model.eval_auc(ub, train_ptr, train_items, test_ptr, test_items)
-            sums = (sums / n).cpu().numpy()
-            ret = {'recall': list(sums[0]), 'precision': [np.float32(x) for x in sums[1]], 'hr': list(sums[2]),
-                   'ndcg': list(sums[3])}
-            if want_auc:
-                ret['auc'] = [float(auc_sum.item()) / n]
-            return ret
-        return self._epoch_test_dense(model, true_ui, all_users, topks)
+            sums, auc = self._sums_device(model, true_name, true_ui, mine, topks)
+        else:
+            sums, auc = self._sums_dense(model, true_ui, mine, topks)
+        if sharded:
+            import torch.distributed as dist
+            packed = torch.cat([sums.flatten(), auc.flatten()])
+            dist.all_reduce(packed)
+            sums, auc = packed[:sums.numel()].reshape(sums.shape), packed[sums.numel():]
+        sums = (sums / n).cpu().numpy()
+        ret = {'recall': list(sums[0]), 'precision': [np.float32(x) for x in sums[1]], 'hr': list(sums[2]),
+               'ndcg': list(sums[3])}
+        if auc.numel():
+            ret['auc'] = [float(auc[0].item()) / n]
+        return ret
 
-    def _epoch_test_dense(self, model, true_ui, all_users, topks):
+    def _sums_device(self, model, true_name, true_ui, users, topks):
+        """K3 path: masked top-K (tcgen05 / fp32 kernels), metric sums and AUC sums stay on the device."""
+        cfg = config.current()
+        device = cfg['device']
+        max_k = max(topks)
+        train_ptr, train_items = self._csr("train", self.pos_ui, device)
+        test_ptr, test_items = self._csr(true_name, true_ui, device)
+        sums = torch.zeros((4, len(topks)), dtype=torch.float64, device=device)
+        want_auc = cfg.get('eval_auc', True) and hasattr(model, "eval_auc")
+        auc = torch.zeros(2 if want_auc else 0, dtype=torch.float64, device=device)
+        users_t = torch.as_tensor(np.asarray(users, dtype=np.int64), device=device)
+        # no [B, n_item] matrix is ever materialised, so the user chunk is not bounded by test_batch (a memory knob of
+        # the reference): larger chunks keep all SMs on one wave of item splits
+        chunk = max(int(cfg['test_batch']), int(cfg.get('eval_chunk', 16384)))
+        for s in range(0, len(users), chunk):
+            ub = users_t[s:s + chunk]
+            ids, _ = model.eval_topk(ub, max_k, train_ptr, train_items)
+            metric_sums(ub, ids, test_ptr, test_items, topks, out=sums)
+            if want_auc:
+                model.eval_auc(ub, train_ptr, train_items, test_ptr, test_items, out=auc)
+        return sums, auc
+
+    def _sums_dense(self, model, true_ui, users, topks):
         """The reference's own procedure (basic_test.py:30-80) for models that only offer predict_rating."""
         cfg = config.current()
-        max_k, n = max(topks), len(all_users)
+        max_k = max(topks)
         tot = {k: np.zeros(len(topks)) for k in ('recall', 'precision', 'hr', 'ndcg')}
         auc = 0.0
         with torch.no_grad():
-            for user in minibatch(all_users, cfg['test_batch']):
+            for user in minibatch(users, cfg['test_batch']):
                 rating = model.predict_rating(torch.tensor(user, dtype=torch.long, device=cfg['device']))
                 rows, cols = [], []
                 for i, u in enumerate(user):
@@ -138,9 +166,10 @@ class Basic_test():
                         disc = 1.0 / np.log2(np.arange(2, k + 2))
                         idcg = disc[:min(k, len(truth))].sum() or 1.0
                         tot['ndcg'][q] += (label[:k] * disc).sum() / idcg
-        ret = {k: list(v / n) for k, v in tot.items()}
-        ret['auc'] = [auc / n]
-        return ret
+        dev = cfg['device']
+        sums = torch.tensor(np.stack([tot['recall'], tot['precision'], tot['hr'], tot['ndcg']]), dtype=torch.float64,
+                            device=dev)
+        return sums, torch.tensor([auc, float(len(users))], dtype=torch.float64, device=dev)
 
     def run(self, model, istest=False, group_k=0):
         cfg = config.current()

@@ -16,6 +16,8 @@ _DEFAULTS = dict(
     # new keys (no reference equivalent)
     sampler="device",        # "device": Philox sampler kernel | "mt19937": bit-exact numpy-legacy stream (cpu_core=1)
     eval_auc=True,           # compute the reference's per-user AUC (training/utils.py:37-45) on device
+    eval_chunk=16384,        # users per K3 launch (the reference's test_batch bounds a B x n_item matrix we never build)
+    eval_shard=True,         # torch.distributed initialised: shard evaluation users over the ranks
 )
 
 # utility/config.py:1-81

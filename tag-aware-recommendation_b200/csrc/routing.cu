@@ -63,39 +63,51 @@ __device__ __forceinline__ float4 softmax4(float4 x) {
 }
 
 // ---------------------------------------------------------------------------------------------- R1
+// Edge-parallel (hub rows of a power-law graph would serialise a row-per-sub-warp walk): one edge per thread,
+// row sums through red.global.add.v4.f32 after a warp-level merge of the runs of equal rows (edges are row-sorted,
+// so a warp usually covers one or two rows).  edge_row = row id of every edge (int32 [nnz], built once per graph).
 __global__ void __launch_bounds__(256)
-edge_softmax_rowsum_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, const float4* __restrict__ logit,
-                           float4* __restrict__ w, float4* __restrict__ dinv) {
-    const RowCtx c = row_ctx(rowptr, n_rows);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t j = c.s + c.sl; j < c.e; j += RL) {
-        const float4 p = softmax4(__ldg(logit + j));
-        w[j] = p;
-        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+edge_softmax_rowsum_kernel(const int32_t* __restrict__ edge_row, int64_t nnz, const float4* __restrict__ logit,
+                           float4* __restrict__ w, float4* __restrict__ rowsum) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int row = -1;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e < nnz) {
+        row = __ldg(edge_row + e);
+        p = softmax4(__ldg(logit + e));
+        w[e] = p;
     }
-    acc.x = half_sum(acc.x, c.mask);
-    acc.y = half_sum(acc.y, c.mask);
-    acc.z = half_sum(acc.z, c.mask);
-    acc.w = half_sum(acc.w, c.mask);
-    if (c.valid && c.sl == 0) {
-        // dgcf.py:96-97: 1/sqrt(rowsum), inf -> 0; rows without edges are absent from col_sum => 0
-        dinv[c.row] = make_float4(acc.x > 0.f ? 1.f / sqrtf(acc.x) : 0.f, acc.y > 0.f ? 1.f / sqrtf(acc.y) : 0.f,
-                                  acc.z > 0.f ? 1.f / sqrtf(acc.z) : 0.f, acc.w > 0.f ? 1.f / sqrtf(acc.w) : 0.f);
+    // segmented inclusive scan over the lanes of a run of equal rows; the last lane of a run issues the reduction
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int r2 = __shfl_up_sync(0xffffffffu, row, o);
+        const float x = __shfl_up_sync(0xffffffffu, p.x, o), y = __shfl_up_sync(0xffffffffu, p.y, o);
+        const float z = __shfl_up_sync(0xffffffffu, p.z, o), q = __shfl_up_sync(0xffffffffu, p.w, o);
+        if (lane >= o && r2 == row) { p.x += x; p.y += y; p.z += z; p.w += q; }
     }
+    const int next = __shfl_down_sync(0xffffffffu, row, 1);
+    if (row >= 0 && (lane == 31 || next != row)) red_add4(rowsum + row, p);
+}
+
+__global__ void __launch_bounds__(256) rowsum_to_dinv_kernel(float4* __restrict__ d, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 s = d[i];      // dgcf.py:96-97: 1/sqrt(rowsum), inf -> 0; rows without edges are absent => 0
+    d[i] = make_float4(s.x > 0.f ? 1.f / sqrtf(s.x) : 0.f, s.y > 0.f ? 1.f / sqrtf(s.y) : 0.f,
+                       s.z > 0.f ? 1.f / sqrtf(s.z) : 0.f, s.w > 0.f ? 1.f / sqrtf(s.w) : 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------- R2
 __global__ void __launch_bounds__(256)
-edge_scale_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_rows,
+edge_scale_kernel(const int32_t* __restrict__ edge_row, const int32_t* __restrict__ col, int64_t nnz,
                   const float4* __restrict__ w, const float4* __restrict__ dinv, float4* __restrict__ val) {
-    const RowCtx c = row_ctx(rowptr, n_rows);
-    if (!c.valid) return;
-    const float4 dh = __ldg(dinv + c.row);
-    for (int64_t j = c.s + c.sl; j < c.e; j += RL) {
-        const float4 p = __ldg(w + j);
-        const float4 dt = __ldg(dinv + __ldg(col + j));
-        val[j] = make_float4(dh.x * p.x * dt.x, dh.y * p.y * dt.y, dh.z * p.z * dt.z, dh.w * p.w * dt.w);
-    }
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const float4 dh = __ldg(dinv + __ldg(edge_row + e));
+    const float4 p = __ldg(w + e);
+    const float4 dt = __ldg(dinv + __ldg(col + e));
+    val[e] = make_float4(dh.x * p.x * dt.x, dh.y * p.y * dt.y, dh.z * p.z * dt.z, dh.w * p.w * dt.w);
 }
 
 // ---------------------------------------------------------------------------------------------- R3
@@ -109,40 +121,40 @@ struct Spmm4Epi {
     float mean_scale;
 };
 
-__global__ void __launch_bounds__(256)
-spmm4_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_rows,
-             const float* __restrict__ val, const int32_t* __restrict__ perm, const float4* __restrict__ x4,
-             Spmm4Epi ep) {
-    const RowCtx c = row_ctx(rowptr, n_rows);
-    const int k = c.sl >> 2;
+constexpr int LONG4 = 256;      // rows with more edges are produced by spmm4_long_kernel (one block per row)
+
+__device__ __forceinline__ float4 spmm4_gather(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                               const int32_t* __restrict__ perm, const float4* __restrict__ x4,
+                                               int64_t begin, int64_t end, int64_t stride, int sl, unsigned mask) {
+    const int k = sl >> 2;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t base = c.s; base < c.e; base += RL) {
-        const int cnt = (int)min((int64_t)RL, c.e - base);
+    for (int64_t base = begin; base < end; base += stride) {
+        const int cnt = (int)min((int64_t)RL, end - base);
         int cj = 0;
         int64_t pj = 0;
-        if (c.sl < cnt) {
-            cj = __ldg(col + base + c.sl);
-            pj = perm ? (int64_t)__ldg(perm + base + c.sl) : base + c.sl;
+        if (sl < cnt) {
+            cj = __ldg(col + base + sl);
+            pj = perm ? (int64_t)__ldg(perm + base + sl) : base + sl;
         }
         for (int j = 0; j < cnt; ++j) {
-            const int cc = __shfl_sync(c.mask, cj, j, 16);
-            const int64_t pp = __shfl_sync(c.mask, pj, j, 16);
+            const int cc = __shfl_sync(mask, cj, j, 16);
+            const int64_t pp = __shfl_sync(mask, pj, j, 16);
             const float wv = __ldg(val + pp * 4 + k);
-            fma4(acc, wv, ldg4(x4 + (int64_t)cc * RL + c.sl));
+            fma4(acc, wv, ldg4(x4 + (int64_t)cc * RL + sl));
         }
     }
-    if (!c.valid) {
-        // keep the shuffles below convergent for the sub-warp: nothing to do, masks are per sub-warp
-        return;
-    }
-    const int64_t o = c.row * RL + c.sl;
+    return acc;
+}
+
+__device__ __forceinline__ void spmm4_epilogue(const Spmm4Epi& ep, int64_t row, int sl, unsigned mask, float4 acc) {
+    const int64_t o = row * RL + sl;
     if (ep.res) {
         const float4 r = __ldg(reinterpret_cast<const float4*>(ep.res) + o);
         acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
     }
     if (ep.y_raw) reinterpret_cast<float4*>(ep.y_raw)[o] = acc;
     if (ep.y_norm || ep.mean_acc) {
-        const float nn = fmaxf(sqrtf(sum4(dot4(acc, acc), c.mask)), 1e-12f);
+        const float nn = fmaxf(sqrtf(sum4(dot4(acc, acc), mask)), 1e-12f);
         const float4 yn = make_float4(acc.x / nn, acc.y / nn, acc.z / nn, acc.w / nn);
         if (ep.y_norm) reinterpret_cast<float4*>(ep.y_norm)[o] = yn;
         if (ep.mean_acc) {
@@ -155,35 +167,59 @@ spmm4_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col
     }
 }
 
+__global__ void __launch_bounds__(256)
+spmm4_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_rows,
+             const float* __restrict__ val, const int32_t* __restrict__ perm, const float4* __restrict__ x4,
+             Spmm4Epi ep, int skip_long) {
+    const RowCtx c = row_ctx(rowptr, n_rows);
+    if (!c.valid || (skip_long && c.e - c.s > LONG4)) return;      // masks below are per sub-warp
+    const float4 acc = spmm4_gather(col, val, perm, x4, c.s, c.e, RL, c.sl, c.mask);
+    spmm4_epilogue(ep, c.row, c.sl, c.mask, acc);
+}
+
+// One block per long row: its 16 sub-warps take alternating 16-edge chunks, partial rows meet in shared memory.
+__global__ void __launch_bounds__(256)
+spmm4_long_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                  const int32_t* __restrict__ long_rows, const float* __restrict__ val, const int32_t* __restrict__ perm,
+                  const float4* __restrict__ x4, Spmm4Epi ep) {
+    __shared__ float4 part[16][RL];
+    const int lane = threadIdx.x & 31, sub16 = threadIdx.x >> 4, sl = lane & 15;
+    const unsigned mask = 0xffffu << (16 * ((lane >> 4) & 1));
+    const int64_t row = __ldg(long_rows + blockIdx.x);
+    const int64_t s = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+    part[sub16][sl] = spmm4_gather(col, val, perm, x4, s + (int64_t)sub16 * RL, e, 16 * RL, sl, mask);
+    __syncthreads();
+    if (sub16 == 0) {
+        float4 acc = part[0][sl];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) {
+            const float4 p = part[i][sl];
+            acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        }
+        spmm4_epilogue(ep, row, sl, mask, acc);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- R4
+// Edge-parallel: 16 lanes per edge gather a[head] and b[tail] (consecutive edges share the head row: L1 hits).
 template <int MODE>   // 0: logit[e] += d (dgcf.py:109)   1: w[e] = softmax_k(d) (disengcn.py:33-34)
 __global__ void __launch_bounds__(256)
-edge_dot4_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_rows,
+edge_dot4_kernel(const int32_t* __restrict__ edge_row, const int32_t* __restrict__ col, int64_t nnz,
                  const float4* __restrict__ a4, const float4* __restrict__ b4, float4* __restrict__ out) {
-    const RowCtx c = row_ctx(rowptr, n_rows);
-    float4 ar = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c.valid) ar = ldg4(a4 + c.row * RL + c.sl);
-    for (int64_t base = c.s; base < c.e; base += RL) {
-        const int cnt = (int)min((int64_t)RL, c.e - base);
-        int cj = 0;
-        if (c.sl < cnt) cj = __ldg(col + base + c.sl);
-        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);     // lane j ends up with the 4 factor dots of edge base + j
-        for (int j = 0; j < cnt; ++j) {
-            const int cc = __shfl_sync(c.mask, cj, j, 16);
-            const float d = sum4(dot4(ar, ldg4(b4 + (int64_t)cc * RL + c.sl)), c.mask);
-            const float d0 = __shfl_sync(c.mask, d, 0, 16), d1 = __shfl_sync(c.mask, d, 4, 16);
-            const float d2 = __shfl_sync(c.mask, d, 8, 16), d3 = __shfl_sync(c.mask, d, 12, 16);
-            if (c.sl == j) mine = make_float4(d0, d1, d2, d3);
-        }
-        if (c.sl < cnt) {
-            const int64_t eidx = base + c.sl;
-            if (MODE == 0) {
-                float4 l = out[eidx];
-                l.x += mine.x; l.y += mine.y; l.z += mine.z; l.w += mine.w;
-                out[eidx] = l;
-            } else {
-                out[eidx] = softmax4(mine);
-            }
+    const int lane = threadIdx.x & 31, sl = lane & 15;
+    const unsigned mask = 0xffffu << (16 * (lane >> 4));
+    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (e >= nnz) return;                                          // whole sub-warp leaves together
+    const int64_t h = __ldg(edge_row + e), t = __ldg(col + e);
+    const float d = sum4(dot4(ldg4(a4 + h * RL + sl), ldg4(b4 + t * RL + sl)), mask);
+    const float d1 = __shfl_sync(mask, d, 4, 16), d2 = __shfl_sync(mask, d, 8, 16), d3 = __shfl_sync(mask, d, 12, 16);
+    if (sl == 0) {
+        if (MODE == 0) {
+            float4 l = out[e];
+            l.x += d; l.y += d1; l.z += d2; l.w += d3;
+            out[e] = l;
+        } else {
+            out[e] = softmax4(make_float4(d, d1, d2, d3));
         }
     }
 }
@@ -253,50 +289,62 @@ static unsigned row_grid(int64_t n_rows) { return (unsigned)((n_rows + 15) / 16)
 
 using namespace tagrec;
 
-extern "C" int tagrec_edge_softmax_rowsum(const int64_t* rowptr, int64_t n_rows, const float* logit, float* w,
-                                          float* dinv, void* stream) {
-    TAGREC_REQUIRE(rowptr && logit && w && dinv, "null pointer");
+extern "C" int tagrec_edge_softmax_rowsum(const int32_t* edge_row, int64_t nnz, int64_t n_rows, const float* logit,
+                                          float* w, float* dinv, void* stream) {
+    TAGREC_REQUIRE(edge_row && logit && w && dinv, "null pointer");
     if (n_rows == 0) return TAGREC_OK;
-    TAGREC_LAUNCH(edge_softmax_rowsum_kernel, row_grid(n_rows), 256, 0, stream, rowptr, n_rows,
-                  reinterpret_cast<const float4*>(logit), reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(dinv));
+    TAGREC_CUDA(cudaMemsetAsync(dinv, 0, (size_t)n_rows * 4 * sizeof(float), (cudaStream_t)stream));
+    if (nnz > 0)
+        TAGREC_LAUNCH(edge_softmax_rowsum_kernel, (unsigned)((nnz + 255) / 256), 256, 0, stream, edge_row, nnz,
+                      reinterpret_cast<const float4*>(logit), reinterpret_cast<float4*>(w),
+                      reinterpret_cast<float4*>(dinv));
+    TAGREC_LAUNCH(rowsum_to_dinv_kernel, (unsigned)((n_rows + 255) / 256), 256, 0, stream,
+                  reinterpret_cast<float4*>(dinv), n_rows);
     return TAGREC_OK;
 }
 
-extern "C" int tagrec_edge_scale(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const float* w,
+extern "C" int tagrec_edge_scale(const int32_t* edge_row, const int32_t* col, int64_t nnz, const float* w,
                                  const float* dinv, float* val, void* stream) {
-    TAGREC_REQUIRE(rowptr && col && w && dinv && val, "null pointer");
-    if (n_rows == 0) return TAGREC_OK;
-    TAGREC_LAUNCH(edge_scale_kernel, row_grid(n_rows), 256, 0, stream, rowptr, col, n_rows,
+    TAGREC_REQUIRE(edge_row && col && w && dinv && val, "null pointer");
+    if (nnz == 0) return TAGREC_OK;
+    TAGREC_LAUNCH(edge_scale_kernel, (unsigned)((nnz + 255) / 256), 256, 0, stream, edge_row, col, nnz,
                   reinterpret_cast<const float4*>(w), reinterpret_cast<const float4*>(dinv), reinterpret_cast<float4*>(val));
     return TAGREC_OK;
 }
 
-extern "C" int tagrec_spmm4(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const float* val,
-                            const int32_t* perm, const float* x, const float* res, float* y_raw, float* y_norm,
-                            float* mean_acc, const float* mean_x0, int mean_first, int mean_last, float mean_scale,
-                            void* stream) {
+extern "C" int tagrec_spmm4(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const int32_t* long_rows,
+                            int64_t n_long, const float* val, const int32_t* perm, const float* x, const float* res,
+                            float* y_raw, float* y_norm, float* mean_acc, const float* mean_x0, int mean_first,
+                            int mean_last, float mean_scale, void* stream) {
     TAGREC_REQUIRE(rowptr && col && val && x, "null pointer");
     TAGREC_REQUIRE(y_raw || y_norm || mean_acc, "no output requested");
     TAGREC_REQUIRE(!mean_acc || !mean_first || mean_x0, "mean_first needs mean_x0");
+    TAGREC_REQUIRE(n_long == 0 || long_rows, "long_rows missing");
     if (n_rows == 0) return TAGREC_OK;
     Spmm4Epi ep{res, y_raw, y_norm, mean_acc, mean_x0, mean_first, mean_last, mean_scale};
-    TAGREC_LAUNCH(spmm4_kernel, row_grid(n_rows), 256, 0, stream, rowptr, col, n_rows, val, perm,
-                  reinterpret_cast<const float4*>(x), ep);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    TAGREC_LAUNCH(spmm4_kernel, row_grid(n_rows), 256, 0, stream, rowptr, col, n_rows, val, perm, x4, ep,
+                  (int)(n_long > 0));
+    if (n_long > 0)
+        TAGREC_LAUNCH(spmm4_long_kernel, (unsigned)n_long, 256, 0, stream, rowptr, col, long_rows, val, perm, x4, ep);
     return TAGREC_OK;
 }
 
-extern "C" int tagrec_edge_dot4(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const float* a,
+extern "C" int tagrec_spmm4_long_threshold(void) { return LONG4; }
+
+extern "C" int tagrec_edge_dot4(const int32_t* edge_row, const int32_t* col, int64_t nnz, const float* a,
                                 const float* b, float* out, int mode, void* stream) {
-    TAGREC_REQUIRE(rowptr && col && a && b && out, "null pointer");
+    TAGREC_REQUIRE(edge_row && col && a && b && out, "null pointer");
     TAGREC_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (accumulate) or 1 (softmax)");
-    if (n_rows == 0) return TAGREC_OK;
+    if (nnz == 0) return TAGREC_OK;
     const float4* a4 = reinterpret_cast<const float4*>(a);
     const float4* b4 = reinterpret_cast<const float4*>(b);
     float4* o4 = reinterpret_cast<float4*>(out);
+    const unsigned grid = (unsigned)((nnz * 16 + 255) / 256);
     if (mode == 0) {
-        TAGREC_LAUNCH(edge_dot4_kernel<0>, row_grid(n_rows), 256, 0, stream, rowptr, col, n_rows, a4, b4, o4);
+        TAGREC_LAUNCH(edge_dot4_kernel<0>, grid, 256, 0, stream, edge_row, col, nnz, a4, b4, o4);
     } else {
-        TAGREC_LAUNCH(edge_dot4_kernel<1>, row_grid(n_rows), 256, 0, stream, rowptr, col, n_rows, a4, b4, o4);
+        TAGREC_LAUNCH(edge_dot4_kernel<1>, grid, 256, 0, stream, edge_row, col, nnz, a4, b4, o4);
     }
     return TAGREC_OK;
 }

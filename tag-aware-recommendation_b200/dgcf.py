@@ -9,12 +9,12 @@ import torch.nn as nn
 
 from . import adj as utils
 from . import config
-from .eval_ops import topk_scores
+from .eval_ops import EvalMixin
 from .functional import BprLossFn
 from .routing import DgcfPropagateFn
 
 
-class DGCF(nn.Module):
+class DGCF(nn.Module, EvalMixin):
     def __init__(self, data, args=None):
         super().__init__()
         self._config(config.current())
@@ -79,8 +79,3 @@ class DGCF(nn.Module):
     def predict_rating(self, users):
         all_users, all_items = self.forward()[:2]
         return torch.sigmoid(torch.matmul(all_users[users], all_items.t()))
-
-    def eval_topk(self, users, k, train_ptr, train_items):
-        with torch.no_grad():
-            all_users, all_items = self.forward()[:2]
-            return topk_scores(users, all_users, all_items, train_ptr, train_items, k)

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from . import adj as utils
 from . import config
-from .eval_ops import topk_scores
+from .eval_ops import EvalMixin
 from .functional import BprLossFn
 from .routing import ChunkNormFn, DisenRouteFn
 
@@ -33,7 +33,7 @@ class Layer(nn.Module):
         return DisenRouteFn.apply(adj, self.iter_k, fac)
 
 
-class DisenGCN(nn.Module):
+class DisenGCN(nn.Module, EvalMixin):
     def __init__(self, data, args=None):
         super().__init__()
         self._config(config.current())
@@ -97,8 +97,3 @@ class DisenGCN(nn.Module):
     def predict_rating(self, users):
         all_users, all_items = self.forward()[:2]
         return torch.sigmoid(torch.matmul(all_users[users], all_items.t()))
-
-    def eval_topk(self, users, k, train_ptr, train_items):
-        with torch.no_grad():
-            all_users, all_items = self.forward()[:2]
-            return topk_scores(users, all_users, all_items, train_ptr, train_items, k)

@@ -37,3 +37,39 @@ def metric_sums(users, topk_ids, test_ptr, test_items, ks, out=None):
                                     ptr(test_items), ptr(ks_t), len(ks), ptr(out), stream_ptr(dev)),
           "tagrec_eval_metrics")
     return out
+
+
+def auc_sums(users, user_table, item_table, train_ptr, train_items, test_ptr, test_items, out=None):
+    """training/utils.py:37-45 summed over ``users``: float64 [2] = (sum of per-user AUC, users with both classes)."""
+    L = lib()
+    dev = user_table.device
+    users = users.to(device=dev, dtype=torch.int64).contiguous()
+    ut, it = user_table.contiguous(), item_table.contiguous()
+    if out is None:
+        out = torch.zeros(2, dtype=torch.float64, device=dev)
+    n_test = int(test_items.numel())
+    ws = torch.empty(int(L.tagrec_eval_auc_workspace_bytes(users.numel(), n_test)), dtype=torch.uint8, device=dev)
+    check(L.tagrec_eval_auc(ptr(users), users.numel(), ptr(ut), ptr(it), it.shape[0], it.shape[1], ptr(train_ptr),
+                            ptr(train_items), ptr(test_ptr), ptr(test_items), n_test, ptr(ws), ws.numel(), ptr(out),
+                            stream_ptr(dev)), "tagrec_eval_auc")
+    return out
+
+
+class EvalMixin:
+    """K3 entry points shared by the drop-in models: everything the evaluation loop needs from ``forward()``'s
+    (user, item) tables without materialising predict_rating's [B, n_item] matrix."""
+
+    def _eval_tables(self):
+        with torch.no_grad():
+            all_users, all_items = self.forward()[:2]
+        return all_users.contiguous(), all_items.contiguous()
+
+    def eval_topk(self, users, k, train_ptr, train_items, path="auto"):
+        """Top-k item ids / scores per user with the user's train items masked (basic_test.py:40-48)."""
+        all_users, all_items = self._eval_tables()
+        return topk_scores(users, all_users, all_items, train_ptr, train_items, k, path=path)
+
+    def eval_auc(self, users, train_ptr, train_items, test_ptr, test_items, out=None):
+        """Sum of the per-user AUC (training/utils.py:37-45) and the number of users it is defined for."""
+        all_users, all_items = self._eval_tables()
+        return auc_sums(users, all_users, all_items, train_ptr, train_items, test_ptr, test_items, out=out)

@@ -6,11 +6,11 @@ import torch.nn.functional as F
 
 from . import adj as utils
 from . import config
-from .eval_ops import topk_scores
+from .eval_ops import EvalMixin
 from .functional import LightGCNLossFn, LightGCNPropagateFn, lightgcn_forward_layers
 
 
-class LightGCN(nn.Module):
+class LightGCN(nn.Module, EvalMixin):
     def __init__(self, data, args=None):
         super().__init__()
         self._config(config.current())
@@ -116,9 +116,3 @@ class LightGCN(nn.Module):
         package uses :meth:`eval_topk` instead and never materialises it."""
         all_users, all_items = self.forward()[:2]
         return torch.sigmoid(torch.matmul(all_users[users], all_items.t()))
-
-    def eval_topk(self, users, k, train_ptr, train_items):
-        """K3: top-k item ids / scores per user with the user's train items masked (basic_test.py:40-48)."""
-        with torch.no_grad():
-            all_users, all_items = self.forward()[:2]
-            return topk_scores(users, all_users, all_items, train_ptr, train_items, k)

@@ -14,11 +14,11 @@ import torch.nn.functional as F
 
 from . import adj as utils
 from . import config
-from .eval_ops import topk_scores
+from .eval_ops import EvalMixin
 from .functional import BprLossFn, NgcfDenseFn
 
 
-class NGCF(nn.Module):
+class NGCF(nn.Module, EvalMixin):
     def __init__(self, data, args=None):
         super().__init__()
         self._config(config.current())
@@ -110,8 +110,3 @@ class NGCF(nn.Module):
     def predict_rating(self, users):
         all_users, all_items = self.forward()[:2]
         return torch.sigmoid(torch.matmul(all_users[users], all_items.t()))
-
-    def eval_topk(self, users, k, train_ptr, train_items):
-        with torch.no_grad():
-            all_users, all_items = self.forward()[:2]
-            return topk_scores(users, all_users, all_items, train_ptr, train_items, k)

@@ -30,26 +30,42 @@ def reverse_perm(graph):
     return rev
 
 
+def edge_rows(graph):
+    """Row id of every CSR entry (int32 [nnz]) and the ids of the rows longer than the R3 long-row threshold; cached."""
+    cached = getattr(graph, "_edge_rows", None)
+    if cached is None:
+        er = graph.row_ids().to(torch.int32).contiguous()
+        deg = graph.rowptr[1:] - graph.rowptr[:-1]
+        long_rows = torch.nonzero(deg > int(lib().tagrec_spmm4_long_threshold())).flatten().to(torch.int32).contiguous()
+        cached = graph._edge_rows = (er, long_rows)
+    return cached
+
+
 def edge_softmax_rowsum(graph, logit, w, dinv):
-    check(lib().tagrec_edge_softmax_rowsum(ptr(graph.rowptr), graph.n_rows, ptr(logit), ptr(w), ptr(dinv), _st(logit)),
+    er, _ = edge_rows(graph)
+    check(lib().tagrec_edge_softmax_rowsum(ptr(er), er.numel(), graph.n_rows, ptr(logit), ptr(w), ptr(dinv), _st(logit)),
           "tagrec_edge_softmax_rowsum")
 
 
 def edge_scale(graph, w, dinv, val):
-    check(lib().tagrec_edge_scale(ptr(graph.rowptr), ptr(graph.col), graph.n_rows, ptr(w), ptr(dinv), ptr(val), _st(w)),
+    er, _ = edge_rows(graph)
+    check(lib().tagrec_edge_scale(ptr(er), ptr(graph.col), er.numel(), ptr(w), ptr(dinv), ptr(val), _st(w)),
           "tagrec_edge_scale")
 
 
 def spmm4(graph, val, x, perm=None, res=None, y_raw=None, y_norm=None, mean_acc=None, mean_x0=None, mean_first=False,
           mean_last=False, mean_scale=1.0):
-    check(lib().tagrec_spmm4(ptr(graph.rowptr), ptr(graph.col), graph.n_rows, ptr(val), ptr(perm), ptr(x), ptr(res),
-                             ptr(y_raw), ptr(y_norm), ptr(mean_acc), ptr(mean_x0), int(mean_first), int(mean_last),
-                             float(mean_scale), _st(x)), "tagrec_spmm4")
+    _, long_rows = edge_rows(graph)
+    check(lib().tagrec_spmm4(ptr(graph.rowptr), ptr(graph.col), graph.n_rows, ptr(long_rows) if long_rows.numel() else None,
+                             long_rows.numel(), ptr(val), ptr(perm), ptr(x), ptr(res), ptr(y_raw), ptr(y_norm),
+                             ptr(mean_acc), ptr(mean_x0), int(mean_first), int(mean_last), float(mean_scale), _st(x)),
+          "tagrec_spmm4")
 
 
 def edge_dot4(graph, a, b, out, softmax):
-    check(lib().tagrec_edge_dot4(ptr(graph.rowptr), ptr(graph.col), graph.n_rows, ptr(a), ptr(b), ptr(out),
-                                 int(bool(softmax)), _st(a)), "tagrec_edge_dot4")
+    er, _ = edge_rows(graph)
+    check(lib().tagrec_edge_dot4(ptr(er), ptr(graph.col), er.numel(), ptr(a), ptr(b), ptr(out), int(bool(softmax)),
+                                 _st(a)), "tagrec_edge_dot4")
 
 
 def chunk_normalize(x, tanh=False, out=None):

@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 from . import config
 from ._lib import check, lib, ptr, stream_ptr
-from .eval_ops import topk_scores
+from .eval_ops import EvalMixin
 from .functional import BprLossFn
 
 
@@ -135,7 +135,7 @@ class BasicLayer(nn.Module):
         return self._fusion(self._conv(euN)), self._fusion(self._conv(eiN)), self._fusion(self._conv(etN))
 
 
-class TGCN(nn.Module):
+class TGCN(nn.Module, EvalMixin):
     def __init__(self, data):
         super().__init__()
         self._config(config.current())
@@ -248,8 +248,3 @@ class TGCN(nn.Module):
     def predict_rating(self, users):
         all_users, all_items = self.forward()[:2]
         return torch.sigmoid(torch.matmul(all_users[users], all_items.t()))
-
-    def eval_topk(self, users, k, train_ptr, train_items):
-        with torch.no_grad():
-            all_users, all_items = self.forward()[:2]
-            return topk_scores(users, all_users.contiguous(), all_items.contiguous(), train_ptr, train_items, k)

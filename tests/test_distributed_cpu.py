@@ -73,3 +73,56 @@ def test_sharded_forward_world2_gloo(tmp_path):
     err, moved = np.load(out)
     assert err < 1e-12
     assert moved > 0
+
+
+class _FixedScores(torch.nn.Module):
+    """Stand-in model that only offers predict_rating (the reference's own evaluation procedure is then used)."""
+
+    def __init__(self, scores):
+        super().__init__()
+        self.scores = scores
+
+    def predict_rating(self, users):
+        return self.scores[users].clone()
+
+
+def _eval_worker(rank, world, port, out):
+    if world > 1:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    import tagrec_b200 as T
+    from helpers import user_lists
+    g = dict(np.load(GOLDEN))
+    U, I, _, _ = nums(g)
+    T.set_config("lightgcn", test_batch=7, topks=[5, 20], device=torch.device("cpu"), has_val=False)
+
+    class D:
+        pass
+    d = D()
+    d.num = {"user": U, "item": I}
+    d.user_items = {"train": user_lists(g, "train"), "test": user_lists(g, "test")}
+    scores = torch.sigmoid(torch.tensor(g["lgcn_fwd_0"]) @ torch.tensor(g["lgcn_fwd_1"]).T)
+    res = T.Basic_test(d).run(_FixedScores(scores))
+    if rank == 0:
+        np.save(out, np.array([res[k][j] for k in ("recall", "precision", "hr", "ndcg") for j in range(2)] + res["auc"],
+                              dtype=np.float64))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def test_sharded_evaluation_world2_gloo(tmp_path):
+    """Basic_test under torch.distributed: users sharded over 2 ranks + all-reduce == single process == the
+    reference's epoch_test (golden eval_* of the tiny dataset)."""
+    outs = []
+    for world in (1, 2):
+        out = str(tmp_path / f"eval{world}.npy")
+        port = 31500 + os.getpid() % 2000 + world
+        if world == 1:
+            _eval_worker(0, 1, port, out)
+        else:
+            mp.spawn(_eval_worker, args=(world, port, out), nprocs=world, join=True)
+        outs.append(np.load(out))
+    assert np.allclose(outs[0], outs[1], rtol=0, atol=1e-12)
+    g = dict(np.load(GOLDEN))
+    want = np.r_[[g[f"eval_{k}"][j] for k in ("recall", "precision", "hr", "ndcg") for j in range(2)], g["eval_auc"]]
+    assert np.allclose(outs[0], want, atol=1e-6), (outs[0], want)

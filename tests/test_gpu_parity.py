@@ -269,8 +269,13 @@ def test_k3_topk_and_metrics_vs_reference(medium):
     assert np.allclose(scores[:, 0], ref_scores[:, 0], atol=1e-6)
     # (b) metrics through the drop-in Basic_test vs the reference's epoch_test
     res = T.Basic_test(d).run(model)
-    for k in ("recall", "precision", "hr", "ndcg"):
+    for k in ("recall", "precision", "hr", "ndcg", "auc"):
         assert np.allclose(res[k], medium[f"eval_{k}"], atol=1e-4), (k, res[k], medium[f"eval_{k}"])
+    # small user chunks (several K3 launches) give the same sums
+    T.CFG["eval_chunk"] = 16
+    res2 = T.Basic_test(d).run(model)
+    for k in ("recall", "precision", "hr", "ndcg", "auc"):
+        assert np.allclose(res2[k], res[k], atol=1e-12)
 
 
 def test_k3_masked_items_fill_the_tail():
@@ -534,12 +539,12 @@ def test_disengcn_forward_loss_grad_vs_reference(tiny):
 
 def test_k5_routing_kernels_vs_torch():
     """Each K5 kernel against a dense torch fp64 restatement on a ragged random symmetric structure (isolated
-    nodes, a hub row longer than one 16-edge chunk, odd row count)."""
+    nodes, a hub row that takes the block-per-row long path, odd row count)."""
     from tagrec_b200 import routing as R
     rng = np.random.RandomState(4)
-    U, I = 37, 54
-    e_u = np.r_[rng.randint(0, U - 2, 300), np.zeros(40, dtype=np.int64)]       # user U-1, U-2 isolated; user 0 = hub
-    e_i = np.r_[rng.randint(0, I - 1, 300), np.arange(40)]
+    U, I = 37, 540
+    e_u = np.r_[rng.randint(0, U - 2, 300), np.zeros(400, dtype=np.int64)]      # user U-1, U-2 isolated; user 0 = hub
+    e_i = np.r_[rng.randint(0, I - 1, 300), np.arange(400)]                     # hub row > 256 edges: long-row kernel
     g = T.build_csr(U, I, (e_u, e_i), "plain", dev())
     n, nnz = g.n, g._nnz()
     rows = g.row_ids().cpu().numpy()
@@ -696,6 +701,65 @@ def test_k4_neighbour_attention_vs_torch():
         assert relerr(got.grad.cpu().numpy(), want.grad.numpy()) < TOL
     for n, p in att.named_parameters():
         assert relerr(p.grad.cpu().numpy(), P[n].grad.numpy()) < TOL, n
+
+
+@pytest.mark.parametrize("nu,n_item,dim,scale", [(70, 3000, 64, 1.0), (33, 700, 256, 0.05), (130, 9000, 64, 30.0)])
+def test_k3b_auc_vs_oracle(nu, n_item, dim, scale):
+    """Device AUC (csrc/eval_auc.cu) == the oracle's restatement of roc_auc_score (rank-sum with tie averaging) per
+    user: ragged test sets, test items that are also train items (masked, not positives), users without positives,
+    duplicated item rows (exact score ties), a user with a long train row."""
+    from tagrec_b200.eval_ops import auc_sums
+    g = torch.Generator().manual_seed(nu)
+    n_tab = nu + 4
+    ut = torch.randn(n_tab, dim, generator=g) * scale
+    it = torch.randn(n_item, dim, generator=g) * scale
+    it[n_item // 2:n_item // 2 + 50] = it[:50]                    # exact ties between positives and negatives
+    rng = np.random.RandomState(nu)
+    users = rng.permutation(n_tab)[:nu]
+    train, test = {}, {}
+    for u in range(n_tab):
+        n_tr = n_item // 2 if u == users[0] else rng.randint(0, 40)
+        train[u] = sorted(rng.choice(n_item, n_tr, replace=False).tolist())
+        n_te = 0 if u == users[1] else rng.randint(1, 30)
+        te = set(rng.choice(n_item, n_te, replace=False).tolist())
+        if u == users[2] and train[u]:
+            te |= set(train[u][:3])                               # test items that are masked by the train set
+        test[u] = sorted(te)
+    tp, ti = T.bpr_training_data.user_items_to_csr(train, n_tab)
+    sp, si = T.bpr_training_data.user_items_to_csr(test, n_tab)
+    out = auc_sums(torch.tensor(users, device=dev()), ut.to(dev()), it.to(dev()), torch.tensor(tp, device=dev()),
+                   torch.tensor(ti, device=dev()).int(), torch.tensor(sp, device=dev()),
+                   torch.tensor(si, device=dev()).int()).cpu().numpy()
+    # oracle on the SAME fp32 scores the kernel ranks (sequential-fmaf dot): use the fp32 K3 path's score definition
+    scores = np.zeros((nu, n_item), dtype=np.float32)
+    ut_n, it_n = ut.numpy(), it.numpy()
+    for r, u in enumerate(users):
+        acc = np.zeros(n_item, dtype=np.float32)
+        for k in range(dim):
+            acc = np.float32(ut_n[u, k]) * it_n[:, k] + acc       # numpy has no fma: compare with a tie-tolerant bar
+        scores[r] = acc
+    tot, cnt = 0.0, 0
+    for r, u in enumerate(users):
+        row = scores[r].astype(np.float64)
+        row[train[u]] = -1e30                                     # masked
+        pos = [i for i in test[u] if i not in set(train[u])]
+        if not pos or len(pos) + len(train[u]) >= n_item:
+            continue
+        keep = row > -1e29
+        y = np.zeros(n_item, dtype=bool)
+        y[pos] = True
+        s, yy = row[keep], y[keep]
+        order = np.argsort(s, kind="stable")
+        ss = s[order]
+        ranks = np.empty(len(s))
+        bounds = np.flatnonzero(np.r_[True, ss[1:] != ss[:-1], True])
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            ranks[order[a:b]] = 0.5 * (a + 1 + b)
+        npos = yy.sum()
+        tot += (ranks[yy].sum() - npos * (npos + 1) / 2.0) / (npos * (len(s) - npos))
+        cnt += 1
+    assert out[1] == cnt
+    assert abs(out[0] - tot) <= 1e-5 * cnt, (out[0], tot)
 
 
 # ------------------------------------------------------------------------------------------------------- sampler
