@@ -225,15 +225,30 @@ int tagrec_edge_softmax_rowsum(const int32_t* edge_row, int64_t nnz, int64_t n_r
 /* val[e,k] = dinv[h,k] * w[e,k] * dinv[t,k]: the per-factor operator D A_k D of dgcf.py:98-101 as edge values. */
 int tagrec_edge_scale(const int32_t* edge_row, const int32_t* col, int64_t nnz, const float* w, const float* dinv,
                       float* val, void* stream);
+/* Long rows of a power-law graph (more than tagrec_spmm4_long_threshold() entries) are cut into pieces of at most
+ * TAGREC_ROUTE_PIECE entries: long_rows int32 [n_long] row ids; piece_slot int32 / piece_begin, piece_end int64
+ * [n_pieces] = (slot in long_rows, entry range); scratch float [n_long, 64], zero on entry, left zero on exit. */
+#define TAGREC_ROUTE_PIECE 2048
+typedef struct {
+    const int32_t* long_rows;
+    int64_t n_long;
+    const int32_t* piece_slot;
+    const int64_t* piece_begin;
+    const int64_t* piece_end;
+    int64_t n_pieces;
+    float* scratch;
+} tagrec_route_plan_t;
+
 /* y[h, chunk k] = (res ? res[h] : 0) + sum_{e=(h,t)} val[perm ? perm[e] : e, k] * x[t, chunk k]
  *   y_raw  (optional) the sum;  y_norm (optional) each 16-d chunk L2-normalised (dgcf.py:79, disengcn.py:41);
  *   mean_acc (optional) running mean of the normalised layers: (first ? mean_x0 : mean_acc) + y_norm, times
  *   mean_scale when last (dgcf.py:59-61).  perm = reverse-edge permutation => multiplies by the TRANSPOSED operator.
- *   long_rows int32 [n_long] = ids of the rows with more than tagrec_spmm4_long_threshold() entries (one block each). */
-int tagrec_spmm4(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const int32_t* long_rows, int64_t n_long,
+ *   plan may be NULL when no row exceeds the threshold. */
+int tagrec_spmm4(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const tagrec_route_plan_t* plan,
                  const float* val, const int32_t* perm, const float* x, const float* res, float* y_raw, float* y_norm,
                  float* mean_acc, const float* mean_x0, int mean_first, int mean_last, float mean_scale, void* stream);
 int tagrec_spmm4_long_threshold(void);
+int tagrec_spmm4_piece(void);
 /* d[e,k] = <a[h, chunk k], b[t, chunk k]>;  mode 0: out[e,:] += d (dgcf.py:103-109, A_values += A_score)
  *                                           mode 1: out[e,:] = softmax_k(d) (disengcn.py:31-34). */
 int tagrec_edge_dot4(const int32_t* edge_row, const int32_t* col, int64_t nnz, const float* a, const float* b,

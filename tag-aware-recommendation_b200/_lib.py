@@ -28,6 +28,12 @@ class CsrDesc(C.Structure):
                 ("long_counter", _p)]
 
 
+class RoutePlan(C.Structure):
+    """tagrec_route_plan_t"""
+    _fields_ = [("long_rows", _p), ("n_long", _i64), ("piece_slot", _p), ("piece_begin", _p), ("piece_end", _p),
+                ("n_pieces", _i64), ("scratch", _p)]
+
+
 class MirrorDesc(C.Structure):
     """tagrec_mirror_t"""
     _fields_ = [("n", C.c_int32), ("self", C.c_int32), ("base", _p * 8)]
@@ -60,8 +66,9 @@ PROTOTYPES = {
     "tagrec_ngcf_dense_bwd": (_i32, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "tagrec_edge_softmax_rowsum": (_i32, [_p, _i64, _i64, _p, _p, _p, _p]),
     "tagrec_edge_scale": (_i32, [_p, _p, _i64, _p, _p, _p, _p]),
-    "tagrec_spmm4": (_i32, [_p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f32, _p]),
+    "tagrec_spmm4": (_i32, [_p, _p, _i64, C.POINTER(RoutePlan), _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f32, _p]),
     "tagrec_spmm4_long_threshold": (_i32, []),
+    "tagrec_spmm4_piece": (_i32, []),
     "tagrec_edge_dot4": (_i32, [_p, _p, _i64, _p, _p, _p, _i32, _p]),
     "tagrec_chunk_normalize": (_i32, [_p, _i64, _i32, _p, _p]),
     "tagrec_chunk_normalize_bwd": (_i32, [_p, _p, _i64, _p, _p]),

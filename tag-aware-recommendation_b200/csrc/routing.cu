@@ -121,7 +121,7 @@ struct Spmm4Epi {
     float mean_scale;
 };
 
-constexpr int LONG4 = 256;      // rows with more edges are produced by spmm4_long_kernel (one block per row)
+constexpr int LONG4 = 256;      // rows with more entries are produced piecewise (spmm4_piece_kernel)
 
 __device__ __forceinline__ float4 spmm4_gather(const int32_t* __restrict__ col, const float* __restrict__ val,
                                                const int32_t* __restrict__ perm, const float4* __restrict__ x4,
@@ -177,16 +177,18 @@ spmm4_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col
     spmm4_epilogue(ep, c.row, c.sl, c.mask, acc);
 }
 
-// One block per long row: its 16 sub-warps take alternating 16-edge chunks, partial rows meet in shared memory.
+// Long rows are cut into pieces of at most LONG4_PIECE entries; one block per piece: its 16 sub-warps take alternating
+// 16-edge chunks, partial rows meet in shared memory and leave through one red.global.add.v4.f32 per lane into the
+// row's scratch slot; a second tiny launch runs the fused epilogue on the complete rows and re-zeroes the scratch.
 __global__ void __launch_bounds__(256)
-spmm4_long_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                  const int32_t* __restrict__ long_rows, const float* __restrict__ val, const int32_t* __restrict__ perm,
-                  const float4* __restrict__ x4, Spmm4Epi ep) {
+spmm4_piece_kernel(const int32_t* __restrict__ col, const int32_t* __restrict__ piece_slot,
+                   const int64_t* __restrict__ piece_begin, const int64_t* __restrict__ piece_end,
+                   const float* __restrict__ val, const int32_t* __restrict__ perm, const float4* __restrict__ x4,
+                   float4* __restrict__ scratch) {
     __shared__ float4 part[16][RL];
     const int lane = threadIdx.x & 31, sub16 = threadIdx.x >> 4, sl = lane & 15;
     const unsigned mask = 0xffffu << (16 * ((lane >> 4) & 1));
-    const int64_t row = __ldg(long_rows + blockIdx.x);
-    const int64_t s = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+    const int64_t s = __ldg(piece_begin + blockIdx.x), e = __ldg(piece_end + blockIdx.x);
     part[sub16][sl] = spmm4_gather(col, val, perm, x4, s + (int64_t)sub16 * RL, e, 16 * RL, sl, mask);
     __syncthreads();
     if (sub16 == 0) {
@@ -196,8 +198,20 @@ spmm4_long_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict_
             const float4 p = part[i][sl];
             acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
         }
-        spmm4_epilogue(ep, row, sl, mask, acc);
+        red_add4(scratch + (int64_t)__ldg(piece_slot + blockIdx.x) * RL + sl, acc);
     }
+}
+
+__global__ void __launch_bounds__(256)
+spmm4_long_epilogue_kernel(const int32_t* __restrict__ long_rows, int64_t n_long, float4* __restrict__ scratch,
+                           Spmm4Epi ep) {
+    const int lane = threadIdx.x & 31, sl = lane & 15;
+    const unsigned mask = 0xffffu << (16 * (lane >> 4));
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (i >= n_long) return;
+    const float4 acc = __ldcg(scratch + i * RL + sl);
+    __stcg(scratch + i * RL + sl, make_float4(0.f, 0.f, 0.f, 0.f));
+    spmm4_epilogue(ep, __ldg(long_rows + i), sl, mask, acc);
 }
 
 // ---------------------------------------------------------------------------------------------- R4
@@ -312,25 +326,34 @@ extern "C" int tagrec_edge_scale(const int32_t* edge_row, const int32_t* col, in
     return TAGREC_OK;
 }
 
-extern "C" int tagrec_spmm4(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const int32_t* long_rows,
-                            int64_t n_long, const float* val, const int32_t* perm, const float* x, const float* res,
-                            float* y_raw, float* y_norm, float* mean_acc, const float* mean_x0, int mean_first,
-                            int mean_last, float mean_scale, void* stream) {
+extern "C" int tagrec_spmm4(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const tagrec_route_plan_t* plan,
+                            const float* val, const int32_t* perm, const float* x, const float* res, float* y_raw,
+                            float* y_norm, float* mean_acc, const float* mean_x0, int mean_first, int mean_last,
+                            float mean_scale, void* stream) {
     TAGREC_REQUIRE(rowptr && col && val && x, "null pointer");
     TAGREC_REQUIRE(y_raw || y_norm || mean_acc, "no output requested");
     TAGREC_REQUIRE(!mean_acc || !mean_first || mean_x0, "mean_first needs mean_x0");
-    TAGREC_REQUIRE(n_long == 0 || long_rows, "long_rows missing");
+    const int64_t n_long = plan ? plan->n_long : 0;
+    if (n_long > 0)
+        TAGREC_REQUIRE(plan->long_rows && plan->piece_slot && plan->piece_begin && plan->piece_end && plan->scratch &&
+                           plan->n_pieces > 0, "long-row plan arrays missing");
     if (n_rows == 0) return TAGREC_OK;
     Spmm4Epi ep{res, y_raw, y_norm, mean_acc, mean_x0, mean_first, mean_last, mean_scale};
     const float4* x4 = reinterpret_cast<const float4*>(x);
     TAGREC_LAUNCH(spmm4_kernel, row_grid(n_rows), 256, 0, stream, rowptr, col, n_rows, val, perm, x4, ep,
                   (int)(n_long > 0));
-    if (n_long > 0)
-        TAGREC_LAUNCH(spmm4_long_kernel, (unsigned)n_long, 256, 0, stream, rowptr, col, long_rows, val, perm, x4, ep);
+    if (n_long > 0) {
+        float4* scr = reinterpret_cast<float4*>(plan->scratch);
+        TAGREC_LAUNCH(spmm4_piece_kernel, (unsigned)plan->n_pieces, 256, 0, stream, col, plan->piece_slot,
+                      plan->piece_begin, plan->piece_end, val, perm, x4, scr);
+        TAGREC_LAUNCH(spmm4_long_epilogue_kernel, (unsigned)((n_long * 16 + 255) / 256), 256, 0, stream, plan->long_rows,
+                      n_long, scr, ep);
+    }
     return TAGREC_OK;
 }
 
 extern "C" int tagrec_spmm4_long_threshold(void) { return LONG4; }
+extern "C" int tagrec_spmm4_piece(void) { return TAGREC_ROUTE_PIECE; }
 
 extern "C" int tagrec_edge_dot4(const int32_t* edge_row, const int32_t* col, int64_t nnz, const float* a,
                                 const float* b, float* out, int mode, void* stream) {

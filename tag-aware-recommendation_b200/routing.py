@@ -5,9 +5,11 @@ No gradient flows through the routing weights in the reference (`.detach()`, dgc
 backward of a layer is the transposed per-factor operator of its LAST routing iteration.  Those weights are not
 symmetric, hence the reverse-edge permutation.
 """
+import ctypes as C
+
 import torch
 
-from ._lib import check, lib, ptr, stream_ptr
+from ._lib import RoutePlan, check, lib, ptr, stream_ptr
 
 FACTORS = 4
 
@@ -31,14 +33,31 @@ def reverse_perm(graph):
 
 
 def edge_rows(graph):
-    """Row id of every CSR entry (int32 [nnz]) and the ids of the rows longer than the R3 long-row threshold; cached."""
+    """Row id of every CSR entry (int32 [nnz]) + the long-row plan of R3 (tagrec_route_plan_t); cached on the graph."""
     cached = getattr(graph, "_edge_rows", None)
     if cached is None:
+        L = lib()
+        dev = graph.device
         er = graph.row_ids().to(torch.int32).contiguous()
         deg = graph.rowptr[1:] - graph.rowptr[:-1]
-        long_rows = torch.nonzero(deg > int(lib().tagrec_spmm4_long_threshold())).flatten().to(torch.int32).contiguous()
-        cached = graph._edge_rows = (er, long_rows)
-    return cached
+        long_rows = torch.nonzero(deg > int(L.tagrec_spmm4_long_threshold())).flatten()
+        plan, keep = None, None
+        if long_rows.numel():
+            piece = int(L.tagrec_spmm4_piece())
+            npieces = (deg[long_rows] + piece - 1) // piece
+            slot = torch.repeat_interleave(torch.arange(long_rows.numel(), device=dev), npieces)
+            first = torch.cumsum(npieces, 0) - npieces
+            k = torch.arange(slot.numel(), device=dev) - first[slot]
+            begin = (graph.rowptr[long_rows][slot] + k * piece).contiguous()
+            end = torch.minimum(begin + piece, graph.rowptr[long_rows + 1][slot]).contiguous()
+            keep = (long_rows.to(torch.int32).contiguous(), slot.to(torch.int32).contiguous(), begin, end,
+                    torch.zeros((long_rows.numel(), 16 * FACTORS), dtype=torch.float32, device=dev))
+            plan = RoutePlan()
+            plan.long_rows, plan.n_long = ptr(keep[0]), long_rows.numel()
+            plan.piece_slot, plan.piece_begin, plan.piece_end = ptr(keep[1]), ptr(keep[2]), ptr(keep[3])
+            plan.n_pieces, plan.scratch = slot.numel(), ptr(keep[4])
+        cached = graph._edge_rows = (er, plan, keep)
+    return cached[0], cached[1]
 
 
 def edge_softmax_rowsum(graph, logit, w, dinv):
@@ -55,11 +74,10 @@ def edge_scale(graph, w, dinv, val):
 
 def spmm4(graph, val, x, perm=None, res=None, y_raw=None, y_norm=None, mean_acc=None, mean_x0=None, mean_first=False,
           mean_last=False, mean_scale=1.0):
-    _, long_rows = edge_rows(graph)
-    check(lib().tagrec_spmm4(ptr(graph.rowptr), ptr(graph.col), graph.n_rows, ptr(long_rows) if long_rows.numel() else None,
-                             long_rows.numel(), ptr(val), ptr(perm), ptr(x), ptr(res), ptr(y_raw), ptr(y_norm),
-                             ptr(mean_acc), ptr(mean_x0), int(mean_first), int(mean_last), float(mean_scale), _st(x)),
-          "tagrec_spmm4")
+    _, plan = edge_rows(graph)
+    check(lib().tagrec_spmm4(ptr(graph.rowptr), ptr(graph.col), graph.n_rows, C.byref(plan) if plan is not None else None,
+                             ptr(val), ptr(perm), ptr(x), ptr(res), ptr(y_raw), ptr(y_norm), ptr(mean_acc), ptr(mean_x0),
+                             int(mean_first), int(mean_last), float(mean_scale), _st(x)), "tagrec_spmm4")
 
 
 def edge_dot4(graph, a, b, out, softmax):

@@ -603,6 +603,32 @@ def test_k5_routing_kernels_vs_torch():
     assert relerr(got[keep], xr.grad.numpy()[keep]) < TOL
 
 
+def test_k5_spmm4_multi_piece_rows():
+    """R3 on rows cut into several TAGREC_ROUTE_PIECE pieces (a 5000-neighbour hub) incl. the transposed operator,
+    twice in a row (the scratch rows must come back zeroed)."""
+    from tagrec_b200 import routing as R
+    rng = np.random.RandomState(8)
+    U, I = 3, 5000
+    e_u = np.r_[np.zeros(I, dtype=np.int64), rng.randint(1, U, 600)]
+    e_i = np.r_[np.arange(I), rng.randint(0, I, 600)]
+    g = T.build_csr(U, I, (e_u, e_i), "plain", dev())
+    n, nnz = g.n, g._nnz()
+    rows = torch.tensor(g.row_ids().cpu().numpy())
+    cols = torch.tensor(g.col.cpu().numpy().astype(np.int64))
+    gen = torch.Generator().manual_seed(3)
+    val = torch.rand(nnz, 4, generator=gen)
+    x = torch.randn(n, 64, generator=gen)
+    vd, xd = val.to(dev()), x.to(dev())
+    rev = R.reverse_perm(g)
+    for perm, v_eff in ((None, val), (rev, val[rev.cpu().long()])):
+        contrib = (v_eff.double()[:, :, None] * x.double()[cols].reshape(nnz, 4, 16)).reshape(nnz, 64)
+        ref = torch.zeros(n, 64, dtype=torch.float64).index_add_(0, rows, contrib)
+        for _ in range(2):
+            out = torch.empty(n, 64, device=dev())
+            R.spmm4(g, vd, xd, perm=perm, y_raw=out)
+            assert relerr(out.cpu().numpy(), ref.numpy()) < TOL
+
+
 def test_dgcf_device_sampler_properties(tiny):
     """Throughput-mode DGCF_training_data: (data, cor) shapes, positives are train items, negatives are not."""
     T.set_config("dgcf", train_batch=16, use_tag=True, cor_batch=10, sampler="device", device=dev())
