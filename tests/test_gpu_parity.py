@@ -838,3 +838,123 @@ def test_multi_gpu_sharded_step_matches_single():
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------------------- large-scale, size-independent properties
+@pytest.fixture(scope="module")
+def big_graph():
+    """A 30 M-interaction synthetic graph of the C5 family (600 K users x 120 K items), built entirely on the device."""
+    U, I, E = 600_000, 120_000, 30_000_000
+    row, col = T.data.synth_bipartite_device(U, I, E, dev(), seed=7)
+    g = T.build_csr(U, I, (row, col), "bi_norm", dev())
+    return U, I, row, col, g
+
+
+def test_large_k0_structure_properties(big_graph):
+    """K0 at scale: rowptr monotone and consistent, columns strictly ascending inside every row, block structure
+    (user rows only reach item columns and vice versa), bi_norm values symmetric through the reverse-edge permutation
+    and equal to d_r^-1/2 d_c^-1/2 up to the two fp32 roundings, long-row plan covers exactly the rows above the cut."""
+    from tagrec_b200 import routing as R
+    U, I, row, col, g = big_graph
+    n, nnz = g.n, g._nnz()
+    assert n == U + I and nnz == 2 * row.numel()
+    rp = g.rowptr
+    assert int(rp[0]) == 0 and int(rp[-1]) == nnz and bool((rp[1:] >= rp[:-1]).all())
+    rid = g.row_ids()
+    same_row = rid[1:] == rid[:-1]
+    assert bool((g.col[1:][same_row] > g.col[:-1][same_row]).all())
+    assert bool((g.col[: int(rp[U])] >= U).all()) and bool((g.col[int(rp[U]):] < U).all())
+    rev = R.reverse_perm(g).long()
+    assert torch.equal(g.val[rev], g.val)                                  # exact symmetry of D^-1/2 A D^-1/2
+    deg = (rp[1:] - rp[:-1]).double()
+    want = 1.0 / torch.sqrt(deg[rid] * deg[g.col.long()])
+    assert float(((g.val.double() - want).abs() / want).max()) < 5e-7
+    assert g.n_long == int((deg > T._lib.LONG_ROW).sum())
+
+
+def test_large_k1_linearity_and_adjointness(big_graph):
+    """K1 at scale (60 M nnz, long-row path active): linearity, <y, A x> == <A y, x> (A symmetric), and the fused
+    LightGCN layer == plain SpMM + normalise + accumulate computed separately."""
+    U, I, _, _, g = big_graph
+    gen = torch.Generator(device=dev()).manual_seed(1)
+    x = torch.randn(g.n, 64, device=dev(), generator=gen)
+    y = torch.randn(g.n, 64, device=dev(), generator=gen)
+    ax, ay = T.spmm_raw(g, x), T.spmm_raw(g, y)
+    lin = T.spmm_raw(g, 2.0 * x - 3.0 * y)
+    assert float((lin - (2.0 * ax - 3.0 * ay)).abs().max() / ax.abs().max()) < 1e-5
+    a, b = float((y.double() * ax.double()).sum()), float((ay.double() * x.double()).sum())
+    scale = float(y.double().norm() * ax.double().norm())           # the inner products are sums of 46 M signed terms
+    assert abs(a - b) <= 1e-6 * scale
+    from tagrec_b200.functional import lightgcn_forward_layers
+    raw = [torch.empty_like(x)]
+    final = torch.empty_like(x)
+    lightgcn_forward_layers(g, x, 1, raw, final)
+    assert torch.equal(raw[0], ax)
+    want = (x + torch.nn.functional.normalize(ax, dim=1)) * 0.5
+    assert float((final - want).abs().max()) < 1e-6
+
+
+def test_large_k3_paths_identical_and_ordered(big_graph):
+    """K3 at scale (8 192 users x 120 K items, real train rows as masks): tcgen05 path == fp32 path bit for bit;
+    scores non-increasing; no train item in any list; re-scoring the returned ids reproduces their scores."""
+    from tagrec_b200.eval_ops import topk_scores
+    U, I, _, _, g = big_graph
+    gen = torch.Generator(device=dev()).manual_seed(2)
+    ut = torch.randn(U, 64, device=dev(), generator=gen) * 0.2
+    it = torch.randn(I, 64, device=dev(), generator=gen) * 0.2
+    users = torch.randperm(U, device=dev(), generator=gen)[:8192]
+    tp = g.rowptr[:U + 1].contiguous()
+    ti = (g.col[: int(tp[-1])] - U).contiguous()
+    ids_a, sc_a = topk_scores(users, ut, it, tp, ti, 20, path="fp32")
+    ids_b, sc_b = topk_scores(users, ut, it, tp, ti, 20, path="tf32")
+    assert torch.equal(ids_a, ids_b) and torch.equal(sc_a, sc_b)
+    assert bool((sc_b[:, 1:] <= sc_b[:, :-1]).all())              # (id order on exact ties: the duplicate-row test)
+    # masked: binary search every returned id in the user's train row
+    lo, hi = tp[users][:, None].expand(-1, 20).clone(), tp[users + 1][:, None].expand(-1, 20).clone()
+    key = ids_b.long()
+    for _ in range(20):
+        mid = (lo + hi) // 2
+        go = (ti[mid.clamp(max=ti.numel() - 1)].long() < key) & (lo < hi)
+        lo = torch.where(go, mid + 1, lo)
+        hi = torch.where(go, hi, torch.minimum(hi, mid))
+    found = (lo < tp[users + 1][:, None]) & (ti[lo.clamp(max=ti.numel() - 1)].long() == key)
+    assert not bool(found.any())
+    dots = (ut[users][:, None, :] * it[ids_b.long()]).sum(-1)
+    assert float((torch.sigmoid(dots) - sc_b).abs().max()) < 1e-6
+
+
+def test_large_device_sampler_and_bpr_step(big_graph):
+    """Device sampler at scale: every negative is a non-train item, every positive an edge; one fused BPR step on the
+    sampled batch: loss finite, gradient rows non-zero exactly on the batch's nodes, gradient sums to zero over the
+    item side minus user side pairing (each triple adds +s f_u to i- and -s f_u to i+)."""
+    U, I, row, col, g = big_graph
+    E = row.numel()
+    tp = g.rowptr[:U + 1].contiguous()
+    ti = (g.col[: int(tp[-1])] - U).contiguous()
+    sel = torch.randint(0, E, (1 << 20,), device=dev())
+    edges = torch.stack([row[sel], col[sel]], 1).contiguous()
+    out = torch.empty((edges.shape[0], 3), dtype=torch.int64, device=dev())
+    L = T._lib
+    L.check(L.lib().tagrec_sample_bpr_device(L.ptr(edges), edges.shape[0], L.ptr(tp), L.ptr(ti), I, 5, 0, L.ptr(out),
+                                             L.stream_ptr(dev())), "sampler")
+    key_train = row * I + col                                   # sorted (row-major unique pairs)
+    def member(u, i):
+        k = u * I + i
+        pos = torch.searchsorted(key_train, k).clamp(max=E - 1)
+        return key_train[pos] == k
+    assert bool(member(out[:, 0], out[:, 1]).all())
+    assert not bool(member(out[:, 0], out[:, 2]).any())
+    assert int(out[:, 2].min()) >= 0 and int(out[:, 2].max()) < I
+    from tagrec_b200.functional import bpr_fwd_bwd
+    final = torch.randn(U + I, 64, device=dev()) * 0.1
+    gf = torch.zeros_like(final)
+    loss = torch.empty(2, device=dev())
+    batch = out[:2048].contiguous()
+    bpr_fwd_bwd(batch, U, final, final, 0.0, "softplus", gf, None, loss)
+    assert bool(torch.isfinite(loss[0]))
+    touched = torch.zeros(U + I, dtype=torch.bool, device=dev())
+    touched[batch[:, 0]] = True
+    touched[batch[:, 1] + U] = True
+    touched[batch[:, 2] + U] = True
+    assert not bool(gf[~touched].any())
+    assert float(gf[U:].sum(0).abs().max()) < 1e-4               # +s f_u and -s f_u cancel over the item rows
