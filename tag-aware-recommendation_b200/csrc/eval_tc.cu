@@ -152,6 +152,9 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int c16) {
 #ifndef TC_TS
 #define TC_TS 1
 #endif
+#ifndef TC_INTERLEAVE
+#define TC_INTERLEAVE 0      // 1: issue the two halves' MMAs alternately (independent accumulators back to back)
+#endif
 #ifndef TC_EXPERIMENT
 #define TC_EXPERIMENT 0      // 1 / 2: timing experiments (wrong results), see tools/tune_eval.sh
 #endif
@@ -306,6 +309,35 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
 #endif
                 mbar_wait(smem_u32(full + s), (t / S) & 1);
                 const uint32_t b0 = smem_u32(Bs + s * TC_TILE_BYTES);
+#if TC_INTERLEAVE && TC_EXPERIMENT != 5
+                // Consecutive MMAs into the SAME accumulator form a dependent chain (each waits for the previous
+                // accumulate to retire); alternating the two halves' accumulators keeps the tensor pipe busy.
+                {
+                    uint32_t dd[NH];
+#pragma unroll
+                    for (int hh = 0; hh < NH; ++hh) {
+                        const int n = t * NH + hh, r = n % TC_NACC;
+                        mbar_wait(smem_u32(accfree + r), ((n / TC_NACC) & 1) ^ 1);
+                        dd[hh] = acc_base + (uint32_t)(r * TC_N);
+                    }
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint32_t off = (uint32_t)((kk >> 2) * TC_KH_BYTES + (kk & 3) * 32);
+                        const uint64_t bd = umma_desc_sw128(b0 + off);
+#pragma unroll
+                        for (int hh = 0; hh < NH; ++hh) {
+                            if constexpr (kTS)
+                                umma_tf32_ts(dd[hh], tmem_base + (uint32_t)(hh * 64 + kk * 8), bd, kk > 0);
+                            else
+                                umma_tf32(dd[hh], umma_desc_sw128(smem_u32(As + hh * TC_TILE_BYTES) + off), bd, kk > 0);
+                        }
+                    }
+#pragma unroll
+                    for (int hh = 0; hh < NH; ++hh) umma_commit(smem_u32(accfull + (t * NH + hh) % TC_NACC));
+                    continue;
+                }
+#endif
 #pragma unroll
                 for (int hh = 0; hh < NH; ++hh) {
                     const int n = t * NH + hh, r = n % TC_NACC;

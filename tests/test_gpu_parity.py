@@ -889,7 +889,7 @@ def test_large_k1_linearity_and_adjointness(big_graph):
     raw = [torch.empty_like(x)]
     final = torch.empty_like(x)
     lightgcn_forward_layers(g, x, 1, raw, final)
-    assert torch.equal(raw[0], ax)
+    assert float((raw[0] - ax).abs().max() / ax.abs().max()) < 1e-6   # long rows meet through atomics: order varies
     want = (x + torch.nn.functional.normalize(ax, dim=1)) * 0.5
     assert float((final - want).abs().max()) < 1e-6
 
