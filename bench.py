@@ -148,7 +148,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_of(args, shape), "cpu_baseline": cb,
+            "config": dict(config_of(args, shape), optimizer="torch.optim.Adam (com.py:25, as the reference composes it)"),
+            "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
