@@ -151,7 +151,7 @@ def run_reference(args):
             "config": dict(config_of(args, shape), optimizer="torch.optim.Adam (com.py:25, as the reference composes it)"),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(_finite(line)))
 
 
 def config_of(args, shape):
@@ -187,7 +187,8 @@ def run_ours(args):
                  device=dev, init_device=dev, lr=0.001, sampler="device")
     if world > 1:
         from tagrec_b200 import distributed as D
-        model, triples, info = D.build_sharded_lightgcn(shape, dev, rank, world, BATCH * (args.steps + args.warmup))
+        model, triples, info = D.build_sharded_lightgcn(shape, dev, rank, world, BATCH * (args.steps + args.warmup),
+                                                        eval_users_per_rank=args.eval_users)
     else:
         ui_row, ui_col = T.data.synth_bipartite_device(shape["n_user"], shape["n_item"], int(shape["n_edge"]),
                                                        dev, seed=2020)
@@ -293,6 +294,9 @@ def run_ours(args):
     e2e = {"value": BATCH * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 8, "d2h_bytes_per_step": 8,
            "last_loss": last}
 
+    eval_sharded = None
+    if world > 1 and args.eval_users > 0 and info.get("eval_mask") is not None:
+        eval_sharded = eval_leg_sharded(T, model, shape, dev, info["eval_mask"], world, dist)
     per_rank = None
     if world > 1:
         mine = {"rank": rank, "fwd_ms": timer.mean_ms("spmm_fwd"), "bwd_ms": timer.mean_ms("spmm_bwd"),
@@ -337,9 +341,53 @@ def run_ours(args):
         line["cpu_baseline"] = cb
     if args.eval_users > 0 and world == 1:
         line["eval"] = eval_leg(T, model, shape, dev, args.eval_users)
-    print(json.dumps(line))
+    if eval_sharded is not None:
+        line["eval"] = eval_sharded
+    print(json.dumps(_finite(line)))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _finite(x):
+    """NaN / inf are not JSON: replace them with null."""
+    if isinstance(x, float):
+        return x if x == x and abs(x) != float("inf") else None
+    if isinstance(x, dict):
+        return {k: _finite(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_finite(v) for v in x]
+    return x
+
+
+def eval_leg_sharded(T, model, shape, dev, eval_mask, world, dist):
+    """Full-rank evaluation sharded by user batch (BASELINE metric "eval users/sec at 1/2/4/8 GPU"): every rank scores
+    its own share of the users (weak scaling: the same number of users per GPU as the 1-GPU leg) against the full item
+    table with its users' train rows as masks; time = max over ranks."""
+    import torch
+    from tagrec_b200.eval_ops import topk_scores
+    lo, ptr_l, items_l = eval_mask
+    n = ptr_l.numel() - 1
+    model.eval()
+    with torch.no_grad():
+        all_users, all_items = model.forward()[:2]            # collective: every rank calls it
+    ut, it = all_users[lo:lo + n].contiguous(), all_items.contiguous()
+    users = torch.arange(n, device=dev)
+    for _ in range(2):
+        topk_scores(users, ut, it, ptr_l, items_l, 20)
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    ids, _ = topk_scores(users, ut, it, ptr_l, items_l, 20)
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    total = n * world
+    return {"users_per_s": total / (ms / 1e3), "users": total, "users_per_gpu": n, "items": shape["n_item"], "k": 20,
+            "ms": ms, "tflops": 2.0 * total * shape["n_item"] * DIM / (ms * 1e-3) / 1e12, "scaling": "weak",
+            "kernel": "eval_tc_kernel (tcgen05.mma kind::tf32 filter + exact fp32 re-score), users sharded over ranks"}
 
 
 def eval_leg(T, model, shape, dev, n_users):

@@ -250,9 +250,11 @@ def rebalance_by_measurement(full, graph, rank, world, dim=64, n_layer=3):
     return new
 
 
-def build_sharded_lightgcn(shape, dev, rank, world, n_triples, seed=2020):
+def build_sharded_lightgcn(shape, dev, rank, world, n_triples, seed=2020, eval_users_per_rank=0):
     """bench.py helper for N > 1: every rank generates the same synthetic graph (same device RNG stream), builds the
-    CSR, keeps its row block, and samples the same batch stream.  Returns (model, triples, info)."""
+    CSR, keeps its row block, and samples the same batch stream.  Returns (model, triples, info).
+    ``eval_users_per_rank`` > 0 also keeps the train rows (evaluation masks) of this rank's share of the evaluation
+    users — users [rank*E, (rank+1)*E) — as a local CSR in ``info["eval_mask"] = (first_user, ptr, items)``."""
     import tagrec_b200 as T
     ui_row, ui_col = T.data.synth_bipartite_device(shape["n_user"], shape["n_item"], int(shape["n_edge"]), dev, seed=seed)
     n_train = ui_row.numel()
@@ -269,6 +271,12 @@ def build_sharded_lightgcn(shape, dev, rank, world, n_triples, seed=2020):
     T._lib.check(T._lib.lib().tagrec_sample_bpr_device(T._lib.ptr(edges), n_triples, T._lib.ptr(train_ptr),
                                                        T._lib.ptr(train_items), shape["n_item"], seed, 0,
                                                        T._lib.ptr(triples), T._lib.stream_ptr(dev)), "sampler")
+    eval_mask = None
+    if eval_users_per_rank > 0:
+        e_n = min(int(eval_users_per_rank), U // world)
+        lo = rank * e_n
+        a, b = int(train_ptr[lo]), int(train_ptr[lo + e_n])
+        eval_mask = (lo, (train_ptr[lo:lo + e_n + 1] - a).contiguous(), train_items[a:b].contiguous())
     del edges, train_items, train_ptr
     graph = shard_graph(full, rank, world)
     mode = "nccl all-gather per layer"
@@ -294,5 +302,5 @@ def build_sharded_lightgcn(shape, dev, rank, world, n_triples, seed=2020):
     info = {"nnz": graph._nnz(), "n": graph.n_rows, "n_long_rows": graph.n_long, "nnz_global": nnz_full,
             "parallelism": f"node-range row blocks x{world}, {mode}, replicated parameters",
             "rows_local": graph.n_rows, "bounds": graph.comm.bounds, "type_weight_s_per_nnz": graph.type_weight,
-            "balance_feedback": getattr(graph, "balance_feedback", None)}
+            "balance_feedback": getattr(graph, "balance_feedback", None), "eval_mask": eval_mask}
     return model, triples, info
