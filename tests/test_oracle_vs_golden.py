@@ -1,4 +1,6 @@
 """Pins the CPU oracle against outputs of the UNMODIFIED reference (tests/golden/*.npz, made by make_golden.py)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -159,3 +161,79 @@ def test_eval_pipeline_medium(medium):
     ref = medium["eval_top40_ids"][:, :20]
     same = sum(set(a) == set(b) for a, b in zip(top[:, :20], ref))
     assert same >= len(users) - 2, f"{len(users) - same} users differ in top-20 set"
+
+
+# ------------------------------------------------------------------------------ DGCF / DisenGCN / TGCN oracles
+def _edges(g, use_tag):
+    U, I, Tg, _ = nums(g)
+    ui, ut, it = blocks(g)
+    n, rowptr, col, _ = OA.creat_adj(U, I, ui, "plain", Tg if use_tag else 0, ut if use_tag else None,
+                                     it if use_tag else None)
+    head = torch.as_tensor(np.repeat(np.arange(n), np.diff(rowptr)), dtype=torch.int64)
+    return n, head, torch.as_tensor(np.asarray(col), dtype=torch.int64)
+
+
+def _bpr_autograd(final_u, final_i, reg_u, reg_i, batch, reg, kind):
+    b = torch.as_tensor(batch, dtype=torch.int64)
+    loss = OP.bpr_loss(final_u[b[:, 0]], final_i[b[:, 1]], final_i[b[:, 2]], kind)
+    return loss, reg * OP.l2reg(reg_u[b[:, 0]], reg_i[b[:, 1]], reg_i[b[:, 2]])
+
+
+def test_dgcf_oracle_vs_reference(tiny):
+    """oracle.routing.dgcf_forward + autograd == model/dgcf.py (forward, loss tuple, embedding gradients)."""
+    from oracle import routing as OR
+    U, I, _, _ = nums(tiny)
+    n, head, tail = _edges(tiny, False)
+    emb = [torch.tensor(tiny[f"dgcf_param_embed.{k}"], requires_grad=True) for k in range(2)]
+    final = OR.dgcf_forward(head, tail, n, torch.cat(emb), 3, 2)
+    fu, fi = final[:U], final[U:]
+    assert relerr(fu.detach().numpy(), tiny["dgcf_fwd_0"]) < 1e-6 and relerr(fi.detach().numpy(), tiny["dgcf_fwd_1"]) < 1e-6
+    loss, reg = _bpr_autograd(fu, fi, emb[0], emb[1], tiny["dgcf_batch"], 1e-3, "softplus")
+    assert abs(loss.item() - tiny["dgcf_loss"][0]) < 1e-6 and abs(reg.item() - tiny["dgcf_loss"][1]) < 1e-9
+    (loss + reg).backward()
+    for k in range(2):
+        assert relerr(emb[k].grad.numpy(), tiny[f"dgcf_grad_embed.{k}"]) < 1e-5
+
+
+def test_disengcn_oracle_vs_reference(tiny):
+    """oracle.routing.disengcn_forward == model/disengcn.py on the tripartite graph; gradients against the float64
+    run of the reference (the float32 ones are ill-conditioned, see tests/golden/make_golden_fp64.py)."""
+    from oracle import routing as OR
+    U, I, Tg, _ = nums(tiny)
+    n, head, tail = _edges(tiny, True)
+    truth = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "routing_fp64.npz")))
+    for dtype, fwd_tol in ((torch.float32, 1e-6), (torch.float64, 1e-12)):
+        emb = [torch.tensor(tiny[f"disengcn_param_embed.{k}"], dtype=dtype, requires_grad=True) for k in range(3)]
+        ws = [(torch.tensor(tiny[f"disengcn_param_layer.{k}.W"], dtype=dtype, requires_grad=True),
+               torch.tensor(tiny[f"disengcn_param_layer.{k}.b"], dtype=dtype, requires_grad=True)) for k in range(3)]
+        final = OR.disengcn_forward(head, tail, n, torch.cat(emb), ws, 2)
+        parts = torch.split(final, [U, I, Tg])
+        want = [truth[f"disengcn_fwd64_{k}"] if dtype == torch.float64 else tiny[f"disengcn_fwd_{k}"] for k in range(3)]
+        for k in range(3):
+            assert relerr(parts[k].detach().numpy(), want[k]) < fwd_tol
+        loss, reg = _bpr_autograd(parts[0], parts[1], parts[0], parts[1], tiny["disengcn_batch"], 1e-3, "softplus")
+        (loss + reg).backward()
+        if dtype == torch.float64:
+            for k in range(3):
+                assert relerr(emb[k].grad.numpy(), truth[f"disengcn_grad64_embed.{k}"]) < 1e-9
+                assert relerr(ws[k][0].grad.numpy(), truth[f"disengcn_grad64_layer.{k}.W"]) < 1e-9
+                assert relerr(ws[k][1].grad.numpy(), truth[f"disengcn_grad64_layer.{k}.b"]) < 1e-9
+
+
+def test_tgcn_oracle_vs_reference(tiny, tiny_tgcn):
+    """oracle.tgcn.tgcn_forward + autograd == model/tgcn.py with the reference's own neighbour tables."""
+    from oracle import tgcn as OT
+    U = nums(tiny)[0]
+    P = {k[len("tgcn_param_"):]: torch.tensor(v, requires_grad=True) for k, v in tiny_tgcn.items()
+         if k.startswith("tgcn_param_")}
+    tables = [(tiny_tgcn[f"tgcn_nbr_{n}"], tiny_tgcn[f"tgcn_nbw_{n}"]) for n in ("ui", "ut", "iu", "it", "tu", "ti")]
+    fu, fi, ft = OT.tgcn_forward(P, tables, 2, 5)
+    for k, t in enumerate((fu, fi, ft)):
+        assert relerr(t.detach().numpy(), tiny_tgcn[f"tgcn_fwd_{k}"]) < 1e-6
+    loss, reg = _bpr_autograd(fu, fi, fu, fi, tiny_tgcn["tgcn_batch"], 1e-3, "logsigmoid")
+    assert abs(loss.item() - tiny_tgcn["tgcn_loss"][0]) < 1e-6 and abs(reg.item() - tiny_tgcn["tgcn_loss"][1]) < 1e-8
+    (loss + reg).backward()
+    for name, p in P.items():
+        want = tiny_tgcn[f"tgcn_grad_{name}"]
+        got = p.grad.numpy() if p.grad is not None else np.zeros_like(want)
+        assert relerr(got, want) < 2e-4, name            # O(1e-9) second-layer attention gradients: fp32 noise
