@@ -295,6 +295,13 @@ int tagrec_sample_bpr_device(const int64_t* edges, int64_t e, const int64_t* tra
 int tagrec_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int64_t step, void* stream);
 
+/* CUDA-graph-capturable form: the step counter and this step's bias corrections live in device memory.
+ * tagrec_adam_advance: *step_dev += 1; scal_dev[0] = lr / (1 - beta1^step), scal_dev[1] = 1 / sqrt(1 - beta2^step)
+ * (once per optimizer step); tagrec_adam_step_dev: the update of one tensor with those scalars. */
+int tagrec_adam_advance(int64_t* step_dev, float lr, float beta1, float beta2, float* scal_dev, void* stream);
+int tagrec_adam_step_dev(float* param, const float* grad, float* m, float* v, int64_t n, float beta1, float beta2,
+                         float eps, float weight_decay, const float* scal_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

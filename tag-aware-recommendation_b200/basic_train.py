@@ -21,6 +21,9 @@ def epoch_training(training_data, loss_func, opt):
         lossx = loss_func(data)
         parts.append(torch.stack([x.detach() for x in lossx]))
         loss = sum(lossx)
+        if getattr(loss_func, "graphed", False):     # graph_step.GraphedStep: backward + optimizer ran in the graph
+            totals.append(loss.detach())
+            continue
         if isinstance(opt, list):
             [op.zero_grad() for op in opt]
             loss.backward()

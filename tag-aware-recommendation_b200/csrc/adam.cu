@@ -9,7 +9,11 @@ namespace tagrec {
 __global__ void __launch_bounds__(256)
 adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
             int64_t n4, float* ps, const float* gs, float* ms, float* vs, int64_t n, float b1, float b2, float eps,
-            float wd, float step_size, float inv_sqrt_bc2) {
+            float wd, float step_size, float inv_sqrt_bc2, const float* __restrict__ scal) {
+    if (scal) {     // capturable mode: the bias corrections of THIS step live in device memory
+        step_size = __ldg(scal);
+        inv_sqrt_bc2 = __ldg(scal + 1);
+    }
     auto upd = [&](float& pp, float gg, float& mm, float& vv) {
         if (wd != 0.f) gg = fmaf(wd, pp, gg);
         mm = mm + (gg - mm) * (1.f - b1);
@@ -52,6 +56,39 @@ extern "C" int tagrec_adam_step(float* param, const float* grad, float* m, float
     if (blocks > kSMs * 16) blocks = kSMs * 16;
     TAGREC_LAUNCH(adam_kernel, (unsigned)blocks, 256, 0, stream, reinterpret_cast<float4*>(param),
                   reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n4,
-                  param, grad, m, v, n, beta1, beta2, eps, weight_decay, step_size, inv_sqrt_bc2);
+                  param, grad, m, v, n, beta1, beta2, eps, weight_decay, step_size, inv_sqrt_bc2,
+                  static_cast<const float*>(nullptr));
+    return TAGREC_OK;
+}
+
+namespace tagrec {
+// step += 1;  scal = { lr / (1 - b1^step), 1 / sqrt(1 - b2^step) }   (one thread; CUDA-graph capturable)
+__global__ void adam_scalars_kernel(int64_t* step, float lr, float b1, float b2, float* scal) {
+    const int64_t t = *step + 1;
+    *step = t;
+    scal[0] = (float)((double)lr / (1.0 - pow((double)b1, (double)t)));
+    scal[1] = (float)(1.0 / sqrt(1.0 - pow((double)b2, (double)t)));
+}
+}  // namespace tagrec
+
+extern "C" int tagrec_adam_advance(int64_t* step_dev, float lr, float beta1, float beta2, float* scal_dev,
+                                   void* stream) {
+    TAGREC_REQUIRE(step_dev && scal_dev, "null pointer");
+    TAGREC_LAUNCH(adam_scalars_kernel, 1, 1, 0, stream, step_dev, lr, beta1, beta2, scal_dev);
+    return TAGREC_OK;
+}
+
+extern "C" int tagrec_adam_step_dev(float* param, const float* grad, float* m, float* v, int64_t n, float beta1,
+                                    float beta2, float eps, float weight_decay, const float* scal_dev, void* stream) {
+    TAGREC_REQUIRE(param && grad && m && v && scal_dev, "null pointer");
+    if (n == 0) return TAGREC_OK;
+    const bool aligned = (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+    const int64_t n4 = aligned ? n / 4 : 0;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > kSMs * 16) blocks = kSMs * 16;
+    TAGREC_LAUNCH(adam_kernel, (unsigned)blocks, 256, 0, stream, reinterpret_cast<float4*>(param),
+                  reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n4,
+                  param, grad, m, v, n, beta1, beta2, eps, weight_decay, 0.f, 0.f, scal_dev);
     return TAGREC_OK;
 }

@@ -190,15 +190,21 @@ class LightGCNLossFn(torch.autograd.Function):
         batch = batch.contiguous()
         nodes = torch.cat([batch[:, 0], batch[:, 1] + model.num_list[0], batch[:, 2] + model.num_list[0]])
         # gradient tables are zero outside the rows the previous batch touched: re-zero just those rows
+        # (the "dirty rows" live in a persistent buffer that is updated in place, so the step can be recorded into a
+        # CUDA graph; a batch of another size — the tail of an epoch — falls back to clearing the whole table)
         for name in ("g_final", "g_reg"):
             if name == "g_reg" and model.reg == 0:
                 continue
-            tns = ws.get(name)
+            tns, dirty = ws.get(name), ws.get(name + "_dirty")
             if tns is None or tns.shape != (n, dim) or tns.device != dev:
                 ws[name] = torch.zeros((n, dim), dtype=torch.float32, device=dev)
-            elif ws.get(name + "_dirty") is not None:
-                tns.index_fill_(0, ws[name + "_dirty"], 0.0)
-            ws[name + "_dirty"] = nodes
+                ws[name + "_dirty"] = nodes.clone()
+            elif dirty is None or dirty.shape != nodes.shape:
+                tns.zero_()
+                ws[name + "_dirty"] = nodes.clone()
+            else:
+                tns.index_fill_(0, dirty, 0.0)
+                dirty.copy_(nodes)
         g_final = ws["g_final"]
         g_reg = ws["g_reg"] if model.reg != 0 else None
         loss_out = torch.empty(2, dtype=torch.float32, device=dev)

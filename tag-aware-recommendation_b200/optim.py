@@ -10,8 +10,11 @@ from ._lib import check, lib, ptr, stream_ptr
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+    """``capturable=True`` keeps the step counter and the bias corrections in device memory (one extra 1-thread launch
+    per step) so that ``step()`` can be recorded into a CUDA graph (``graph_step.GraphedStep``)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, capturable=False):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, capturable=capturable))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -20,8 +23,11 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         L = lib()
-        for group in self.param_groups:
+        dev_state = self.__dict__.setdefault("_dev", {})
+        for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
+            cap = group.get("capturable", False)
+            scal = None
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -29,12 +35,27 @@ class FusedAdam(torch.optim.Optimizer):
                     raise RuntimeError("FusedAdam needs contiguous float32 CUDA parameters (no CPU fallback)")
                 st = self.state[p]
                 if not st:
-                    st["step"] = 0
+                    st["step"] = torch.zeros((), dtype=torch.int64, device=p.device) if cap else 0
                     st["exp_avg"] = torch.zeros_like(p)
                     st["exp_avg_sq"] = torch.zeros_like(p)
-                st["step"] += 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                check(L.tagrec_adam_step(ptr(p), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(),
-                                         group["lr"], b1, b2, group["eps"], group["weight_decay"], st["step"],
-                                         stream_ptr(p.device)), "tagrec_adam_step")
+                if cap:
+                    if scal is None:
+                        # one device-side counter per group (every tensor of the group steps together)
+                        gs = dev_state.setdefault(gi, {})
+                        if "step" not in gs:
+                            gs["step"] = torch.zeros((), dtype=torch.int64, device=p.device)
+                            gs["scal"] = torch.zeros(2, dtype=torch.float32, device=p.device)
+                        check(L.tagrec_adam_advance(ptr(gs["step"]), group["lr"], b1, b2, ptr(gs["scal"]),
+                                                    stream_ptr(p.device)), "tagrec_adam_advance")
+                        scal = gs["scal"]
+                    st["step"] = dev_state[gi]["step"]
+                    check(L.tagrec_adam_step_dev(ptr(p), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), b1,
+                                                 b2, group["eps"], group["weight_decay"], ptr(scal), stream_ptr(p.device)),
+                          "tagrec_adam_step_dev")
+                else:
+                    st["step"] += 1
+                    check(L.tagrec_adam_step(ptr(p), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(),
+                                             group["lr"], b1, b2, group["eps"], group["weight_decay"], st["step"],
+                                             stream_ptr(p.device)), "tagrec_adam_step")
         return loss

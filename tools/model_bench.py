@@ -57,6 +57,7 @@ def main():
     ap.add_argument("--models", default="lightgcn,lightgcn_tag,ngcf,dgcf,disengcn,tgcn")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="record the step into a CUDA graph (T.GraphedStep)")
     args = ap.parse_args()
     import __graft_entry__ as G
     G.build()
@@ -78,7 +79,11 @@ def main():
         else:
             model = {"lightgcn": T.LightGCN, "ngcf": T.NGCF, "dgcf": T.DGCF, "disengcn": T.DisenGCN}[model_name](ds).to(dev)
         data = (T.DGCF_training_data if sampler == "DGCF" else T.BPR_training_data)(ds, None)
-        opt = torch.optim.Adam(model.parameters(), lr=0.001)
+        if args.graph:
+            opt = T.FusedAdam(model.parameters(), lr=0.001, capturable=True)
+            graphed = T.GraphedStep(model, opt, warmup=2)
+        else:
+            opt = torch.optim.Adam(model.parameters(), lr=0.001)
         test = T.Basic_test(ds, None)
         model.train()
         data.reset()
@@ -92,6 +97,8 @@ def main():
         setup_s = time.time() - t0
 
         def step(b):
+            if args.graph:
+                return graphed.loss(b)
             lossx = model.loss(b)
             loss = sum(lossx)
             opt.zero_grad()
@@ -130,7 +137,7 @@ def main():
         print(json.dumps({
             "case": name, "model": model_name, "shape": shape, "users": ds.num["user"], "items": ds.num["item"],
             "tags": ds.num.get("tag", 0), "nnz": graph._nnz() if graph is not None else None, "batch": int(bsz),
-            "ms_per_step": ms, "triples_per_s": bsz / ms * 1e3, "tagrec_launches_per_step": launches,
+            "cuda_graph": bool(args.graph), "ms_per_step": ms, "triples_per_s": bsz / ms * 1e3, "tagrec_launches_per_step": launches,
             "eval_users": len(ds.user_items["test"]), "eval_s": eval_s,
             "eval_users_per_s": len(ds.user_items["test"]) / eval_s,
             "loss": [float(x) for x in lossx], "ndcg@20": res["ndcg"][0], "auc": res.get("auc", [None])[0],
