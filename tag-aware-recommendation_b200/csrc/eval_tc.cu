@@ -38,9 +38,11 @@ namespace tagrec {
 constexpr int TC_M = 128;                 // user rows per accumulator half (UMMA M)
 constexpr int TC_N = 128;                 // items per tile (UMMA N)
 constexpr int TC_D = 64;                  // feature dim == GEMM K
+constexpr int TC_UPITCH = TC_D + 4;       // floats per user row in the plain smem copy (spreads rows over banks)
 constexpr int TC_KH_BYTES = TC_N * 128;   // one 128B-swizzled k-half of a tile: 128 rows x 32 floats = 16 KB
 constexpr int TC_TILE_BYTES = 2 * TC_KH_BYTES;   // 32 KB (A half or B stage)
 constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_MAX_SPLITS = 32;
 constexpr float TC_MARGIN = 2.2e-3f;
 
 struct TcArgs {
@@ -52,6 +54,8 @@ struct TcArgs {
     const int64_t* train_ptr;
     const int32_t* train_items;
     const float* item_maxnorm;   // device scalar: max_i ||I_i||_2
+    float* shared_thr;           // [nu] or NULL: per-user lower bound of the final K-th best score, shared by the item
+                                 // splits of that user (max over splits of their own exact K-th best)
     int k;
     int splits;
     int stages;
@@ -137,6 +141,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// atomicMax on a float that may have either sign (order-preserving integer views; the slot starts at -inf)
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
 // Byte offset of 16-byte chunk c16 (0..15) of row `row` inside a [128 x 64] fp32 tile stored as two SW128 k-halves.
 __device__ __forceinline__ uint32_t sw128_off(int row, int c16) {
     return (uint32_t)((c16 >> 3) * TC_KH_BYTES + row * 128 + (((c16 & 7) ^ (row & 7)) << 4));
@@ -158,7 +168,7 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int c16) {
 #ifndef TC_EXPERIMENT
 #define TC_EXPERIMENT 0      // 1 / 2: timing experiments (wrong results), see tools/tune_eval.sh
 #endif
-constexpr int TC_NACC = 3;        // accumulator ring (128 columns each)
+constexpr int TC_NACC = TC_TS ? 3 : 4;   // accumulator ring (128 TMEM columns each; A takes 128 columns in TS form)
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
@@ -193,7 +203,8 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
     const int S = a.stages, K = a.k;
     unsigned char* As = base;                                         // SS form only: NH x 32 KB
     unsigned char* Bs = base + A_SMEM;                                // S x 32 KB
-    float* ls = reinterpret_cast<float*>(Bs + S * TC_TILE_BYTES);     // [K][ROWS] scores (unsorted K-lists)
+    float* Uf = reinterpret_cast<float*>(Bs + S * TC_TILE_BYTES);     // [ROWS][TC_UPITCH] user rows, plain fp32 (re-scores)
+    float* ls = Uf + (size_t)ROWS * TC_UPITCH;                        // [K][ROWS] scores (unsorted K-lists)
     int32_t* li = reinterpret_cast<int32_t*>(ls + (size_t)K * ROWS);  // [K][ROWS] item ids
     uint64_t* bars = reinterpret_cast<uint64_t*>(li + (size_t)K * ROWS);
     uint64_t* full = bars;                                    // [S]     TMA -> MMA
@@ -209,6 +220,10 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
     const int64_t i_end = min(a.n_item, i_begin + a.items_per_split);
     const int n_tiles = (int)((i_end - i_begin + TC_N - 1) / TC_N);
 
+#if TC_EXPERIMENT == 9
+    __shared__ long long dbg_acc[16][4];        // [warp][wait_full | fast | slow | n_slow_iters]
+    long long d_wait = 0, d_fast = 0, d_slow = 0, d_iters = 0;
+#endif
 #if TC_EXPERIMENT != 0
     long long dbg_c0 = clock64();
     unsigned long long dbg_t0;
@@ -273,6 +288,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
                 r[4 * c + 1] = __float_as_uint(v.y);
                 r[4 * c + 2] = __float_as_uint(v.z);
                 r[4 * c + 3] = __float_as_uint(v.w);
+                *reinterpret_cast<float4*>(Uf + (size_t)row * TC_UPITCH + 4 * (half * 8 + c)) = v;
             }
             if constexpr (kTS) tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 64 + half * 32), r);
         }
@@ -288,7 +304,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % S;
                 mbar_wait(smem_u32(bfree + s), ((t / S) & 1) ^ 1);
-#if TC_EXPERIMENT >= 4
+#if TC_EXPERIMENT == 4 || TC_EXPERIMENT == 5
                 if (t >= S) continue;                         // timing experiment: no item-tile traffic (pure MMA rate)
 #endif
                 const uint32_t bar = smem_u32(full + s);
@@ -304,7 +320,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
         if (lane == 0) {
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % S;
-#if TC_EXPERIMENT >= 4
+#if TC_EXPERIMENT == 4 || TC_EXPERIMENT == 5
                 if (t < S)
 #endif
                 mbar_wait(smem_u32(full + s), (t / S) & 1);
@@ -377,6 +393,8 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
     } else {
         // ================= epilogue: thread = user row =================
         float thr = -INFINITY, thr_lo = valid ? -INFINITY : INFINITY, margin = 0.f;
+        float thr_sh = -INFINITY;               // bound published by the other item splits of this user
+        float* sh_slot = (valid && a.shared_thr) ? a.shared_thr + (u0 + row) : nullptr;
         int cnt = 0, minpos = 0;                // the K-list is UNSORTED; minpos = entry to evict ((score, -id) minimum)
         int64_t tc = 0, te = 0;
         int32_t nxt = INT32_MAX;                // smallest train item of this user not yet passed
@@ -398,24 +416,28 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
             const int n = t * NH + h, r = n % TC_NACC;
             const int64_t it0 = i_begin + (int64_t)t * TC_N;
             const unsigned char* brow = Bs + s * TC_TILE_BYTES;
+#if TC_EXPERIMENT == 9
+            long long d_t0 = clock64();
+#endif
+            // another split may have raised the bound (a stale read only prunes less); issued before the wait
+            const float sh_new = sh_slot ? __ldcg(sh_slot) : -INFINITY;
             mbar_wait(smem_u32(accfull + r), (n / TC_NACC) & 1);
             tc_fence_after();
+#if TC_EXPERIMENT == 9
+            long long d_t1 = clock64();
+            d_wait += d_t1 - d_t0;
+#endif
             const uint32_t taddr = acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * TC_N);
+            if (sh_new > thr_sh) {
+                thr_sh = sh_new;
+                thr_lo = fmaxf(thr, thr_sh) - margin;
+            }
             // ---- fast path: 128 TF32 scores of this row -> a 128-bit candidate mask (usually empty) ----
             uint32_t cm[TC_N / 32];
 #if TC_EXPERIMENT == 1
             if (t == 8) thr_lo = INFINITY;                    // timing experiment: no candidate work after warm-up
 #endif
-#pragma unroll
-            for (int c = 0; c < TC_N / 32; ++c) {
-                uint32_t v[32];
-#if TC_EXPERIMENT == 2
-                if (c >= 2) { cm[c] = 0; continue; }          // timing experiment: drain only half of the accumulator
-#elif TC_EXPERIMENT >= 3
-                if (t > 0) { cm[c] = 0; continue; }           // timing experiment: no drain at all (MMA + TMA floor)
-#endif
-                tmem_ld32(taddr + c * 32, v);
-                tmem_ld_wait();
+            auto scan32 = [&](const uint32_t (&v)[32]) -> uint32_t {
                 float m = __uint_as_float(v[0]);
 #pragma unroll
                 for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
@@ -424,15 +446,36 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr_lo) ? (1u << j) : 0u;
                 }
-                cm[c] = mask;
+                return mask;
+            };
+#pragma unroll
+            for (int c = 0; c < TC_N / 32; c += 2) {      // two 32-column loads in flight per wait
+#if TC_EXPERIMENT == 2
+                if (c >= 2) { cm[c] = cm[c + 1] = 0; continue; }   // timing experiment: drain half of the accumulator
+#elif TC_EXPERIMENT >= 3 && TC_EXPERIMENT <= 5
+                if (t > 0) { cm[c] = cm[c + 1] = 0; continue; }    // timing experiment: no drain (MMA + TMA floor)
+#endif
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr + c * 32, v0);
+                tmem_ld32(taddr + (c + 1) * 32, v1);
+                tmem_ld_wait();
+                cm[c] = scan32(v0);
+                cm[c + 1] = scan32(v1);
             }
             // the accumulator is drained: hand it back to the MMA warp before the (rare, slow) candidate work
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(accfree + r));
+#if TC_EXPERIMENT == 9
+            long long d_t2 = clock64();
+            d_fast += d_t2 - d_t1;
+#endif
             // ---- slow path: all lanes' candidates of this tile in lockstep ----
             uint64_t lo64 = (uint64_t)cm[0] | ((uint64_t)cm[1] << 32), hi64 = (uint64_t)cm[2] | ((uint64_t)cm[3] << 32);
             while (lo64 | hi64) {
+#if TC_EXPERIMENT == 9
+                ++d_iters;
+#endif
                 int il;
                 if (lo64) {
                     il = __ffsll((long long)lo64) - 1;
@@ -459,19 +502,21 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
                     nxt = tc < te ? __ldg(a.train_items + tc) : INT32_MAX;
                 }
                 if ((int64_t)nxt == item) continue;           // masked (basic_test.py:47)
-                // exact fp32 score, canonical sequential order; item row from the smem stage, user row from L1/L2
+                // exact fp32 score, canonical sequential order; item row from the smem stage, user row from its smem copy
                 float ex = 0.f;
 #pragma unroll
                 for (int c16 = 0; c16 < 16; ++c16) {
-                    const float4 uu = __ldg(urow + c16);
+                    const float4 uu = *reinterpret_cast<const float4*>(Uf + (size_t)row * TC_UPITCH + 4 * c16);
                     const float4 ii = *reinterpret_cast<const float4*>(brow + sw128_off(il, c16));
                     ex = fmaf(uu.x, ii.x, ex);
                     ex = fmaf(uu.y, ii.y, ex);
                     ex = fmaf(uu.z, ii.z, ex);
                     ex = fmaf(uu.w, ii.w, ex);
                 }
-                // items arrive in ascending id order, so on a score tie the incumbent (smaller id) stays: strict >
-                if (cnt < K || ex > thr) {
+                // items arrive in ascending id order, so on a score tie the incumbent (smaller id) stays: strict >.
+                // Against the bound of ANOTHER split only strictly smaller scores may be dropped (its K-th item
+                // may have a larger id than this one).
+                if ((cnt < K || ex > thr) && ex >= thr_sh) {
                     const int pos = cnt < K ? cnt : minpos;
                     ls[(size_t)pos * ROWS + row] = ex;
                     li[(size_t)pos * ROWS + row] = (int32_t)item;
@@ -492,12 +537,16 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
                         }
                         thr = best;
                         minpos = bp;
-                        thr_lo = thr - margin;
+                        thr_lo = fmaxf(thr, thr_sh) - margin;
+                        if (sh_slot && thr > thr_sh) atomic_max_float(sh_slot, thr);
                     }
                 }
             }
             // this warp no longer reads B stage `s`
             __syncwarp();
+#if TC_EXPERIMENT == 9
+            d_slow += clock64() - d_t2;
+#endif
             if (lane == 0) mbar_arrive(smem_u32(bfree + s));
         }
         if (valid) {
@@ -510,6 +559,23 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
     }
     tc_fence_before();
     __syncthreads();
+#if TC_EXPERIMENT == 9
+    {
+        // warp-level maxima over lanes (lanes diverge in the slow path: the slowest lane is the warp's time)
+        long long it_sum = d_iters;
+        for (int o = 16; o > 0; o >>= 1) {
+            d_slow = max(d_slow, __shfl_xor_sync(0xffffffffu, d_slow, o));
+            d_iters = max(d_iters, __shfl_xor_sync(0xffffffffu, d_iters, o));
+            it_sum += __shfl_xor_sync(0xffffffffu, it_sum, o);
+        }
+        if (lane == 0 && warp < 16) { dbg_acc[warp][0] = d_wait; dbg_acc[warp][1] = d_fast; dbg_acc[warp][2] = d_slow; dbg_acc[warp][3] = it_sum; }
+        __syncthreads();
+        if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+            for (int w = 2; w < 2 + 4 * NH; ++w)
+                printf("  epi warp %d: wait_accfull %lld  fast %lld  slow %lld cycles, lane-events %lld\n", w,
+                       dbg_acc[w][0], dbg_acc[w][1], dbg_acc[w][2], dbg_acc[w][3]);
+    }
+#endif
 #if TC_EXPERIMENT != 0
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
         unsigned long long dbg_t1;
@@ -524,6 +590,11 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                      : "memory");
     }
+}
+
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 // max_i ||I_i||_2 (for the TF32 error margin).  16 lanes per 64-float row, coalesced.
@@ -601,7 +672,8 @@ static EncodeTiledFn encode_tiled() {
 
 static size_t tc_smem(int nh, int stages, int k) {
     const size_t a_smem = TC_TS ? 0 : (size_t)nh * TC_TILE_BYTES;
-    return 1024 + a_smem + (size_t)stages * TC_TILE_BYTES + (size_t)2 * k * TC_M * nh * 4 + 256;
+    return 1024 + a_smem + (size_t)stages * TC_TILE_BYTES + (size_t)TC_M * nh * TC_UPITCH * 4 +
+           (size_t)2 * k * TC_M * nh * 4 + 256;
 }
 
 TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
@@ -609,8 +681,15 @@ TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
     p.ok = false;
     if (dim != TC_D || k < 1 || k > 128 || nu < 1 || n_item < 1) return p;
     const size_t budget = 227 * 1024;
-    // two halves per CTA halve the L2 traffic of the item stream; use them when there are enough users
-    p.nh = nu > TC_M ? 2 : 1;
+    const int64_t item_tiles = (n_item + TC_N - 1) / TC_N;
+    // Item splits: every split restarts its thresholds (about K * ln(items/K) exact re-scores per row and split) and
+    // the merge ranks splits*K entries per user, so: at most TC_MAX_SPLITS, at least 8 tiles each, and no more than
+    // fill ONE wave of the 148 SMs.
+    const int64_t max_s = std::max<int64_t>(1, std::min<int64_t>(TC_MAX_SPLITS, item_tiles / 8));
+    // Two 128-user halves per CTA halve the L2 traffic of the item stream; with few users one half per CTA puts twice
+    // as many CTAs on the machine.
+    const int64_t tiles2 = (nu + 2 * TC_M - 1) / (2 * TC_M);
+    p.nh = (nu > TC_M && tiles2 * max_s >= (kSMs * 3) / 4) ? 2 : 1;
     for (;; p.nh = 1) {
         p.stages = TC_MAX_STAGES;
         while (p.stages >= 2 && tc_smem(p.nh, p.stages, k) > budget) --p.stages;
@@ -618,11 +697,8 @@ TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
         if (p.nh == 1) return p;
     }
     const int64_t user_tiles = (nu + TC_M * p.nh - 1) / (TC_M * p.nh);
-    const int64_t item_tiles = (n_item + TC_N - 1) / TC_N;
-    // item splits: every split restarts its thresholds (K * ln(items/K) slow-path candidates per row and split), so
-    // use as few as fill ONE wave of the 148 SMs, with at least 8 tiles per split
     int64_t best_s = user_tiles >= kSMs ? 1 : kSMs / user_tiles;
-    best_s = std::max<int64_t>(1, std::min<int64_t>(best_s, item_tiles / 8));
+    best_s = std::max<int64_t>(1, std::min<int64_t>(best_s, max_s));
     p.splits = (int)best_s;
     p.items_per_split = ((item_tiles + p.splits - 1) / p.splits) * TC_N;
     p.splits = (int)((n_item + p.items_per_split - 1) / p.items_per_split);
@@ -637,7 +713,7 @@ int eval_topk_tc(const int64_t* users, int64_t nu, const float* user_table, cons
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return fail(TAGREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver", __FILE__, __LINE__);
     TAGREC_REQUIRE((reinterpret_cast<uintptr_t>(item_table) & 15) == 0, "item table must be 16-byte aligned");
-    const size_t need = 256 + (size_t)nu * p.splits * k * 8;
+    const size_t need = eval_tc_workspace_bytes(nu, p, k);
     if (!workspace || workspace_bytes < need) return fail(TAGREC_ENOMEM, "eval workspace too small", __FILE__, __LINE__);
     CUtensorMap map;
     const cuuint64_t gdim[2] = {(cuuint64_t)TC_D, (cuuint64_t)n_item};
@@ -657,8 +733,13 @@ int eval_topk_tc(const int64_t* users, int64_t nu, const float* user_table, cons
     a.item_maxnorm = maxnorm;
     a.part_scores = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
     a.part_ids = reinterpret_cast<int32_t*>(a.part_scores + (size_t)nu * p.splits * k);
+    // (the max over splits of their own K-th best is no tighter than one's own bound when two splits advance in
+    // lockstep; it pays with many short splits, where late starters inherit the early ones' bounds)
+    a.shared_thr = p.splits > 2 ? reinterpret_cast<float*>(a.part_ids + (size_t)nu * p.splits * k) : nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     TAGREC_CUDA(cudaMemsetAsync(maxnorm, 0, 4, st));
+    if (a.shared_thr)
+        TAGREC_LAUNCH(fill_f32_kernel, (unsigned)((nu + 255) / 256), 256, 0, stream, a.shared_thr, nu, -INFINITY);
     const int64_t nb = min((int64_t)kSMs * 8, (n_item + 15) / 16);
     TAGREC_LAUNCH(item_maxnorm_kernel, (unsigned)nb, 256, 0, stream, reinterpret_cast<const float4*>(item_table), n_item,
                   maxnorm);
@@ -675,6 +756,8 @@ int eval_topk_tc(const int64_t* users, int64_t nu, const float* user_table, cons
     return TAGREC_OK;
 }
 
-size_t eval_tc_workspace_bytes(int64_t nu, const TcPlan& p, int k) { return 256 + (size_t)nu * p.splits * k * 8; }
+size_t eval_tc_workspace_bytes(int64_t nu, const TcPlan& p, int k) {
+    return 256 + (size_t)nu * p.splits * k * 8 + (size_t)nu * 4;
+}
 
 }  // namespace tagrec
