@@ -326,7 +326,11 @@ def run_ours(args):
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "ms_per_launch": fwd_ms, "launches_timed": timer.count("spmm_fwd"),
                 "bwd_layer_ms": bwd_ms, "bwd_layer_gbs": bytes_per_launch / (bwd_ms * 1e-3) / 1e9,
-                "bpr_ms": timer.mean_ms("bpr"), "bwd_elementwise_ms": timer.mean_ms("bwd_elementwise")}
+                "bpr_ms": timer.mean_ms("bpr"), "bwd_elementwise_ms": timer.mean_ms("bwd_elementwise"),
+                # the backward launches of the last timed step, in order: G_{L-1} (source non-zero on the batch rows
+                # only), G_{L-2} (batch rows + neighbours), ..., dE0 (dense source); zero source rows are skipped
+                "bwd_launch_ms": [round(x.elapsed_time(y), 3) for x, y in timer.pairs.get("spmm_bwd", [])[-LAYERS:]],
+                "row_mask_ms": timer.mean_ms("row_mask")}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": dict(config_of(args, shape), parallelism=info["parallelism"],

@@ -138,6 +138,15 @@ int tagrec_lightgcn_bwd_layer_p2p(const tagrec_csr_t* a, const float* g_next, co
                                   const float* reg_grad, const float* upstream, float inv_layers, float* g_out,
                                   int dim, const tagrec_mirror_t* out_mirror, void* stream);
 
+/* Same with zero-row skipping: g_next_nz (optional) = one byte per row of g_next, 0 where that row is all-zero
+ * (tagrec_row_nonzero).  The upstream gradient of a BPR batch touches 3*B rows, so the first backward tables are
+ * non-zero only on the batch's nodes / their neighbours: the 256 B gathers of the other rows are never issued. */
+int tagrec_lightgcn_bwd_layer_ex(const tagrec_csr_t* a, const float* g_next, const uint8_t* g_next_nz, const float* e_k,
+                                 const float* g_final, const float* reg_grad, const float* upstream, float inv_layers,
+                                 float* g_out, int dim, const tagrec_mirror_t* out_mirror, void* stream);
+/* nz[r] = (row r of the [n, dim] table has a non-zero element). */
+int tagrec_row_nonzero(const float* table, int64_t n, int dim, uint8_t* nz, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K2  fused BPR step            replaces model/lightgcn.py:68-82 / model/ngcf.py:95-105 (3 gathers, mul_loss,
  *                               l2reg_loss: model/help/loss.py:4-12,27-32) and their index_put_ backward.

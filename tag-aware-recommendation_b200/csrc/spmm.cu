@@ -50,6 +50,7 @@ struct Epi {
     const float* g_final;   // bwd: gradient w.r.t. the final (mean) table
     const float* reg_grad;  // bwd0: optional regulariser gradient (may alias y)
     const float* upstream;  // bwd: optional 2 floats {d/dloss, d/dreg} on device
+    const uint8_t* src_nz;  // optional byte per SOURCE row: 0 = the row of x is all-zero, its gather is skipped
     float scale;            // plain: beta | fwd: final_scale | bwd: 1/(L+1)
     int first, last;
 };
@@ -76,10 +77,11 @@ __device__ __forceinline__ float sub_sum(float v, unsigned mask) {
 #endif
 
 // acc = sum_{j in [begin,end), chunk(j) == part (mod nparts)} val[j] * x[col[j]]   for this lane's float4 slice.
-template <int LPR>
+template <int LPR, bool MASKED = false>
 __device__ __forceinline__ float4 gather_rows(const int32_t* __restrict__ col, const float* __restrict__ val,
                                               const float4* __restrict__ x4, int64_t begin, int64_t end, int part,
-                                              int nparts, int sl, unsigned mask) {
+                                              int nparts, int sl, unsigned mask,
+                                              const uint8_t* __restrict__ src_nz = nullptr) {
     constexpr int U = SPMM_U < LPR ? SPMM_U : LPR;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const int32_t* __restrict__ colp = col + begin;
@@ -89,9 +91,13 @@ __device__ __forceinline__ float4 gather_rows(const int32_t* __restrict__ col, c
     int base = part * LPR;
     int c = 0;
     float v = 0.f;
+    // Zero-row skipping (backward tables that are non-zero only near the batch): the lane that loaded a column id
+    // also looks its row up in the byte map and parks the answer in the id's sign bit, so the broadcast below needs no
+    // extra shuffle and the 256 B gather of an all-zero row is never issued.
     if (base + sl < len) {
         c = __ldcs(colp + base + sl);
         v = __ldcs(valp + base + sl);
+        if (MASKED && !__ldg(src_nz + c)) c |= (int)0x80000000;
     }
     const float4* __restrict__ xs = x4 + sl;
     while (base < len) {
@@ -101,6 +107,7 @@ __device__ __forceinline__ float4 gather_rows(const int32_t* __restrict__ col, c
         if (nbase + sl < len) {  // prefetch the next index chunk while this chunk's rows are in flight
             cn = __ldcs(colp + nbase + sl);
             vn = __ldcs(valp + nbase + sl);
+            if (MASKED && !__ldg(src_nz + cn)) cn |= (int)0x80000000;
         }
         const int cnt = min(LPR, len - base);
 #pragma unroll
@@ -110,7 +117,7 @@ __device__ __forceinline__ float4 gather_rows(const int32_t* __restrict__ col, c
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
                     const int cj = __shfl_sync(mask, c, j0 + j, LPR);
-                    xv[j] = (j0 + j < cnt) ? ldg4(xs + (int64_t)cj * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xv[j] = (j0 + j < cnt && (!MASKED || cj >= 0)) ? ldg4(xs + (int64_t)cj * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int j = 0; j < U; ++j) fma4(acc, __shfl_sync(mask, v, j0 + j, LPR), xv[j]);
@@ -213,7 +220,7 @@ __device__ __forceinline__ float4 combine_subs(float4 p) {
 
 constexpr int kWarpsPerBlock = SPMM_WPB;
 
-template <int LPR, int EPI>
+template <int LPR, int EPI, bool MASKED = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, SPMM_MINB)
 spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_blocks, int gather) {
     constexpr int RPW = 32 / LPR;
@@ -229,7 +236,7 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
         if (item >= a.n_items) return;
         const int slot = __ldg(a.item_slot + item);
         const int64_t b = __ldg(a.item_begin + item), e = __ldg(a.item_end + item);
-        float4 p = gather_rows<LPR>(a.col, a.val, x4, b, e, sub, RPW, sl, mask);
+        float4 p = gather_rows<LPR, MASKED>(a.col, a.val, x4, b, e, sub, RPW, sl, mask, ep.src_nz);
         p = combine_subs<LPR>(p);
         float4* scr = reinterpret_cast<float4*>(a.long_scratch) + (int64_t)slot * LPR + sl;
         if (sub == 0) red_add4(scr, p);
@@ -280,13 +287,13 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
             side_by_side = par <= seq;
         }
         if (side_by_side) {
-            acc = gather_rows<LPR>(a.col, a.val, x4, s, e, 0, 1, sl, mask);
+            acc = gather_rows<LPR, MASKED>(a.col, a.val, x4, s, e, 0, 1, sl, mask, ep.src_nz);
         } else {
 #pragma unroll
             for (int i = 0; i < RPW; ++i) {
                 const int64_t si = __shfl_sync(0xffffffffu, s, i * LPR);
                 const int64_t ei = __shfl_sync(0xffffffffu, e, i * LPR);
-                float4 p = gather_rows<LPR>(a.col, a.val, x4, si, ei, sub, RPW, sl, mask);
+                float4 p = gather_rows<LPR, MASKED>(a.col, a.val, x4, si, ei, sub, RPW, sl, mask, ep.src_nz);
                 p = combine_subs<LPR>(p);
                 if (sub == i) acc = p;
             }
@@ -314,7 +321,9 @@ static int launch(const tagrec_csr_t* a, const float* x, const Epi& ep, int dim,
     d.n_items = n_items;
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const dim3 block(kWarpsPerBlock * 32);
-    if (lpr == 16) {
+    if (lpr == 16 && ep.src_nz && gather && (EPI == EPI_BWD || EPI == EPI_BWD0)) {
+        TAGREC_LAUNCH((spmm_kernel<16, EPI, true>), (unsigned)grid, block, 0, stream, d, x4, ep, (int)long_blocks, gather);
+    } else if (lpr == 16) {
         TAGREC_LAUNCH((spmm_kernel<16, EPI>), (unsigned)grid, block, 0, stream, d, x4, ep, (int)long_blocks, gather);
     } else if (lpr == 8) {
         TAGREC_LAUNCH((spmm_kernel<8, EPI>), (unsigned)grid, block, 0, stream, d, x4, ep, (int)long_blocks, gather);
@@ -380,6 +389,14 @@ extern "C" int tagrec_lightgcn_bwd_layer_p2p(const tagrec_csr_t* a, const float*
                                              const float* g_final, const float* reg_grad, const float* upstream,
                                              float inv_layers, float* g_out, int dim,
                                              const tagrec_mirror_t* out_mirror, void* stream) {
+    return tagrec_lightgcn_bwd_layer_ex(a, g_next, nullptr, e_k, g_final, reg_grad, upstream, inv_layers, g_out, dim,
+                                        out_mirror, stream);
+}
+
+extern "C" int tagrec_lightgcn_bwd_layer_ex(const tagrec_csr_t* a, const float* g_next, const uint8_t* g_next_nz,
+                                            const float* e_k, const float* g_final, const float* reg_grad,
+                                            const float* upstream, float inv_layers, float* g_out, int dim,
+                                            const tagrec_mirror_t* out_mirror, void* stream) {
     TAGREC_REQUIRE(g_final && g_out, "g_final/g_out is null");
     Epi ep{};
     if (int rc = set_mirror(ep.my, out_mirror)) return rc;
@@ -389,7 +406,37 @@ extern "C" int tagrec_lightgcn_bwd_layer_p2p(const tagrec_csr_t* a, const float*
     ep.reg_grad = reg_grad;
     ep.upstream = upstream;
     ep.scale = inv_layers;
+    ep.src_nz = (g_next && dim == 64) ? g_next_nz : nullptr;      // masked instantiation exists for dim 64
     const int gather = g_next != nullptr;
     if (e_k) return launch<EPI_BWD>(a, g_next, ep, dim, gather, stream);
     return launch<EPI_BWD0>(a, g_next, ep, dim, gather, stream);
+}
+
+namespace tagrec {
+// nz[r] = 1 if any element of row r of a [n, dim] table is non-zero (one float4 per thread, dim/4 threads per row).
+template <int LPR>
+__global__ void __launch_bounds__(256) row_nonzero_kernel(const float4* __restrict__ t, int64_t n, uint8_t* __restrict__ nz) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < n * LPR;
+    const float4 v = valid ? __ldcs(t + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned b = __ballot_sync(0xffffffffu, v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f);
+    const int lane = threadIdx.x & 31;
+    if (valid && lane % LPR == 0) {
+        const unsigned grp = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << lane);
+        nz[idx / LPR] = (b & grp) ? 1 : 0;
+    }
+}
+}  // namespace tagrec
+
+extern "C" int tagrec_row_nonzero(const float* table, int64_t n, int dim, uint8_t* nz, void* stream) {
+    TAGREC_REQUIRE(table && nz, "null pointer");
+    TAGREC_REQUIRE(dim == 32 || dim == 64 || dim == 128, "dim must be 32, 64 or 128");
+    if (n == 0) return TAGREC_OK;
+    const int lpr = dim / 4;
+    const unsigned grid = (unsigned)((n * lpr + 255) / 256);
+    const float4* t4 = reinterpret_cast<const float4*>(table);
+    if (lpr == 16) { TAGREC_LAUNCH((row_nonzero_kernel<16>), grid, 256, 0, stream, t4, n, nz); }
+    else if (lpr == 8) { TAGREC_LAUNCH((row_nonzero_kernel<8>), grid, 256, 0, stream, t4, n, nz); }
+    else { TAGREC_LAUNCH((row_nonzero_kernel<32>), grid, 256, 0, stream, t4, n, nz); }
+    return TAGREC_OK;
 }

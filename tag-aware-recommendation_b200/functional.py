@@ -10,6 +10,7 @@ import torch
 from ._lib import check, lib, ptr, stream_ptr
 
 LOSS_KIND = {"softplus": 0, "logsigmoid": 1}
+MASK_DEPTH = 1           # backward gather launches that skip all-zero source rows (see lightgcn_backward_layers)
 
 
 class KernelTimer:
@@ -89,7 +90,7 @@ def lightgcn_forward_layers(graph, e0, n_layer, raw, final, mirrors=None):
 
 
 def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad=None, upstream=None, mirrors=None,
-                             sparse_rows=None, g_first=None):
+                             sparse_rows=None, g_first=None, mask_depth=0):
     """Closed-form backward of the above: one elementwise launch (layer L) + L launches of K1 on
     A^T with the normalise-Jacobian epilogue.  ``bufs`` = two scratch tables, ``g_out`` receives dL/dE0.
     Sharded + ``mirrors``: outputs are stored to every rank by the kernels; the first table G_L is non-zero only on
@@ -101,16 +102,36 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
     inv = 1.0 / (n_layer + 1)
     g_next = None
     t = KERNEL_TIMER
+    # The upstream gradient touches only the batch's 3*B rows, so G_L is non-zero on those rows only and G_{L-1} on
+    # them and their neighbours: the first ``mask_depth`` gather launches get a byte map of the non-zero source rows and
+    # never issue the 256 B gathers of all-zero rows (tagrec_lightgcn_bwd_layer_ex).
+    gathers = 0
+
+    def nz_mask(table):
+        nonlocal gathers
+        gathers += 1
+        if table is None or gathers > mask_depth:
+            return None
+        mk = _buf(graph_ws, "nz_mask", (table.shape[0],), table.device, torch.uint8)
+        if t:
+            t.start("row_mask")
+        check(L.tagrec_row_nonzero(ptr(table), table.shape[0], dim, ptr(mk), st), "tagrec_row_nonzero")
+        if t:
+            t.stop("row_mask")
+        return mk
+
+    graph_ws = graph.__dict__.setdefault("_bwd_ws", {})
     for k in range(n_layer, 0, -1):
         first = g_next is None
         sparse = first and mirrors is not None and sparse_rows is not None and g_first is not None
         out = g_first if sparse else bufs[k % 2]
         m = mirrors.get(id(out)) if (mirrors and not sparse) else None
         name = "bwd_elementwise" if first else "spmm_bwd"
+        mk = None if first else nz_mask(g_next)
         if t:
             t.start(name)
-        check(L.tagrec_lightgcn_bwd_layer_p2p(C.byref(d), ptr(g_next), ptr(raw[k - 1]), ptr(g_final), None,
-                                              ptr(upstream), inv, ptr(out), dim, _mref(m), st),
+        check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d), ptr(g_next), ptr(mk), ptr(raw[k - 1]), ptr(g_final), None,
+                                             ptr(upstream), inv, ptr(out), dim, _mref(m), st),
               "tagrec_lightgcn_bwd_layer")
         if t:
             t.stop(name)
@@ -125,10 +146,11 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
             else:
                 comm.all_gather_rows(g_next)
     m = mirrors.get(id(g_out)) if mirrors else None
+    mk = nz_mask(g_next)
     if t:
         t.start("spmm_bwd")
-    check(L.tagrec_lightgcn_bwd_layer_p2p(C.byref(d), ptr(g_next), None, ptr(g_final), ptr(reg_grad), ptr(upstream), inv,
-                                          ptr(g_out), dim, _mref(m), st), "tagrec_lightgcn_bwd_layer")
+    check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d), ptr(g_next), ptr(mk), None, ptr(g_final), ptr(reg_grad), ptr(upstream),
+                                         inv, ptr(g_out), dim, _mref(m), st), "tagrec_lightgcn_bwd_layer")
     if t:
         t.stop("spmm_bwd")
     if comm is not None:
@@ -189,22 +211,18 @@ class LightGCNLossFn(torch.autograd.Function):
         lightgcn_forward_layers(graph, e0, nl, raw, final, mirrors)
         batch = batch.contiguous()
         nodes = torch.cat([batch[:, 0], batch[:, 1] + model.num_list[0], batch[:, 2] + model.num_list[0]])
-        # gradient tables are zero outside the rows the previous batch touched: re-zero just those rows
-        # (the "dirty rows" live in a persistent buffer that is updated in place, so the step can be recorded into a
-        # CUDA graph; a batch of another size — the tail of an epoch — falls back to clearing the whole table)
+        # The gradient tables are all-zero between steps: K2 scatters into the batch's rows, backward() consumes them
+        # and re-zeroes exactly those rows (no state crosses a step, so eager and CUDA-graph steps can alternate).
+        # If a previous forward was never followed by its backward, its rows are cleared here first.
         for name in ("g_final", "g_reg"):
             if name == "g_reg" and model.reg == 0:
                 continue
-            tns, dirty = ws.get(name), ws.get(name + "_dirty")
+            tns = ws.get(name)
             if tns is None or tns.shape != (n, dim) or tns.device != dev:
                 ws[name] = torch.zeros((n, dim), dtype=torch.float32, device=dev)
-                ws[name + "_dirty"] = nodes.clone()
-            elif dirty is None or dirty.shape != nodes.shape:
-                tns.zero_()
-                ws[name + "_dirty"] = nodes.clone()
-            else:
-                tns.index_fill_(0, dirty, 0.0)
-                dirty.copy_(nodes)
+            elif ws.get("pending_nodes") is not None:
+                tns.index_fill_(0, ws["pending_nodes"], 0.0)
+        ws["pending_nodes"] = nodes
         g_final = ws["g_final"]
         g_reg = ws["g_reg"] if model.reg != 0 else None
         loss_out = torch.empty(2, dtype=torch.float32, device=dev)
@@ -232,7 +250,11 @@ class LightGCNLossFn(torch.autograd.Function):
                 g_first = ws["g_first"] = torch.zeros((n, dim), dtype=torch.float32, device=dev)
         lightgcn_backward_layers(graph, raw, g_final, nl, [tabs["gbuf0"], tabs["gbuf1"]], g_e0,
                                  ws["g_reg"] if ctx.has_reg else None, upstream, mirrors,
-                                 ctx.nodes if p2p else None, g_first)
+                                 ctx.nodes if p2p else None, g_first, mask_depth=MASK_DEPTH)
+        g_final.index_fill_(0, ctx.nodes, 0.0)
+        if ctx.has_reg:
+            ws["g_reg"].index_fill_(0, ctx.nodes, 0.0)
+        ws["pending_nodes"] = None
         return (None, None) + tuple(torch.split(g_e0, ctx.sizes, dim=0))
 
 
