@@ -297,6 +297,12 @@ int tagrec_nbr_attention_bwd(const float* g_out, const float* att, const float* 
 void tagrec_mt19937_seed(uint32_t seed, uint32_t* state);
 int tagrec_sample_bpr_host(uint32_t* state, const int64_t* edges /*[e,2]*/, int64_t e, const int64_t* train_ptr,
                            const int64_t* train_items_sorted, int64_t num_item, int64_t* triples_out /*[e,3]*/);
+/* TransTag / TransE negative tails, host, bit-exact with train_data/transe_training_data.py:42-70 +
+ * train_data/utils.py:31-37 (sample_neg_tail) for cpu_core == 1: for every (h, r, t) draw np.random.randint(0, num)
+ * until the draw is not a tail of (h, r).  group[e] = id of the (h, r) pair of triple e; group_ptr / group_items_sorted =
+ * CSR of the tails per pair (ascending).  `state` (625 words) is read, NOT advanced (the worker is a fork). */
+int tagrec_sample_neg_tail_host(const uint32_t* state, const int64_t* group, int64_t e, const int64_t* group_ptr,
+                                const int64_t* group_items_sorted, int64_t num, int64_t* neg_out);
 int tagrec_sample_bpr_device(const int64_t* edges, int64_t e, const int64_t* train_ptr, const int32_t* train_items,
                              int64_t num_item, uint64_t seed, uint64_t epoch, int64_t* triples_out, void* stream);
 

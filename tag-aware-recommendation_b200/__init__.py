@@ -19,7 +19,8 @@ from .dgcf import DGCF                                         # noqa: F401
 from .disengcn import DisenGCN                                 # noqa: F401
 from .tgcn import TGCN                                         # noqa: F401
 from . import routing                                          # noqa: F401
-from .bpr_training_data import Abstract_training_data, BPR_training_data, DGCF_training_data   # noqa: F401
+from .bpr_training_data import (Abstract_training_data, BPR_training_data, DGCF_training_data,   # noqa: F401
+                                TransTag_training_data)
 from .basic_train import Basic_train, epoch_training           # noqa: F401
 from .basic_test import Basic_test                             # noqa: F401
 from .early_stop import Early_stop                             # noqa: F401

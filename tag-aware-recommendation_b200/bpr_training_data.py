@@ -194,3 +194,64 @@ class DGCF_training_data(Abstract_training_data):
     def mini_batch(self):
         for _ in range(0, self.tot_inter):
             yield self.mini_sample()
+
+
+class TransTag_training_data(Abstract_training_data):
+    """Drop-in for train_data/transe_training_data.py:42-70 — TGCN's second training phase (com.py:68-70): for every
+    (user, tag, item) triple of ``data.uit_data`` one negative item that the user never tagged with that tag; no
+    shuffle; re-sampled by ``reset()`` every epoch; batches of ``transtag_batch`` rows ``[u, t, i+, i-]``.
+
+    CFG['sampler'] == 'mt19937': numpy-legacy stream restated in C++ (``tagrec_sample_neg_tail_host``), bit-exact with
+    the reference at ``cpu_core == 1`` — a forked worker samples from a COPY of the global generator, so (as in the
+    reference) the parent's state does not move and every epoch draws the same negatives unless something else
+    advanced it.  'device': Philox rejection kernel (rows come out in a pseudo-random order)."""
+
+    def __init__(self, data, args=None):
+        super().__init__(args)
+        cfg = config.current()
+        self.args = args
+        self.batch_size = cfg['transtag_batch']
+        self.mode = cfg.get('sampler', 'device')
+        self.seed = int(cfg.get('seed', 2020))
+        self.num = int(data.num['item'])
+        self.uti_data = np.ascontiguousarray(np.asarray(data.uit_data)[:, [0, 2, 1]], dtype=np.int64)
+        # (u, t) groups -> ascending tails: the reference's u_t_dict (train_data/utils.py:40-46) as a CSR
+        n_tag = int(self.uti_data[:, 1].max()) + 1 if len(self.uti_data) else 1
+        key = self.uti_data[:, 0] * n_tag + self.uti_data[:, 1]
+        uniq, self._group = np.unique(key, return_inverse=True)
+        order = np.lexsort((self.uti_data[:, 2], self._group))
+        self._gitems = np.ascontiguousarray(self.uti_data[order, 2])
+        self._gptr = np.zeros(len(uniq) + 1, dtype=np.int64)
+        np.cumsum(np.bincount(self._group, minlength=len(uniq)), out=self._gptr[1:])
+        self._group = np.ascontiguousarray(self._group, dtype=np.int64)
+        self.epoch = 0
+        if self.mode == "device":
+            dev = self.device
+            e = len(self.uti_data)
+            self._edges_d = torch.as_tensor(np.stack([self._group, np.arange(e)], 1), device=dev)
+            self._gptr_d = torch.as_tensor(self._gptr, device=dev)
+            self._gitems_d = torch.as_tensor(self._gitems, device=dev).to(torch.int32)
+            self._uti_d = torch.as_tensor(self.uti_data, device=dev)
+        start = time.time()
+        self.all_train_data = self.get_all_training_data()
+        self.tot_inter = self.all_train_data.shape[0] // self.batch_size
+        print(f"TransTag_training_data producer, tot_inter: {self.tot_inter},"
+              f"[all_training_data time:{time.time()-start}]")
+
+    def get_all_training_data(self):
+        e = len(self.uti_data)
+        if self.mode != "device":
+            kind, keyw, pos, has_gauss, cached = np.random.get_state()
+            state = np.empty(625, dtype=np.uint32)
+            state[:624], state[624] = keyw, pos
+            neg = np.empty(e, dtype=np.int64)
+            check(lib().tagrec_sample_neg_tail_host(ptr(state), ptr(self._group), e, ptr(self._gptr), ptr(self._gitems),
+                                                    self.num, ptr(neg)), "tagrec_sample_neg_tail_host")
+            out = np.concatenate([self.uti_data, neg[:, None]], axis=1)
+            return torch.as_tensor(out, dtype=torch.long, device=self.device)
+        tri = torch.empty((e, 3), dtype=torch.int64, device=self.device)
+        check(lib().tagrec_sample_bpr_device(ptr(self._edges_d), e, ptr(self._gptr_d), ptr(self._gitems_d), self.num,
+                                             self.seed + 1, self.epoch, ptr(tri), stream_ptr(tri.device)),
+              "tagrec_sample_bpr_device")
+        self.epoch += 1
+        return torch.cat([self._uti_d[tri[:, 1]], tri[:, 2:3]], dim=1)

@@ -174,6 +174,33 @@ extern "C" int tagrec_sample_bpr_host(uint32_t* state, const int64_t* edges, int
     return TAGREC_OK;
 }
 
+extern "C" int tagrec_sample_neg_tail_host(const uint32_t* state, const int64_t* group, int64_t e,
+                                           const int64_t* group_ptr, const int64_t* group_items_sorted, int64_t num,
+                                           int64_t* neg_out) {
+    TAGREC_REQUIRE(state && group && group_ptr && group_items_sorted && neg_out, "null pointer");
+    TAGREC_REQUIRE(num > 0 && num <= 0xffffffffll, "num out of range");
+    // the forked worker of transe_training_data.py:61-66 with cpu_core == 1: a COPY of the generator, the parent's
+    // state is not advanced (there is no shuffle in this sampler)
+    std::vector<uint32_t> wstate(state, state + 625);
+    Mt worker{wstate.data(), wstate.data() + 624};
+    for (int64_t k = 0; k < e; ++k) {
+        const int64_t* lo = group_items_sorted + group_ptr[group[k]];
+        const int64_t* hi = group_items_sorted + group_ptr[group[k] + 1];
+        int64_t neg;
+        for (;;) {                                               // train_data/utils.py:31-37 sample_neg_tail
+            neg = (int64_t)worker.bounded((uint32_t)(num - 1));
+            const int64_t *a = lo, *b = hi;
+            while (a < b) {
+                const int64_t* mid = a + (b - a) / 2;
+                if (*mid < neg) a = mid + 1; else b = mid;
+            }
+            if (!(a < hi && *a == neg)) break;
+        }
+        neg_out[k] = neg;
+    }
+    return TAGREC_OK;
+}
+
 extern "C" int tagrec_sample_bpr_device(const int64_t* edges, int64_t e, const int64_t* train_ptr,
                                         const int32_t* train_items, int64_t num_item, uint64_t seed, uint64_t epoch,
                                         int64_t* triples_out, void* stream) {

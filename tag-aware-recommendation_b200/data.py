@@ -157,3 +157,50 @@ def synth_bipartite_device(n_user, n_item, n_edge, device, seed=2020, zipf=0.9, 
     key = torch.unique(users * n_item + items)        # sorted, duplicates removed
     del users, items
     return torch.div(key, n_item, rounding_mode="floor"), key % n_item
+
+
+def all_neighbor_sample(matrix, max_deg):
+    """data/utils.py:87-106 — one padded neighbour table: per row ``max_deg`` neighbour ids (+1; 0 = padding, only in
+    empty rows) sampled WITH replacement when the row is shorter than the table, a random permutation prefix otherwise,
+    and the matching integer edge weights.  Same ``np.random.choice`` calls in the same order as the reference (so the
+    same numpy state gives the same tables), but straight from the CSR arrays — the reference densifies every row with
+    ``matrix[i].toarray()``."""
+    m = matrix.tocsr()
+    m.sum_duplicates()
+    n = m.shape[0]
+    data = np.zeros((n, max_deg), dtype=np.int64)
+    weight = np.zeros((n, max_deg), dtype=np.int64)
+    indptr, indices, vals = m.indptr, m.indices, m.data
+    for i in range(n):
+        lo, hi = indptr[i], indptr[i + 1]
+        keep = vals[lo:hi] != 0
+        ids = indices[lo:hi][keep]
+        x = len(ids)
+        if x == 0:
+            continue
+        if x < max_deg:
+            sample = np.random.choice(ids, max_deg)
+        else:
+            sample = np.random.choice(ids, max_deg, replace=False)
+        data[i] = sample + 1
+        weight[i] = vals[lo:hi][keep][np.searchsorted(ids, sample)].astype(np.int64)
+    return [data, weight]
+
+
+def get_all_neighbor(ds, fork_semantics=True, width=None):
+    """data/tgcn_load.py:41-53 TGCN_load.get_all_neighbor: the six tables (ui, ut, iu, it, tu, ti).  The reference
+    builds them in a forked worker (cpu_core == 1: one worker, the six matrices in order), i.e. from a COPY of numpy's
+    global generator; ``fork_semantics`` reproduces that by restoring the global state afterwards.  The reference's
+    tables are as wide as the largest stored row (thousands of columns on tag graphs) although TGCN reads the first
+    ``neighbor_k`` columns only (tgcn.py:199); ``width`` caps them (different random stream, same distribution)."""
+    mats = [ds.ui_adj, ds.ut_adj, ds.ui_adj.transpose(), ds.it_adj, ds.ut_adj.transpose(), ds.it_adj.transpose()]
+    # tgcn_load.py:44: getnnz(1) of the COO as stored — duplicate (u, t) entries count, so the table can be wider than
+    # the number of DISTINCT neighbours (rows are then filled by sampling with replacement)
+    max_deg = [int(max(a.getnnz(1))) for a in mats]
+    if width is not None:      # NOT stream-identical to the reference: tables only as wide as the model reads (neighbor_k)
+        max_deg = [min(d, int(width)) for d in max_deg]
+    saved = np.random.get_state() if fork_semantics else None
+    out = [all_neighbor_sample(a, d) for a, d in zip(mats, max_deg)]
+    if saved is not None:
+        np.random.set_state(saved)
+    return out

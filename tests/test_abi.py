@@ -113,3 +113,50 @@ def test_dgcf_sampler_host_mode_bit_exact_vs_reference(tiny):
         np.random.seed(6)
         s = T.DGCF_training_data(d, None)
         assert np.array_equal(np.stack([b[0].numpy() for b in s.mini_batch()]), gold[f"{tag}_small_data"])
+
+
+def test_transtag_sampler_host_mode_bit_exact_vs_reference(tiny):
+    """T.TransTag_training_data (C++ numpy-legacy stream) == train_data/transe_training_data.py:42-70, two epochs; the
+    global generator is left untouched, like the reference's forked worker leaves the parent's."""
+    import torch
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "transtag_sampler.npz")))
+    U, I, Tg, _ = nums(tiny)
+
+    class D:
+        pass
+    d = D()
+    d.num = {"user": U, "item": I, "tag": Tg}
+    d.uit_data = tiny["uit_data"]
+    T.set_config("tgcn", transtag_batch=64, sampler="mt19937", device=torch.device("cpu"), cpu_core=1)
+    np.random.seed(2020)
+    before = np.random.get_state()[1].copy()
+    s = T.TransTag_training_data(d, None)
+    assert np.array_equal(s.all_train_data.numpy(), gold["first"])
+    s.reset()
+    assert np.array_equal(s.all_train_data.numpy(), gold["second"])
+    assert np.array_equal(before, np.random.get_state()[1])
+    sizes = [b.shape[0] for b in s.mini_batch()]
+    assert sum(sizes[:-1]) + sizes[-1] >= len(gold["first"]) and sizes[0] == 64
+
+
+def test_neighbour_tables_bit_exact_vs_reference(tiny, tiny_tgcn):
+    """T.data.get_all_neighbor == TGCN_load.get_all_neighbor (data/tgcn_load.py:41-53, data/utils.py:87-106): the six
+    padded neighbour / weight tables the reference built after init_seed(2020), incl. table widths that count
+    duplicate COO entries."""
+    import scipy.sparse as sp
+    from helpers import blocks
+    U, I, Tg, _ = nums(tiny)
+    ui, ut, it = blocks(tiny)
+
+    class D:
+        pass
+    d = D()
+    coo = lambda rc, shape: sp.coo_matrix((np.ones(len(rc[0])), rc), dtype=np.float32, shape=shape)  # noqa: E731
+    d.ui_adj, d.ut_adj, d.it_adj = coo(ui, (U, I)), coo(ut, (U, Tg)), coo(it, (I, Tg))
+    np.random.seed(2020)
+    before = np.random.get_state()[1].copy()
+    tabs = T.data.get_all_neighbor(d)
+    for name, (ids, w) in zip(["ui", "ut", "iu", "it", "tu", "ti"], tabs):
+        assert np.array_equal(ids, tiny_tgcn[f"tgcn_nbr_{name}"]), name
+        assert np.array_equal(w, tiny_tgcn[f"tgcn_nbw_{name}"]), name
+    assert np.array_equal(before, np.random.get_state()[1])

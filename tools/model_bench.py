@@ -31,27 +31,6 @@ CASES = {
 }
 
 
-def neighbour_tables(ds, k_cap=64):
-    """Stand-in for TGCN_load.get_all_neighbor (data/tgcn_load.py:41-53, host-side, out of scope): padded neighbour /
-    weight tables (ids + 1, 0 = padding), rows sampled with replacement up to the table width."""
-    rng = np.random.RandomState(0)
-    mats = [ds.ui_adj, ds.ut_adj, ds.ui_adj.T, ds.it_adj, ds.ut_adj.T, ds.it_adj.T]
-    out = []
-    for m in mats:
-        m = m.tocsr()
-        width = min(int(m.getnnz(1).max()), k_cap)
-        idx = np.zeros((m.shape[0], width), dtype=np.int64)
-        wgt = np.zeros((m.shape[0], width), dtype=np.int64)
-        for i in range(m.shape[0]):
-            lo, hi = m.indptr[i], m.indptr[i + 1]
-            if hi > lo:
-                sel = rng.randint(lo, hi, width)
-                idx[i] = m.indices[sel] + 1
-                wgt[i] = m.data[sel].astype(np.int64)
-        out.append((idx, wgt))
-    return out
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--models", default="lightgcn,lightgcn_tag,ngcf,dgcf,disengcn,tgcn")
@@ -74,7 +53,7 @@ def main():
         T.set_config(model_name, **cfg)
         torch.manual_seed(2020)
         if model_name == "tgcn":
-            ds.get_all_neighbor = lambda ds=ds: neighbour_tables(ds)
+            ds.get_all_neighbor = lambda ds=ds: T.data.get_all_neighbor(ds, width=25)      # data/tgcn_load.py:41-53, restated
             model = T.TGCN(ds).to(dev)
         else:
             model = {"lightgcn": T.LightGCN, "ngcf": T.NGCF, "dgcf": T.DGCF, "disengcn": T.DisenGCN}[model_name](ds).to(dev)
