@@ -181,7 +181,10 @@ class DGCF_training_data(Abstract_training_data):
                                              self.seed, self.calls, ptr(out), stream_ptr(dev)),
               "tagrec_sample_bpr_device")
         sizes = [self.num_user, self.num_item] + ([self.num_tag] if self.use_tag else [])
-        cor = torch.stack([torch.randperm(n, device=dev, generator=g)[:self.cor_batch] for n in sizes])
+        # (the reference's random.sample raises when a population is smaller than cor_batch; here: with replacement)
+        cb = self.cor_batch
+        cor = torch.stack([torch.randperm(n, device=dev, generator=g)[:cb] if n >= cb
+                           else torch.randint(0, n, (cb,), device=dev, generator=g) for n in sizes])
         return out, cor
 
     def mini_sample(self):

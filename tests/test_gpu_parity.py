@@ -888,6 +888,62 @@ def test_graphed_step_matches_eager(tiny, model_name):
         assert relerr(b.cpu().numpy(), a.cpu().numpy()) < 2e-4
 
 
+# ------------------------------------------------------------------------------------------- end-to-end drop-in loops
+class _Args:
+    pool = None
+    writer = None
+
+    def __init__(self, out_dir):
+        self.out_dir = out_dir
+
+
+@pytest.mark.parametrize("name", ["lightgcn", "ngcf", "dgcf", "disengcn", "tgcn"])
+def test_end_to_end_training_loop(tiny, tiny_tgcn, name, tmp_path):
+    """The composition of com.py:10-86 with the drop-in classes: sampler(s) -> Basic_train.run (2 epochs, evaluation
+    every epoch, early-stop checkpoint) -> Basic_test.run(istest=True, group_k=2).  TGCN runs its two phases (BPR +
+    TransTag, one shared Adam) like tgcn_comp.  Checks: loss goes down, result dicts have the reference's keys and
+    lengths, the checkpoint holds the reference's state_dict keys."""
+    use_tag = name in ("disengcn", "tgcn")
+    layers = [64, 64] if name == "tgcn" else [64, 64, 64]
+    T.set_config(name, use_tag=use_tag, reg=1e-4, dim_layer_list=layers, device=dev(), lr=0.01, train_batch=64,
+                 test_batch=16, topks=[5, 20], epochs=2, test_interval=1, patient_epoch=5, sampler="device",
+                 neighbor_k=5, transtag_batch=64)
+    d = make_data(tiny, tags=True)
+    d.uit_data = tiny["uit_data"]
+    args = _Args(str(tmp_path))
+    torch.manual_seed(0)
+    if name == "tgcn":
+        names = ["ui", "ut", "iu", "it", "tu", "ti"]
+        d.get_all_neighbor = lambda: [(tiny_tgcn[f"tgcn_nbr_{n}"], tiny_tgcn[f"tgcn_nbw_{n}"]) for n in names]
+        model = T.TGCN(d).to(dev())
+        opt = torch.optim.Adam(model.parameters(), lr=0.01)
+        train_data = [T.BPR_training_data(d, args), T.TransTag_training_data(d, args)]
+        loss_func, opts = [model.loss, model.transtag_loss], [opt, opt]
+    else:
+        cls = {"lightgcn": T.LightGCN, "ngcf": T.NGCF, "dgcf": T.DGCF, "disengcn": T.DisenGCN}[name]
+        model = cls(d).to(dev())
+        sampler = T.DGCF_training_data if name in ("dgcf", "disengcn") else T.BPR_training_data
+        train_data = [sampler(d, args)]
+        loss_func, opts = [model.loss], [torch.optim.Adam(model.parameters(), lr=0.01)]
+    test = T.Basic_test(d, args)
+    keys_before = list(model.state_dict().keys())
+    first = T.basic_train.epoch_training(train_data[0], loss_func[0], opts[0])
+    train = T.Basic_train(train_data, loss_func, opts, test, args)
+    train.run(model)
+    last = T.basic_train.epoch_training(train_data[0], loss_func[0], opts[0])
+    assert np.isfinite(first).all() and np.isfinite(last).all()
+    assert np.mean(last) < np.mean(first), (np.mean(first), np.mean(last))
+    res = test.run(model, istest=True)
+    assert set(res) == {"recall", "precision", "hr", "ndcg", "auc"}
+    assert all(len(res[k]) == 2 for k in ("recall", "precision", "hr", "ndcg")) and len(res["auc"]) == 1
+    assert 0.0 <= res["auc"][0] <= 1.0 and 0.0 <= res["recall"][1] <= 1.0
+    grouped = test.run(model, istest=True, group_k=2)
+    assert len(grouped) == 2 and all(k.startswith("inter<") for k in grouped)
+    ckpt = os.path.join(str(tmp_path), "model.pth.tar")
+    assert os.path.exists(ckpt)
+    assert list(torch.load(ckpt, map_location="cpu").keys()) == keys_before
+
+
 # ------------------------------------------------------------------------------- large-scale, size-independent properties
 @pytest.fixture(scope="module")
 def big_graph():
