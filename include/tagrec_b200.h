@@ -175,9 +175,10 @@ size_t tagrec_eval_workspace_bytes(int64_t nu, int64_t n_item, int k);
 /* Same, with the scoring path chosen by the caller.  Both paths return the same top-K (by (-score, id) of the exact
  * fp32 dot product, sequential fmaf over the feature index):
  *   TAGREC_EVAL_FP32  CUDA-core fp32 tiles (any dim % 32 == 0);
- *   TAGREC_EVAL_TF32  dim == 64: tcgen05.mma kind::tf32 (accumulators in TMEM, item tiles by TMA) as a filter with a
- *                     proven error margin, every candidate re-scored in exact fp32 (csrc/eval_tc.cu);
- *   TAGREC_EVAL_AUTO  TF32 when dim == 64, else FP32 (what tagrec_eval_topk does). */
+ *   TAGREC_EVAL_TF32  dim in {64, 128, 192, 256}: tcgen05.mma kind::tf32 (accumulators and user rows in TMEM, item
+ *                     tiles by TMA) as a filter with a proven error margin, every candidate re-scored in exact fp32
+ *                     (csrc/eval_tc.cu);
+ *   TAGREC_EVAL_AUTO  TF32 when the dim allows it, else FP32 (what tagrec_eval_topk does). */
 #define TAGREC_EVAL_AUTO 0
 #define TAGREC_EVAL_FP32 1
 #define TAGREC_EVAL_TF32 2

@@ -592,22 +592,282 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------- wide tables
+// dim = 64 * KB, KB = 2..4 (NGCF's 256-d concat, ngcf.py:89; TGCN's 192-d, tgcn.py:227-229; 128-d tables).  Same roles
+// as eval_tc_kernel with one 128-user half per CTA; a tile is KB item k-blocks of [128 x 64] that stream through the
+// stage ring one after the other (stages are released by tcgen05.commit as soon as the MMAs that read them retire),
+// the user rows occupy 64*KB TMEM columns, the accumulator ring has two 128-column slots, and the exact re-score
+// reads both rows from global memory (L2: the item rows were streamed through it a moment ago).
+__global__ void __launch_bounds__(64 + 128, 1)
+eval_tc_wide_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a, int KB) {
+    constexpr int ROWS = TC_M;
+    constexpr int NACC = 2;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int S = a.stages, K = a.k, D = KB * TC_D;
+    unsigned char* Bs = base;                                         // S x 32 KB
+    float* ls = reinterpret_cast<float*>(Bs + S * TC_TILE_BYTES);     // [K][ROWS]
+    int32_t* li = reinterpret_cast<int32_t*>(ls + (size_t)K * ROWS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(li + (size_t)K * ROWS);
+    uint64_t* full = bars;                            // [S]
+    uint64_t* bfree = bars + TC_MAX_STAGES;           // [S]   released by tcgen05.commit
+    uint64_t* accfull = bars + 2 * TC_MAX_STAGES;     // [2]
+    uint64_t* accfree = accfull + NACC;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfree + NACC);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t u0 = (int64_t)blockIdx.x * ROWS;
+    const int split = blockIdx.y;
+    const int64_t i_begin = (int64_t)split * a.items_per_split;
+    const int64_t i_end = min(a.n_item, i_begin + a.items_per_split);
+    const int n_tiles = (int)((i_end - i_begin + TC_N - 1) / TC_N);
+    const int a_cols = KB * TC_D;                     // TMEM columns of the user rows
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(smem_u32(full + s), 1);
+            mbar_init(smem_u32(bfree + s), 1);
+        }
+        for (int x = 0; x < NACC; ++x) {
+            mbar_init(smem_u32(accfull + x), 1);
+            mbar_init(smem_u32(accfree + x), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_base = tmem_base + (uint32_t)a_cols;
+
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool is_epi = warp >= 2;
+    const bool valid = is_epi && (u0 + row < a.nu);
+    const float* urow = nullptr;
+    float unorm2 = 0.f;
+    if (is_epi) {
+        if (valid) urow = a.user_table + __ldg(a.users + u0 + row) * (int64_t)D;
+        for (int ch = 0; ch < 2 * KB; ++ch) {          // 32 floats per tcgen05.st
+            uint32_t r[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) v = __ldg(reinterpret_cast<const float4*>(urow) + ch * 8 + c);
+                unorm2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, unorm2))));
+                r[4 * c + 0] = __float_as_uint(v.x);
+                r[4 * c + 1] = __float_as_uint(v.y);
+                r[4 * c + 2] = __float_as_uint(v.z);
+                r[4 * c + 3] = __float_as_uint(v.w);
+            }
+            tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int t = 0; t < n_tiles; ++t) {
+                const int row0 = (int)(i_begin + (int64_t)t * TC_N);
+                for (int kb = 0; kb < KB; ++kb) {
+                    const int g = t * KB + kb, s = g % S;
+                    mbar_wait(smem_u32(bfree + s), ((g / S) & 1) ^ 1);
+                    const uint32_t bar = smem_u32(full + s);
+                    mbar_expect_tx(bar, TC_TILE_BYTES);
+                    const uint32_t dst = smem_u32(Bs + s * TC_TILE_BYTES);
+                    tma_load_2d(dst, &item_map, bar, kb * TC_D, row0);
+                    tma_load_2d(dst + TC_KH_BYTES, &item_map, bar, kb * TC_D + 32, row0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int t = 0; t < n_tiles; ++t) {
+                const int r = t % NACC;
+                mbar_wait(smem_u32(accfree + r), ((t / NACC) & 1) ^ 1);
+                const uint32_t d = acc_base + (uint32_t)(r * TC_N);
+                for (int kb = 0; kb < KB; ++kb) {
+                    const int g = t * KB + kb, s = g % S;
+                    mbar_wait(smem_u32(full + s), (g / S) & 1);
+                    tc_fence_after();
+                    const uint32_t b0 = smem_u32(Bs + s * TC_TILE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint32_t off = (uint32_t)((kk >> 2) * TC_KH_BYTES + (kk & 3) * 32);
+                        umma_tf32_ts(d, tmem_base + (uint32_t)(kb * TC_D + kk * 8), umma_desc_sw128(b0 + off),
+                                     (kb | kk) > 0);
+                    }
+                    umma_commit(smem_u32(bfree + s));       // the stage is free once these MMAs have read it
+                }
+                umma_commit(smem_u32(accfull + r));
+            }
+        }
+    } else {
+        float thr = -INFINITY, thr_lo = valid ? -INFINITY : INFINITY, margin = 0.f;
+        float thr_sh = -INFINITY;
+        float* sh_slot = (valid && a.shared_thr) ? a.shared_thr + (u0 + row) : nullptr;
+        int cnt = 0, minpos = 0;
+        int64_t tc = 0, te = 0;
+        int32_t nxt = INT32_MAX;
+        if (valid) {
+            const int64_t u = __ldg(a.users + u0 + row);
+            margin = TC_MARGIN * sqrtf(unorm2) * __ldg(a.item_maxnorm) + FLT_MIN;
+            tc = __ldg(a.train_ptr + u);
+            te = __ldg(a.train_ptr + u + 1);
+            int64_t lo = tc, hi = te;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if ((int64_t)__ldg(a.train_items + mid) < i_begin) lo = mid + 1; else hi = mid;
+            }
+            tc = lo;
+            nxt = tc < te ? __ldg(a.train_items + tc) : INT32_MAX;
+        }
+        for (int t = 0; t < n_tiles; ++t) {
+            const int r = t % NACC;
+            const int64_t it0 = i_begin + (int64_t)t * TC_N;
+            const float sh_new = sh_slot ? __ldcg(sh_slot) : -INFINITY;
+            mbar_wait(smem_u32(accfull + r), (t / NACC) & 1);
+            tc_fence_after();
+            if (sh_new > thr_sh) {
+                thr_sh = sh_new;
+                thr_lo = fmaxf(thr, thr_sh) - margin;
+            }
+            const uint32_t taddr = acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * TC_N);
+            uint32_t cm[TC_N / 32];
+            auto scan32 = [&](const uint32_t (&v)[32]) -> uint32_t {
+                float m = __uint_as_float(v[0]);
+#pragma unroll
+                for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+                uint32_t mask = 0;
+                if (m > thr_lo) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr_lo) ? (1u << j) : 0u;
+                }
+                return mask;
+            };
+#pragma unroll
+            for (int c = 0; c < TC_N / 32; c += 2) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr + c * 32, v0);
+                tmem_ld32(taddr + (c + 1) * 32, v1);
+                tmem_ld_wait();
+                cm[c] = scan32(v0);
+                cm[c + 1] = scan32(v1);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(accfree + r));
+            uint64_t lo64 = (uint64_t)cm[0] | ((uint64_t)cm[1] << 32), hi64 = (uint64_t)cm[2] | ((uint64_t)cm[3] << 32);
+            while (lo64 | hi64) {
+                int il;
+                if (lo64) {
+                    il = __ffsll((long long)lo64) - 1;
+                    lo64 &= lo64 - 1;
+                } else {
+                    il = 64 + __ffsll((long long)hi64) - 1;
+                    hi64 &= hi64 - 1;
+                }
+                const int64_t item = it0 + il;
+                if (item >= i_end) break;
+                if ((int64_t)nxt < item) {
+                    int64_t step = 1, lo = tc + 1;
+                    while (lo + step < te && (int64_t)__ldg(a.train_items + lo + step) < item) {
+                        lo += step;
+                        step <<= 1;
+                    }
+                    int64_t hi = min(te, lo + step + 1);
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if ((int64_t)__ldg(a.train_items + mid) < item) lo = mid + 1; else hi = mid;
+                    }
+                    tc = lo;
+                    nxt = tc < te ? __ldg(a.train_items + tc) : INT32_MAX;
+                }
+                if ((int64_t)nxt == item) continue;
+                // exact fp32 score, canonical sequential order over all D features
+                const float4* irow = reinterpret_cast<const float4*>(a.item_table + item * (int64_t)D);
+                const float4* ur4 = reinterpret_cast<const float4*>(urow);
+                float ex = 0.f;
+                for (int c16 = 0; c16 < D / 4; ++c16) {
+                    const float4 uu = __ldg(ur4 + c16);
+                    const float4 ii = __ldg(irow + c16);
+                    ex = fmaf(uu.x, ii.x, ex);
+                    ex = fmaf(uu.y, ii.y, ex);
+                    ex = fmaf(uu.z, ii.z, ex);
+                    ex = fmaf(uu.w, ii.w, ex);
+                }
+                if ((cnt < K || ex > thr) && ex >= thr_sh) {
+                    const int pos = cnt < K ? cnt : minpos;
+                    ls[(size_t)pos * ROWS + row] = ex;
+                    li[(size_t)pos * ROWS + row] = (int32_t)item;
+                    if (cnt < K) ++cnt;
+                    if (cnt == K) {
+                        float best = INFINITY;
+                        int32_t besti = -1;
+                        int bp = 0;
+#pragma unroll 4
+                        for (int j = 0; j < K; ++j) {
+                            const float sj = ls[(size_t)j * ROWS + row];
+                            const int32_t ij = li[(size_t)j * ROWS + row];
+                            if (sj < best || (sj == best && ij > besti)) {
+                                best = sj;
+                                besti = ij;
+                                bp = j;
+                            }
+                        }
+                        thr = best;
+                        minpos = bp;
+                        thr_lo = fmaxf(thr, thr_sh) - margin;
+                        if (sh_slot && thr > thr_sh) atomic_max_float(sh_slot, thr);
+                    }
+                }
+            }
+        }
+        if (valid) {
+            const size_t o = ((size_t)(u0 + row) * a.splits + split) * K;
+            for (int j = 0; j < K; ++j) {
+                a.part_scores[o + j] = j < cnt ? ls[(size_t)j * ROWS + row] : -INFINITY;
+                a.part_ids[o + j] = j < cnt ? li[(size_t)j * ROWS + row] : -1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 __global__ void fill_f32_kernel(float* p, int64_t n, float v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
 
-// max_i ||I_i||_2 (for the TF32 error margin).  16 lanes per 64-float row, coalesced.
-__global__ void __launch_bounds__(256) item_maxnorm_kernel(const float4* __restrict__ it, int64_t n_item, float* out) {
-    const int lane = threadIdx.x & 31, sub = lane >> 4, sl = lane & 15;
-    const unsigned mask = 0xffffu << (sub * 16);
+// max_i ||I_i||_2 (for the TF32 error margin).  One warp per row, lanes stride over the row's float4s.
+__global__ void __launch_bounds__(256) item_maxnorm_kernel(const float4* __restrict__ it, int64_t n_item, int c4,
+                                                           float* out) {
+    const int lane = threadIdx.x & 31;
     float best = 0.f;
-    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 4);
-    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); r < n_item; r += stride) {
-        const float4 v = __ldg(it + r * 16 + sl);
-        best = fmaxf(best, half_sum(dot4(v, v), mask));
+    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_item; r += stride) {
+        float ss = 0.f;
+        for (int c = lane; c < c4; c += 32) {
+            const float4 v = __ldg(it + r * c4 + c);
+            ss += dot4(v, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        best = fmaxf(best, ss);
     }
-    best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 16));
     if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(best) * 1.0001f));   // non-negative floats order as ints
 }
 
@@ -676,25 +936,39 @@ static size_t tc_smem(int nh, int stages, int k) {
            (size_t)2 * k * TC_M * nh * 4 + 256;
 }
 
+static size_t tc_smem_wide(int stages, int k) {
+    return 1024 + (size_t)stages * TC_TILE_BYTES + (size_t)2 * k * TC_M * 4 + 256;
+}
+
 TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
     TcPlan p{};
     p.ok = false;
-    if (dim != TC_D || k < 1 || k > 128 || nu < 1 || n_item < 1) return p;
+    if (dim < TC_D || dim % TC_D != 0 || dim > 4 * TC_D || k < 1 || k > 128 || nu < 1 || n_item < 1) return p;
+    p.kb = dim / TC_D;
     const size_t budget = 227 * 1024;
     const int64_t item_tiles = (n_item + TC_N - 1) / TC_N;
     // Item splits: every split restarts its thresholds (about K * ln(items/K) exact re-scores per row and split) and
     // the merge ranks splits*K entries per user, so: at most TC_MAX_SPLITS, at least 8 tiles each, and no more than
     // fill ONE wave of the 148 SMs.
     const int64_t max_s = std::max<int64_t>(1, std::min<int64_t>(TC_MAX_SPLITS, item_tiles / 8));
-    // Two 128-user halves per CTA halve the L2 traffic of the item stream; with few users one half per CTA puts twice
-    // as many CTAs on the machine.
-    const int64_t tiles2 = (nu + 2 * TC_M - 1) / (2 * TC_M);
-    p.nh = (nu > TC_M && tiles2 * max_s >= (kSMs * 3) / 4) ? 2 : 1;
-    for (;; p.nh = 1) {
+    if (p.kb > 1) {     // wide tables: one 128-user half per CTA, stages released by tcgen05.commit
+        p.nh = 1;
         p.stages = TC_MAX_STAGES;
-        while (p.stages >= 2 && tc_smem(p.nh, p.stages, k) > budget) --p.stages;
-        if (p.stages >= (p.nh == 2 ? 3 : 2)) break;
-        if (p.nh == 1) return p;
+        while (p.stages >= 2 && tc_smem_wide(p.stages, k) > budget) --p.stages;
+        if (p.stages < 2) return p;
+        p.smem = tc_smem_wide(p.stages, k);
+    } else {
+        // Two 128-user halves per CTA halve the L2 traffic of the item stream; with few users one half per CTA puts
+        // twice as many CTAs on the machine.
+        const int64_t tiles2 = (nu + 2 * TC_M - 1) / (2 * TC_M);
+        p.nh = (nu > TC_M && tiles2 * max_s >= (kSMs * 3) / 4) ? 2 : 1;
+        for (;; p.nh = 1) {
+            p.stages = TC_MAX_STAGES;
+            while (p.stages >= 2 && tc_smem(p.nh, p.stages, k) > budget) --p.stages;
+            if (p.stages >= (p.nh == 2 ? 3 : 2)) break;
+            if (p.nh == 1) return p;
+        }
+        p.smem = tc_smem(p.nh, p.stages, k);
     }
     const int64_t user_tiles = (nu + TC_M * p.nh - 1) / (TC_M * p.nh);
     int64_t best_s = user_tiles >= kSMs ? 1 : kSMs / user_tiles;
@@ -702,7 +976,6 @@ TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
     p.splits = (int)best_s;
     p.items_per_split = ((item_tiles + p.splits - 1) / p.splits) * TC_N;
     p.splits = (int)((n_item + p.items_per_split - 1) / p.items_per_split);
-    p.smem = tc_smem(p.nh, p.stages, k);
     p.ok = true;
     return p;
 }
@@ -716,8 +989,9 @@ int eval_topk_tc(const int64_t* users, int64_t nu, const float* user_table, cons
     const size_t need = eval_tc_workspace_bytes(nu, p, k);
     if (!workspace || workspace_bytes < need) return fail(TAGREC_ENOMEM, "eval workspace too small", __FILE__, __LINE__);
     CUtensorMap map;
-    const cuuint64_t gdim[2] = {(cuuint64_t)TC_D, (cuuint64_t)n_item};
-    const cuuint64_t gstride[1] = {(cuuint64_t)TC_D * 4};
+    const int dim = p.kb * TC_D;
+    const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n_item};
+    const cuuint64_t gstride[1] = {(cuuint64_t)dim * 4};
     const cuuint32_t box[2] = {32, (cuuint32_t)TC_N};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(item_table), gdim, gstride, box,
@@ -740,11 +1014,14 @@ int eval_topk_tc(const int64_t* users, int64_t nu, const float* user_table, cons
     TAGREC_CUDA(cudaMemsetAsync(maxnorm, 0, 4, st));
     if (a.shared_thr)
         TAGREC_LAUNCH(fill_f32_kernel, (unsigned)((nu + 255) / 256), 256, 0, stream, a.shared_thr, nu, -INFINITY);
-    const int64_t nb = min((int64_t)kSMs * 8, (n_item + 15) / 16);
+    const int64_t nb = min((int64_t)kSMs * 8, (n_item + 7) / 8);
     TAGREC_LAUNCH(item_maxnorm_kernel, (unsigned)nb, 256, 0, stream, reinterpret_cast<const float4*>(item_table), n_item,
-                  maxnorm);
+                  dim / 4, maxnorm);
     const dim3 grid((unsigned)((nu + TC_M * p.nh - 1) / (TC_M * p.nh)), (unsigned)p.splits);
-    if (p.nh == 2) {
+    if (p.kb > 1) {
+        TAGREC_CUDA(cudaFuncSetAttribute(eval_tc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        TAGREC_LAUNCH(eval_tc_wide_kernel, grid, 64 + 128, p.smem, stream, map, a, p.kb);
+    } else if (p.nh == 2) {
         TAGREC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
         TAGREC_LAUNCH(eval_tc_kernel<2>, grid, 64 + 256, p.smem, stream, map, a);
     } else {

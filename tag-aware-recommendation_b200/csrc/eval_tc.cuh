@@ -6,7 +6,7 @@ namespace tagrec {
 
 // Shape of a tensor-core launch: NH 128-user halves per CTA, item splits, B stages — derived from (nu, n_item, k).
 struct TcPlan {
-    int nh, splits, stages;
+    int nh, splits, stages, kb;      // kb = dim / 64 feature blocks (1: eval_tc_kernel, 2..4: eval_tc_wide_kernel)
     int64_t items_per_split;
     size_t smem;
     bool ok;

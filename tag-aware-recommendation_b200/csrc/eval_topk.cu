@@ -298,8 +298,10 @@ extern "C" size_t tagrec_eval_workspace_bytes(int64_t nu, int64_t n_item, int k)
     // large enough for either path (the tensor-core plan depends on dim only through dim == 64)
     const int s = pick_splits(nu, n_item);
     size_t need = (size_t)nu * s * k * 8 + 256;
-    const TcPlan p = tc_plan(nu, n_item, 64, k);
-    if (p.ok) need = std::max(need, eval_tc_workspace_bytes(nu, p, k));
+    for (int dim = 64; dim <= 256; dim += 192) {      // the split count differs between the 64-d and the wide kernel
+        const TcPlan p = tc_plan(nu, n_item, dim, k);
+        if (p.ok) need = std::max(need, eval_tc_workspace_bytes(nu, p, k));
+    }
     return need;
 }
 
@@ -324,7 +326,7 @@ extern "C" int tagrec_eval_topk_ex(const int64_t* users, int64_t nu, const float
         if (p.ok)
             return eval_topk_tc(users, nu, user_table, item_table, n_item, train_ptr, train_items, k, topk_ids,
                                 topk_scores, workspace, workspace_bytes, stream, p);
-        TAGREC_REQUIRE(path == TAGREC_EVAL_AUTO, "tensor-core path needs dim == 64 and k <= 128");
+        TAGREC_REQUIRE(path == TAGREC_EVAL_AUTO, "tensor-core path needs dim in {64, 128, 192, 256} and k <= 128");
     }
     TAGREC_REQUIRE(dim >= 4 && dim % KC == 0, "dim must be a multiple of 32");
     TAGREC_REQUIRE(n_item > 0 && n_item < (1ll << 31), "n_item out of range");

@@ -350,6 +350,30 @@ def test_k3_tensor_core_path_equals_fp32_path(nu, n_item, k, scale, heavy):
     assert torch.equal(sc_a, sc_b)
 
 
+@pytest.mark.parametrize("nu,n_item,dim,k", [(70, 3000, 256, 20), (200, 9000, 192, 10), (33, 700, 128, 100),
+                                             (300, 20000, 256, 20)])
+def test_k3_tensor_core_wide_tables_equal_fp32_path(nu, n_item, dim, k):
+    """eval_tc_wide_kernel (dim = 128 / 192 / 256: NGCF's and TGCN's concatenated tables) returns the same ids and
+    scores as the exact fp32 CUDA-core path, bit for bit."""
+    from tagrec_b200.eval_ops import topk_scores
+    g = torch.Generator().manual_seed(nu + dim)
+    n_tab = nu + 5
+    ut = torch.randn(n_tab, dim, generator=g) * 0.3
+    it = torch.randn(n_item, dim, generator=g) * 0.3
+    it[n_item // 2:n_item // 2 + 20] = it[:20]                       # exact ties
+    rng = np.random.RandomState(dim)
+    users = rng.permutation(n_tab)[:nu]
+    train = {u: sorted(rng.choice(n_item, rng.randint(0, 60), replace=False).tolist()) for u in range(n_tab)}
+    ptr_, items = T.bpr_training_data.user_items_to_csr(train, n_tab)
+    args = (torch.tensor(users, device=dev()), ut.to(dev()), it.to(dev()), torch.tensor(ptr_, device=dev()),
+            torch.tensor(items, device=dev()).int(), k)
+    ids_a, sc_a = topk_scores(*args, path="fp32")
+    ids_b, sc_b = topk_scores(*args, path="tf32")
+    torch.cuda.synchronize()
+    assert torch.equal(ids_a, ids_b)
+    assert torch.equal(sc_a, sc_b)
+
+
 def test_k3_tensor_core_ties_and_masked_tail():
     """Duplicate item rows (exact score ties -> lower id first) and a user with fewer than k un-masked items."""
     from tagrec_b200.eval_ops import topk_scores

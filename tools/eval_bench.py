@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--deg", type=int, default=100)
     ap.add_argument("--paths", default="tf32,fp32")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--dim", type=int, default=64)
     args = ap.parse_args()
     import __graft_entry__ as G
     G.build()
@@ -36,8 +37,8 @@ def main():
     g.manual_seed(0)
     U, I = args.users, args.items
     # LightGCN-like tables: mean of unit rows + small ego term => norms ~0.5-1
-    ut = torch.nn.functional.normalize(torch.randn(U, 64, device=dev, generator=g), dim=1) * 0.8
-    it = torch.nn.functional.normalize(torch.randn(I, 64, device=dev, generator=g), dim=1) * 0.8
+    ut = torch.nn.functional.normalize(torch.randn(U, args.dim, device=dev, generator=g), dim=1) * 0.8
+    it = torch.nn.functional.normalize(torch.randn(I, args.dim, device=dev, generator=g), dim=1) * 0.8
     deg = torch.full((U,), args.deg, dtype=torch.int64, device=dev)
     ptr = torch.zeros(U + 1, dtype=torch.int64, device=dev)
     ptr[1:] = torch.cumsum(deg, 0)
@@ -59,7 +60,7 @@ def main():
         ms = float(np.median(times))
         res[path] = ids
         print(json.dumps({"path": path, "users": U, "items": I, "k": args.k, "ms": ms, "users_per_s": U / ms * 1e3,
-                          "tflops": 2.0 * U * I * 64 / (ms * 1e-3) / 1e12, "launches": T.launch_count()}))
+                          "dim": args.dim, "tflops": 2.0 * U * I * args.dim / (ms * 1e-3) / 1e12, "launches": T.launch_count()}))
     if len(res) == 2:
         a, b = res.values()
         print(json.dumps({"paths_identical": bool(torch.equal(a, b))}))
