@@ -11,7 +11,6 @@ Documented deviations: (i) ties are ordered by item id (the reference's torch.to
 (ii) no crash when ``len(users) % test_batch == 0`` (the reference yields an empty batch and raises IndexError,
 training/utils.py:48-54).
 """
-import time
 from collections import defaultdict
 
 import numpy as np

@@ -15,7 +15,6 @@ of the gradient is computed by exactly one rank and broadcast, so the replicas s
 """
 import os
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -203,7 +202,6 @@ def shard_graph(full: CsrGraph, rank, world, group=None, calibrate=True, weights
 def rebalance_by_measurement(full, graph, rank, world, dim=64, n_layer=3):
     """One feedback step: time the REAL fused forward layer (mirrored epilogue stores included) on the current row
     blocks, scale each block's modelled cost by measured/mean, and cut again.  Collective."""
-    from .functional import lightgcn_forward_layers
     dev = full.device
     n = full.n
     comm = graph.comm
