@@ -196,9 +196,19 @@ def split_mm(norm_adj, all_embed):
 
 
 def node_drop(graph, keep_prob, training=False):
-    """adj.py:170-191.  Identity at the default p == 0 / eval; edge dropout with p > 0 is not implemented on the
-    CSR path (statistical parity only)."""
+    """adj.py:170-191 (the argument is the DROP probability p, as in the reference): every stored entry is kept with
+    probability 1 - p, independently, and the kept values are divided by 1 - p.  Identity at p == 0 or in eval.
+    The draw comes from torch's CUDA generator (the reference draws on the CPU), so parity with p > 0 is statistical
+    (SURVEY A19).  Entries are dropped independently of their mirror entry, so the result is not symmetric: the values
+    of its transpose (for the backward SpMM) go through the reverse-edge permutation."""
     assert 0 <= keep_prob < 1
     if keep_prob == 0 or not training:
         return graph
-    raise NotImplementedError("node_drop > 0 is not supported by the CSR path")
+    import copy
+    from .routing import reverse_perm
+    k = 1.0 - keep_prob
+    keep = (torch.rand(graph._nnz(), device=graph.device) >= keep_prob).to(torch.float32) / k
+    g = copy.copy(graph)
+    g.val = graph.val * keep
+    g.val_t = graph.val_t * keep[reverse_perm(graph).long()]
+    return g

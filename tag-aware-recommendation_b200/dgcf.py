@@ -64,7 +64,15 @@ class DGCF(nn.Module, EvalMixin):
 
     def forward(self, out_A=False):
         if out_A:
-            raise NotImplementedError("out_A=True (per-layer factor adjacencies, dgcf.py:62-63) is not exported")
+            # dgcf.py:57,62-63,81: per layer, per factor, the sparse adjacency carrying that factor's routing weights
+            # (softmax over the factors of the edge logits) of the layer's last iteration
+            from .routing import dgcf_propagate
+            with torch.no_grad():
+                ego = torch.cat([p.detach() for p in self.embed], dim=0)
+                _, _, _, weights = dgcf_propagate(self.norm_adj, self.num_layer, self.iterate_k, ego, True)
+            idx = self.norm_adj._indices()
+            return [[torch.sparse_coo_tensor(idx, w[:, i].contiguous(), self.norm_adj.shape) for i in range(self.factor_k)]
+                    for w in weights]
         return torch.split(self._final_table(), self.num_list, dim=0)
 
     def get_ego_embed(self):

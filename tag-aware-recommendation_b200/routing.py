@@ -103,6 +103,46 @@ def _check_table(t):
         "routing kernels need contiguous float32 CUDA tables of width 64 (4 factors x 16)"
 
 
+def dgcf_propagate(graph, n_layer, iterate_k, ego, collect_weights=False):
+    """The launch sequence of DGCF.forward (dgcf.py:49-110).  Returns (mean table, per-layer operator values of the
+    last routing iteration, per-layer un-normalised outputs, per-layer softmax weights if ``collect_weights``)."""
+    ego = ego.detach().contiguous()
+    _check_table(ego)
+    dev, n, nnz = ego.device, ego.shape[0], graph._nnz()
+    logits = torch.ones((nnz, FACTORS), dtype=torch.float32, device=dev)          # A_values, dgcf.py:50
+    w = torch.empty_like(logits)
+    dinv = torch.empty((n, FACTORS), dtype=torch.float32, device=dev)
+    mean = torch.empty_like(ego)
+    tn = torch.empty_like(ego)
+    fnorm = torch.empty_like(ego)
+    vals, raws, weights = [], [], []
+    x = ego
+    for layer in range(n_layer):
+        chunk_normalize(x, tanh=True, out=tn)                  # tanh(normalize(ego_split[tail])), dgcf.py:106-108
+        val = torch.empty_like(logits)
+        raw = torch.empty_like(ego)
+        nxt = torch.empty_like(ego)
+        for t in range(iterate_k):
+            edge_softmax_rowsum(graph, logits, w, dinv)
+            edge_scale(graph, w, dinv, val)
+            last_it = t == iterate_k - 1
+            if last_it:
+                spmm4(graph, val, x, y_raw=raw, y_norm=nxt, mean_acc=mean, mean_x0=ego, mean_first=layer == 0,
+                      mean_last=layer == n_layer - 1, mean_scale=1.0 / (n_layer + 1))
+                head = nxt          # normalize(factor_emb[head]) — the chunk-normalised layer output itself
+                if collect_weights:
+                    weights.append(w.clone())
+            else:
+                spmm4(graph, val, x, y_norm=fnorm)
+                head = fnorm
+            if not (last_it and layer == n_layer - 1):         # the very last score update is never read
+                edge_dot4(graph, head, tn, logits, softmax=False)
+        vals.append(val)
+        raws.append(raw)
+        x = nxt
+    return mean, vals, raws, weights
+
+
 class DgcfPropagateFn(torch.autograd.Function):
     """DGCF.forward (dgcf.py:49-65): L layers x iterate_k routing iterations over 4 intents, mean over layers.
     Returns the [N, 64] mean table.  Per (layer, iteration): R1 softmax+rowsum, R2 edge values, R3 SpMM over the four
@@ -111,38 +151,7 @@ class DgcfPropagateFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, graph, n_layer, iterate_k, ego):
-        ego = ego.detach().contiguous()
-        _check_table(ego)
-        dev, n, nnz = ego.device, ego.shape[0], graph._nnz()
-        logits = torch.ones((nnz, FACTORS), dtype=torch.float32, device=dev)          # A_values, dgcf.py:50
-        w = torch.empty_like(logits)
-        dinv = torch.empty((n, FACTORS), dtype=torch.float32, device=dev)
-        mean = torch.empty_like(ego)
-        tn = torch.empty_like(ego)
-        fnorm = torch.empty_like(ego)
-        vals, raws = [], []
-        x = ego
-        for layer in range(n_layer):
-            chunk_normalize(x, tanh=True, out=tn)                  # tanh(normalize(ego_split[tail])), dgcf.py:106-108
-            val = torch.empty_like(logits)
-            raw = torch.empty_like(ego)
-            nxt = torch.empty_like(ego)
-            for t in range(iterate_k):
-                edge_softmax_rowsum(graph, logits, w, dinv)
-                edge_scale(graph, w, dinv, val)
-                last_it = t == iterate_k - 1
-                if last_it:
-                    spmm4(graph, val, x, y_raw=raw, y_norm=nxt, mean_acc=mean, mean_x0=ego, mean_first=layer == 0,
-                          mean_last=layer == n_layer - 1, mean_scale=1.0 / (n_layer + 1))
-                    head = nxt          # normalize(factor_emb[head]) — the chunk-normalised layer output itself
-                else:
-                    spmm4(graph, val, x, y_norm=fnorm)
-                    head = fnorm
-                if not (last_it and layer == n_layer - 1):         # the very last score update is never read
-                    edge_dot4(graph, head, tn, logits, softmax=False)
-            vals.append(val)
-            raws.append(raw)
-            x = nxt
+        mean, vals, raws, _ = dgcf_propagate(graph, n_layer, iterate_k, ego)
         ctx.graph, ctx.n_layer = graph, n_layer
         ctx.vals, ctx.raws = vals, raws
         return mean

@@ -527,6 +527,11 @@ def test_dgcf_forward_loss_grad_vs_reference(tiny):
     with torch.no_grad():
         r = model.predict_rating(torch.tensor(tiny["dgcf_pred_users"], device=dev()))
     assert relerr(r.cpu().numpy(), tiny["dgcf_pred"]) < TOL
+    # forward(out_A=True): per layer, per factor sparse adjacencies whose values sum to 1 over the factors
+    out_a = model.forward(out_A=True)
+    assert len(out_a) == 3 and all(len(f) == 4 for f in out_a)
+    tot = sum(a._values() for a in out_a[0])
+    assert out_a[0][0].shape == model.norm_adj.shape and torch.allclose(tot, torch.ones_like(tot), atol=1e-6)
 
 
 def test_disengcn_forward_loss_grad_vs_reference(tiny):
@@ -862,6 +867,35 @@ def test_multi_gpu_sharded_step_matches_single():
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_edge_dropout_and_message_dropout_path(tiny):
+    """adj.py:170-191 node_drop on the CSR path: kept fraction ~ 1 - p, kept values scaled by 1/(1-p), val_t is the
+    exact transpose of the dropped matrix; a LightGCN step with node_drop + message dropout runs through the unfused
+    path (split_mm autograd on the dropped graph) and produces finite gradients; eval ignores dropout."""
+    import scipy.sparse as sp
+    U, I, _, _ = nums(tiny)
+    g = T.build_csr(U, I, blocks(tiny)[0], "bi_norm", dev())
+    torch.manual_seed(0)
+    gd = T.node_drop(g, 0.3, training=True)
+    assert T.node_drop(g, 0.3, training=False) is g and T.node_drop(g, 0.0, training=True) is g
+    kept = gd.val != 0
+    assert 0.55 < float(kept.float().mean()) < 0.85
+    assert torch.allclose(gd.val[kept], g.val[kept] / 0.7)
+    a = sp.csr_matrix((gd.val.cpu().numpy(), g.col.cpu().numpy(), g.rowptr.cpu().numpy()), shape=g.shape)
+    at = sp.csr_matrix((gd.val_t.cpu().numpy(), g.col.cpu().numpy(), g.rowptr.cpu().numpy()), shape=g.shape)
+    assert abs(a.T - at).max() == 0
+    T.set_config("lightgcn", use_tag=False, reg=1e-3, dim_layer_list=[64, 64, 64], device=dev(), node_drop=0.2,
+                 message_drop_list=[0.1, 0.1, 0.1])
+    model = T.LightGCN(make_data(tiny)).to(dev())
+    model.train()
+    lossx = model.loss(torch.tensor(tiny["lgcn_batch"], device=dev()))
+    sum(lossx).backward()
+    assert all(torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0 for p in model.embed)
+    model.eval()
+    with torch.no_grad():
+        a1, a2 = model.forward()[0].clone(), model.forward()[0].clone()
+    assert torch.equal(a1, a2)
 
 
 # ------------------------------------------------------------------------------------------------ CUDA-graph step
