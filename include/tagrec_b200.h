@@ -79,8 +79,8 @@ int tagrec_csr_normalise(const int64_t* rowptr, const int32_t* col, const float*
  * long_rows[n_long] = row ids; item_slot/item_begin/item_end[n_items] = chunk -> (slot in long_rows, nnz range).
  * All five may be NULL when n_long == 0.
  * ---------------------------------------------------------------------------------------------------------- */
-#define TAGREC_LONG_ROW 4096
-#define TAGREC_LONG_CHUNK 2048
+#define TAGREC_LONG_ROW 4096      /* defaults, tuned on the 1.9e9-nnz graph; small graphs (everything L2-resident, a few */
+#define TAGREC_LONG_CHUNK 2048    /* waves of rows) balance better with 256 / 256 — the caller's plan decides */
 
 typedef struct {
     const int64_t* rowptr;      /* n_rows + 1 entries, local (rowptr[0] == 0 for a row block) */
@@ -97,6 +97,8 @@ typedef struct {
     int64_t n_items;
     float* long_scratch;
     int32_t* long_counter;
+    int32_t long_row;           /* rows with more entries than this are "long"; 0 = TAGREC_LONG_ROW */
+    int32_t long_chunk;         /* entries per chunk of a long row;             0 = TAGREC_LONG_CHUNK */
 } tagrec_csr_t;
 
 /* Fused compute + collective (multi-GPU, no reference equivalent — the reference is single-device): where an
@@ -209,8 +211,10 @@ int tagrec_eval_metrics(const int64_t* users, int64_t nu, const int32_t* topk_id
  *   fwd: out = lrelu((nei+e)(w1+b1)) + lrelu((nei*e)(w2+b2)); nrm = out / max(||out||, 1e-12);
  *        s_act / t_act = the two activations (saved for backward).
  *   bwd: g = g_out (may be NULL) + J_normalize(out)^T g_nrm (rows g_nrm_ld floats apart: a column slice of the
- *        concatenated gradient); gs = g*lrelu'(s), gt = g*lrelu'(t) (outputs: the caller forms dW = x^T gs with a
- *        library GEMM); g_nei = gs(w1+b1)^T + (gt(w2+b2)^T)*e;  g_e = gs(w1+b1)^T + (gt(w2+b2)^T)*nei.
+ *        concatenated gradient); gs = g*lrelu'(s), gt = g*lrelu'(t) (optional outputs, may be NULL);
+ *        g_nei = gs(w1+b1)^T + (gt(w2+b2)^T)*e;  g_e = gs(w1+b1)^T + (gt(w2+b2)^T)*nei;
+ *        dw1 += (nei+e)^T gs, dw2 += (nei*e)^T gt  ([64, 64] each = the gradient of W and, summed over rows, of the
+ *        bias that ngcf.py:78,82 adds to the WEIGHT; caller zeroes them; both NULL to skip).
  * ---------------------------------------------------------------------------------------------------------- */
 int tagrec_ngcf_dense_fwd(const float* nei, const float* e, const float* w1, const float* b1, const float* w2,
                           const float* b2, int64_t n, int dim, float* out, float* nrm, float* s_act, float* t_act,
@@ -218,7 +222,7 @@ int tagrec_ngcf_dense_fwd(const float* nei, const float* e, const float* w1, con
 int tagrec_ngcf_dense_bwd(const float* g_out, const float* g_nrm, int64_t g_nrm_ld, const float* out,
                           const float* s_act, const float* t_act, const float* nei, const float* e, const float* w1,
                           const float* b1, const float* w2, const float* b2, int64_t n, int dim, float* g_nei,
-                          float* g_e, float* gs, float* gt, void* stream);
+                          float* g_e, float* gs, float* gt, float* dw1, float* dw2, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K5  disentangled routing (DGCF / DisenGCN)     replaces model/dgcf.py:68-110 (iterate_update, factor_update) and

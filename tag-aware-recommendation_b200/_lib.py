@@ -9,8 +9,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TAGREC_LIB") or os.path.join(_HERE, "libtagrec_b200.so")   # TAGREC_LIB: tuning builds
 
-LONG_ROW = 4096       # TAGREC_LONG_ROW
+LONG_ROW = 4096       # TAGREC_LONG_ROW   (defaults of the long-row plan, tuned on the 1.9e9-nnz graph)
 LONG_CHUNK = 2048     # TAGREC_LONG_CHUNK
+SMALL_GRAPH_NNZ = 1 << 25     # below this many entries a graph is a few waves of rows: plan with 256 / 256 instead
+SMALL_LONG_ROW = 256
+SMALL_LONG_CHUNK = 256
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -25,7 +28,7 @@ class CsrDesc(C.Structure):
     """tagrec_csr_t"""
     _fields_ = [("rowptr", _p), ("col", _p), ("val", _p), ("n_rows", _i64), ("row_offset", _i64), ("long_rows", _p), ("item_slot", _p),
                 ("item_begin", _p), ("item_end", _p), ("n_long", _i64), ("n_items", _i64), ("long_scratch", _p),
-                ("long_counter", _p)]
+                ("long_counter", _p), ("long_row", C.c_int32), ("long_chunk", C.c_int32)]
 
 
 class RoutePlan(C.Structure):
@@ -66,7 +69,8 @@ PROTOTYPES = {
     "tagrec_eval_auc": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _sz, _p, _p]),
     "tagrec_eval_metrics": (_i32, [_p, _i64, _p, _i32, _p, _p, _p, _i32, _p, _p]),
     "tagrec_ngcf_dense_fwd": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
-    "tagrec_ngcf_dense_bwd": (_i32, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
+    "tagrec_ngcf_dense_bwd": (_i32, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p,
+                                     _p]),
     "tagrec_edge_softmax_rowsum": (_i32, [_p, _i64, _i64, _p, _p, _p, _p]),
     "tagrec_edge_scale": (_i32, [_p, _p, _i64, _p, _p, _p, _p]),
     "tagrec_spmm4": (_i32, [_p, _p, _i64, C.POINTER(RoutePlan), _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f32, _p]),

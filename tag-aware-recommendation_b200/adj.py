@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import CsrDesc, LONG_CHUNK, LONG_ROW, check, lib, ptr, stream_ptr
+from ._lib import CsrDesc, check, lib, ptr, stream_ptr
 
 _NORM = {"bi_norm": (0, 0, -0.5), "si_norm": (1, 0, -1), "si_norm_self": (1, 1, -1), "ngcf": (1, 2, -1)}
 
@@ -49,7 +49,13 @@ class CsrGraph:
         return self.val
 
     def _build_plan(self):
-        """Rows above TAGREC_LONG_ROW nnz are cut into TAGREC_LONG_CHUNK pieces (see csrc/spmm.cu)."""
+        """Rows above ``long_row`` nnz are cut into ``long_chunk`` pieces (see csrc/spmm.cu).  The thresholds are the
+        tuned 4096 / 2048 on big graphs; a small graph is only a few waves of rows, where one sub-warp walking a
+        2000-entry hub row IS the launch time, so it is planned with 256 / 256."""
+        small = self._nnz() < _lib.SMALL_GRAPH_NNZ
+        self.long_row = _lib.SMALL_LONG_ROW if small else _lib.LONG_ROW
+        self.long_chunk = _lib.SMALL_LONG_CHUNK if small else _lib.LONG_CHUNK
+        LONG_ROW, LONG_CHUNK = self.long_row, self.long_chunk
         dev = self.device
         deg = self.rowptr[1:] - self.rowptr[:-1]
         long_rows = torch.nonzero(deg > LONG_ROW).flatten()
@@ -79,6 +85,7 @@ class CsrGraph:
         d.n_rows = self.n_rows
         d.row_offset = self.row_offset
         d.n_long, d.n_items = self.n_long, self.n_items
+        d.long_row, d.long_chunk = self.long_row, self.long_chunk
         if self.n_long:
             if dim not in self._scratch:
                 self._scratch[dim] = (torch.zeros(self.n_long, dim, dtype=torch.float32, device=self.device),

@@ -9,7 +9,9 @@
 //             nrm = out / max(||out||_2, 1e-12)                      writes out, nrm, s, t   (s, t: saved activations)
 //   backward  g  = g_out + J_normalize(out)^T g_nrm;  gs = g * lrelu'(s), gt = g * lrelu'(t)
 //             gx1 = gs (W1+b1)^T, gx2 = gt (W2+b2)^T;  g_nei = gx1 + gx2 * e;  g_e = gx1 + gx2 * nei
-//             writes g_nei, g_e, gs, gt  (dW = x^T gs is a plain [64 x N] x [N x 64] GEMM left to cuBLAS)
+//             d(W1+b1) = (nei+e)^T gs, d(W2+b2) = (nei*e)^T gt   (outer products over the tile's rows, accumulated in
+//             registers over all tiles of a block, one atomicAdd per element and block at the end)
+//             writes g_nei, g_e, dW1, dW2 (+ gs, gt on request)
 //
 // Mapping: a block owns 64-row tiles; the two 64x64 weight matrices live in smem for the whole kernel; a thread
 // owns a 4x4 micro-tile of the 64x64 output tile and walks the contraction index in float4 steps (sequential fp32
@@ -116,31 +118,38 @@ ngcf_dense_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__
                       const float* __restrict__ nei, const float* __restrict__ e, const float* __restrict__ W1,
                       const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
                       int64_t n, float* __restrict__ g_nei, float* __restrict__ g_e, float* __restrict__ gs_out,
-                      float* __restrict__ gt_out) {
+                      float* __restrict__ gt_out, float* __restrict__ dw1, float* __restrict__ dw2) {
     extern __shared__ __align__(16) float sm[];
     float* W1t = sm;                 // [64][NLD]  (W1 + b1)^T : W1t[j][i]
     float* W2t = W1t + ND * NLD;
     float* Gs = W2t + ND * NLD;      // [64][NLD]  gs tile
     float* Gt = Gs + NR * NLD;
+    float* Ns = Gt + NR * NLD;       // [64][NLD]  nei tile
+    float* Es = Ns + NR * NLD;       // [64][NLD]  e tile
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     for (int idx = tid; idx < ND * ND; idx += 256) {
         const int i = idx >> 6, j = idx & 63;
         W1t[j * NLD + i] = __ldg(W1 + idx) + __ldg(b1 + j);
         W2t[j * NLD + i] = __ldg(W2 + idx) + __ldg(b2 + j);
     }
+    // weight gradients of this block: dW1[i][j] = sum_r (nei+e)[r][i] gs[r][j], dW2 likewise with nei*e and gt;
+    // thread (ty, tx) owns rows 4ty..4ty+3, columns 4tx..4tx+3, accumulated over all tiles of the block
+    float a1[4][4] = {}, a2[4][4] = {};
     const int64_t tiles = (n + NR - 1) / NR;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t r0 = tile * NR;
         __syncthreads();
-        // ---- g = g_out + J^T g_nrm ; gs, gt -> smem + global (16 lanes per row, 4 rows per pass) ----
+        // ---- g = g_out + J^T g_nrm ; gs, gt, nei, e -> smem (16 lanes per row, 4 rows per pass) ----
         for (int rr = ty; rr < NR; rr += 16) {
             const int64_t row = r0 + rr;
-            float4 gs4 = make_float4(0.f, 0.f, 0.f, 0.f), gt4 = gs4;
+            float4 gs4 = make_float4(0.f, 0.f, 0.f, 0.f), gt4 = gs4, n4 = gs4, e4 = gs4;
             if (row < n) {          // uniform per half-warp (16 lanes share rr)
                 const int64_t off = row * (ND / 4) + tx;
                 const float4 o = __ldg(reinterpret_cast<const float4*>(out) + off);
                 const float4 gn = __ldg(reinterpret_cast<const float4*>(g_nrm + row * g_nrm_ld) + tx);
                 float4 g = g_out ? __ldg(reinterpret_cast<const float4*>(g_out) + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                n4 = __ldg(reinterpret_cast<const float4*>(nei) + off);
+                e4 = __ldg(reinterpret_cast<const float4*>(e) + off);
                 const unsigned hm = 0xffffu << (16 * ((tid >> 4) & 1));
                 const float ss = half_sum(dot4(o, o), hm);
                 const float dt = half_sum(dot4(o, gn), hm);
@@ -160,11 +169,13 @@ ngcf_dense_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__
                                   sa.z > 0.f ? g.z : 0.2f * g.z, sa.w > 0.f ? g.w : 0.2f * g.w);
                 gt4 = make_float4(ta.x > 0.f ? g.x : 0.2f * g.x, ta.y > 0.f ? g.y : 0.2f * g.y,
                                   ta.z > 0.f ? g.z : 0.2f * g.z, ta.w > 0.f ? g.w : 0.2f * g.w);
-                reinterpret_cast<float4*>(gs_out)[off] = gs4;
-                reinterpret_cast<float4*>(gt_out)[off] = gt4;
+                if (gs_out) reinterpret_cast<float4*>(gs_out)[off] = gs4;
+                if (gt_out) reinterpret_cast<float4*>(gt_out)[off] = gt4;
             }
             *reinterpret_cast<float4*>(Gs + rr * NLD + 4 * tx) = gs4;
             *reinterpret_cast<float4*>(Gt + rr * NLD + 4 * tx) = gt4;
+            *reinterpret_cast<float4*>(Ns + rr * NLD + 4 * tx) = n4;
+            *reinterpret_cast<float4*>(Es + rr * NLD + 4 * tx) = e4;
         }
         __syncthreads();
         float gx1[4][4] = {}, gx2[4][4] = {};
@@ -172,11 +183,12 @@ ngcf_dense_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__
         tile_mm(Gt, W2t, ty, tx, gx2);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const int64_t row = r0 + ty * 4 + r;
+            const int rr = ty * 4 + r;
+            const int64_t row = r0 + rr;
             if (row < n) {
                 const int64_t off = row * (ND / 4) + tx;
-                const float4 a = __ldg(reinterpret_cast<const float4*>(nei) + off);
-                const float4 b = __ldg(reinterpret_cast<const float4*>(e) + off);
+                const float4 a = *reinterpret_cast<const float4*>(Ns + rr * NLD + 4 * tx);
+                const float4 b = *reinterpret_cast<const float4*>(Es + rr * NLD + 4 * tx);
                 reinterpret_cast<float4*>(g_nei)[off] =
                     make_float4(fmaf(gx2[r][0], b.x, gx1[r][0]), fmaf(gx2[r][1], b.y, gx1[r][1]),
                                 fmaf(gx2[r][2], b.z, gx1[r][2]), fmaf(gx2[r][3], b.w, gx1[r][3]));
@@ -185,10 +197,40 @@ ngcf_dense_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__
                                 fmaf(gx2[r][2], a.z, gx1[r][2]), fmaf(gx2[r][3], a.w, gx1[r][3]));
             }
         }
+        if (dw1) {      // outer products over the tile's rows (rows past n hold zeros)
+#pragma unroll 4
+            for (int r = 0; r < NR; ++r) {
+                const float4 nn4 = *reinterpret_cast<const float4*>(Ns + r * NLD + 4 * ty);
+                const float4 ee4 = *reinterpret_cast<const float4*>(Es + r * NLD + 4 * ty);
+                const float4 gs4 = *reinterpret_cast<const float4*>(Gs + r * NLD + 4 * tx);
+                const float4 gt4 = *reinterpret_cast<const float4*>(Gt + r * NLD + 4 * tx);
+                const float x1[4] = {nn4.x + ee4.x, nn4.y + ee4.y, nn4.z + ee4.z, nn4.w + ee4.w};
+                const float x2[4] = {nn4.x * ee4.x, nn4.y * ee4.y, nn4.z * ee4.z, nn4.w * ee4.w};
+                const float gsv[4] = {gs4.x, gs4.y, gs4.z, gs4.w};
+                const float gtv[4] = {gt4.x, gt4.y, gt4.z, gt4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        a1[i][j] = fmaf(x1[i], gsv[j], a1[i][j]);
+                        a2[i][j] = fmaf(x2[i], gtv[j], a2[i][j]);
+                    }
+            }
+        }
+    }
+    if (dw1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(dw1 + (ty * 4 + i) * ND + tx * 4 + j, a1[i][j]);
+                atomicAdd(dw2 + (ty * 4 + i) * ND + tx * 4 + j, a2[i][j]);
+            }
     }
 }
 
 constexpr size_t kNgcfSmem = (size_t)(2 * ND + 2 * NR) * NLD * sizeof(float);
+constexpr size_t kNgcfSmemBwd = (size_t)(2 * ND + 4 * NR) * NLD * sizeof(float);
 
 }  // namespace tagrec
 
@@ -210,17 +252,19 @@ extern "C" int tagrec_ngcf_dense_fwd(const float* nei, const float* e, const flo
 extern "C" int tagrec_ngcf_dense_bwd(const float* g_out, const float* g_nrm, int64_t g_nrm_ld, const float* out,
                                      const float* s_act, const float* t_act, const float* nei, const float* e,
                                      const float* w1, const float* b1, const float* w2, const float* b2, int64_t n,
-                                     int dim, float* g_nei, float* g_e, float* gs, float* gt, void* stream) {
-    TAGREC_REQUIRE(g_nrm && out && s_act && t_act && nei && e && w1 && b1 && w2 && b2 && g_nei && g_e && gs && gt,
-                   "null pointer");
+                                     int dim, float* g_nei, float* g_e, float* gs, float* gt, float* dw1, float* dw2,
+                                     void* stream) {
+    TAGREC_REQUIRE(g_nrm && out && s_act && t_act && nei && e && w1 && b1 && w2 && b2 && g_nei && g_e, "null pointer");
+    TAGREC_REQUIRE((dw1 == nullptr) == (dw2 == nullptr), "dw1 and dw2 go together");
     TAGREC_REQUIRE(dim == ND, "the fused NGCF layer is built for 64 -> 64 layers");
     TAGREC_REQUIRE(g_nrm_ld >= ND && g_nrm_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(g_nrm) & 15) == 0,
                    "g_nrm rows must be 16-byte aligned");
     if (n == 0) return TAGREC_OK;
-    TAGREC_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNgcfSmem));
+    TAGREC_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kNgcfSmemBwd));
     const int64_t tiles = (n + NR - 1) / NR;
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * kSMs);
-    TAGREC_LAUNCH(ngcf_dense_bwd_kernel, grid, 256, kNgcfSmem, stream, g_out, g_nrm, g_nrm_ld, out, s_act, t_act, nei, e,
-                  w1, b1, w2, b2, n, g_nei, g_e, gs, gt);
+    TAGREC_LAUNCH(ngcf_dense_bwd_kernel, grid, 256, kNgcfSmemBwd, stream, g_out, g_nrm, g_nrm_ld, out, s_act, t_act, nei,
+                  e, w1, b1, w2, b2, n, g_nei, g_e, gs, gt, dw1, dw2);
     return TAGREC_OK;
 }

@@ -244,7 +244,7 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
         __syncwarp();
         const int64_t r = __ldg(a.long_rows + slot);
         const int64_t deg = __ldg(a.rowptr + r + 1) - __ldg(a.rowptr + r);
-        const int nchunks = (int)((deg + TAGREC_LONG_CHUNK - 1) / TAGREC_LONG_CHUNK);
+        const int nchunks = (int)((deg + a.long_chunk - 1) / a.long_chunk);
         int ticket = 0;
         if (lane == 0) ticket = atomicAdd(a.long_counter + slot, 1);
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
@@ -269,7 +269,7 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
         s = __ldg(a.rowptr + r);
         e = __ldg(a.rowptr + r + 1);
     }
-    const bool is_long = gather && (e - s) > TAGREC_LONG_ROW;
+    const bool is_long = gather && (e - s) > a.long_row;
     if (is_long || !gather) e = s;  // long rows are produced by the chunk blocks above
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -319,6 +319,8 @@ static int launch(const tagrec_csr_t* a, const float* x, const Epi& ep, int dim,
     TAGREC_REQUIRE(grid < (1ll << 31), "grid too large");
     tagrec_csr_t d = *a;
     d.n_items = n_items;
+    if (d.long_row <= 0) d.long_row = TAGREC_LONG_ROW;
+    if (d.long_chunk <= 0) d.long_chunk = TAGREC_LONG_CHUNK;
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const dim3 block(kWarpsPerBlock * 32);
     if (lpr == 16 && ep.src_nz && gather && (EPI == EPI_BWD || EPI == EPI_BWD0)) {

@@ -313,7 +313,7 @@ class BprLossFn(torch.autograd.Function):
 
 class NgcfDenseFn(torch.autograd.Function):
     """K6: the dense half of one NGCF layer (ngcf.py:77-86) as one autograd node — one fused forward launch, one
-    fused backward launch + the two weight-gradient GEMMs (x^T g, plain cuBLAS through torch)."""
+    fused backward launch (input gradients AND the two 64x64 weight gradients)."""
 
     @staticmethod
     def forward(ctx, nei, e, w1, b1, w2, b2):
@@ -339,11 +339,11 @@ class NgcfDenseFn(torch.autograd.Function):
         if g_out is not None:
             g_out = g_out.contiguous()
         g_nei, g_e = torch.empty_like(e), torch.empty_like(e)
-        gs, gt = torch.empty_like(e), torch.empty_like(e)
+        dw = torch.zeros((2, dim, dim), dtype=torch.float32, device=e.device)       # d(W1 + b1), d(W2 + b2)
         check(lib().tagrec_ngcf_dense_bwd(ptr(g_out), ptr(g_nrm), g_nrm.stride(0), ptr(out), ptr(s_act), ptr(t_act),
                                           ptr(nei), ptr(e), ptr(w1), ptr(b1), ptr(w2), ptr(b2), n, dim, ptr(g_nei),
-                                          ptr(g_e), ptr(gs), ptr(gt), stream_ptr(e.device)), "tagrec_ngcf_dense_bwd")
-        gw1 = torch.mm((nei + e).t(), gs)          # d/d(W1 + b1)
-        gw2 = torch.mm((nei * e).t(), gt)
+                                          ptr(g_e), None, None, ptr(dw[0]), ptr(dw[1]), stream_ptr(e.device)),
+              "tagrec_ngcf_dense_bwd")
         # the bias is broadcast over the ROWS of W (ngcf.py:78): its gradient is the column sum of dW
-        return g_nei, g_e, gw1, gw1.sum(0, keepdim=True), gw2, gw2.sum(0, keepdim=True)
+        gb = dw.sum(1, keepdim=True)
+        return g_nei, g_e, dw[0], gb[0], dw[1], gb[1]

@@ -3,8 +3,8 @@ predict_rating / get_ego_emb), on the kernels of libtagrec_b200.so.
 
 Per layer (ngcf.py:73-90):  nei = A E   -> K1 ``tagrec_spmm`` (backward: the same kernel on the values of A^T);
 the two 64x64 products with the bias added to the WEIGHT matrix (ngcf.py:78,82), LeakyReLU(0.2), the row
-normalisation and the concat -> K6 ``tagrec_ngcf_dense_fwd`` / ``tagrec_ngcf_dense_bwd`` (one fused pass each; the
-weight-gradient contraction X^T dZ over the N rows is the only library call, a plain cuBLAS GEMM through torch).
+normalisation and the concat -> K6 ``tagrec_ngcf_dense_fwd`` / ``tagrec_ngcf_dense_bwd`` (one fused pass each, weight
+gradients included: no library GEMM on the 64-d path).
 Loss (ngcf.py:95-105): K2 on the 256-d propagated rows, logsigmoid form, L2 term on the PROPAGATED rows.
 Evaluation: K3 (fp32 CUDA-core tiles for the 256-d concat table).
 """

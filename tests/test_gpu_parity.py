@@ -1031,7 +1031,7 @@ def test_large_k0_structure_properties(big_graph):
     deg = (rp[1:] - rp[:-1]).double()
     want = 1.0 / torch.sqrt(deg[rid] * deg[g.col.long()])
     assert float(((g.val.double() - want).abs() / want).max()) < 5e-7
-    assert g.n_long == int((deg > T._lib.LONG_ROW).sum())
+    assert g.long_row == T._lib.LONG_ROW and g.n_long == int((deg > g.long_row).sum())
 
 
 def test_large_k1_linearity_and_adjointness(big_graph):
