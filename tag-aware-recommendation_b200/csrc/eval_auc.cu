@@ -17,10 +17,15 @@
 //
 //   A1 auc_pos_kernel       positives' scores per user (train members -> +inf = "not a positive"), rank-sorted
 //   A2 auc_all_kernel       64-user x 128-item fp32 tiles (same tiling as eval_topk_kernel); per score one or two
-//                           register compares against the row's [min, max] positive, else a binary search in the
-//                           row's sorted positives (L1-resident)
+//                           register compares against the row's [min, max] positive, else a branch-free bisection
+//                           over the row's sorted positives staged in shared memory (rows with more than 32
+//                           positives search their global copy).  The search, not the scoring, bounds this pass when
+//                           positives are spread over the whole score range (a 128 x 128 / 8 x 8 variant of the tile
+//                           measured SLOWER for that reason: fewer warps to hide the search latency).
 //   A3 auc_finalize_kernel  subtract train / positive contributions, divide, accumulate sum and user count
 #include <float.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -29,6 +34,7 @@ namespace tagrec {
 constexpr int AUT = 64;       // users per block
 constexpr int AIT = 128;      // items per tile
 constexpr int AKC = 32;       // feature chunk
+constexpr int APC = 32;       // positives per row staged in shared memory
 
 __device__ __forceinline__ float dot_seq(const float* __restrict__ a, const float* __restrict__ b, int dim) {
     float acc = 0.f;
@@ -122,7 +128,8 @@ __global__ void __launch_bounds__(256) auc_all_kernel(AucArgs a) {
     const int D = a.dim;
     float* Us = reinterpret_cast<float*>(smem_raw);              // [D][AUT+4] user tile, feature-major
     float* Is = Us + (size_t)D * (AUT + 4);                       // [AKC][AIT+4] item chunk
-    int64_t* uid = reinterpret_cast<int64_t*>(Is + (size_t)AKC * (AIT + 4));   // [AUT]
+    float* Ps = Is + (size_t)AKC * (AIT + 4);                     // [AUT][APC]   sorted positives (+inf padded)
+    int64_t* uid = reinterpret_cast<int64_t*>(Ps + (size_t)AUT * APC);         // [AUT]
     const int tid = threadIdx.x;
     const int tu = tid >> 4, ti = tid & 15;
     const int64_t u0 = (int64_t)blockIdx.x * AUT;
@@ -130,6 +137,12 @@ __global__ void __launch_bounds__(256) auc_all_kernel(AucArgs a) {
     const int64_t i_end = min(a.n_item, i_begin + a.items_per_split);
     if (tid < AUT) uid[tid] = (u0 + tid < a.nu) ? a.users[u0 + tid] : -1;
     __syncthreads();
+    for (int idx = tid; idx < AUT * APC; idx += 256) {
+        const int u = idx / APC, j = idx % APC;
+        float v = INFINITY;
+        if (uid[u] >= 0 && j < a.n_pos[u0 + u]) v = __ldg(a.pos_sorted + a.test_ptr[uid[u]] + j);
+        Ps[idx] = v;
+    }
     for (int idx = tid; idx < AUT * (D / 4); idx += 256) {
         const int u = idx / (D / 4), c4 = idx % (D / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -201,7 +214,19 @@ __global__ void __launch_bounds__(256) auc_all_kernel(AucArgs a) {
                 const float s = acc[r][c];
                 if (s < pmin[r]) tot[r] += 2ull * (unsigned long long)pm[r];      // below every positive
                 else if (s > pmax[r]) {}                                         // above every positive
-                else tot[r] += twice_f(pp[r], pm[r], s);
+                else if (pm[r] <= APC) {
+                    // branch-free bisection in shared memory: lb = #{p < s}, then the (rare) run of equal positives
+                    const float* ps = Ps + (size_t)(4 * tu + r) * APC;
+                    int lb = 0;
+#pragma unroll
+                    for (int st = APC / 2; st > 0; st >>= 1) lb += (ps[lb + st - 1] < s) ? st : 0;
+                    lb += (ps[lb] < s) ? 1 : 0;
+                    int eq = 0;
+                    while (lb + eq < pm[r] && ps[lb + eq] == s) ++eq;
+                    tot[r] += 2ull * (unsigned long long)(pm[r] - lb - eq) + (unsigned long long)eq;
+                } else {
+                    tot[r] += twice_f(pp[r], pm[r], s);
+                }
             }
         }
     }
@@ -286,7 +311,7 @@ extern "C" int tagrec_eval_auc(const int64_t* users, int64_t nu, const float* us
     const int splits = auc_splits(nu, n_item);
     const int64_t tiles = (n_item + AIT - 1) / AIT;
     a.items_per_split = ((tiles + splits - 1) / splits) * AIT;
-    const size_t smem = ((size_t)dim * (AUT + 4) + (size_t)AKC * (AIT + 4)) * 4 + AUT * 8;
+    const size_t smem = ((size_t)dim * (AUT + 4) + (size_t)AKC * (AIT + 4) + (size_t)AUT * APC) * 4 + AUT * 8;
     TAGREC_REQUIRE(smem <= 227 * 1024, "dim too large for shared memory");
     TAGREC_CUDA(cudaFuncSetAttribute(auc_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const dim3 grid((unsigned)((nu + AUT - 1) / AUT), (unsigned)splits);

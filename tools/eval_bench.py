@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--paths", default="tf32,fp32")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--dim", type=int, default=64)
+    ap.add_argument("--auc", action="store_true", help="also time the per-user AUC pass (K3b)")
     args = ap.parse_args()
     import __graft_entry__ as G
     G.build()
@@ -64,6 +65,25 @@ def main():
     if len(res) == 2:
         a, b = res.values()
         print(json.dumps({"paths_identical": bool(torch.equal(a, b))}))
+    if args.auc:
+        from tagrec_b200.eval_ops import auc_sums
+        n_test = 25
+        tptr = torch.arange(0, (U + 1) * n_test, n_test, device=dev, dtype=torch.int64)
+        titems = torch.randint(0, I, (U, n_test), device=dev, generator=g).sort(dim=1).values.to(torch.int32).flatten()
+        for _ in range(2):
+            out = auc_sums(users, ut, it, ptr, items, tptr, titems)
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(args.reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = auc_sums(users, ut, it, ptr, items, tptr, titems)
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        ms = float(np.median(times))
+        print(json.dumps({"path": "auc_fp32", "users": U, "items": I, "dim": args.dim, "ms": ms, "users_per_s": U / ms * 1e3,
+                          "tflops": 2.0 * U * I * args.dim / (ms * 1e-3) / 1e12, "mean_auc": float(out[0] / out[1])}))
 
 
 if __name__ == "__main__":
