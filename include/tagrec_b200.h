@@ -294,6 +294,26 @@ int tagrec_nbr_attention_bwd(const float* g_out, const float* att, const float* 
                              float* g_ej, float* g_v, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * K7  TGCN dense tail              replaces model/tgcn.py:86-106 (BasicLayer._conv bit-level branch + _fusion) and
+ *                                  their autograd: the [N, 2096] feature matrix is generated and consumed on chip.
+ *   z  [n, 3, 64]   output of the type-level attention (tgcn.py:78-84)
+ *   wb [C, 3]       conv.bit_level.weight[:, 0, :, 0]   (C = num_bit_conv)
+ *   xf [n, E]       rectified vector-level features, cat of conv_1..3 channel-major (tgcn.py:92-98), E = 6*num_vec_conv
+ *   wf [C*64+E, 64] fusion weight, bf [64] fusion bias
+ *   fwd: out[n,64] = relu([relu(bit_conv(z)) | xf] wf + bf)
+ *   bwd: g_z [n,3,64], g_xf [n,E] written; g_wb [C,3], g_wf, g_bf [64] OVERWRITTEN (zeroed inside, then reduced).
+ *        workspace: tagrec_tgcn_tail_workspace_bytes(n, C) device bytes.
+ * dim must be 64; E a multiple of 4, <= 64.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t tagrec_tgcn_tail_workspace_bytes(int64_t n, int n_bit_conv);
+int tagrec_tgcn_tail_fwd(const float* z, const float* wb, const float* xf, const float* wf, const float* bf, int64_t n,
+                         int dim, int n_bit_conv, int n_extra, float* out, void* stream);
+int tagrec_tgcn_tail_bwd(const float* g_out, const float* out, const float* z, const float* wb, const float* xf,
+                         const float* wf, int64_t n, int dim, int n_bit_conv, int n_extra, void* workspace,
+                         size_t workspace_bytes, float* g_z, float* g_wb, float* g_xf, float* g_wf, float* g_bf,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * BPR negative sampler          replaces train_data/bpr_training_data.py:29-45 + train_data/utils.py:19-28,52-55.
  * Host version: bit-exact numpy-legacy MT19937 stream for cpu_core == 1 (parity mode).  All pointers HOST.
  *   state: 625 uint32 (624 words + position), advanced exactly as the parent's RandomState is (shuffle only).

@@ -25,25 +25,13 @@
 // row keeps the next masked item id in a register (items are visited in ascending id order).  Masked items are never
 // candidates; if a user has fewer than K un-masked items the merge kernel appends the first masked ids with score
 // -1024, which is exactly the (-score, id) order the reference's -1024 fill produces (basic_test.py:47).
-#include <cuda.h>
-#include <float.h>
-
 #include <algorithm>
 
-#include "common.cuh"
 #include "eval_tc.cuh"
+#include "tc_ptx.cuh"
 
 namespace tagrec {
 
-constexpr int TC_M = 128;                 // user rows per accumulator half (UMMA M)
-constexpr int TC_N = 128;                 // items per tile (UMMA N)
-constexpr int TC_D = 64;                  // feature dim == GEMM K
-constexpr int TC_UPITCH = TC_D + 4;       // floats per user row in the plain smem copy (spreads rows over banks)
-constexpr int TC_KH_BYTES = TC_N * 128;   // one 128B-swizzled k-half of a tile: 128 rows x 32 floats = 16 KB
-constexpr int TC_TILE_BYTES = 2 * TC_KH_BYTES;   // 32 KB (A half or B stage)
-constexpr int TC_MAX_STAGES = 6;
-constexpr int TC_MAX_SPLITS = 32;
-constexpr float TC_MARGIN = 2.2e-3f;
 
 struct TcArgs {
     const int64_t* users;
@@ -64,93 +52,6 @@ struct TcArgs {
     int32_t* part_ids;           // [nu, splits, k]  -1 when absent
 };
 
-// ---------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) {
-            printf("tagrec eval_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y,
-                   threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);     // start address            bits [0,14)
-    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset = 1024  bits [32,46)
-    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
-    return d;
-}
-// Instruction descriptor: D = f32, A = B = tf32, both K-major, N = 128, M = 128.
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
-                              ((uint32_t)(TC_M >> 4) << 24);
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// atomicMax on a float that may have either sign (order-preserving integer views; the slot starts at -inf)
-__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
-    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
-}
-
-// Byte offset of 16-byte chunk c16 (0..15) of row `row` inside a [128 x 64] fp32 tile stored as two SW128 k-halves.
-__device__ __forceinline__ uint32_t sw128_off(int row, int c16) {
-    return (uint32_t)((c16 >> 3) * TC_KH_BYTES + row * 128 + (((c16 & 7) ^ (row & 7)) << 4));
-}
 
 // ---------------------------------------------------------------------------------------------- the kernel
 // TC_TS == 1 (default): the A operand (user rows) lives in TENSOR MEMORY (tcgen05.mma "TS" form): every epilogue
@@ -170,25 +71,6 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int c16) {
 #endif
 constexpr int TC_NACC = TC_TS ? 3 : 4;   // accumulator ring (128 TMEM columns each; A takes 128 columns in TS form)
 
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
-          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
-          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int NH>
 __global__ void __launch_bounds__(64 + 128 * NH, 1)
@@ -914,11 +796,7 @@ eval_tc_merge_kernel(const float* __restrict__ ps, const int32_t* __restrict__ p
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled() {
+EncodeTiledFn encode_tiled() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -980,24 +858,37 @@ TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
     return p;
 }
 
+int make_row_table_map(CUtensorMap* map, const float* table, int64_t n_rows, int dim) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(TAGREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver", __FILE__, __LINE__);
+    const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n_rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)dim * 4};
+    const cuuint32_t box[2] = {32, (cuuint32_t)TC_N};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(table), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TAGREC_ECUDA, "cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+    return TAGREC_OK;
+}
+
+int launch_item_maxnorm(const float* item_table, int64_t n_item, int dim, float* out, void* stream) {
+    TAGREC_CUDA(cudaMemsetAsync(out, 0, 4, (cudaStream_t)stream));
+    const int64_t nb = min((int64_t)kSMs * 8, (n_item + 7) / 8);
+    TAGREC_LAUNCH(item_maxnorm_kernel, (unsigned)nb, 256, 0, stream, reinterpret_cast<const float4*>(item_table), n_item,
+                  dim / 4, out);
+    return TAGREC_OK;
+}
+
 int eval_topk_tc(const int64_t* users, int64_t nu, const float* user_table, const float* item_table, int64_t n_item,
                  const int64_t* train_ptr, const int32_t* train_items, int k, int32_t* topk_ids, float* topk_scores,
                  void* workspace, size_t workspace_bytes, void* stream, const TcPlan& p) {
-    EncodeTiledFn enc = encode_tiled();
-    if (!enc) return fail(TAGREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver", __FILE__, __LINE__);
     TAGREC_REQUIRE((reinterpret_cast<uintptr_t>(item_table) & 15) == 0, "item table must be 16-byte aligned");
     const size_t need = eval_tc_workspace_bytes(nu, p, k);
     if (!workspace || workspace_bytes < need) return fail(TAGREC_ENOMEM, "eval workspace too small", __FILE__, __LINE__);
     CUtensorMap map;
     const int dim = p.kb * TC_D;
-    const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n_item};
-    const cuuint64_t gstride[1] = {(cuuint64_t)dim * 4};
-    const cuuint32_t box[2] = {32, (cuuint32_t)TC_N};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(item_table), gdim, gstride, box,
-                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(TAGREC_ECUDA, "cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+    if (int rc = make_row_table_map(&map, item_table, n_item, dim)) return rc;
 
     TcArgs a{};
     a.users = users; a.nu = nu; a.user_table = user_table; a.item_table = item_table; a.n_item = n_item;
@@ -1010,13 +901,9 @@ int eval_topk_tc(const int64_t* users, int64_t nu, const float* user_table, cons
     // (the max over splits of their own K-th best is no tighter than one's own bound when two splits advance in
     // lockstep; it pays with many short splits, where late starters inherit the early ones' bounds)
     a.shared_thr = p.splits > 2 ? reinterpret_cast<float*>(a.part_ids + (size_t)nu * p.splits * k) : nullptr;
-    cudaStream_t st = (cudaStream_t)stream;
-    TAGREC_CUDA(cudaMemsetAsync(maxnorm, 0, 4, st));
     if (a.shared_thr)
         TAGREC_LAUNCH(fill_f32_kernel, (unsigned)((nu + 255) / 256), 256, 0, stream, a.shared_thr, nu, -INFINITY);
-    const int64_t nb = min((int64_t)kSMs * 8, (n_item + 7) / 8);
-    TAGREC_LAUNCH(item_maxnorm_kernel, (unsigned)nb, 256, 0, stream, reinterpret_cast<const float4*>(item_table), n_item,
-                  dim / 4, maxnorm);
+    if (int rc = launch_item_maxnorm(item_table, n_item, dim, maxnorm, stream)) return rc;
     const dim3 grid((unsigned)((nu + TC_M * p.nh - 1) / (TC_M * p.nh)), (unsigned)p.splits);
     if (p.kb > 1) {
         TAGREC_CUDA(cudaFuncSetAttribute(eval_tc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));

@@ -5,8 +5,9 @@ and creation order (state_dict keys ``embed.user|item|tag|weight``, ``layer.<k>.
 
 Neighbour attention (tgcn.py:11-37) — the gather/scatter family that is 45 % of the reference's step — runs on K4
 (csrc/nbr_attention.cu) through :class:`NbrAttentionFn`; its three dense projections, the type-level attention
-(tgcn.py:78-84), the bit-/vector-level Conv2d (tgcn.py:86-101, evaluated as fp32 matmuls) and the fusion layer
-(tgcn.py:103-106) are dense library ops (cuBLAS through torch).  The BPR loss runs on K2 over the 64*(L+1)-d concat
+(tgcn.py:78-84) and the 48 vector-level conv features (tgcn.py:92-98) are small dense library ops (cuBLAS through
+torch); the bit-level Conv2d, the concat and the 2096 -> 64 fusion layer (tgcn.py:86-106) run fused on K7
+(csrc/tgcn_tail.cu) through :class:`TgcnTailFn`.  The BPR loss runs on K2 over the 64*(L+1)-d concat
 rows (L2 term on the propagated rows, tgcn.py:247), evaluation on K3.
 """
 import time
@@ -49,6 +50,35 @@ class NbrAttentionFn(torch.autograd.Function):
                                              pv.shape[1], ptr(g_pv), ptr(g_ww), ptr(g_pj), ptr(g_ej), ptr(g_v),
                                              stream_ptr(pv.device)), "tagrec_nbr_attention_bwd")
         return g_pv, g_ww, g_pj, g_ej, g_v, None, None, None
+
+
+class TgcnTailFn(torch.autograd.Function):
+    """out = relu([relu(bit_conv(z)) | xf] Wf + bf) on K7 (csrc/tgcn_tail.cu); the [N, 2096] feature matrix of
+    tgcn.py:86-106 is generated and consumed on chip, forward and backward."""
+
+    @staticmethod
+    def forward(ctx, z, wb, xf, wf, bf):
+        z, wb, xf, wf, bf = (t.detach().contiguous() for t in (z, wb, xf, wf, bf))
+        n, c, e = z.shape[0], wb.shape[0], xf.shape[1]
+        out = torch.empty((n, z.shape[2]), dtype=torch.float32, device=z.device)
+        check(lib().tagrec_tgcn_tail_fwd(ptr(z), ptr(wb), ptr(xf), ptr(wf), ptr(bf), n, z.shape[2], c, e, ptr(out),
+                                         stream_ptr(z.device)), "tagrec_tgcn_tail_fwd")
+        ctx.save_for_backward(z, wb, xf, wf, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        z, wb, xf, wf, out = ctx.saved_tensors
+        n, c, e = z.shape[0], wb.shape[0], xf.shape[1]
+        g_out = g_out.contiguous()
+        g_z, g_wb, g_xf, g_wf = (torch.empty_like(t) for t in (z, wb, xf, wf))
+        g_bf = torch.empty(z.shape[2], dtype=torch.float32, device=z.device)
+        nbytes = int(lib().tagrec_tgcn_tail_workspace_bytes(n, c))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
+        check(lib().tagrec_tgcn_tail_bwd(ptr(g_out), ptr(out), ptr(z), ptr(wb), ptr(xf), ptr(wf), n, z.shape[2], c, e,
+                                         ptr(ws), nbytes, ptr(g_z), ptr(g_wb), ptr(g_xf), ptr(g_wf), ptr(g_bf),
+                                         stream_ptr(z.device)), "tagrec_tgcn_tail_bwd")
+        return g_z, g_wb, g_xf, g_wf, g_bf
 
 
 class Attention1(nn.Module):
@@ -103,22 +133,23 @@ class BasicLayer(nn.Module):
         x = torch.matmul(F.relu(x), self.p.T)
         return torch.softmax(x, dim=1) * uit
 
-    def _conv(self, eN):
-        """tgcn.py:86-101.  The four Conv2d are tiny contractions over a [N, 3, 64] stack; they are evaluated as fp32
-        matmuls on the modules' own weights (same values as F.conv2d) — cuDNN is free to run convolutions, forward
-        AND backward, in TF32 under torch's defaults, which would break fp32 parity of every upstream gradient."""
+    def _vec_conv(self, eN):
+        """Vector-level branch of tgcn.py:92-98: Conv2d(1 -> 8, (j, 64)), j = 1..3, over a [N, 3, 64] stack — tiny
+        contractions, evaluated as fp32 matmuls on the modules' own weights (same values as F.conv2d; cuDNN is free
+        to run convolutions, forward AND backward, in TF32 under torch's defaults, which would break fp32 parity of
+        every upstream gradient).  Returns the rectified [N, 6 * 8] features, channel-major per conv."""
         n = eN.shape[0]
-        wb = self.conv["bit_level"].weight[:, 0, :, 0]                       # [32, 3]
-        bit_e = F.relu(torch.einsum('cr,nrd->ncd', wb, eN)).reshape(n, -1)   # [N, 32*64], channel-major
         vec_e = []
         for j, model in enumerate(self.conv["vec_level"].values(), start=1):
             w = model.weight.reshape(model.weight.shape[0], -1)              # [8, j*64]
             pos = [torch.matmul(eN[:, p:p + j, :].reshape(n, -1), w.t()) for p in range(4 - j)]
             vec_e.append(F.relu(torch.stack(pos, dim=2)).reshape(n, -1))     # [N, 8*(4-j)], channel-major
-        return torch.cat([bit_e, torch.cat(vec_e, dim=-1)], dim=1)
+        return torch.cat(vec_e, dim=-1)
 
-    def _fusion(self, x):
-        return F.relu(torch.addmm(self.bf, x, self.Wf))
+    def _conv_fusion(self, eN):
+        """tgcn.py:86-106 (_conv + _fusion) on K7: bit-level conv, concat and the 2096 -> 64 fusion layer fused."""
+        wb = self.conv["bit_level"].weight[:, 0, :, 0]                       # [32, 3]
+        return TgcnTailFn.apply(eN, wb, self._vec_conv(eN), self.Wf, self.bf.reshape(-1))
 
     def forward(self, eu, ei, et, ew, u_iw, u_tw, i_uw, i_tw, t_uw, t_iw):
         a_u, a_i, a_t = self.atten1["user"], self.atten1["item"], self.atten1["tag"]
@@ -129,10 +160,11 @@ class BasicLayer(nn.Module):
         ei_tN = a_t.forward(ei, et, ew, i_tw, pj_t)
         et_uN = a_u.forward(et, eu, ew, t_uw, pj_u)
         et_iN = a_i.forward(et, ei, ew, t_iw, pj_i)
-        euN = self._atten2(eu, eu_iN, eu_tN)
-        eiN = self._atten2(ei_uN, ei, ei_tN)
-        etN = self._atten2(et_uN, et_iN, et)
-        return self._fusion(self._conv(euN)), self._fusion(self._conv(eiN)), self._fusion(self._conv(etN))
+        # the three node types share U/q/p, the convolutions and the fusion layer: one pass over their concatenation
+        # (the reference's own commented-out variant, tgcn.py:131-137)
+        zN = self._atten2(torch.cat([eu, ei_uN, et_uN], 0), torch.cat([eu_iN, ei, et_iN], 0),
+                          torch.cat([eu_tN, ei_tN, et], 0))
+        return torch.split(self._conv_fusion(zN), [eu.shape[0], ei.shape[0], et.shape[0]], dim=0)
 
 
 class TGCN(nn.Module, EvalMixin):
@@ -169,6 +201,9 @@ class TGCN(nn.Module, EvalMixin):
         if any(d != 64 for d in self.dim_layer_list) or self.dim_atten != 32 or self.neighbor_k > 32:
             raise NotImplementedError("K4 is built for 64-d layers, dim_atten 32 and neighbor_k <= 32 "
                                       "(utility/config.py:41-51 defaults: 64 / 32 / 25)")
+        if (6 * self.num_vec_conv) % 4 or 6 * self.num_vec_conv > 64 or self.num_bit_conv > 256:
+            raise NotImplementedError("K7 needs 6 * num_vec_conv to be a multiple of 4, at most 64, and "
+                                      "num_bit_conv <= 256 (utility/config.py defaults: 8 / 32)")
 
     def _init_weight(self):
         self.embed = nn.ParameterDict({

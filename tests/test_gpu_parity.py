@@ -758,6 +758,43 @@ def test_k4_neighbour_attention_vs_torch():
         assert relerr(p.grad.cpu().numpy(), P[n].grad.numpy()) < TOL, n
 
 
+@pytest.mark.parametrize("n", [1, 127, 128, 700])
+def test_k7_tgcn_tail_vs_conv2d(n):
+    """K7 (bit-level conv + concat + fusion, fused) forward/backward against the reference formulation with real
+    Conv2d modules (tgcn.py:86-106) in torch fp64: every input and parameter gradient; tile edges (n = 1, 127, 128)
+    and several tiles per CTA (n = 700 > 4 * 128)."""
+    from tagrec_b200.tgcn import BasicLayer
+    g = torch.Generator().manual_seed(11 + n)
+    layer = BasicLayer(64, 64, 32, 10, 32, 8).to(dev())
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.2)
+    z = torch.randn(n, 3, 64, generator=g)
+    up = torch.randn(n, 64, generator=g)
+    zd = z.clone().to(dev()).requires_grad_(True)
+    out = layer._conv_fusion(zd)
+    (out * up.to(dev())).sum().backward()
+    # reference formulation, float64, F.conv2d
+    P = {k: v.detach().cpu().double().requires_grad_(True) for k, v in layer.named_parameters()}
+    zr = z.clone().double().requires_grad_(True)
+    x = zr.unsqueeze(1)
+    bit = torch.relu(torch.nn.functional.conv2d(x, P["conv.bit_level.weight"]))
+    bit = bit.squeeze().reshape(bit.shape[0], -1)
+    vec = []
+    for j in range(1, 4):
+        y = torch.relu(torch.nn.functional.conv2d(x, P[f"conv.vec_level.conv_{j}.weight"])).squeeze(dim=-1)
+        vec.append(y.reshape(y.shape[0], -1))
+    ref = torch.relu(torch.cat([bit, torch.cat(vec, dim=-1)], dim=1) @ P["Wf"] + P["bf"])
+    (ref * up.double()).sum().backward()
+    assert relerr(out.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+    assert relerr(zd.grad.cpu().numpy(), zr.grad.numpy()) < TOL
+    for k in ("conv.bit_level.weight", "conv.vec_level.conv_1.weight", "conv.vec_level.conv_2.weight",
+              "conv.vec_level.conv_3.weight", "Wf", "bf"):
+        got = dict(layer.named_parameters())[k].grad
+        assert relerr(got.cpu().numpy(), P[k].grad.numpy()) < TOL, k
+
+
+
 @pytest.mark.parametrize("nu,n_item,dim,scale", [(70, 3000, 64, 1.0), (33, 700, 256, 0.05), (130, 9000, 64, 30.0)])
 def test_k3b_auc_vs_oracle(nu, n_item, dim, scale):
     """Device AUC (csrc/eval_auc.cu) == the oracle's restatement of roc_auc_score (rank-sum with tie averaging) per
