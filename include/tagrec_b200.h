@@ -314,6 +314,23 @@ int tagrec_tgcn_tail_bwd(const float* g_out, const float* out, const float* z, c
                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * K7a TGCN type attention + vector-level conv     replaces model/tgcn.py:78-84 (BasicLayer._atten2) and the
+ *                                  vector-level branch of _conv (tgcn.py:92-98) with their autograd graphs.
+ *   x0, x1, x2 [n, 64]  the (user, item, tag) slots of one node type: its own rows and its two neighbour-attention outputs
+ *   U [64, 32], q [32], p [32]      type-attention parameters;  wv_j [V, j*64] = conv.vec_level.conv_j.weight, V in {4, 8}
+ *   fwd: z [n,3,64] = softmax_r(relu(x_r U + q) . p) * x_r;   xf [n, 6V] = relu(conv_1..3(z)), channel-major per conv
+ *   bwd: g_x0..2 written; g_U, g_q, g_p, g_wv1..3 ACCUMULATED (caller zeroes them).
+ * ---------------------------------------------------------------------------------------------------------- */
+int tagrec_tgcn_mix_fwd(const float* x0, const float* x1, const float* x2, const float* U, const float* q,
+                        const float* p, const float* wv1, const float* wv2, const float* wv3, int64_t n, int dim,
+                        int dim_atten, int n_vec_conv, float* z, float* xf, void* stream);
+int tagrec_tgcn_mix_bwd(const float* x0, const float* x1, const float* x2, const float* U, const float* q,
+                        const float* p, const float* wv1, const float* wv2, const float* wv3, int64_t n, int dim,
+                        int dim_atten, int n_vec_conv, const float* g_z, const float* g_xf, const float* xf,
+                        float* g_x0, float* g_x1, float* g_x2, float* g_U, float* g_q, float* g_p, float* g_wv1,
+                        float* g_wv2, float* g_wv3, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * BPR negative sampler          replaces train_data/bpr_training_data.py:29-45 + train_data/utils.py:19-28,52-55.
  * Host version: bit-exact numpy-legacy MT19937 stream for cpu_core == 1 (parity mode).  All pointers HOST.
  *   state: 625 uint32 (624 words + position), advanced exactly as the parent's RandomState is (shuffle only).

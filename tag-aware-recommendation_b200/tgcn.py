@@ -5,9 +5,9 @@ and creation order (state_dict keys ``embed.user|item|tag|weight``, ``layer.<k>.
 
 Neighbour attention (tgcn.py:11-37) — the gather/scatter family that is 45 % of the reference's step — runs on K4
 (csrc/nbr_attention.cu) through :class:`NbrAttentionFn`; its three dense projections, the type-level attention
-(tgcn.py:78-84) and the 48 vector-level conv features (tgcn.py:92-98) are small dense library ops (cuBLAS through
-torch); the bit-level Conv2d, the concat and the 2096 -> 64 fusion layer (tgcn.py:86-106) run fused on K7
-(csrc/tgcn_tail.cu) through :class:`TgcnTailFn`.  The BPR loss runs on K2 over the 64*(L+1)-d concat
+(tgcn.py:78-84) and the 48 vector-level conv features (tgcn.py:92-98) run per node on K7a (csrc/tgcn_mix.cu,
+:class:`TgcnMixFn`); the bit-level Conv2d, the concat and the 2096 -> 64 fusion layer (tgcn.py:86-106) run fused on K7
+(csrc/tgcn_tail.cu, :class:`TgcnTailFn`).  ``BasicLayer._atten2`` / ``_vec_conv`` keep the torch formulation (tests).  The BPR loss runs on K2 over the 64*(L+1)-d concat
 rows (L2 term on the propagated rows, tgcn.py:247), evaluation on K3.
 """
 import time
@@ -79,6 +79,36 @@ class TgcnTailFn(torch.autograd.Function):
                                          ptr(ws), nbytes, ptr(g_z), ptr(g_wb), ptr(g_xf), ptr(g_wf), ptr(g_bf),
                                          stream_ptr(z.device)), "tagrec_tgcn_tail_bwd")
         return g_z, g_wb, g_xf, g_wf, g_bf
+
+
+class TgcnMixFn(torch.autograd.Function):
+    """(z, xf) = type-level attention over the (user, item, tag) slots of one node type + rectified vector-level conv
+    features, on K7a (csrc/tgcn_mix.cu) — tgcn.py:78-84 and 92-98."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, x2, U, q, p, w1, w2, w3):
+        x0, x1, x2, U, q, p, w1, w2, w3 = (t.detach().contiguous() for t in (x0, x1, x2, U, q, p, w1, w2, w3))
+        n, v = x0.shape[0], w1.shape[0]
+        z = torch.empty((n, 3, x0.shape[1]), dtype=torch.float32, device=x0.device)
+        xf = torch.empty((n, 6 * v), dtype=torch.float32, device=x0.device)
+        check(lib().tagrec_tgcn_mix_fwd(ptr(x0), ptr(x1), ptr(x2), ptr(U), ptr(q), ptr(p), ptr(w1), ptr(w2), ptr(w3), n,
+                                        x0.shape[1], U.shape[1], v, ptr(z), ptr(xf), stream_ptr(x0.device)),
+              "tagrec_tgcn_mix_fwd")
+        ctx.save_for_backward(x0, x1, x2, U, q, p, w1, w2, w3, xf)
+        return z, xf
+
+    @staticmethod
+    def backward(ctx, g_z, g_xf):
+        x0, x1, x2, U, q, p, w1, w2, w3, xf = ctx.saved_tensors
+        n, v = x0.shape[0], w1.shape[0]
+        g_z = torch.zeros((n, 3, x0.shape[1]), dtype=torch.float32, device=x0.device) if g_z is None else g_z.contiguous()
+        g_xf = torch.zeros_like(xf) if g_xf is None else g_xf.contiguous()
+        gx = [torch.empty_like(x0) for _ in range(3)]
+        gp = [torch.zeros_like(t) for t in (U, q, p, w1, w2, w3)]
+        check(lib().tagrec_tgcn_mix_bwd(ptr(x0), ptr(x1), ptr(x2), ptr(U), ptr(q), ptr(p), ptr(w1), ptr(w2), ptr(w3), n,
+                                        x0.shape[1], U.shape[1], v, ptr(g_z), ptr(g_xf), ptr(xf), ptr(gx[0]), ptr(gx[1]),
+                                        ptr(gx[2]), *(ptr(t) for t in gp), stream_ptr(x0.device)), "tagrec_tgcn_mix_bwd")
+        return (*gx, *gp)
 
 
 class Attention1(nn.Module):
@@ -160,11 +190,17 @@ class BasicLayer(nn.Module):
         ei_tN = a_t.forward(ei, et, ew, i_tw, pj_t)
         et_uN = a_u.forward(et, eu, ew, t_uw, pj_u)
         et_iN = a_i.forward(et, ei, ew, t_iw, pj_i)
-        # the three node types share U/q/p, the convolutions and the fusion layer: one pass over their concatenation
-        # (the reference's own commented-out variant, tgcn.py:131-137)
-        zN = self._atten2(torch.cat([eu, ei_uN, et_uN], 0), torch.cat([eu_iN, ei, et_iN], 0),
-                          torch.cat([eu_tN, ei_tN, et], 0))
-        return torch.split(self._conv_fusion(zN), [eu.shape[0], ei.shape[0], et.shape[0]], dim=0)
+        # per node type: type-level attention + vector-level conv on K7a; then the three types share the bit-level
+        # conv and the fusion layer: one K7 pass over their concatenation (the reference's own commented-out
+        # variant, tgcn.py:131-137)
+        par = (self.U, self.q.reshape(-1), self.p.reshape(-1)) + tuple(
+            m.weight.reshape(m.weight.shape[0], -1) for m in self.conv["vec_level"].values())
+        zu, xu = TgcnMixFn.apply(eu, eu_iN, eu_tN, *par)
+        zi, xi = TgcnMixFn.apply(ei_uN, ei, ei_tN, *par)
+        zt, xt = TgcnMixFn.apply(et_uN, et_iN, et, *par)
+        wb = self.conv["bit_level"].weight[:, 0, :, 0]                       # [32, 3]
+        out = TgcnTailFn.apply(torch.cat([zu, zi, zt], 0), wb, torch.cat([xu, xi, xt], 0), self.Wf, self.bf.reshape(-1))
+        return torch.split(out, [eu.shape[0], ei.shape[0], et.shape[0]], dim=0)
 
 
 class TGCN(nn.Module, EvalMixin):
@@ -201,9 +237,9 @@ class TGCN(nn.Module, EvalMixin):
         if any(d != 64 for d in self.dim_layer_list) or self.dim_atten != 32 or self.neighbor_k > 32:
             raise NotImplementedError("K4 is built for 64-d layers, dim_atten 32 and neighbor_k <= 32 "
                                       "(utility/config.py:41-51 defaults: 64 / 32 / 25)")
-        if (6 * self.num_vec_conv) % 4 or 6 * self.num_vec_conv > 64 or self.num_bit_conv > 256:
-            raise NotImplementedError("K7 needs 6 * num_vec_conv to be a multiple of 4, at most 64, and "
-                                      "num_bit_conv <= 256 (utility/config.py defaults: 8 / 32)")
+        if self.num_vec_conv not in (4, 8) or self.num_bit_conv > 256:
+            raise NotImplementedError("K7 is built for num_vec_conv in (4, 8) and num_bit_conv <= 256 "
+                                      "(utility/config.py defaults: 8 / 32)")
 
     def _init_weight(self):
         self.embed = nn.ParameterDict({

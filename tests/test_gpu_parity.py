@@ -691,7 +691,7 @@ def _tgcn_model(tiny, tiny_tgcn):
 
 
 def test_tgcn_forward_loss_grad_vs_reference(tiny, tiny_tgcn):
-    """T.TGCN (neighbour attention on K4, dense parts on cuBLAS/cuDNN, K2 on 192-d rows) == model/tgcn.py with the
+    """T.TGCN (neighbour attention on K4, type attention + convs + fusion on K7a/K7, K2 on 192-d rows) == model/tgcn.py with the
     reference's own neighbour tables: concat outputs, loss tuple, the gradient of EVERY parameter."""
     model = _tgcn_model(tiny, tiny_tgcn)
     model.train()
@@ -706,14 +706,20 @@ def test_tgcn_forward_loss_grad_vs_reference(tiny, tiny_tgcn):
     # Bar per tensor: within 1e-5 of the reference, or — for the O(1e-9) second-layer attention gradients, where the
     # reference's own float32 run is up to 9e-5 away from its float64 run (tests/golden/make_golden_fp64.py) —
     # within 4x of the reference's own float32 error against that float64 truth.
+    # Noise floor: a tensor whose ABSOLUTE error is below 1e-10 x the largest gradient entry of the whole model (600x
+    # below one float32 ulp of that entry) also passes — layer.1.atten1.user.v has |grad| = 3.6e-10 next to 1.6e-2 for
+    # the embeddings (a softmax gradient that cancels to ~0), and which float32 rounding realisation one gets there
+    # depends on the summation order of every kernel upstream (K7a measured alone is within 3e-7 of float64, as
+    # torch's float32 ops are).
     truth = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "routing_fp64.npz")))
+    gmax = max(float(np.abs(truth[f"tgcn_grad64_{name}"]).max()) for name, _ in model.named_parameters())
     bad = []
     for name, p in model.named_parameters():
         want = tiny_tgcn[f"tgcn_grad_{name}"]
         got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(want)
         t64 = truth[f"tgcn_grad64_{name}"]
         err, err_ref = relerr(got, t64), relerr(want, t64)
-        if err > max(TOL, 4 * err_ref):
+        if err > max(TOL, 4 * err_ref) and float(np.abs(got - t64).max()) > 1e-10 * gmax:
             bad.append((name, err, err_ref))
     assert not bad, bad
 
@@ -756,6 +762,45 @@ def test_k4_neighbour_attention_vs_torch():
         assert relerr(got.grad.cpu().numpy(), want.grad.numpy()) < TOL
     for n, p in att.named_parameters():
         assert relerr(p.grad.cpu().numpy(), P[n].grad.numpy()) < TOL, n
+
+
+@pytest.mark.parametrize("n", [1, 9, 333])
+def test_k7a_type_attention_and_vec_conv_vs_torch(n):
+    """K7a forward/backward against the torch formulation of BasicLayer._atten2 + the vector-level Conv2d branch
+    (tgcn.py:78-84, 92-98) in fp64: z, xf and the gradients of the three slot tables and of U, q, p, conv_1..3."""
+    from tagrec_b200.tgcn import BasicLayer, TgcnMixFn
+    g = torch.Generator().manual_seed(5 + n)
+    layer = BasicLayer(64, 64, 32, 10, 32, 8).to(dev())
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.2)
+    xs = [torch.randn(n, 64, generator=g) for _ in range(3)]
+    up_z, up_f = torch.randn(n, 3, 64, generator=g), torch.randn(n, 48, generator=g)
+    leaves = [t.clone().to(dev()).requires_grad_(True) for t in xs]
+    par = (layer.U, layer.q.reshape(-1), layer.p.reshape(-1)) + tuple(
+        m.weight.reshape(m.weight.shape[0], -1) for m in layer.conv["vec_level"].values())
+    z, xf = TgcnMixFn.apply(*leaves, *par)
+    ((z * up_z.to(dev())).sum() + (xf * up_f.to(dev())).sum()).backward()
+    P = {k: v.detach().cpu().double().requires_grad_(True) for k, v in layer.named_parameters()}
+    rx = [t.clone().double().requires_grad_(True) for t in xs]
+    uit = torch.stack(rx, dim=1)
+    a = torch.relu(uit @ P["U"] + P["q"]) @ P["p"].T
+    zr = torch.softmax(a, dim=1) * uit
+    x = zr.unsqueeze(1)
+    vec = []
+    for j in range(1, 4):
+        y = torch.relu(torch.nn.functional.conv2d(x, P[f"conv.vec_level.conv_{j}.weight"])).squeeze(dim=-1)
+        vec.append(y.reshape(y.shape[0], -1))
+    xr = torch.cat(vec, dim=-1)
+    ((zr * up_z.double()).sum() + (xr * up_f.double()).sum()).backward()
+    assert relerr(z.detach().cpu().numpy(), zr.detach().numpy()) < TOL
+    assert relerr(xf.detach().cpu().numpy(), xr.detach().numpy()) < TOL
+    for got, want in zip(leaves, rx):
+        assert relerr(got.grad.cpu().numpy(), want.grad.numpy()) < TOL
+    named = dict(layer.named_parameters())
+    for k in ("U", "q", "p", "conv.vec_level.conv_1.weight", "conv.vec_level.conv_2.weight",
+              "conv.vec_level.conv_3.weight"):
+        assert relerr(named[k].grad.cpu().numpy(), P[k].grad.numpy()) < TOL, k
 
 
 @pytest.mark.parametrize("n", [1, 127, 128, 700])
