@@ -331,6 +331,13 @@ int tagrec_tgcn_mix_bwd(const float* x0, const float* x1, const float* x2, const
                         float* g_wv2, float* g_wv3, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * K8  skinny X^T Y                 out[a, b] = x[n, a]^T y[n, b]  (OVERWRITTEN), a and b multiples of 4 in 4..64.
+ * The weight gradient of the small dense layers on the path (attention projections model/tgcn.py:26-31, factor
+ * projection model/disengcn.py:25): a row reduction spread over all SMs instead of a one-tile GEMM with K = n.
+ * ---------------------------------------------------------------------------------------------------------- */
+int tagrec_xty(const float* x, const float* y, int64_t n, int a, int b, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * BPR negative sampler          replaces train_data/bpr_training_data.py:29-45 + train_data/utils.py:19-28,52-55.
  * Host version: bit-exact numpy-legacy MT19937 stream for cpu_core == 1 (parity mode).  All pointers HOST.
  *   state: 625 uint32 (624 words + position), advanced exactly as the parent's RandomState is (shuffle only).

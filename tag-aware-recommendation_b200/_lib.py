@@ -88,6 +88,7 @@ PROTOTYPES = {
     "tagrec_tgcn_tail_bwd": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _sz, _p, _p, _p, _p, _p, _p]),
     "tagrec_tgcn_mix_fwd": (_i32, [_p] * 9 + [_i64, _i32, _i32, _i32, _p, _p, _p]),
     "tagrec_tgcn_mix_bwd": (_i32, [_p] * 9 + [_i64, _i32, _i32, _i32] + [_p] * 13),
+    "tagrec_xty": (_i32, [_p, _p, _i64, _i32, _i32, _p, _p]),
     "tagrec_mt19937_seed": (None, [_u32, _p]),
     "tagrec_sample_bpr_host": (_i32, [_p, _p, _i64, _p, _p, _i64, _p]),
     "tagrec_sample_neg_tail_host": (_i32, [_p, _p, _i64, _p, _p, _i64, _p]),

@@ -66,15 +66,16 @@ __device__ __forceinline__ void type_attention(const float* __restrict__ xs, con
     float lg[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        float a = ql;
+        float a0 = ql, a1 = 0.f, a2 = 0.f, a3 = 0.f;    // four independent chains (FMA latency, few warps per SM)
 #pragma unroll
         for (int d4 = 0; d4 < MW / 4; ++d4) {
             const float4 xv = *reinterpret_cast<const float4*>(xs + r * MW + 4 * d4);
-            a = fmaf(xv.x, ucol[4 * d4 + 0], a);
-            a = fmaf(xv.y, ucol[4 * d4 + 1], a);
-            a = fmaf(xv.z, ucol[4 * d4 + 2], a);
-            a = fmaf(xv.w, ucol[4 * d4 + 3], a);
+            a0 = fmaf(xv.x, ucol[4 * d4 + 0], a0);
+            a1 = fmaf(xv.y, ucol[4 * d4 + 1], a1);
+            a2 = fmaf(xv.z, ucol[4 * d4 + 2], a2);
+            a3 = fmaf(xv.w, ucol[4 * d4 + 3], a3);
         }
+        const float a = (a0 + a1) + (a2 + a3);
         h[r] = a;
         lg[r] = mix_warp_sum(fmaxf(a, 0.f) * pl);
     }
@@ -251,14 +252,18 @@ tgcn_mix_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, 
                 gU[4 * d4 + 2] = fmaf(xv.z, gh, gU[4 * d4 + 2]);
                 gU[4 * d4 + 3] = fmaf(xv.w, gh, gU[4 * d4 + 3]);
             }
+            float2 gx1 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int l = 0; l < MA; ++l) {
-                const float ghl = __shfl_sync(0xffffffffu, gh, l);
-                const float2 u2 = *reinterpret_cast<const float2*>(UT + l * MW + 2 * lane);
-                gx.x = fmaf(ghl, u2.x, gx.x);
-                gx.y = fmaf(ghl, u2.y, gx.y);
+            for (int l = 0; l < MA; l += 2) {
+                const float gh0 = __shfl_sync(0xffffffffu, gh, l), gh1 = __shfl_sync(0xffffffffu, gh, l + 1);
+                const float2 u0 = *reinterpret_cast<const float2*>(UT + l * MW + 2 * lane);
+                const float2 u1 = *reinterpret_cast<const float2*>(UT + (l + 1) * MW + 2 * lane);
+                gx.x = fmaf(gh0, u0.x, gx.x);
+                gx.y = fmaf(gh0, u0.y, gx.y);
+                gx1.x = fmaf(gh1, u1.x, gx1.x);
+                gx1.y = fmaf(gh1, u1.y, gx1.y);
             }
-            *reinterpret_cast<float2*>(gxr[r] + node * MW + 2 * lane) = gx;
+            *reinterpret_cast<float2*>(gxr[r] + node * MW + 2 * lane) = make_float2(gx.x + gx1.x, gx.y + gx1.y);
         }
     }
     // per-CTA sums, then one atomic per parameter element and CTA

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from . import adj as utils
 from . import config
 from .eval_ops import EvalMixin
-from .functional import BprLossFn
+from .functional import BprLossFn, skinny_mm
 from .routing import ChunkNormFn, DisenRouteFn
 
 
@@ -28,7 +28,7 @@ class Layer(nn.Module):
     def forward(self, adj, all_emb):
         # [K, in, dk] -> [in, K*dk]: column block k is factor k, so chunk k of a row == fac_emb[k] of the reference
         wc = (self.W + self.b).permute(1, 0, 2).reshape(self.in_dim, self.out_dim)
-        fac = F.leaky_relu(torch.matmul(all_emb, wc), negative_slope=0.2)
+        fac = F.leaky_relu(skinny_mm(all_emb, wc), negative_slope=0.2)
         fac = ChunkNormFn.apply(fac)
         return DisenRouteFn.apply(adj, self.iter_k, fac)
 

@@ -311,6 +311,40 @@ class BprLossFn(torch.autograd.Function):
         return None, None, None, None, gf, gr
 
 
+def xty(x, y):
+    """x[n, a]^T y[n, b] on K8 (csrc/xty.cu): the weight gradient of a small dense layer as a row reduction over all
+    SMs (cuBLAS runs the [a x n] x [n x b] form on one tile's worth of SMs)."""
+    x, y = x.contiguous(), y.contiguous()
+    out = torch.empty((x.shape[1], y.shape[1]), dtype=torch.float32, device=x.device)
+    check(lib().tagrec_xty(ptr(x), ptr(y), x.shape[0], x.shape[1], y.shape[1], ptr(out), stream_ptr(x.device)),
+          "tagrec_xty")
+    return out
+
+
+class SkinnyMmFn(torch.autograd.Function):
+    """x[n, a] @ w[a, b] for tall x and a, b <= 64 (attention projections tgcn.py:26-31, factor projection
+    disengcn.py:25).  Forward and input gradient are plain GEMMs (the latter on a contiguous copy of w^T: cuBLAS picks
+    a 6x slower kernel for the transposed-operand form with K = 32); the weight gradient runs on K8."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return torch.mm(x, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        gx = torch.mm(g, w.t().contiguous()) if ctx.needs_input_grad[0] else None
+        gw = xty(x.detach(), g) if ctx.needs_input_grad[1] else None
+        return gx, gw
+
+
+def skinny_mm(x, w):
+    ok = x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and all(4 <= d <= 64 and d % 4 == 0 for d in w.shape)
+    return SkinnyMmFn.apply(x, w) if ok else torch.mm(x, w)
+
+
 class NgcfDenseFn(torch.autograd.Function):
     """K6: the dense half of one NGCF layer (ngcf.py:77-86) as one autograd node — one fused forward launch, one
     fused backward launch (input gradients AND the two 64x64 weight gradients)."""

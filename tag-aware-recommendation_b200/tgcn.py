@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from . import config
 from ._lib import check, lib, ptr, stream_ptr
 from .eval_ops import EvalMixin
-from .functional import BprLossFn
+from .functional import BprLossFn, skinny_mm
 
 
 class NbrAttentionFn(torch.autograd.Function):
@@ -104,7 +104,8 @@ class TgcnMixFn(torch.autograd.Function):
         g_z = torch.zeros((n, 3, x0.shape[1]), dtype=torch.float32, device=x0.device) if g_z is None else g_z.contiguous()
         g_xf = torch.zeros_like(xf) if g_xf is None else g_xf.contiguous()
         gx = [torch.empty_like(x0) for _ in range(3)]
-        gp = [torch.zeros_like(t) for t in (U, q, p, w1, w2, w3)]
+        flat = torch.zeros(sum(t.numel() for t in (U, q, p, w1, w2, w3)), dtype=torch.float32, device=x0.device)
+        gp = [c.view_as(t) for c, t in zip(flat.split([t.numel() for t in (U, q, p, w1, w2, w3)]), (U, q, p, w1, w2, w3))]
         check(lib().tagrec_tgcn_mix_bwd(ptr(x0), ptr(x1), ptr(x2), ptr(U), ptr(q), ptr(p), ptr(w1), ptr(w2), ptr(w3), n,
                                         x0.shape[1], U.shape[1], v, ptr(g_z), ptr(g_xf), ptr(xf), ptr(gx[0]), ptr(gx[1]),
                                         ptr(gx[2]), *(ptr(t) for t in gp), stream_ptr(x0.device)), "tagrec_tgcn_mix_bwd")
@@ -124,10 +125,10 @@ class Attention1(nn.Module):
         """tgcn.py:20-37.  ``pj`` = ej @ W_2 may be passed in when two calls share the neighbour type."""
         v_j, v_w = v_jw
         d = self.in_features
-        pv = torch.addmm(self.b, ev, self.W_1[:d])             # [e_v | e_w] W1 + b, split by rows of W1
+        pv = skinny_mm(ev, self.W_1[:d]) + self.b          # [e_v | e_w] W1 + b, split by rows of W1
         ww = torch.matmul(ew, self.W_1[d:])
         if pj is None:
-            pj = torch.matmul(ej, self.W_2)
+            pj = skinny_mm(ej, self.W_2)
         return NbrAttentionFn.apply(pv, ww, pj, ej, self.v.reshape(-1), v_j, v_w, v_j.shape[1])
 
 
@@ -183,23 +184,21 @@ class BasicLayer(nn.Module):
 
     def forward(self, eu, ei, et, ew, u_iw, u_tw, i_uw, i_tw, t_uw, t_iw):
         a_u, a_i, a_t = self.atten1["user"], self.atten1["item"], self.atten1["tag"]
-        pj_u, pj_i, pj_t = torch.matmul(eu, a_u.W_2), torch.matmul(ei, a_i.W_2), torch.matmul(et, a_t.W_2)
+        pj_u, pj_i, pj_t = skinny_mm(eu, a_u.W_2), skinny_mm(ei, a_i.W_2), skinny_mm(et, a_t.W_2)
         eu_iN = a_i.forward(eu, ei, ew, u_iw, pj_i)
         eu_tN = a_t.forward(eu, et, ew, u_tw, pj_t)
         ei_uN = a_u.forward(ei, eu, ew, i_uw, pj_u)
         ei_tN = a_t.forward(ei, et, ew, i_tw, pj_t)
         et_uN = a_u.forward(et, eu, ew, t_uw, pj_u)
         et_iN = a_i.forward(et, ei, ew, t_iw, pj_i)
-        # per node type: type-level attention + vector-level conv on K7a; then the three types share the bit-level
-        # conv and the fusion layer: one K7 pass over their concatenation (the reference's own commented-out
-        # variant, tgcn.py:131-137)
+        # The three node types share U/q/p, the convolutions and the fusion layer: one K7a and one K7 pass over their
+        # concatenation (the reference's own commented-out variant, tgcn.py:131-137).
         par = (self.U, self.q.reshape(-1), self.p.reshape(-1)) + tuple(
             m.weight.reshape(m.weight.shape[0], -1) for m in self.conv["vec_level"].values())
-        zu, xu = TgcnMixFn.apply(eu, eu_iN, eu_tN, *par)
-        zi, xi = TgcnMixFn.apply(ei_uN, ei, ei_tN, *par)
-        zt, xt = TgcnMixFn.apply(et_uN, et_iN, et, *par)
+        z, xf = TgcnMixFn.apply(torch.cat([eu, ei_uN, et_uN], 0), torch.cat([eu_iN, ei, et_iN], 0),
+                                torch.cat([eu_tN, ei_tN, et], 0), *par)
         wb = self.conv["bit_level"].weight[:, 0, :, 0]                       # [32, 3]
-        out = TgcnTailFn.apply(torch.cat([zu, zi, zt], 0), wb, torch.cat([xu, xi, xt], 0), self.Wf, self.bf.reshape(-1))
+        out = TgcnTailFn.apply(z, wb, xf, self.Wf, self.bf.reshape(-1))
         return torch.split(out, [eu.shape[0], ei.shape[0], et.shape[0]], dim=0)
 
 

@@ -764,6 +764,21 @@ def test_k4_neighbour_attention_vs_torch():
         assert relerr(p.grad.cpu().numpy(), P[n].grad.numpy()) < TOL, n
 
 
+@pytest.mark.parametrize("n,a,b", [(1, 64, 32), (63, 4, 64), (5000, 64, 64), (70001, 64, 32), (300, 12, 8)])
+def test_k8_skinny_xty_vs_torch(n, a, b):
+    """K8 out = x^T y against torch float64, and through SkinnyMmFn's autograd (input and weight gradient)."""
+    from tagrec_b200.functional import skinny_mm, xty
+    g = torch.Generator().manual_seed(n + a)
+    x, y = torch.randn(n, a, generator=g), torch.randn(n, b, generator=g)
+    got = xty(x.to(dev()), y.to(dev())).cpu().numpy()
+    assert relerr(got, (x.double().t() @ y.double()).numpy()) < TOL
+    w = torch.randn(a, b, generator=g)
+    xd, wd = x.clone().to(dev()).requires_grad_(True), w.clone().to(dev()).requires_grad_(True)
+    (skinny_mm(xd, wd) * y.to(dev())).sum().backward()
+    assert relerr(xd.grad.cpu().numpy(), (y.double() @ w.double().t()).numpy()) < TOL
+    assert relerr(wd.grad.cpu().numpy(), (x.double().t() @ y.double()).numpy()) < TOL
+
+
 @pytest.mark.parametrize("n", [1, 9, 333])
 def test_k7a_type_attention_and_vec_conv_vs_torch(n):
     """K7a forward/backward against the torch formulation of BasicLayer._atten2 + the vector-level Conv2d branch

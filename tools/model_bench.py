@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--graph", action="store_true", help="record the step into a CUDA graph (T.GraphedStep)")
+    ap.add_argument("--kineto", action="store_true", help="print the in-pipeline kernel times of 3 extra steps (CUPTI)")
     args = ap.parse_args()
     import __graft_entry__ as G
     G.build()
@@ -103,6 +104,17 @@ def main():
         if args.profile:
             torch.cuda.profiler.stop()
         ms = float(np.median([a.elapsed_time(e) for a, e in evs]))
+        if args.kineto:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for b in batches[3:6]:
+                    step(b)
+                torch.cuda.synchronize()
+            rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)
+            tot = sum(r.device_time_total for r in rows)
+            print(f"# {name}: {tot / 3e3:.2f} ms of kernel time per step (in-pipeline, warm)")
+            for r in rows[:24]:
+                print(f"#  {r.device_time_total / 3:9.1f} us {r.count / 3:6.1f}x  {100 * r.device_time_total / tot:5.1f} %  {r.key[:90]}")
         launches = (T.launch_count() - l0) / args.steps
         bsz = (batches[0][0] if isinstance(batches[0], tuple) else batches[0]).shape[0]
         # evaluation (K3 + K3b + metrics) through the drop-in Basic_test
