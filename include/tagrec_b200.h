@@ -319,16 +319,19 @@ int tagrec_tgcn_tail_bwd(const float* g_out, const float* out, const float* z, c
  *   x0, x1, x2 [n, 64]  the (user, item, tag) slots of one node type: its own rows and its two neighbour-attention outputs
  *   U [64, 32], q [32], p [32]      type-attention parameters;  wv_j [V, j*64] = conv.vec_level.conv_j.weight, V in {4, 8}
  *   fwd: z [n,3,64] = softmax_r(relu(x_r U + q) . p) * x_r;   xf [n, 6V] = relu(conv_1..3(z)), channel-major per conv
- *   bwd: g_x0..2 written; g_U, g_q, g_p, g_wv1..3 ACCUMULATED (caller zeroes them).
+ *   bwd: takes the forward's z and xf; g_x0..2 written; g_U, g_q, g_p, g_wv1..3 ACCUMULATED (caller zeroes them);
+ *        workspace: tagrec_tgcn_mix_workspace_bytes(n) device bytes.
  * ---------------------------------------------------------------------------------------------------------- */
 int tagrec_tgcn_mix_fwd(const float* x0, const float* x1, const float* x2, const float* U, const float* q,
                         const float* p, const float* wv1, const float* wv2, const float* wv3, int64_t n, int dim,
                         int dim_atten, int n_vec_conv, float* z, float* xf, void* stream);
 int tagrec_tgcn_mix_bwd(const float* x0, const float* x1, const float* x2, const float* U, const float* q,
                         const float* p, const float* wv1, const float* wv2, const float* wv3, int64_t n, int dim,
-                        int dim_atten, int n_vec_conv, const float* g_z, const float* g_xf, const float* xf,
-                        float* g_x0, float* g_x1, float* g_x2, float* g_U, float* g_q, float* g_p, float* g_wv1,
-                        float* g_wv2, float* g_wv3, void* stream);
+                        int dim_atten, int n_vec_conv, const float* z, const float* g_z, const float* g_xf,
+                        const float* xf, float* g_x0, float* g_x1, float* g_x2, float* g_U, float* g_q, float* g_p,
+                        float* g_wv1, float* g_wv2, float* g_wv3, void* workspace, size_t workspace_bytes,
+                        void* stream);
+size_t tagrec_tgcn_mix_workspace_bytes(int64_t n);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K8  skinny X^T Y                 out[a, b] = x[n, a]^T y[n, b]  (OVERWRITTEN), a and b multiples of 4 in 4..64.
@@ -336,6 +339,8 @@ int tagrec_tgcn_mix_bwd(const float* x0, const float* x1, const float* x2, const
  * projection model/disengcn.py:25): a row reduction spread over all SMs instead of a one-tile GEMM with K = n.
  * ---------------------------------------------------------------------------------------------------------- */
 int tagrec_xty(const float* x, const float* y, int64_t n, int a, int b, float* out, void* stream);
+/* same; accumulate != 0 adds to out instead of overwriting it */
+int tagrec_xty_acc(const float* x, const float* y, int64_t n, int a, int b, float* out, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * BPR negative sampler          replaces train_data/bpr_training_data.py:29-45 + train_data/utils.py:19-28,52-55.

@@ -87,7 +87,9 @@ PROTOTYPES = {
     "tagrec_tgcn_tail_fwd": (_i32, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p]),
     "tagrec_tgcn_tail_bwd": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _sz, _p, _p, _p, _p, _p, _p]),
     "tagrec_tgcn_mix_fwd": (_i32, [_p] * 9 + [_i64, _i32, _i32, _i32, _p, _p, _p]),
-    "tagrec_tgcn_mix_bwd": (_i32, [_p] * 9 + [_i64, _i32, _i32, _i32] + [_p] * 13),
+    "tagrec_tgcn_mix_bwd": (_i32, [_p] * 9 + [_i64, _i32, _i32, _i32] + [_p] * 13 + [_p, _sz, _p]),
+    "tagrec_tgcn_mix_workspace_bytes": (_sz, [_i64]),
+    "tagrec_xty_acc": (_i32, [_p, _p, _i64, _i32, _i32, _p, _i32, _p]),
     "tagrec_xty": (_i32, [_p, _p, _i64, _i32, _i32, _p, _p]),
     "tagrec_mt19937_seed": (None, [_u32, _p]),
     "tagrec_sample_bpr_host": (_i32, [_p, _p, _i64, _p, _p, _i64, _p]),

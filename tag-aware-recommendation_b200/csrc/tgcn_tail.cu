@@ -44,19 +44,27 @@ __device__ __forceinline__ float bit_pre(float w0, float w1, float w2, float z0,
 }
 
 // acc[i][j] += sum_k Af[k][8 ty + i] * Wk[k][4 tx + j]      (Af feature-major pitch TP, Wk row-major pitch TW)
+__device__ __forceinline__ void tile_gemm_step(const float* __restrict__ Af, const float* __restrict__ Wk, int k, int ty,
+                                               int tx, float (&acc)[8][4]) {
+    const float4 a0 = *reinterpret_cast<const float4*>(Af + k * TP + 8 * ty);
+    const float4 a1 = *reinterpret_cast<const float4*>(Af + k * TP + 8 * ty + 4);
+    const float4 w = *reinterpret_cast<const float4*>(Wk + k * TW + 4 * tx);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], wv[j], acc[i][j]);
+}
+
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ Af, const float* __restrict__ Wk, int kc, int ty,
                                           int tx, float (&acc)[8][4]) {
-#pragma unroll 8
-    for (int k = 0; k < kc; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(Af + k * TP + 8 * ty);
-        const float4 a1 = *reinterpret_cast<const float4*>(Af + k * TP + 8 * ty + 4);
-        const float4 w = *reinterpret_cast<const float4*>(Wk + k * TW + 4 * tx);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], wv[j], acc[i][j]);
+    if (kc == TW) {                                 // the 64-feature chunks: compile-time trip count
+#pragma unroll 16
+        for (int k = 0; k < TW; ++k) tile_gemm_step(Af, Wk, k, ty, tx, acc);
+    } else {
+#pragma unroll 4
+        for (int k = 0; k < kc; ++k) tile_gemm_step(Af, Wk, k, ty, tx, acc);
     }
 }
 

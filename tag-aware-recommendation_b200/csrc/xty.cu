@@ -88,14 +88,19 @@ xty_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n, 
 
 using namespace tagrec;
 
-extern "C" int tagrec_xty(const float* x, const float* y, int64_t n, int a, int b, float* out, void* stream) {
+extern "C" int tagrec_xty_acc(const float* x, const float* y, int64_t n, int a, int b, float* out, int accumulate,
+                              void* stream) {
     TAGREC_REQUIRE(x && y && out, "null pointer");
     TAGREC_REQUIRE(a >= 4 && a <= 64 && a % 4 == 0 && b >= 4 && b <= 64 && b % 4 == 0,
                    "both widths must be multiples of 4 in 4..64");
     TAGREC_REQUIRE(n >= 0, "negative row count");
-    TAGREC_CUDA(cudaMemsetAsync(out, 0, (size_t)a * b * 4, (cudaStream_t)stream));
+    if (!accumulate) TAGREC_CUDA(cudaMemsetAsync(out, 0, (size_t)a * b * 4, (cudaStream_t)stream));
     if (n == 0) return TAGREC_OK;
     const int64_t n_chunks = (n + XR - 1) / XR;
     TAGREC_LAUNCH(xty_kernel, (unsigned)std::min<int64_t>(n_chunks, (int64_t)kSMs * 4), 256, 0, stream, x, y, n, a, b, out);
     return TAGREC_OK;
+}
+
+extern "C" int tagrec_xty(const float* x, const float* y, int64_t n, int a, int b, float* out, void* stream) {
+    return tagrec_xty_acc(x, y, n, a, b, out, 0, stream);
 }

@@ -94,21 +94,24 @@ class TgcnMixFn(torch.autograd.Function):
         check(lib().tagrec_tgcn_mix_fwd(ptr(x0), ptr(x1), ptr(x2), ptr(U), ptr(q), ptr(p), ptr(w1), ptr(w2), ptr(w3), n,
                                         x0.shape[1], U.shape[1], v, ptr(z), ptr(xf), stream_ptr(x0.device)),
               "tagrec_tgcn_mix_fwd")
-        ctx.save_for_backward(x0, x1, x2, U, q, p, w1, w2, w3, xf)
+        ctx.save_for_backward(x0, x1, x2, U, q, p, w1, w2, w3, z, xf)
         return z, xf
 
     @staticmethod
     def backward(ctx, g_z, g_xf):
-        x0, x1, x2, U, q, p, w1, w2, w3, xf = ctx.saved_tensors
+        x0, x1, x2, U, q, p, w1, w2, w3, z, xf = ctx.saved_tensors
         n, v = x0.shape[0], w1.shape[0]
         g_z = torch.zeros((n, 3, x0.shape[1]), dtype=torch.float32, device=x0.device) if g_z is None else g_z.contiguous()
         g_xf = torch.zeros_like(xf) if g_xf is None else g_xf.contiguous()
         gx = [torch.empty_like(x0) for _ in range(3)]
+        nbytes = int(lib().tagrec_tgcn_mix_workspace_bytes(n))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x0.device)
         flat = torch.zeros(sum(t.numel() for t in (U, q, p, w1, w2, w3)), dtype=torch.float32, device=x0.device)
         gp = [c.view_as(t) for c, t in zip(flat.split([t.numel() for t in (U, q, p, w1, w2, w3)]), (U, q, p, w1, w2, w3))]
         check(lib().tagrec_tgcn_mix_bwd(ptr(x0), ptr(x1), ptr(x2), ptr(U), ptr(q), ptr(p), ptr(w1), ptr(w2), ptr(w3), n,
-                                        x0.shape[1], U.shape[1], v, ptr(g_z), ptr(g_xf), ptr(xf), ptr(gx[0]), ptr(gx[1]),
-                                        ptr(gx[2]), *(ptr(t) for t in gp), stream_ptr(x0.device)), "tagrec_tgcn_mix_bwd")
+                                        x0.shape[1], U.shape[1], v, ptr(z), ptr(g_z), ptr(g_xf), ptr(xf), ptr(gx[0]), ptr(gx[1]),
+                                        ptr(gx[2]), *(ptr(t) for t in gp), ptr(ws), nbytes, stream_ptr(x0.device)),
+              "tagrec_tgcn_mix_bwd")
         return (*gx, *gp)
 
 
