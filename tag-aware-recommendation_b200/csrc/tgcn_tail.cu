@@ -30,6 +30,7 @@ constexpr int TW = 64;            // layer width (in_features == out_features ==
 constexpr int TM = 128;           // nodes per tile
 constexpr int TP = TM + 4;        // pitch (floats) of the feature-major tiles X[k][node]
 constexpr int T3C = 4;            // chunks per CTA in T3
+constexpr int ZNP = 3 * TW + 4;   // pitch (floats) of the node-major z tile of T2
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
@@ -83,15 +84,27 @@ __device__ __forceinline__ void load_tile_fm(float* __restrict__ X, const float*
     }
 }
 
-// A[d][node] = relu(bit_pre(wb[c], Z[., d][node]))  for the 64 features of conv channel c
-__device__ __forceinline__ void gen_bit_chunk(float* __restrict__ A, const float* __restrict__ Z, const float* WB, int c,
-                                              int tid) {
+// Feature generation: thread `tid` produces, for EVERY conv channel, the same 8 groups of 4 nodes x 1 dim — so its 24
+// float4 of z are chunk-invariant and live in registers (the first version re-read them from shared memory for each
+// of the 32 chunks: half again as many shared-memory wavefronts as the GEMM itself).
+struct ZRegs {
+    float4 v[8][3];
+};
+__device__ __forceinline__ void load_zregs(ZRegs& zr, const float* __restrict__ Z, int tid) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int idx = tid + 256 * it, d = idx >> 5, n4 = (idx & 31) * 4;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) zr.v[it][r] = *reinterpret_cast<const float4*>(Z + (r * TW + d) * TP + n4);
+    }
+}
+// A[d][node] = relu(bit_pre(wb[c], z[., d][node]))  for the 64 features of conv channel c
+__device__ __forceinline__ void gen_bit_chunk(float* __restrict__ A, const ZRegs& zr, const float* WB, int c, int tid) {
     const float w0 = WB[3 * c], w1 = WB[3 * c + 1], w2 = WB[3 * c + 2];
-    for (int idx = tid; idx < TW * (TM / 4); idx += 256) {
-        const int d = idx >> 5, n4 = (idx & 31) * 4;
-        const float4 z0 = *reinterpret_cast<const float4*>(Z + d * TP + n4);
-        const float4 z1 = *reinterpret_cast<const float4*>(Z + (TW + d) * TP + n4);
-        const float4 z2 = *reinterpret_cast<const float4*>(Z + (2 * TW + d) * TP + n4);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int idx = tid + 256 * it, d = idx >> 5, n4 = (idx & 31) * 4;
+        const float4 z0 = zr.v[it][0], z1 = zr.v[it][1], z2 = zr.v[it][2];
         float4 r;
         r.x = fmaxf(bit_pre(w0, w1, w2, z0.x, z1.x, z2.x), 0.f);
         r.y = fmaxf(bit_pre(w0, w1, w2, z0.y, z1.y, z2.y), 0.f);
@@ -123,7 +136,9 @@ tgcn_tail_fwd_kernel(const float* __restrict__ z, const float* __restrict__ wb, 
     load_tile_fm(Z, z, n0, n, 3 * TW, tid);
     load_w_async(W, wf, C > 0 ? TW : E, tid);
     __syncthreads();
-    if (C > 0) gen_bit_chunk(A, Z, WB, 0, tid); else load_tile_fm(A, xf, n0, n, E, tid);
+    ZRegs zr;
+    load_zregs(zr, Z, tid);
+    if (C > 0) gen_bit_chunk(A, zr, WB, 0, tid); else load_tile_fm(A, xf, n0, n, E, tid);
     cp_async_wait_all();
     __syncthreads();
     float acc[8][4];
@@ -136,7 +151,7 @@ tgcn_tail_fwd_kernel(const float* __restrict__ z, const float* __restrict__ wb, 
         float* Wn = W + ((c + 1) & 1) * TW * TW;
         if (c + 1 < NC) {                           // next chunk: weights in flight, features generated
             load_w_async(Wn, wf + (size_t)(c + 1) * TW * TW, c + 1 < C ? TW : E, tid);
-            if (c + 1 < C) gen_bit_chunk(An, Z, WB, c + 1, tid); else load_tile_fm(An, xf, n0, n, E, tid);
+            if (c + 1 < C) gen_bit_chunk(An, zr, WB, c + 1, tid); else load_tile_fm(An, xf, n0, n, E, tid);
         }
         tile_gemm(A + (c & 1) * TW * TP, W + (c & 1) * TW * TW, c < C ? TW : E, ty, tx, acc);
         cp_async_wait_all();
@@ -174,8 +189,8 @@ tgcn_tail_bwd_z_kernel(const float* __restrict__ g_out, const float* __restrict_
                        float* __restrict__ g_pre, float* __restrict__ g_z, float* __restrict__ g_wb,
                        float* __restrict__ g_xf, float* __restrict__ g_bf) {
     extern __shared__ __align__(16) float sm[];
-    float* Z = sm;                                  // [192][TP]
-    float* GP = Z + 3 * TW * TP;                    // [64][TP]   g_pre, feature-major
+    float* Z = sm;                                  // [TM][ZNP]  z, NODE-major: the mask stage reads float4 over 4 dims
+    float* GP = Z + TM * ZNP;                       // [64][TP]   g_pre, feature-major
     float* W = GP + TW * TP;                        // [2][64][64]
     float* WB = W + 2 * TW * TW;                    // [C][3]
     float* GWB = WB + 3 * C;                        // [C][3]  per-CTA sums
@@ -191,7 +206,10 @@ tgcn_tail_bwd_z_kernel(const float* __restrict__ g_out, const float* __restrict_
         const int64_t n0 = tile * TM;
         __syncthreads();                            // the previous tile's readers are done
         load_w_async(W, wft, TW, tid);
-        load_tile_fm(Z, z, n0, n, 3 * TW, tid);
+        for (int idx = tid; idx < TM * (3 * TW / 4); idx += 256) {
+            const int node = idx / (3 * TW / 4), q4 = idx % (3 * TW / 4);
+            cp_async16(Z + node * ZNP + 4 * q4, z + (min(n0 + node, n - 1)) * 3 * TW + 4 * q4);   // rows past n: g = 0
+        }
         for (int idx = tid; idx < TM * (TW / 4); idx += 256) {
             const int node = idx & (TM - 1), c4 = idx >> 7;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -235,24 +253,21 @@ tgcn_tail_bwd_z_kernel(const float* __restrict__ g_out, const float* __restrict_
                 const float w[3] = {WB[3 * c], WB[3 * c + 1], WB[3 * c + 2]};
                 float t[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float zz[3][8];
+                for (int i = 0; i < 8; ++i) {
+                    float zz[3][4];
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
-                        const float* zp = Z + (r * TW + 4 * tx + j) * TP + 8 * ty;
-                        const float4 q0 = *reinterpret_cast<const float4*>(zp);
-                        const float4 q1 = *reinterpret_cast<const float4*>(zp + 4);
-                        zz[r][0] = q0.x; zz[r][1] = q0.y; zz[r][2] = q0.z; zz[r][3] = q0.w;
-                        zz[r][4] = q1.x; zz[r][5] = q1.y; zz[r][6] = q1.z; zz[r][7] = q1.w;
+                        const float4 q = *reinterpret_cast<const float4*>(Z + (8 * ty + i) * ZNP + r * TW + 4 * tx);
+                        zz[r][0] = q.x; zz[r][1] = q.y; zz[r][2] = q.z; zz[r][3] = q.w;
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float pre = bit_pre(w[0], w[1], w[2], zz[0][i], zz[1][i], zz[2][i]);
+                    for (int j = 0; j < 4; ++j) {
+                        const float pre = bit_pre(w[0], w[1], w[2], zz[0][j], zz[1][j], zz[2][j]);
                         const float g = pre > 0.f ? acc[i][j] : 0.f;
 #pragma unroll
                         for (int r = 0; r < 3; ++r) {
                             gz[r][i][j] = fmaf(w[r], g, gz[r][i][j]);
-                            t[r] = fmaf(g, zz[r][i], t[r]);
+                            t[r] = fmaf(g, zz[r][j], t[r]);
                         }
                     }
                 }
@@ -292,19 +307,72 @@ tgcn_tail_bwd_z_kernel(const float* __restrict__ g_out, const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------ T3 backward to Wf
-// grid (chunk groups, node splits).  acc[cc][i][j] = g_Wf[(c0 + cc)*64 + 4 ty + i][4 tx + j]
+// grid (chunk groups, node splits).  acc[cc][i][j] = g_Wf[(c0 + cc)*64 + 4 ty + i][4 tx + j].
+// Half tiles of 64 nodes, double buffered: the global loads of half h+1 (z, g_pre, xf) are issued before the FMA loop
+// of half h and turned into features after it, so their latency hides behind the arithmetic.
+constexpr int T3H = 64;           // nodes per half tile
+
+struct T3Pre {                    // one thread's share of a half tile: 4 (node, 4-dim group) items
+    float4 g[4], z0[4], z1[4], z2[4], e[4];
+};
+
+__device__ __forceinline__ void t3_fetch(T3Pre& p, const float* __restrict__ z, const float* __restrict__ xf,
+                                         const float* __restrict__ g_pre, int64_t n0, int64_t n, int E, bool extra,
+                                         int tid) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int idx = tid + 256 * it, node = idx >> 4, d4 = idx & 15;
+        const bool ok = n0 + node < n;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        p.g[it] = p.z0[it] = p.z1[it] = p.z2[it] = p.e[it] = zero;
+        if (ok) {
+            p.g[it] = __ldg(reinterpret_cast<const float4*>(g_pre + (n0 + node) * TW) + d4);
+            const float4* zr = reinterpret_cast<const float4*>(z + (n0 + node) * 3 * TW);
+            p.z0[it] = __ldg(zr + d4);
+            p.z1[it] = __ldg(zr + 16 + d4);
+            p.z2[it] = __ldg(zr + 32 + d4);
+            if (extra && 4 * d4 < E) p.e[it] = __ldg(reinterpret_cast<const float4*>(xf + (n0 + node) * E) + d4);
+        }
+    }
+}
+
+__device__ __forceinline__ void t3_store(const T3Pre& p, float* __restrict__ An, float* __restrict__ Gn,
+                                         const float (&w)[T3C][3], int c0, int C, int tid) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int idx = tid + 256 * it, node = idx >> 4, d4 = idx & 15;
+        *reinterpret_cast<float4*>(Gn + node * TW + 4 * d4) = p.g[it];
+        const float4 z0 = p.z0[it], z1 = p.z1[it], z2 = p.z2[it];
+#pragma unroll
+        for (int cc = 0; cc < T3C; ++cc) {
+            const int c = c0 + cc;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < C) {
+                a.x = fmaxf(bit_pre(w[cc][0], w[cc][1], w[cc][2], z0.x, z1.x, z2.x), 0.f);
+                a.y = fmaxf(bit_pre(w[cc][0], w[cc][1], w[cc][2], z0.y, z1.y, z2.y), 0.f);
+                a.z = fmaxf(bit_pre(w[cc][0], w[cc][1], w[cc][2], z0.z, z1.z, z2.z), 0.f);
+                a.w = fmaxf(bit_pre(w[cc][0], w[cc][1], w[cc][2], z0.w, z1.w, z2.w), 0.f);
+            } else if (c == C) {
+                a = p.e[it];
+            }
+            *reinterpret_cast<float4*>(An + ((size_t)cc * T3H + node) * TW + 4 * d4) = a;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256, 1)
 tgcn_tail_bwd_w_kernel(const float* __restrict__ z, const float* __restrict__ wb, const float* __restrict__ xf,
-                       const float* __restrict__ g_pre, int64_t n, int C, int E, int64_t tiles_per_split,
+                       const float* __restrict__ g_pre, int64_t n, int C, int E, int64_t halves_per_split,
                        float* __restrict__ g_wf) {
     extern __shared__ __align__(16) float sm[];
-    float* An = sm;                                 // [T3C][TM][64]   features, node-major
-    float* Gn = An + T3C * TM * TW;                 // [TM][64]        g_pre, node-major
+    float* An = sm;                                 // [2][T3C][T3H][64]   features, node-major
+    float* Gn = An + 2 * T3C * T3H * TW;            // [2][T3H][64]        g_pre, node-major
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int c0 = blockIdx.x * T3C;
-    const int64_t n_tiles = (n + TM - 1) / TM;
-    const int64_t t_begin = (int64_t)blockIdx.y * tiles_per_split;
-    const int64_t t_end = min(n_tiles, t_begin + tiles_per_split);
+    const bool extra = E > 0 && c0 <= C && C < c0 + T3C;
+    const int64_t n_halves = (n + T3H - 1) / T3H;
+    const int64_t h_begin = (int64_t)blockIdx.y * halves_per_split;
+    const int64_t h_end = min(n_halves, h_begin + halves_per_split);
     float w[T3C][3];
 #pragma unroll
     for (int cc = 0; cc < T3C; ++cc)
@@ -317,44 +385,25 @@ tgcn_tail_bwd_w_kernel(const float* __restrict__ z, const float* __restrict__ wb
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[cc][i][j] = 0.f;
-    for (int64_t tile = t_begin; tile < t_end; ++tile) {
-        const int64_t n0 = tile * TM;
-        __syncthreads();
-        for (int idx = tid; idx < TM * (TW / 4); idx += 256) {
-            const int node = idx >> 4, d4 = idx & 15;
-            const bool ok = n0 + node < n;
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f), z0 = g, z1 = g, z2 = g;
-            if (ok) {
-                g = __ldg(reinterpret_cast<const float4*>(g_pre + (n0 + node) * TW) + d4);
-                const float4* zr = reinterpret_cast<const float4*>(z + (n0 + node) * 3 * TW);
-                z0 = __ldg(zr + d4);
-                z1 = __ldg(zr + 16 + d4);
-                z2 = __ldg(zr + 32 + d4);
-            }
-            *reinterpret_cast<float4*>(Gn + node * TW + 4 * d4) = g;
-#pragma unroll
-            for (int cc = 0; cc < T3C; ++cc) {
-                const int c = c0 + cc;
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < C) {
-                    a.x = fmaxf(bit_pre(w[cc][0], w[cc][1], w[cc][2], z0.x, z1.x, z2.x), 0.f);
-                    a.y = fmaxf(bit_pre(w[cc][0], w[cc][1], w[cc][2], z0.y, z1.y, z2.y), 0.f);
-                    a.z = fmaxf(bit_pre(w[cc][0], w[cc][1], w[cc][2], z0.z, z1.z, z2.z), 0.f);
-                    a.w = fmaxf(bit_pre(w[cc][0], w[cc][1], w[cc][2], z0.w, z1.w, z2.w), 0.f);
-                } else if (c == C && ok && 4 * d4 < E) {
-                    a = __ldg(reinterpret_cast<const float4*>(xf + (n0 + node) * E) + d4);
-                }
-                *reinterpret_cast<float4*>(An + ((size_t)cc * TM + node) * TW + 4 * d4) = a;
-            }
-        }
-        __syncthreads();
+    T3Pre pre;
+    if (h_begin < h_end) {
+        t3_fetch(pre, z, xf, g_pre, h_begin * T3H, n, E, extra, tid);
+        t3_store(pre, An, Gn, w, c0, C, tid);
+    }
+    __syncthreads();
+    for (int64_t h = h_begin; h < h_end; ++h) {
+        const int buf = (int)((h - h_begin) & 1);
+        const bool more = h + 1 < h_end;
+        if (more) t3_fetch(pre, z, xf, g_pre, (h + 1) * T3H, n, E, extra, tid);
+        const float* Ab = An + (size_t)buf * T3C * T3H * TW;
+        const float* Gb = Gn + (size_t)buf * T3H * TW;
 #pragma unroll 4
-        for (int node = 0; node < TM; ++node) {
-            const float4 g = *reinterpret_cast<const float4*>(Gn + node * TW + 4 * tx);
+        for (int node = 0; node < T3H; ++node) {
+            const float4 g = *reinterpret_cast<const float4*>(Gb + node * TW + 4 * tx);
             const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
             for (int cc = 0; cc < T3C; ++cc) {
-                const float4 a = *reinterpret_cast<const float4*>(An + ((size_t)cc * TM + node) * TW + 4 * ty);
+                const float4 a = *reinterpret_cast<const float4*>(Ab + ((size_t)cc * T3H + node) * TW + 4 * ty);
                 const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -362,6 +411,8 @@ tgcn_tail_bwd_w_kernel(const float* __restrict__ z, const float* __restrict__ wb
                     for (int j = 0; j < 4; ++j) acc[cc][i][j] = fmaf(av[i], gv[j], acc[cc][i][j]);
             }
         }
+        if (more) t3_store(pre, An + (size_t)(buf ^ 1) * T3C * T3H * TW, Gn + (size_t)(buf ^ 1) * T3H * TW, w, c0, C, tid);
+        __syncthreads();
     }
     const int F = C * TW + E;
 #pragma unroll
@@ -376,8 +427,8 @@ tgcn_tail_bwd_w_kernel(const float* __restrict__ z, const float* __restrict__ wb
 }
 
 static size_t tail_smem_fwd(int C) { return ((size_t)3 * TW * TP + 2 * TW * TP + 2 * TW * TW + 3 * C) * 4; }
-static size_t tail_smem_bwd_z(int C) { return ((size_t)3 * TW * TP + TW * TP + 2 * TW * TW + 6 * C) * 4; }
-static size_t tail_smem_bwd_w() { return ((size_t)T3C * TM * TW + TM * TW) * 4; }
+static size_t tail_smem_bwd_z(int C) { return ((size_t)TM * ZNP + TW * TP + 2 * TW * TW + 6 * C) * 4; }
+static size_t tail_smem_bwd_w() { return ((size_t)2 * T3C * T3H * TW + 2 * T3H * TW) * 4; }
 
 }  // namespace tagrec
 
@@ -433,9 +484,10 @@ extern "C" int tagrec_tgcn_tail_bwd(const float* g_out, const float* out, const 
     TAGREC_LAUNCH(tgcn_tail_bwd_z_kernel, (unsigned)std::min<int64_t>(n_tiles, kSMs), 256, smem_z, stream, g_out, out, z, wb,
                   wft, n, C, E, g_pre, g_z, g_wb, g_xf, g_bf);
     const int groups = (NC + T3C - 1) / T3C;
-    int64_t splits = std::max<int64_t>(1, std::min<int64_t>(n_tiles, kSMs / groups));
-    const int64_t tps = (n_tiles + splits - 1) / splits;
-    splits = (n_tiles + tps - 1) / tps;
+    const int64_t n_halves = (n + T3H - 1) / T3H;
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>(n_halves, kSMs / groups));
+    const int64_t tps = (n_halves + splits - 1) / splits;
+    splits = (n_halves + tps - 1) / tps;
     const size_t smem_w = tail_smem_bwd_w();
     TAGREC_CUDA(cudaFuncSetAttribute(tgcn_tail_bwd_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
     TAGREC_LAUNCH(tgcn_tail_bwd_w_kernel, dim3((unsigned)groups, (unsigned)splits), 256, smem_w, stream, z, wb, xf, g_pre, n,
