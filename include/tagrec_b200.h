@@ -198,6 +198,12 @@ int tagrec_eval_auc(const int64_t* users, int64_t nu, const float* user_table, c
                     int dim, const int64_t* train_ptr, const int32_t* train_items, const int64_t* test_ptr,
                     const int32_t* test_items, int64_t n_test_total, void* workspace, size_t workspace_bytes, double* out,
                     void* stream);
+/* same, with the path of the dense pass chosen explicitly: TAGREC_EVAL_AUTO (tensor cores when dim == 64), _FP32 (CUDA-core
+ * tiles), _TF32 (3xTF32 tcgen05 MMAs + exact re-scores inside the error margin; the sums are identical to _FP32's). */
+int tagrec_eval_auc_ex(const int64_t* users, int64_t nu, const float* user_table, const float* item_table,
+                       int64_t n_item, int dim, const int64_t* train_ptr, const int32_t* train_items,
+                       const int64_t* test_ptr, const int32_t* test_items, int64_t n_test_total, void* workspace,
+                       size_t workspace_bytes, double* out, int path, void* stream);
 
 /* metric sums over users (training/utils.py:15-35): out[4*nk] = recall|precision|hr|ndcg per k (double, +=). */
 int tagrec_eval_metrics(const int64_t* users, int64_t nu, const int32_t* topk_ids, int kmax,

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "tagrec_eval_topk_ex": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _sz, _i32, _p]),
     "tagrec_eval_auc_workspace_bytes": (_sz, [_i64, _i64]),
     "tagrec_eval_auc": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _sz, _p, _p]),
+    "tagrec_eval_auc_ex": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _sz, _p, _i32, _p]),
     "tagrec_eval_metrics": (_i32, [_p, _i64, _p, _i32, _p, _p, _p, _i32, _p, _p]),
     "tagrec_ngcf_dense_fwd": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "tagrec_ngcf_dense_bwd": (_i32, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p,

@@ -278,6 +278,12 @@ static int auc_splits(int64_t nu, int64_t n_item) {
     return (int)s;
 }
 
+// eval_auc_tc.cu
+bool auc_tc_available(int dim);
+int eval_auc_tc(const int64_t* users, int64_t nu, const float* user_table, const float* item_table, int64_t n_item,
+                const int64_t* test_ptr, const float* pos_sorted, const int32_t* n_pos, float* maxnorm,
+                unsigned long long* acc2, void* stream);
+
 }  // namespace tagrec
 
 using namespace tagrec;
@@ -290,7 +296,18 @@ extern "C" int tagrec_eval_auc(const int64_t* users, int64_t nu, const float* us
                                int64_t n_item, int dim, const int64_t* train_ptr, const int32_t* train_items,
                                const int64_t* test_ptr, const int32_t* test_items, int64_t n_test_total,
                                void* workspace, size_t workspace_bytes, double* out, void* stream) {
+    return tagrec_eval_auc_ex(users, nu, user_table, item_table, n_item, dim, train_ptr, train_items, test_ptr, test_items,
+                              n_test_total, workspace, workspace_bytes, out, TAGREC_EVAL_AUTO, stream);
+}
+
+extern "C" int tagrec_eval_auc_ex(const int64_t* users, int64_t nu, const float* user_table, const float* item_table,
+                                  int64_t n_item, int dim, const int64_t* train_ptr, const int32_t* train_items,
+                                  const int64_t* test_ptr, const int32_t* test_items, int64_t n_test_total,
+                                  void* workspace, size_t workspace_bytes, double* out, int path, void* stream) {
     TAGREC_REQUIRE(users && user_table && item_table && train_ptr && test_ptr && out, "null pointer");
+    TAGREC_REQUIRE(path == TAGREC_EVAL_AUTO || path == TAGREC_EVAL_FP32 || path == TAGREC_EVAL_TF32, "bad path");
+    const bool use_tc = path != TAGREC_EVAL_FP32 && auc_tc_available(dim);
+    TAGREC_REQUIRE(use_tc || path != TAGREC_EVAL_TF32, "tensor-core AUC path needs dim 64");
     TAGREC_REQUIRE(dim >= 4 && dim % AKC == 0, "dim must be a multiple of 32");
     TAGREC_REQUIRE(n_item > 0 && n_item < (1ll << 31), "n_item out of range");
     if (nu == 0) return TAGREC_OK;
@@ -305,6 +322,23 @@ extern "C" int tagrec_eval_auc(const int64_t* users, int64_t nu, const float* us
     TAGREC_CUDA(cudaMemsetAsync(acc2, 0, (size_t)nu * 8, st));
     TAGREC_LAUNCH(auc_pos_kernel, (unsigned)((nu + 7) / 8), 256, 0, stream, users, nu, user_table, item_table, dim,
                   train_ptr, train_items, test_ptr, test_items, pos_raw, pos_sorted, n_pos);
+    if (use_tc) {
+        float* maxnorm = reinterpret_cast<float*>(n_pos + nu);        // the 64 spare bytes behind n_pos
+        if (int rc = eval_auc_tc(users, nu, user_table, item_table, n_item, test_ptr, pos_sorted, n_pos, maxnorm, acc2,
+                                 stream))
+            return rc;
+#if defined(AT_EXPERIMENT) && AT_EXPERIMENT == 4
+        {
+            float h[2];
+            cudaMemcpyAsync(h, maxnorm, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+            cudaStreamSynchronize((cudaStream_t)stream);
+            printf("AT_EXPERIMENT 4: max |3xTF32 - exact| / (||u|| max||i||) = %.3e (max item norm %.3f)\n", h[1], h[0]);
+        }
+#endif
+        TAGREC_LAUNCH(auc_finalize_kernel, (unsigned)((nu + 7) / 8), 256, 0, stream, users, nu, user_table, item_table,
+                      n_item, dim, train_ptr, train_items, test_ptr, pos_sorted, n_pos, acc2, out);
+        return TAGREC_OK;
+    }
     AucArgs a{};
     a.users = users; a.nu = nu; a.user_table = user_table; a.item_table = item_table; a.n_item = n_item; a.dim = dim;
     a.test_ptr = test_ptr; a.pos_sorted = pos_sorted; a.n_pos = n_pos; a.acc2 = acc2;

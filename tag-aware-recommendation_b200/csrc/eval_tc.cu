@@ -81,7 +81,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
     constexpr int TMEM_COLS = 512;                            // A_COLS + TC_NACC * 128 <= 512, power of two
     constexpr int A_SMEM = kTS ? 0 : NH * TC_TILE_BYTES;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS, not generic LD)
     const int S = a.stages, K = a.k;
     unsigned char* As = base;                                         // SS form only: NH x 32 KB
     unsigned char* Bs = base + A_SMEM;                                // S x 32 KB
@@ -485,7 +485,7 @@ eval_tc_wide_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a, int 
     constexpr int ROWS = TC_M;
     constexpr int NACC = 2;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS, not generic LD)
     const int S = a.stages, K = a.k, D = KB * TC_D;
     unsigned char* Bs = base;                                         // S x 32 KB
     float* ls = reinterpret_cast<float*>(Bs + S * TC_TILE_BYTES);     // [K][ROWS]

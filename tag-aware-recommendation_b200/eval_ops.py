@@ -39,8 +39,9 @@ def metric_sums(users, topk_ids, test_ptr, test_items, ks, out=None):
     return out
 
 
-def auc_sums(users, user_table, item_table, train_ptr, train_items, test_ptr, test_items, out=None):
-    """training/utils.py:37-45 summed over ``users``: float64 [2] = (sum of per-user AUC, users with both classes)."""
+def auc_sums(users, user_table, item_table, train_ptr, train_items, test_ptr, test_items, out=None, path="auto"):
+    """training/utils.py:37-45 summed over ``users``: float64 [2] = (sum of per-user AUC, users with both classes).
+    ``path``: "auto" (tensor cores for 64-d tables), "fp32", "tf32" — identical sums."""
     L = lib()
     dev = user_table.device
     users = users.to(device=dev, dtype=torch.int64).contiguous()
@@ -49,9 +50,9 @@ def auc_sums(users, user_table, item_table, train_ptr, train_items, test_ptr, te
         out = torch.zeros(2, dtype=torch.float64, device=dev)
     n_test = int(test_items.numel())
     ws = torch.empty(int(L.tagrec_eval_auc_workspace_bytes(users.numel(), n_test)), dtype=torch.uint8, device=dev)
-    check(L.tagrec_eval_auc(ptr(users), users.numel(), ptr(ut), ptr(it), it.shape[0], it.shape[1], ptr(train_ptr),
-                            ptr(train_items), ptr(test_ptr), ptr(test_items), n_test, ptr(ws), ws.numel(), ptr(out),
-                            stream_ptr(dev)), "tagrec_eval_auc")
+    check(L.tagrec_eval_auc_ex(ptr(users), users.numel(), ptr(ut), ptr(it), it.shape[0], it.shape[1], ptr(train_ptr),
+                               ptr(train_items), ptr(test_ptr), ptr(test_items), n_test, ptr(ws), ws.numel(), ptr(out),
+                               {"auto": 0, "fp32": 1, "tf32": 2}[path], stream_ptr(dev)), "tagrec_eval_auc_ex")
     return out
 
 

@@ -914,6 +914,39 @@ def test_k3b_auc_vs_oracle(nu, n_item, dim, scale):
     assert abs(out[0] - tot) <= 1e-5 * cnt, (out[0], tot)
 
 
+@pytest.mark.parametrize("nu,n_item,scale,max_pos", [(70, 3000, 1.0, 30), (200, 100, 1.0, 10), (130, 9001, 30.0, 30),
+                                                     (300, 20000, 0.05, 80), (129, 128, 1.0, 5)])
+def test_k3b_tensor_core_auc_equals_fp32_path(nu, n_item, scale, max_pos):
+    """The 3xTF32 tensor-core AUC pass (csrc/eval_auc_tc.cu) gives the SAME integer rank sums as the fp32 pass: equal
+    user counts and AUC sums equal to double rounding (the sums are reduced by atomics in both).  Exact score ties
+    (duplicated item rows, positives among them), rows with more positives than the 32 staged in shared memory, tables
+    smaller than one tile, tile-edge sizes, large and small score scales."""
+    from tagrec_b200.eval_ops import auc_sums
+    g = torch.Generator().manual_seed(nu + n_item)
+    n_tab = nu + 3
+    ut = torch.randn(n_tab, 64, generator=g) * scale
+    it = torch.randn(n_item, 64, generator=g) * scale
+    it[n_item // 2:n_item // 2 + 20] = it[:20]                    # exact ties
+    it[7] = it[3] * (1 + 2e-7)                                    # near ties: inside the TF32 margin, distinct in fp32
+    rng = np.random.RandomState(n_item)
+    users = rng.permutation(n_tab)[:nu]
+    train, test = {}, {}
+    for u in range(n_tab):
+        train[u] = sorted(rng.choice(n_item, rng.randint(0, min(40, n_item // 2)), replace=False).tolist())
+        te = set(rng.choice(n_item, rng.randint(0, min(max_pos, n_item // 2)), replace=False).tolist())
+        if u % 3 == 0:
+            te |= {3, 7, n_item // 2 + 3}                         # tied / near-tied items as positives
+        test[u] = sorted(te)
+    tp, ti = T.bpr_training_data.user_items_to_csr(train, n_tab)
+    sp, si = T.bpr_training_data.user_items_to_csr(test, n_tab)
+    args = (torch.tensor(users, device=dev()), ut.to(dev()), it.to(dev()), torch.tensor(tp, device=dev()),
+            torch.tensor(ti, device=dev()).int(), torch.tensor(sp, device=dev()), torch.tensor(si, device=dev()).int())
+    a = auc_sums(*args, path="tf32").cpu().numpy()
+    b = auc_sums(*args, path="fp32").cpu().numpy()
+    assert a[1] == b[1] and a[1] > 0
+    assert abs(a[0] - b[0]) <= 1e-12 * max(1.0, b[1]), (a, b)
+
+
 # ------------------------------------------------------------------------------------------------------- sampler
 def test_device_sampler_properties(medium):
     U, I, _, _ = nums(medium)

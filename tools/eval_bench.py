@@ -70,21 +70,27 @@ def main():
         n_test = 25
         tptr = torch.arange(0, (U + 1) * n_test, n_test, device=dev, dtype=torch.int64)
         titems = torch.randint(0, I, (U, n_test), device=dev, generator=g).sort(dim=1).values.to(torch.int32).flatten()
-        for _ in range(2):
-            out = auc_sums(users, ut, it, ptr, items, tptr, titems)
-        torch.cuda.synchronize()
-        times = []
-        for _ in range(args.reps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            out = auc_sums(users, ut, it, ptr, items, tptr, titems)
-            b.record()
+        outs = {}
+        for apath in (["tf32", "fp32"] if args.dim == 64 else ["fp32"]):
+            for _ in range(2):
+                out = auc_sums(users, ut, it, ptr, items, tptr, titems, path=apath)
             torch.cuda.synchronize()
-            times.append(a.elapsed_time(b))
-        ms = float(np.median(times))
-        print(json.dumps({"path": "auc_fp32", "users": U, "items": I, "dim": args.dim, "ms": ms, "users_per_s": U / ms * 1e3,
-                          "tflops": 2.0 * U * I * args.dim / (ms * 1e-3) / 1e12, "mean_auc": float(out[0] / out[1])}))
-
+            times = []
+            for _ in range(args.reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                out = auc_sums(users, ut, it, ptr, items, tptr, titems, path=apath)
+                b.record()
+                torch.cuda.synchronize()
+                times.append(a.elapsed_time(b))
+            ms = float(np.median(times))
+            outs[apath] = out
+            print(json.dumps({"path": "auc_" + apath, "users": U, "items": I, "dim": args.dim, "ms": ms,
+                              "users_per_s": U / ms * 1e3, "tflops": 2.0 * U * I * args.dim / (ms * 1e-3) / 1e12,
+                              "mean_auc": float(out[0] / out[1])}))
+        if len(outs) == 2:
+            d = (outs["tf32"] - outs["fp32"]).abs().cpu().numpy()
+            print(json.dumps({"auc_paths_abs_diff_of_sum": float(d[0]), "users_counted_equal": bool(d[1] == 0)}))
 
 if __name__ == "__main__":
     main()
