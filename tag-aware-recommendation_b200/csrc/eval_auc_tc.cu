@@ -40,6 +40,7 @@ constexpr int AT_PC = 32;                   // positives per row staged in share
 constexpr float AT_MARGIN = 1.0e-5f;
 constexpr int AT_THREADS = 640;             // 20 warps: TMA, MMA, 16 epilogue (4 per scheduler: the searches are latency-bound), 2 converter
 constexpr int AT_STAGE_BYTES = 2 * TC_TILE_BYTES;        // hi tile + lo tile
+constexpr int AT_Q = 256;                                // a warp's queue of in-range scores (of 32 rows x 32 columns)
 #ifndef AT_EXPERIMENT
 #define AT_EXPERIMENT 0      // timing experiments (WRONG results): 1 no exact re-scores, 2 no bisection, 3 no scan at all;
                              // 4: measure max |3xTF32 score - exact score| / (||u|| max||i||) into item_maxnorm[1]
@@ -102,6 +103,10 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
     uint64_t* accfull = sfree + AT_STAGES;        // [NACC] MMA -> epilogue
     uint64_t* accfree = accfull + AT_NACC;        // [NACC] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfree + AT_NACC);
+    float* Qs = reinterpret_cast<float*>(tmem_slot + 2);              // [16 warps][AT_Q] queued scores
+    uint32_t* Qc = reinterpret_cast<uint32_t*>(Qs + 16 * AT_Q);       // [16][AT_Q]  (row in warp) << 5 | column
+    uint32_t* Racc = Qc + 16 * AT_Q;                                  // [16][32]    per-row sums of (m - lb)
+    uint32_t* Rum = Racc + 16 * 32;                                   // [16][32]    per-row masks of uncertain columns
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t u0 = (int64_t)blockIdx.x * TC_M;
@@ -258,6 +263,7 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
         const float* urow_s = Uf + (size_t)row * TC_UPITCH;
         const bool in_smem = pm <= AT_PC;
         unsigned long long tot = 0;
+        bool dense_mode = false;
         for (int t = 0; t < n_tiles; ++t) {
             const int r = t % AT_NACC;
             const int64_t it0 = i_begin + (int64_t)t * TC_N + half * 32;
@@ -336,7 +342,76 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
             };
             const bool warp_big = __any_sync(0xffffffffu, !in_smem);
 #if AT_EXPERIMENT != 3
-            const Scan r0 = warp_big ? scan(v0, 0, std::true_type{}) : scan(v0, 0, std::false_type{});
+            // Which columns are in range at all?  For a trained model (AUC 0.9+) it is a few per cent, spread over
+            // all rows — so the dense search above (every lane, all its 32 columns) would run for nearly every tile
+            // with nearly every result "below all".  Sparse case: the warp's in-range (row, column) pairs go to a
+            // queue in shared memory and are searched 32 at a time, any lane serving any row.
+            // (while the dense regime lasts the classification is skipped; it is re-probed every 16th tile)
+            unsigned int inr = 0;
+            int n_below = 0, cnt = 0, total = AT_Q + 1;
+            if (!dense_mode || (t & 15) == 0) {              // warp-uniform
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float s = __uint_as_float(v0[j]);
+                    const bool real = j < nvalid;
+                    const bool below = real && s < below_thr;
+                    n_below += below ? 1 : 0;
+                    inr |= (real && !below && s <= above_thr) ? (1u << j) : 0u;
+                }
+                cnt = __popc(inr);
+                total = __reduce_add_sync(0xffffffffu, cnt);
+                dense_mode = total > AT_Q;
+            }
+            Scan r0{(unsigned int)(n_below * pm), 0u};
+            if (total > AT_Q) {
+                r0 = warp_big ? scan(v0, 0, std::true_type{}) : scan(v0, 0, std::false_type{});
+            } else if (total > 0) {
+                const int ew = warp - 2;
+                float* qs = Qs + ew * AT_Q;
+                uint32_t* qc = Qc + ew * AT_Q;
+                uint32_t* racc = Racc + ew * 32;
+                uint32_t* rum = Rum + ew * 32;
+                int pos = cnt;                               // exclusive prefix sum over the lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t2 = __shfl_up_sync(0xffffffffu, pos, o);
+                    pos += lane >= o ? t2 : 0;
+                }
+                pos -= cnt;
+                racc[lane] = 0u;
+                rum[lane] = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if ((inr >> j) & 1u) {
+                        qs[pos] = __uint_as_float(v0[j]);
+                        qc[pos] = ((uint32_t)lane << 5) | (uint32_t)j;
+                        ++pos;
+                    }
+                }
+                __syncwarp();
+                for (int b0 = 0; b0 < total; b0 += 32) {
+                    const bool act = b0 + lane < total;
+                    const float s = act ? qs[b0 + lane] : 0.f;
+                    const uint32_t code = act ? qc[b0 + lane] : ((uint32_t)lane << 5);
+                    const int rl = (int)(code >> 5), col = (int)(code & 31u);
+                    const int pm_r = __shfl_sync(0xffffffffu, pm, rl);
+                    const float mg_r = __shfl_sync(0xffffffffu, mg, rl);
+                    const float* pr = Ps + TC_M + (q * 32 + rl);
+                    const float* cur = pr;
+#pragma unroll
+                    for (int st = AT_PC / 2; st > 0; st >>= 1) cur += (cur[(st - 1) * TC_M] < s) ? st * TC_M : 0;
+                    cur += (cur[0] < s) ? TC_M : 0;
+                    const float lo_p = cur[-TC_M], hi_p = cur[0];
+                    const bool sure = pm_r <= AT_PC && s - lo_p > mg_r && hi_p - s > mg_r;
+                    if (act) {
+                        if (sure) atomicAdd(racc + rl, (uint32_t)(pm_r - (int)(cur - pr) / TC_M));
+                        else atomicOr(rum + rl, 1u << col);
+                    }
+                }
+                __syncwarp();
+                r0.certain += racc[lane];
+                r0.um = rum[lane];
+            }
 #else
             const Scan r0{v0[3], 0u};
 #endif
@@ -381,7 +456,7 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
 
 static size_t auc_tc_smem() {
     return 1024 + (size_t)AT_STAGES * AT_STAGE_BYTES + ((size_t)TC_M * TC_UPITCH + TC_M * (AT_PC + 2) + 2) * 4 +
-           (3 * AT_STAGES + 2 * AT_NACC) * 8 + 64;
+           (3 * AT_STAGES + 2 * AT_NACC) * 8 + 64 + (size_t)16 * (2 * AT_Q + 64) * 4;
 }
 
 bool auc_tc_available(int dim) { return dim == TC_D && encode_tiled() != nullptr; }

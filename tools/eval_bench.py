@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--dim", type=int, default=64)
     ap.add_argument("--auc", action="store_true", help="also time the per-user AUC pass (K3b)")
+    ap.add_argument("--auc-skew", type=int, default=0,
+                    help="0: random test items (AUC 0.5, every score lands between positives: worst case); C > 0: each "
+                         "user's 25 test items are its best of C random candidates (trained-model-like, AUC -> 1)")
     args = ap.parse_args()
     import __graft_entry__ as G
     G.build()
@@ -69,7 +72,12 @@ def main():
         from tagrec_b200.eval_ops import auc_sums
         n_test = 25
         tptr = torch.arange(0, (U + 1) * n_test, n_test, device=dev, dtype=torch.int64)
-        titems = torch.randint(0, I, (U, n_test), device=dev, generator=g).sort(dim=1).values.to(torch.int32).flatten()
+        if args.auc_skew > 0:
+            cand = torch.randperm(I, device=dev, generator=g)[:args.auc_skew]
+            best = (ut[users] @ it[cand].T).topk(n_test, dim=1).indices
+            titems = cand[best].sort(dim=1).values.to(torch.int32).flatten()
+        else:
+            titems = torch.randint(0, I, (U, n_test), device=dev, generator=g).sort(dim=1).values.to(torch.int32).flatten()
         outs = {}
         for apath in (["tf32", "fp32"] if args.dim == 64 else ["fp32"]):
             for _ in range(2):
