@@ -429,12 +429,35 @@ def eval_leg(T, model, shape, dev, n_users):
         ids_by_path[path] = ids
         out[path] = {"users_per_s": n_users / (ms / 1e3), "ms": ms, "tflops": flops / (ms * 1e-3) / 1e12}
     same = bool(torch.equal(ids_by_path["tf32"], ids_by_path["fp32"]))
+    # per-user AUC (training/utils.py:37-45) over the same users: 20 random test items each (a random-init model: AUC
+    # 0.5, the worst case for the search among the positives); both dense-pass implementations, sums compared
+    from tagrec_b200.eval_ops import auc_sums
+    gen = torch.Generator(device=dev).manual_seed(5)
+    auc_ptr = torch.clamp(torch.arange(U + 1, device=dev), max=n_users) * 20
+    auc_items = torch.randint(0, shape["n_item"], (n_users, 20), device=dev, generator=gen).sort(dim=1).values
+    auc_items = auc_items.to(torch.int32).flatten().contiguous()
+    auc = {}
+    for path in ("tf32", "fp32"):
+        auc_sums(users, all_users, all_items, train_ptr, train_items, auc_ptr, auc_items, path=path)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        sums = auc_sums(users, all_users, all_items, train_ptr, train_items, auc_ptr, auc_items, path=path)
+        b.record()
+        torch.cuda.synchronize()
+        auc[path] = (a.elapsed_time(b), sums.cpu().numpy())
+    auc_same = bool(auc["tf32"][1][1] == auc["fp32"][1][1] and
+                    abs(auc["tf32"][1][0] - auc["fp32"][1][0]) <= 1e-9 * max(1.0, auc["fp32"][1][1]))
+    auc_out = {"ms": auc["tf32"][0], "users_per_s": n_users / (auc["tf32"][0] / 1e3),
+               "mean_auc": _finite(float(auc["tf32"][1][0] / max(auc["tf32"][1][1], 1.0))),
+               "kernel": "auc_tc_kernel (3xTF32 tcgen05.mma + exact band, canonical fp32 re-scores)",
+               "fp32_cuda_core_path_ms": auc["fp32"][0], "sums_identical": auc_same}
     tf32_peak = 1100.0      # nominal dense TF32 TFLOP/s (B200_PROFILING.md); no measured TF32 figure in MEASURED_PEAKS
     return {"users_per_s": out["tf32"]["users_per_s"], "users": n_users, "items": shape["n_item"], "k": 20,
             "ms": out["tf32"]["ms"], "tflops": out["tf32"]["tflops"],
             "tensor_frac_of_nominal_tf32": out["tf32"]["tflops"] / tf32_peak,
             "kernel": "eval_tc_kernel (tcgen05.mma kind::tf32 filter + exact fp32 re-score)",
-            "fp32_cuda_core_path": out["fp32"], "paths_identical": same}
+            "fp32_cuda_core_path": out["fp32"], "paths_identical": same, "auc": auc_out}
 
 
 def main():
