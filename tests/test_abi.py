@@ -36,6 +36,38 @@ def test_version_and_error_text():
     assert rc == -1 and b"null" in L.tagrec_last_error()
 
 
+def test_argument_validation_of_the_dense_kernels_needs_no_gpu():
+    """Every entry point validates its arguments before it touches the device: wrong widths / paths / null pointers
+    come back as TAGREC_EINVAL (-1) with the reason in tagrec_last_error() — the error behaviour the Python layer
+    turns into TagrecError."""
+    L = _lib.lib()
+    one = ctypes.c_void_p(16)          # a non-null dummy pointer; never dereferenced by the checks
+    cases = [
+        (lambda: L.tagrec_xty(one, one, 10, 5, 32, one, None), b"multiples of 4"),
+        (lambda: L.tagrec_xty(one, one, 10, 64, 68, one, None), b"multiples of 4"),
+        (lambda: L.tagrec_xty(None, one, 10, 64, 32, one, None), b"null"),
+        (lambda: L.tagrec_tgcn_tail_fwd(one, one, one, one, one, 10, 32, 32, 48, one, None), b"64-d"),
+        (lambda: L.tagrec_tgcn_tail_fwd(one, one, one, one, one, 10, 64, 32, 50, one, None), b"multiple of 4"),
+        (lambda: L.tagrec_tgcn_tail_fwd(one, None, one, one, one, 10, 64, 32, 48, one, None), b"null"),
+        (lambda: L.tagrec_tgcn_mix_fwd(one, one, one, one, one, one, one, one, one, 10, 64, 32, 5, one, one, None),
+         b"num_vec_conv"),
+        (lambda: L.tagrec_tgcn_mix_fwd(one, one, one, one, one, one, one, one, one, 10, 64, 16, 8, one, one, None),
+         b"dim_atten"),
+        (lambda: L.tagrec_eval_auc_ex(one, 4, one, one, 100, 64, one, one, one, one, 8, one, 1 << 20, one, 7, None),
+         b"bad path"),
+        (lambda: L.tagrec_eval_auc_ex(one, 4, one, one, 100, 96, one, one, one, one, 8, one, 1 << 20, one, 2, None),
+         b"dim 64"),
+        (lambda: L.tagrec_nbr_attention_fwd(one, one, one, one, one, one, one, 10, 40, 40, 64, 32, one, one, None),
+         b"neighbor_k"),
+    ]
+    for call, text in cases:
+        assert call() == -1
+        assert text in L.tagrec_last_error(), (text, L.tagrec_last_error())
+    # n == 0 is a no-op that succeeds (no launch)
+    assert L.tagrec_tgcn_tail_fwd(one, one, one, one, one, 0, 64, 32, 48, one, None) == 0
+    assert L.tagrec_tgcn_mix_fwd(one, one, one, one, one, one, one, one, one, 0, 64, 32, 8, one, one, None) == 0
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libtagrec_b200.so")

@@ -947,6 +947,30 @@ def test_k3b_tensor_core_auc_equals_fp32_path(nu, n_item, scale, max_pos):
     assert abs(a[0] - b[0]) <= 1e-12 * max(1.0, b[1]), (a, b)
 
 
+def test_k3b_tensor_core_auc_large_trained_like():
+    """2 048 users x 200 000 items, test items = each user's best 25 of 512 candidates (AUC ~ 0.97: the sparse-queue
+    regime of the epilogue) and random ones (dense regime): tensor-core sums == fp32 sums."""
+    from tagrec_b200.eval_ops import auc_sums
+    g = torch.Generator(device=dev()).manual_seed(3)
+    U, I = 2048, 200_000
+    ut = torch.nn.functional.normalize(torch.randn(U, 64, device=dev(), generator=g), dim=1)
+    it = torch.nn.functional.normalize(torch.randn(I, 64, device=dev(), generator=g), dim=1) * \
+        (0.5 + torch.rand(I, 1, device=dev(), generator=g))
+    users = torch.arange(U, device=dev())
+    tp = torch.arange(0, (U + 1) * 50, 50, device=dev())
+    ti = torch.randint(0, I, (U, 50), device=dev(), generator=g).sort(dim=1).values.int().flatten()
+    sp = torch.arange(0, (U + 1) * 25, 25, device=dev())
+    cand = torch.randperm(I, device=dev(), generator=g)[:512]
+    best = cand[(ut @ it[cand].T).topk(25, dim=1).indices].sort(dim=1).values.int().flatten()
+    rand = torch.randint(0, I, (U, 25), device=dev(), generator=g).sort(dim=1).values.int().flatten()
+    for si, lo, hi in ((best, 0.9, 1.0), (rand, 0.45, 0.55)):
+        a = auc_sums(users, ut, it, tp, ti, sp, si, path="tf32").cpu().numpy()
+        b = auc_sums(users, ut, it, tp, ti, sp, si, path="fp32").cpu().numpy()
+        assert a[1] == b[1] == U
+        assert abs(a[0] - b[0]) <= 1e-12 * U, (a, b)
+        assert lo < a[0] / a[1] < hi
+
+
 # ------------------------------------------------------------------------------------------------------- sampler
 def test_device_sampler_properties(medium):
     U, I, _, _ = nums(medium)
