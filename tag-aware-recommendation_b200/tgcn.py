@@ -185,15 +185,24 @@ class BasicLayer(nn.Module):
         wb = self.conv["bit_level"].weight[:, 0, :, 0]                       # [32, 3]
         return TgcnTailFn.apply(eN, wb, self._vec_conv(eN), self.Wf, self.bf.reshape(-1))
 
+    def _cat_tables(self, a, b):
+        """Row-wise concatenation of two (neighbour, weight-id) table pairs, cached by storage (the tables are built
+        once per model, tgcn.py:194-202)."""
+        key = (a[0].data_ptr(), b[0].data_ptr(), a[0].shape, b[0].shape)
+        cache = self.__dict__.setdefault("_table_cache", {})
+        if key not in cache:
+            cache[key] = (torch.cat([a[0], b[0]], 0).contiguous(), torch.cat([a[1], b[1]], 0).contiguous())
+        return cache[key]
+
     def forward(self, eu, ei, et, ew, u_iw, u_tw, i_uw, i_tw, t_uw, t_iw):
         a_u, a_i, a_t = self.atten1["user"], self.atten1["item"], self.atten1["tag"]
         pj_u, pj_i, pj_t = skinny_mm(eu, a_u.W_2), skinny_mm(ei, a_i.W_2), skinny_mm(et, a_t.W_2)
-        eu_iN = a_i.forward(eu, ei, ew, u_iw, pj_i)
-        eu_tN = a_t.forward(eu, et, ew, u_tw, pj_t)
-        ei_uN = a_u.forward(ei, eu, ew, i_uw, pj_u)
-        ei_tN = a_t.forward(ei, et, ew, i_tw, pj_t)
-        et_uN = a_u.forward(et, eu, ew, t_uw, pj_u)
-        et_iN = a_i.forward(et, ei, ew, t_iw, pj_i)
+        # Each Attention1 module serves two node types (e.g. "item" neighbours of users and of tags): one K4 pass over
+        # both (node rows and neighbour tables concatenated; the tables are static, their concatenation is cached).
+        nu, ni, nt = eu.shape[0], ei.shape[0], et.shape[0]
+        eu_iN, et_iN = torch.split(a_i.forward(torch.cat([eu, et], 0), ei, ew, self._cat_tables(u_iw, t_iw), pj_i), [nu, nt])
+        eu_tN, ei_tN = torch.split(a_t.forward(torch.cat([eu, ei], 0), et, ew, self._cat_tables(u_tw, i_tw), pj_t), [nu, ni])
+        ei_uN, et_uN = torch.split(a_u.forward(torch.cat([ei, et], 0), eu, ew, self._cat_tables(i_uw, t_uw), pj_u), [ni, nt])
         # The three node types share U/q/p, the convolutions and the fusion layer: one K7a and one K7 pass over their
         # concatenation (the reference's own commented-out variant, tgcn.py:131-137).
         par = (self.U, self.q.reshape(-1), self.p.reshape(-1)) + tuple(
