@@ -44,29 +44,57 @@ __device__ __forceinline__ float bit_pre(float w0, float w1, float w2, float z0,
     return fmaf(w2, z2, fmaf(w1, z1, w0 * z0));
 }
 
+// Packed fp32 FMA (fma.rn.f32x2 -> FFMA2): two IEEE fp32 FMAs per instruction.  Measured on B200
+// (tools/probes/ffma2_probe.cu): the same 128 FMA/clk/SM as scalar FFMA, i.e. HALF the issue slots per flop — and the
+// tile GEMMs below are issue-bound (ncu: issue slots 65 % busy, FMA pipe 55 %, profiles/r1_tgcn_tail_ncu.md).
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // acc[i][j] += sum_k Af[k][8 ty + i] * Wk[k][4 tx + j]      (Af feature-major pitch TP, Wk row-major pitch TW)
+// p[ip][j] holds the pair (acc[2 ip][j], acc[2 ip + 1][j]): the node pairs come straight out of the float4 loads of Af,
+// the weight is duplicated into both halves (4 moves per 16 FFMA2).
 __device__ __forceinline__ void tile_gemm_step(const float* __restrict__ Af, const float* __restrict__ Wk, int k, int ty,
-                                               int tx, float (&acc)[8][4]) {
+                                               int tx, unsigned long long (&p)[4][4]) {
     const float4 a0 = *reinterpret_cast<const float4*>(Af + k * TP + 8 * ty);
     const float4 a1 = *reinterpret_cast<const float4*>(Af + k * TP + 8 * ty + 4);
     const float4 w = *reinterpret_cast<const float4*>(Wk + k * TW + 4 * tx);
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float wv[4] = {w.x, w.y, w.z, w.w};
+    const unsigned long long ap[4] = {pack2(a0.x, a0.y), pack2(a0.z, a0.w), pack2(a1.x, a1.y), pack2(a1.z, a1.w)};
+    const unsigned long long wd[4] = {pack2(w.x, w.x), pack2(w.y, w.y), pack2(w.z, w.z), pack2(w.w, w.w)};
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int ip = 0; ip < 4; ++ip)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], wv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) p[ip][j] = ffma2(ap[ip], wd[j], p[ip][j]);
 }
 
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ Af, const float* __restrict__ Wk, int kc, int ty,
                                           int tx, float (&acc)[8][4]) {
+    unsigned long long p[4][4];
+#pragma unroll
+    for (int ip = 0; ip < 4; ++ip)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[ip][j] = pack2(acc[2 * ip][j], acc[2 * ip + 1][j]);
     if (kc == TW) {                                 // the 64-feature chunks: compile-time trip count
 #pragma unroll 16
-        for (int k = 0; k < TW; ++k) tile_gemm_step(Af, Wk, k, ty, tx, acc);
+        for (int k = 0; k < TW; ++k) tile_gemm_step(Af, Wk, k, ty, tx, p);
     } else {
 #pragma unroll 4
-        for (int k = 0; k < kc; ++k) tile_gemm_step(Af, Wk, k, ty, tx, acc);
+        for (int k = 0; k < kc; ++k) tile_gemm_step(Af, Wk, k, ty, tx, p);
     }
+#pragma unroll
+    for (int ip = 0; ip < 4; ++ip)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) unpack2(p[ip][j], acc[2 * ip][j], acc[2 * ip + 1][j]);
 }
 
 // rows [n0, n0 + TM) of a row-major [n, width] table -> feature-major tile X[f][node] (zero rows past n)
@@ -378,13 +406,13 @@ tgcn_tail_bwd_w_kernel(const float* __restrict__ z, const float* __restrict__ wb
     for (int cc = 0; cc < T3C; ++cc)
 #pragma unroll
         for (int r = 0; r < 3; ++r) w[cc][r] = (c0 + cc < C) ? __ldg(wb + 3 * (c0 + cc) + r) : 0.f;
-    float acc[T3C][4][4];
+    unsigned long long acc2[T3C][2][4];            // acc2[cc][ip][j] = rows (2 ip, 2 ip + 1) of the 4 x 4 block, packed
 #pragma unroll
     for (int cc = 0; cc < T3C; ++cc)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int ip = 0; ip < 2; ++ip)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[cc][i][j] = 0.f;
+            for (int j = 0; j < 4; ++j) acc2[cc][ip][j] = 0ull;
     T3Pre pre;
     if (h_begin < h_end) {
         t3_fetch(pre, z, xf, g_pre, h_begin * T3H, n, E, extra, tid);
@@ -400,21 +428,29 @@ tgcn_tail_bwd_w_kernel(const float* __restrict__ z, const float* __restrict__ wb
 #pragma unroll 4
         for (int node = 0; node < T3H; ++node) {
             const float4 g = *reinterpret_cast<const float4*>(Gb + node * TW + 4 * tx);
-            const float gv[4] = {g.x, g.y, g.z, g.w};
+            const unsigned long long gd[4] = {pack2(g.x, g.x), pack2(g.y, g.y), pack2(g.z, g.z), pack2(g.w, g.w)};
 #pragma unroll
             for (int cc = 0; cc < T3C; ++cc) {
                 const float4 a = *reinterpret_cast<const float4*>(Ab + ((size_t)cc * T3H + node) * TW + 4 * ty);
-                const float av[4] = {a.x, a.y, a.z, a.w};
+                const unsigned long long a01 = pack2(a.x, a.y), a23 = pack2(a.z, a.w);
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[cc][i][j] = fmaf(av[i], gv[j], acc[cc][i][j]);
+                for (int j = 0; j < 4; ++j) {
+                    acc2[cc][0][j] = ffma2(a01, gd[j], acc2[cc][0][j]);
+                    acc2[cc][1][j] = ffma2(a23, gd[j], acc2[cc][1][j]);
+                }
             }
         }
         if (more) t3_store(pre, An + (size_t)(buf ^ 1) * T3C * T3H * TW, Gn + (size_t)(buf ^ 1) * T3H * TW, w, c0, C, tid);
         __syncthreads();
     }
     const int F = C * TW + E;
+    float acc[T3C][4][4];
+#pragma unroll
+    for (int cc = 0; cc < T3C; ++cc)
+#pragma unroll
+        for (int ip = 0; ip < 2; ++ip)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) unpack2(acc2[cc][ip][j], acc[cc][2 * ip][j], acc[cc][2 * ip + 1][j]);
 #pragma unroll
     for (int cc = 0; cc < T3C; ++cc)
 #pragma unroll
