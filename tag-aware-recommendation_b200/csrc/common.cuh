@@ -37,11 +37,41 @@ constexpr int kSMs = 148;   // B200
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
+// Packed fp32 FMA (fma.rn.f32x2 -> SASS FFMA2): two IEEE fp32 FMAs per instruction.  Measured on B200
+// (tools/probes/ffma2_probe.cu): the same 128 FMA/clk/SM as scalar FFMA, i.e. half the issue slots per flop; results
+// are bit-identical to two fmaf.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// fma4 (the gather kernels' accumulate) measured NO different packed or scalar — K1 60.4 vs 60.2 ms per layer on the
+// 1.88e9-nnz graph, K5 / K6 model steps within noise: those kernels wait on memory, not on issue slots.  Scalar kept.
+#ifndef TAGREC_FMA4_PACKED
+#define TAGREC_FMA4_PACKED 0
+#endif
 __device__ __forceinline__ void fma4(float4& acc, float s, const float4& x) {
+#if TAGREC_FMA4_PACKED
+    const unsigned long long sd = pack2(s, s);
+    const unsigned long long lo = ffma2(pack2(x.x, x.y), sd, pack2(acc.x, acc.y));
+    const unsigned long long hi = ffma2(pack2(x.z, x.w), sd, pack2(acc.z, acc.w));
+    unpack2(lo, acc.x, acc.y);
+    unpack2(hi, acc.z, acc.w);
+#else
     acc.x = fmaf(s, x.x, acc.x);
     acc.y = fmaf(s, x.y, acc.y);
     acc.z = fmaf(s, x.z, acc.z);
     acc.w = fmaf(s, x.w, acc.w);
+#endif
 }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {

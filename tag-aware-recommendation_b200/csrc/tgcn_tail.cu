@@ -44,23 +44,8 @@ __device__ __forceinline__ float bit_pre(float w0, float w1, float w2, float z0,
     return fmaf(w2, z2, fmaf(w1, z1, w0 * z0));
 }
 
-// Packed fp32 FMA (fma.rn.f32x2 -> FFMA2): two IEEE fp32 FMAs per instruction.  Measured on B200
-// (tools/probes/ffma2_probe.cu): the same 128 FMA/clk/SM as scalar FFMA, i.e. HALF the issue slots per flop — and the
-// tile GEMMs below are issue-bound (ncu: issue slots 65 % busy, FMA pipe 55 %, profiles/r1_tgcn_tail_ncu.md).
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-
+// The tile GEMMs below were issue-bound on scalar FFMA (ncu: issue slots 65 % busy, FMA pipe 55 %,
+// profiles/r1_tgcn_tail_ncu.md): they use the packed FMAs of common.cuh (pack2 / ffma2).
 // acc[i][j] += sum_k Af[k][8 ty + i] * Wk[k][4 tx + j]      (Af feature-major pitch TP, Wk row-major pitch TW)
 // p[ip][j] holds the pair (acc[2 ip][j], acc[2 ip + 1][j]): the node pairs come straight out of the float4 loads of Af,
 // the weight is duplicated into both halves (4 moves per 16 FFMA2).
