@@ -29,8 +29,16 @@ constexpr int NLD = ND + 4;     // smem row pitch (floats): keeps float4 alignme
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.2f * x; }
 
 // acc[r][c] += sum_i X[(ty*4+r)][i] * W[i][tx*4+c]
+// Packed FMAs (FFMA2, common.cuh): the column pairs come straight out of the float4 loads of W, the x operand is
+// broadcast; every output's own accumulation order over i is unchanged (bit-identical to the scalar form).
 __device__ __forceinline__ void tile_mm(const float* __restrict__ Xs, const float* __restrict__ Ws, int ty, int tx,
                                         float (&acc)[4][4]) {
+    unsigned long long p[4][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        p[r][0] = pack2(acc[r][0], acc[r][1]);
+        p[r][1] = pack2(acc[r][2], acc[r][3]);
+    }
 #pragma unroll 4
     for (int i = 0; i < ND; i += 4) {
         float4 x[4], w[4];
@@ -43,12 +51,16 @@ __device__ __forceinline__ void tile_mm(const float* __restrict__ Xs, const floa
             const float xv[4] = {x[r].x, x[r].y, x[r].z, x[r].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                acc[r][0] = fmaf(xv[k], w[k].x, acc[r][0]);
-                acc[r][1] = fmaf(xv[k], w[k].y, acc[r][1]);
-                acc[r][2] = fmaf(xv[k], w[k].z, acc[r][2]);
-                acc[r][3] = fmaf(xv[k], w[k].w, acc[r][3]);
+                const unsigned long long xd = pack2(xv[k], xv[k]);
+                p[r][0] = ffma2(xd, pack2(w[k].x, w[k].y), p[r][0]);
+                p[r][1] = ffma2(xd, pack2(w[k].z, w[k].w), p[r][1]);
             }
         }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        unpack2(p[r][0], acc[r][0], acc[r][1]);
+        unpack2(p[r][1], acc[r][2], acc[r][3]);
     }
 }
 
@@ -134,7 +146,7 @@ ngcf_dense_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__
     }
     // weight gradients of this block: dW1[i][j] = sum_r (nei+e)[r][i] gs[r][j], dW2 likewise with nei*e and gt;
     // thread (ty, tx) owns rows 4ty..4ty+3, columns 4tx..4tx+3, accumulated over all tiles of the block
-    float a1[4][4] = {}, a2[4][4] = {};
+    unsigned long long a1p[4][2] = {}, a2p[4][2] = {};     // weight-gradient blocks, column pairs packed (FFMA2)
     const int64_t tiles = (n + NR - 1) / NR;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t r0 = tile * NR;
@@ -206,26 +218,30 @@ ngcf_dense_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__
                 const float4 gt4 = *reinterpret_cast<const float4*>(Gt + r * NLD + 4 * tx);
                 const float x1[4] = {nn4.x + ee4.x, nn4.y + ee4.y, nn4.z + ee4.z, nn4.w + ee4.w};
                 const float x2[4] = {nn4.x * ee4.x, nn4.y * ee4.y, nn4.z * ee4.z, nn4.w * ee4.w};
-                const float gsv[4] = {gs4.x, gs4.y, gs4.z, gs4.w};
-                const float gtv[4] = {gt4.x, gt4.y, gt4.z, gt4.w};
+                const unsigned long long gs01 = pack2(gs4.x, gs4.y), gs23 = pack2(gs4.z, gs4.w);
+                const unsigned long long gt01 = pack2(gt4.x, gt4.y), gt23 = pack2(gt4.z, gt4.w);
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        a1[i][j] = fmaf(x1[i], gsv[j], a1[i][j]);
-                        a2[i][j] = fmaf(x2[i], gtv[j], a2[i][j]);
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const unsigned long long x1d = pack2(x1[i], x1[i]), x2d = pack2(x2[i], x2[i]);
+                    a1p[i][0] = ffma2(x1d, gs01, a1p[i][0]);
+                    a1p[i][1] = ffma2(x1d, gs23, a1p[i][1]);
+                    a2p[i][0] = ffma2(x2d, gt01, a2p[i][0]);
+                    a2p[i][1] = ffma2(x2d, gt23, a2p[i][1]);
+                }
             }
         }
     }
     if (dw1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                atomicAdd(dw1 + (ty * 4 + i) * ND + tx * 4 + j, a1[i][j]);
-                atomicAdd(dw2 + (ty * 4 + i) * ND + tx * 4 + j, a2[i][j]);
-            }
+        for (int i = 0; i < 4; ++i) {
+            float4 v1, v2;
+            unpack2(a1p[i][0], v1.x, v1.y);
+            unpack2(a1p[i][1], v1.z, v1.w);
+            unpack2(a2p[i][0], v2.x, v2.y);
+            unpack2(a2p[i][1], v2.z, v2.w);
+            red_add4(reinterpret_cast<float4*>(dw1 + (ty * 4 + i) * ND + tx * 4), v1);
+            red_add4(reinterpret_cast<float4*>(dw2 + (ty * 4 + i) * ND + tx * 4), v2);
+        }
     }
 }
 
