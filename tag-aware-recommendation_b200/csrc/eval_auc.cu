@@ -305,8 +305,9 @@ static int auc_splits(int64_t nu, int64_t n_item) {
 
 // eval_auc_tc.cu
 bool auc_tc_available(int dim);
+size_t auc_tc_workspace_bytes(int64_t nu, int64_t n_test_total);
 int eval_auc_tc(const int64_t* users, int64_t nu, const float* user_table, const float* item_table, int64_t n_item,
-                const int64_t* test_ptr, const float* pos_sorted, const int32_t* n_pos, float* maxnorm,
+                const int64_t* test_ptr, const float* pos_sorted, const int32_t* n_pos, int64_t n_test_total, void* ws,
                 unsigned long long* acc2, void* stream);
 
 }  // namespace tagrec
@@ -314,7 +315,7 @@ int eval_auc_tc(const int64_t* users, int64_t nu, const float* user_table, const
 using namespace tagrec;
 
 extern "C" size_t tagrec_eval_auc_workspace_bytes(int64_t nu, int64_t n_test_total) {
-    return 256 + (size_t)n_test_total * 8 + (size_t)nu * 12 + 64;
+    return 256 + (size_t)n_test_total * 8 + (size_t)nu * 12 + 64 + auc_tc_workspace_bytes(nu, n_test_total);
 }
 
 extern "C" int tagrec_eval_auc(const int64_t* users, int64_t nu, const float* user_table, const float* item_table,
@@ -348,14 +349,14 @@ extern "C" int tagrec_eval_auc_ex(const int64_t* users, int64_t nu, const float*
     TAGREC_LAUNCH(auc_pos_kernel, (unsigned)((nu + 7) / 8), 256, 0, stream, users, nu, user_table, item_table, dim,
                   train_ptr, train_items, test_ptr, test_items, pos_raw, pos_sorted, n_pos);
     if (use_tc) {
-        float* maxnorm = reinterpret_cast<float*>(n_pos + nu);        // the 64 spare bytes behind n_pos
-        if (int rc = eval_auc_tc(users, nu, user_table, item_table, n_item, test_ptr, pos_sorted, n_pos, maxnorm, acc2,
-                                 stream))
+        void* tc_ws = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(n_pos + nu) + 63) & ~(uintptr_t)63);
+        if (int rc = eval_auc_tc(users, nu, user_table, item_table, n_item, test_ptr, pos_sorted, n_pos, n_test_total,
+                                 tc_ws, acc2, stream))
             return rc;
 #if defined(AT_EXPERIMENT) && AT_EXPERIMENT == 4
         {
             float h[2];
-            cudaMemcpyAsync(h, maxnorm, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+            cudaMemcpyAsync(h, tc_ws, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
             cudaStreamSynchronize((cudaStream_t)stream);
             printf("AT_EXPERIMENT 4: max |3xTF32 - exact| / (||u|| max||i||) = %.3e (max item norm %.3f)\n", h[1], h[0]);
         }

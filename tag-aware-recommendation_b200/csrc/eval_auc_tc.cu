@@ -21,6 +21,8 @@
 //                 [min - margin, max + margin] of the row's positives, else a branch-free bisection over the sorted
 //                 positives in shared memory (k-major: conflict-free) + the margin test; uncertain columns are
 //                 re-scored after the accumulator has been handed back.
+// Rows are VIRTUAL rows: a user with more than 32 positives is split into several rows (same embedding, consecutive
+// groups of 32 sorted positives) — 2 f is additive over such a partition (auc_vrows_kernel).
 #include <float.h>
 
 #include <algorithm>
@@ -55,10 +57,44 @@ struct AucTcArgs {
     const int64_t* test_ptr;
     const float* pos_sorted;
     const int32_t* n_pos;
+    const int32_t* vr_owner;                // [nv] index into users[] of the row this virtual row belongs to
+    const int32_t* vr_part;                 // [nv] which group of AT_PC sorted positives of that row it searches
+    const int32_t* nv;                      // device scalar: number of virtual rows
     const float* item_maxnorm;
     int64_t items_per_split;                // multiple of TC_N
     unsigned long long* acc2;
 };
+
+// Virtual rows: 2 f(s) is additive over a partition of the positives, so a user with m positives becomes
+// max(1, ceil(m / AT_PC)) rows with the same embedding and consecutive groups of AT_PC sorted positives — every row's
+// positives fit the shared-memory search, whatever the size of the test set.  One block; exclusive scan of the counts.
+__global__ void __launch_bounds__(1024) auc_vrows_kernel(const int32_t* __restrict__ n_pos, int64_t nu,
+                                                         int32_t* __restrict__ vr_owner, int32_t* __restrict__ vr_part,
+                                                         int32_t* __restrict__ nv) {
+    __shared__ int part_sum[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (nu + 1023) / 1024, lo = t * per, hi = min(nu, lo + per);
+    int mine = 0;
+    for (int64_t w = lo; w < hi; ++w) mine += max(1, (n_pos[w] + AT_PC - 1) / AT_PC);
+    part_sum[t] = mine;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {            // inclusive scan
+        const int v = t >= o ? part_sum[t - o] : 0;
+        __syncthreads();
+        part_sum[t] += v;
+        __syncthreads();
+    }
+    int pos = part_sum[t] - mine;
+    for (int64_t w = lo; w < hi; ++w) {
+        const int parts = max(1, (n_pos[w] + AT_PC - 1) / AT_PC);
+        for (int k = 0; k < parts; ++k) {
+            vr_owner[pos] = (int32_t)w;
+            vr_part[pos] = k;
+            ++pos;
+        }
+    }
+    if (t == 1023) *nv = part_sum[1023];
+}
 
 __device__ __forceinline__ float at_dot_seq(const float* __restrict__ urow, const float* __restrict__ irow) {
     float acc = 0.f;
@@ -113,6 +149,8 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
     const int64_t i_begin = (int64_t)blockIdx.y * a.items_per_split;
     const int64_t i_end = min(a.n_item, i_begin + a.items_per_split);
     const int n_tiles = (int)((i_end - i_begin + TC_N - 1) / TC_N);
+    const int64_t nv = __ldg(a.nv);
+    if (u0 >= nv) return;                       // the grid is sized for the upper bound of the virtual-row count
 
     if (tid == 0) {
         for (int s = 0; s < AT_STAGES; ++s) {
@@ -142,17 +180,20 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;           // column quarter 0..3 (32 columns each)
     const int row = q * 32 + lane;
-    const bool valid = is_epi && (u0 + row < a.nu);
+    const bool valid = is_epi && (u0 + row < nv);
     int pm = 0;
+    int64_t owner = 0;                          // index into users[] / acc2[]
     float unorm2 = 0.f;
     const float* pp = a.pos_sorted;
     if (is_epi) {
         const float4* urow = nullptr;
         if (valid) {
-            const int64_t u = __ldg(a.users + u0 + row);
+            owner = __ldg(a.vr_owner + u0 + row);
+            const int part = __ldg(a.vr_part + u0 + row);
+            const int64_t u = __ldg(a.users + owner);
             urow = reinterpret_cast<const float4*>(a.user_table + u * TC_D);
-            pm = __ldg(a.n_pos + u0 + row);
-            pp = a.pos_sorted + __ldg(a.test_ptr + u);
+            pm = min(AT_PC, max(0, __ldg(a.n_pos + owner) - part * AT_PC));
+            pp = a.pos_sorted + __ldg(a.test_ptr + u) + part * AT_PC;
         }
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -179,7 +220,7 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
         if (half == 0) {
             tmem_st_wait();
             Ps[row] = -INFINITY;
-            for (int j = 0; j <= AT_PC; ++j) Ps[(j + 1) * TC_M + row] = (j < pm && j < AT_PC) ? __ldg(pp + j) : INFINITY;
+            for (int j = 0; j <= AT_PC; ++j) Ps[(j + 1) * TC_M + row] = j < pm ? __ldg(pp + j) : INFINITY;
         }
     }
     tc_fence_before();
@@ -261,7 +302,6 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
         const float* ps = Ps + TC_M + row;                       // positive k of this row: ps[k * TC_M], k = -1 .. AT_PC
         const float piv7 = ps[7 * TC_M], piv15 = ps[15 * TC_M], piv23 = ps[23 * TC_M];
         const float* urow_s = Uf + (size_t)row * TC_UPITCH;
-        const bool in_smem = pm <= AT_PC;
         unsigned long long tot = 0;
         bool dense_mode = false;
         for (int t = 0; t < n_tiles; ++t) {
@@ -282,8 +322,7 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
                 unsigned int certain;                    // sum of (m - lb) over the columns decided here
                 unsigned int um;                         // columns that need the exact score
             };
-            auto scan = [=](const uint32_t (&v)[32], int c0, auto big_tag) -> Scan {
-                constexpr bool BIG = decltype(big_tag)::value;   // some row of the warp has more positives than AT_PC
+            auto scan = [=](const uint32_t (&v)[32], int c0) -> Scan {
                 Scan r{0u, 0u};
                 const int nreal = min(32, max(0, nvalid - c0));  // zero-filled rows past the table end are not items
                 float mx = __uint_as_float(v[0]);
@@ -324,14 +363,8 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
                         const float s = __uint_as_float(v[j]);
                         const float lo_p = cur[g][-TC_M], hi_p = cur[g][0];          // sentinel rows at -1 and AT_PC
                         const bool real = j < nreal;
-                        bool sure = real && s - lo_p > mg && hi_p - s > mg;
-                        bool redo = real && !sure;
-                        if (BIG) {       // rows searched in their global copy: only the range test is valid here
-                            const bool below = s < below_thr, inside = !below && s <= above_thr;
-                            sure = in_smem ? sure : false;
-                            redo = in_smem ? redo : (real && inside);
-                            r.certain += (!in_smem && real && below) ? (unsigned int)pm : 0u;
-                        }
+                        const bool sure = real && s - lo_p > mg && hi_p - s > mg;
+                        const bool redo = real && !sure;
                         off_sum += sure ? (unsigned int)(cur[g] - ps) : 0u;
                         n_sure += sure ? 1u : 0u;
                         r.um |= redo ? (1u << j) : 0u;
@@ -340,7 +373,6 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
                 r.certain += n_sure * (unsigned int)pm - off_sum / TC_M;
                 return r;
             };
-            const bool warp_big = __any_sync(0xffffffffu, !in_smem);
 #if AT_EXPERIMENT != 3
             // Which columns are in range at all?  For a trained model (AUC 0.9+) it is a few per cent, spread over
             // all rows — so the dense search above (every lane, all its 32 columns) would run for nearly every tile
@@ -364,7 +396,7 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
             }
             Scan r0{(unsigned int)(n_below * pm), 0u};
             if (total > AT_Q) {
-                r0 = warp_big ? scan(v0, 0, std::true_type{}) : scan(v0, 0, std::false_type{});
+                r0 = scan(v0, 0);
             } else if (total > 0) {
                 const int ew = warp - 2;
                 float* qs = Qs + ew * AT_Q;
@@ -402,7 +434,7 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
                     for (int st = AT_PC / 2; st > 0; st >>= 1) cur += (cur[(st - 1) * TC_M] < s) ? st * TC_M : 0;
                     cur += (cur[0] < s) ? TC_M : 0;
                     const float lo_p = cur[-TC_M], hi_p = cur[0];
-                    const bool sure = pm_r <= AT_PC && s - lo_p > mg_r && hi_p - s > mg_r;
+                    const bool sure = s - lo_p > mg_r && hi_p - s > mg_r;
                     if (act) {
                         if (sure) atomicAdd(racc + rl, (uint32_t)(pm_r - (int)(cur - pr) / TC_M));
                         else atomicOr(rum + rl, 1u << col);
@@ -441,10 +473,10 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
                 const int j = __ffs((int)um) - 1;
                 um &= um - 1;
                 const float ex = at_dot_seq(urow_s, a.item_table + (it0 + j) * TC_D);
-                tot += in_smem ? at_twice_f<TC_M>(ps, pm, ex) : at_twice_f<1>(pp, pm, ex);
+                tot += at_twice_f<TC_M>(ps, pm, ex);
             }
         }
-        if (valid && tot) atomicAdd(a.acc2 + u0 + row, tot);
+        if (valid && tot) atomicAdd(a.acc2 + owner, tot);
     }
     tc_fence_before();
     __syncthreads();
@@ -461,20 +493,34 @@ static size_t auc_tc_smem() {
 
 bool auc_tc_available(int dim) { return dim == TC_D && encode_tiled() != nullptr; }
 
+size_t auc_tc_workspace_bytes(int64_t nu, int64_t n_test_total) {
+    const int64_t nv_max = nu + n_test_total / AT_PC + 1;
+    return 64 + (size_t)nv_max * 8;
+}
+
+// ws: auc_tc_workspace_bytes(nu, n_test_total) device bytes (max item norm, virtual-row count, the two row tables)
 int eval_auc_tc(const int64_t* users, int64_t nu, const float* user_table, const float* item_table, int64_t n_item,
-                const int64_t* test_ptr, const float* pos_sorted, const int32_t* n_pos, float* maxnorm,
+                const int64_t* test_ptr, const float* pos_sorted, const int32_t* n_pos, int64_t n_test_total, void* ws,
                 unsigned long long* acc2, void* stream) {
     TAGREC_REQUIRE((reinterpret_cast<uintptr_t>(item_table) & 15) == 0, "item table must be 16-byte aligned");
     CUtensorMap map;
     if (int rc = make_row_table_map(&map, item_table, n_item, TC_D)) return rc;
+    float* maxnorm = reinterpret_cast<float*>(ws);
+    int32_t* nv = reinterpret_cast<int32_t*>(ws) + 4;
+    const int64_t nv_max = nu + n_test_total / AT_PC + 1;
+    int32_t* vr_owner = reinterpret_cast<int32_t*>(ws) + 16;
+    int32_t* vr_part = vr_owner + nv_max;
 #if AT_EXPERIMENT == 4
     TAGREC_CUDA(cudaMemsetAsync(maxnorm, 0, 8, (cudaStream_t)stream));
 #endif
     if (int rc = launch_item_maxnorm(item_table, n_item, TC_D, maxnorm, stream)) return rc;
+    TAGREC_LAUNCH(auc_vrows_kernel, 1, 1024, 0, stream, n_pos, nu, vr_owner, vr_part, nv);
     AucTcArgs a{};
     a.users = users; a.nu = nu; a.user_table = user_table; a.item_table = item_table; a.n_item = n_item;
     a.test_ptr = test_ptr; a.pos_sorted = pos_sorted; a.n_pos = n_pos; a.item_maxnorm = maxnorm; a.acc2 = acc2;
-    const int64_t user_tiles = (nu + TC_M - 1) / TC_M;
+    a.vr_owner = vr_owner; a.vr_part = vr_part; a.nv = nv;
+    const int64_t grid_tiles = (nv_max + TC_M - 1) / TC_M;       // CTAs past the actual count return at once
+    const int64_t user_tiles = (nu + TC_M - 1) / TC_M;           // the usual case: about one virtual row per user
     const int64_t item_tiles = (n_item + TC_N - 1) / TC_N;
     int64_t splits = user_tiles >= kSMs ? 1 : kSMs / user_tiles;
     splits = std::max<int64_t>(1, std::min<int64_t>(splits, (item_tiles + 3) / 4));
@@ -482,7 +528,7 @@ int eval_auc_tc(const int64_t* users, int64_t nu, const float* user_table, const
     splits = (n_item + a.items_per_split - 1) / a.items_per_split;
     const size_t smem = auc_tc_smem();
     TAGREC_CUDA(cudaFuncSetAttribute(auc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TAGREC_LAUNCH(auc_tc_kernel, dim3((unsigned)user_tiles, (unsigned)splits), AT_THREADS, smem, stream, map, a);
+    TAGREC_LAUNCH(auc_tc_kernel, dim3((unsigned)grid_tiles, (unsigned)splits), AT_THREADS, smem, stream, map, a);
     return TAGREC_OK;
 }
 
