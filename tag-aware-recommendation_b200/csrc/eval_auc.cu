@@ -18,8 +18,8 @@
 //   A1 auc_pos_kernel       positives' scores per user (train members -> +inf = "not a positive"), rank-sorted
 //   A2 auc_all_kernel       64-user x 128-item fp32 tiles (same tiling as eval_topk_kernel); per score one or two
 //                           register compares against the row's [min, max] positive, else a branch-free bisection
-//                           over the row's sorted positives staged in shared memory (rows with more than 32
-//                           positives search their global copy).  The search, not the scoring, bounds this pass when
+//                           over the row's sorted positives staged in shared memory (a user with more than 32
+//                           positives is several virtual rows, one group of 32 each: 2 f is additive).  The search, not the scoring, bounds this pass when
 //                           positives are spread over the whole score range (a 128 x 128 / 8 x 8 variant of the tile
 //                           measured SLOWER for that reason: fewer warps to hide the search latency).
 //   A3 auc_finalize_kernel  subtract train / positive contributions, divide, accumulate sum and user count
@@ -125,6 +125,11 @@ struct AucArgs {
     const int32_t* n_pos;
     int64_t items_per_split;
     unsigned long long* acc2;     // [nu] sum over all items of 2 f
+    // virtual rows (eval_auc_tc.cu, auc_vrows_kernel): a user with m positives is max(1, ceil(m / APC)) rows, each with
+    // one group of APC sorted positives — 2 f is additive over the groups, and every row's search runs in smem
+    const int32_t* vr_owner;
+    const int32_t* vr_part;
+    const int32_t* nv;
 };
 
 // A2
@@ -134,19 +139,35 @@ __global__ void __launch_bounds__(256) auc_all_kernel(AucArgs a) {
     float* Us = reinterpret_cast<float*>(smem_raw);              // [D][AUT+4] user tile, feature-major
     float* Is = Us + (size_t)D * (AUT + 4);                       // [AKC][AIT+4] item chunk
     float* Ps = Is + (size_t)AKC * (AIT + 4);                     // [AUT][APC]   sorted positives (+inf padded)
-    int64_t* uid = reinterpret_cast<int64_t*>(Ps + (size_t)AUT * APC);         // [AUT]
+    int64_t* uid = reinterpret_cast<int64_t*>(Ps + (size_t)AUT * APC);         // [AUT] user id of the row, -1 = none
+    int64_t* poff = uid + AUT;                                                 // [AUT] offset of the row's positives
+    int32_t* own = reinterpret_cast<int32_t*>(poff + AUT);                     // [AUT] index into users[] / acc2[]
+    int32_t* pcnt = own + AUT;                                                 // [AUT] positives of this (virtual) row
     const int tid = threadIdx.x;
     const int tu = tid >> 4, ti = tid & 15;
     const int64_t u0 = (int64_t)blockIdx.x * AUT;
     const int64_t i_begin = (int64_t)blockIdx.y * a.items_per_split;
     const int64_t i_end = min(a.n_item, i_begin + a.items_per_split);
-    if (tid < AUT) uid[tid] = (u0 + tid < a.nu) ? a.users[u0 + tid] : -1;
+    const int64_t nv = __ldg(a.nv);
+    if (u0 >= nv) return;                       // the grid is sized for the upper bound of the virtual-row count
+    if (tid < AUT) {
+        uid[tid] = -1;
+        own[tid] = 0;
+        pcnt[tid] = 0;
+        poff[tid] = 0;
+        if (u0 + tid < nv) {
+            const int w = __ldg(a.vr_owner + u0 + tid), part = __ldg(a.vr_part + u0 + tid);
+            const int64_t u = a.users[w];
+            uid[tid] = u;
+            own[tid] = w;
+            pcnt[tid] = min(APC, max(0, a.n_pos[w] - part * APC));
+            poff[tid] = a.test_ptr[u] + (int64_t)part * APC;
+        }
+    }
     __syncthreads();
     for (int idx = tid; idx < AUT * APC; idx += 256) {
         const int u = idx / APC, j = idx % APC;
-        float v = INFINITY;
-        if (uid[u] >= 0 && j < a.n_pos[u0 + u]) v = __ldg(a.pos_sorted + a.test_ptr[uid[u]] + j);
-        Ps[idx] = v;
+        Ps[idx] = j < pcnt[u] ? __ldg(a.pos_sorted + poff[u] + j) : INFINITY;
     }
     for (int idx = tid; idx < AUT * (D / 4); idx += 256) {
         const int u = idx / (D / 4), c4 = idx % (D / 4);
@@ -170,8 +191,8 @@ __global__ void __launch_bounds__(256) auc_all_kernel(AucArgs a) {
         pmin[r] = INFINITY;
         pmax[r] = -INFINITY;
         if (uid[u] >= 0) {
-            pm[r] = a.n_pos[u0 + u];
-            pp[r] = a.pos_sorted + a.test_ptr[uid[u]];
+            pm[r] = pcnt[u];
+            pp[r] = a.pos_sorted + poff[u];
             if (pm[r] > 0) {
                 pmin[r] = __ldg(pp[r]);
                 pmax[r] = __ldg(pp[r] + pm[r] - 1);
@@ -239,7 +260,7 @@ __global__ void __launch_bounds__(256) auc_all_kernel(AucArgs a) {
                 const float s = acc[r][c];
                 if (s < pmin[r]) tot[r] += 2ull * (unsigned long long)pm[r];      // below every positive
                 else if (s > pmax[r]) {}                                         // above every positive
-                else if (pm[r] <= APC) {
+                else {
                     // branch-free bisection in shared memory: lb = #{p < s}, then the (rare) run of equal positives
                     const float* ps = Ps + (size_t)(4 * tu + r) * APC;
                     int lb = 0;
@@ -249,8 +270,6 @@ __global__ void __launch_bounds__(256) auc_all_kernel(AucArgs a) {
                     int eq = 0;
                     while (lb + eq < pm[r] && ps[lb + eq] == s) ++eq;
                     tot[r] += 2ull * (unsigned long long)(pm[r] - lb - eq) + (unsigned long long)eq;
-                } else {
-                    tot[r] += twice_f(pp[r], pm[r], s);
                 }
             }
         }
@@ -261,7 +280,7 @@ __global__ void __launch_bounds__(256) auc_all_kernel(AucArgs a) {
         unsigned long long v = tot[r];
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (ti == 0 && uid[4 * tu + r] >= 0 && v) atomicAdd(a.acc2 + u0 + 4 * tu + r, v);
+        if (ti == 0 && uid[4 * tu + r] >= 0 && v) atomicAdd(a.acc2 + own[4 * tu + r], v);
     }
 }
 
@@ -306,6 +325,8 @@ static int auc_splits(int64_t nu, int64_t n_item) {
 // eval_auc_tc.cu
 bool auc_tc_available(int dim);
 size_t auc_tc_workspace_bytes(int64_t nu, int64_t n_test_total);
+int launch_auc_vrows(const int32_t* n_pos, int64_t nu, int64_t n_test_total, void* ws, const int32_t** vr_owner,
+                     const int32_t** vr_part, const int32_t** nv, int64_t* nv_max, void* stream);
 int eval_auc_tc(const int64_t* users, int64_t nu, const float* user_table, const float* item_table, int64_t n_item,
                 const int64_t* test_ptr, const float* pos_sorted, const int32_t* n_pos, int64_t n_test_total, void* ws,
                 unsigned long long* acc2, void* stream);
@@ -371,10 +392,13 @@ extern "C" int tagrec_eval_auc_ex(const int64_t* users, int64_t nu, const float*
     const int splits = auc_splits(nu, n_item);
     const int64_t tiles = (n_item + AIT - 1) / AIT;
     a.items_per_split = ((tiles + splits - 1) / splits) * AIT;
-    const size_t smem = ((size_t)dim * (AUT + 4) + (size_t)AKC * (AIT + 4) + (size_t)AUT * APC) * 4 + AUT * 8;
+    const size_t smem = ((size_t)dim * (AUT + 4) + (size_t)AKC * (AIT + 4) + (size_t)AUT * APC) * 4 + AUT * 24;
     TAGREC_REQUIRE(smem <= 227 * 1024, "dim too large for shared memory");
     TAGREC_CUDA(cudaFuncSetAttribute(auc_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const dim3 grid((unsigned)((nu + AUT - 1) / AUT), (unsigned)splits);
+    void* vr_ws = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(n_pos + nu) + 63) & ~(uintptr_t)63);
+    int64_t nv_max = 0;
+    if (int rc = launch_auc_vrows(n_pos, nu, n_test_total, vr_ws, &a.vr_owner, &a.vr_part, &a.nv, &nv_max, stream)) return rc;
+    const dim3 grid((unsigned)((nv_max + AUT - 1) / AUT), (unsigned)splits);
     TAGREC_LAUNCH(auc_all_kernel, grid, 256, smem, stream, a);
     TAGREC_LAUNCH(auc_finalize_kernel, (unsigned)((nu + 7) / 8), 256, 0, stream, users, nu, user_table, item_table, n_item,
                   dim, train_ptr, train_items, test_ptr, pos_sorted, n_pos, acc2, out);

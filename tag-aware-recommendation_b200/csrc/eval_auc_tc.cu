@@ -498,6 +498,18 @@ size_t auc_tc_workspace_bytes(int64_t nu, int64_t n_test_total) {
     return 64 + (size_t)nv_max * 8;
 }
 
+// Builds the virtual-row tables in ws (layout: [0] max item norm (K3b-TC), [4] row count, [16..] owner, part).
+int launch_auc_vrows(const int32_t* n_pos, int64_t nu, int64_t n_test_total, void* ws, const int32_t** vr_owner,
+                     const int32_t** vr_part, const int32_t** nv, int64_t* nv_max, void* stream) {
+    *nv_max = nu + n_test_total / AT_PC + 1;
+    int32_t* base = reinterpret_cast<int32_t*>(ws);
+    TAGREC_LAUNCH(auc_vrows_kernel, 1, 1024, 0, stream, n_pos, nu, base + 16, base + 16 + *nv_max, base + 4);
+    *nv = base + 4;
+    *vr_owner = base + 16;
+    *vr_part = base + 16 + *nv_max;
+    return TAGREC_OK;
+}
+
 // ws: auc_tc_workspace_bytes(nu, n_test_total) device bytes (max item norm, virtual-row count, the two row tables)
 int eval_auc_tc(const int64_t* users, int64_t nu, const float* user_table, const float* item_table, int64_t n_item,
                 const int64_t* test_ptr, const float* pos_sorted, const int32_t* n_pos, int64_t n_test_total, void* ws,
@@ -506,15 +518,13 @@ int eval_auc_tc(const int64_t* users, int64_t nu, const float* user_table, const
     CUtensorMap map;
     if (int rc = make_row_table_map(&map, item_table, n_item, TC_D)) return rc;
     float* maxnorm = reinterpret_cast<float*>(ws);
-    int32_t* nv = reinterpret_cast<int32_t*>(ws) + 4;
-    const int64_t nv_max = nu + n_test_total / AT_PC + 1;
-    int32_t* vr_owner = reinterpret_cast<int32_t*>(ws) + 16;
-    int32_t* vr_part = vr_owner + nv_max;
+    const int32_t *vr_owner, *vr_part, *nv;
+    int64_t nv_max = 0;
+    if (int rc = launch_auc_vrows(n_pos, nu, n_test_total, ws, &vr_owner, &vr_part, &nv, &nv_max, stream)) return rc;
 #if AT_EXPERIMENT == 4
     TAGREC_CUDA(cudaMemsetAsync(maxnorm, 0, 8, (cudaStream_t)stream));
 #endif
     if (int rc = launch_item_maxnorm(item_table, n_item, TC_D, maxnorm, stream)) return rc;
-    TAGREC_LAUNCH(auc_vrows_kernel, 1, 1024, 0, stream, n_pos, nu, vr_owner, vr_part, nv);
     AucTcArgs a{};
     a.users = users; a.nu = nu; a.user_table = user_table; a.item_table = item_table; a.n_item = n_item;
     a.test_ptr = test_ptr; a.pos_sorted = pos_sorted; a.n_pos = n_pos; a.item_maxnorm = maxnorm; a.acc2 = acc2;
