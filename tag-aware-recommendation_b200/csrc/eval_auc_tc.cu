@@ -232,7 +232,7 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
         if (lane == 0) {
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % AT_STAGES;
-                mbar_wait(smem_u32(sfree + s), ((t / AT_STAGES) & 1) ^ 1);
+                mbar_wait_relaxed(smem_u32(sfree + s), ((t / AT_STAGES) & 1) ^ 1);
                 const uint32_t bar = smem_u32(full + s);
                 mbar_expect_tx(bar, TC_TILE_BYTES);
                 const uint32_t dst = smem_u32(St + s * AT_STAGE_BYTES);
@@ -268,7 +268,7 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
         const int ct = tid - 576;
         for (int t = 0; t < n_tiles; ++t) {
             const int s = t % AT_STAGES;
-            mbar_wait(smem_u32(full + s), (t / AT_STAGES) & 1);
+            mbar_wait_relaxed(smem_u32(full + s), (t / AT_STAGES) & 1);
             unsigned char* hi = St + s * AT_STAGE_BYTES;
             unsigned char* lo = hi + TC_TILE_BYTES;
 #pragma unroll 4
@@ -308,7 +308,7 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
             const int r = t % AT_NACC;
             const int64_t it0 = i_begin + (int64_t)t * TC_N + half * 32;
             const int nvalid = (int)min((int64_t)32, i_end - it0);          // <= 0: nothing of this quarter is a real item
-            mbar_wait(smem_u32(accfull + r), (t / AT_NACC) & 1);
+            mbar_wait_relaxed(smem_u32(accfull + r), (t / AT_NACC) & 1);
             tc_fence_after();
             const uint32_t taddr = acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * TC_N + half * 32);
             uint32_t v0[32];
