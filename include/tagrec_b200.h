@@ -314,6 +314,14 @@ int tagrec_nbr_attention_bwd(const float* g_out, const float* att, const float* 
 size_t tagrec_tgcn_tail_workspace_bytes(int64_t n, int n_bit_conv);
 int tagrec_tgcn_tail_fwd(const float* z, const float* wb, const float* xf, const float* wf, const float* bf, int64_t n,
                          int dim, int n_bit_conv, int n_extra, float* out, void* stream);
+/* same forward with the path chosen explicitly (TAGREC_EVAL_AUTO / _FP32 / _TF32): the tensor-core path runs the
+ * [n, C*64+E] x [C*64+E, 64] product as 3xTF32 tcgen05 MMAs (fp32-level accuracy) with the features generated straight
+ * into the swizzled operand tiles; it needs tagrec_tgcn_tail_fwd_workspace_bytes(C) device bytes.  AUTO = TF32 when a
+ * workspace is given. */
+size_t tagrec_tgcn_tail_fwd_workspace_bytes(int n_bit_conv);
+int tagrec_tgcn_tail_fwd_ex(const float* z, const float* wb, const float* xf, const float* wf, const float* bf, int64_t n,
+                            int dim, int n_bit_conv, int n_extra, float* out, void* workspace, size_t workspace_bytes,
+                            int path, void* stream);
 int tagrec_tgcn_tail_bwd(const float* g_out, const float* out, const float* z, const float* wb, const float* xf,
                          const float* wf, int64_t n, int dim, int n_bit_conv, int n_extra, void* workspace,
                          size_t workspace_bytes, float* g_z, float* g_wb, float* g_xf, float* g_wf, float* g_bf,

@@ -858,12 +858,12 @@ TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
     return p;
 }
 
-int make_row_table_map(CUtensorMap* map, const float* table, int64_t n_rows, int dim) {
+int make_row_table_map(CUtensorMap* map, const float* table, int64_t n_rows, int dim, int box_rows) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return fail(TAGREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver", __FILE__, __LINE__);
     const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n_rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)dim * 4};
-    const cuuint32_t box[2] = {32, (cuuint32_t)TC_N};
+    const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(table), gdim, gstride, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

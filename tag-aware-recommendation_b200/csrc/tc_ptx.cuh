@@ -143,8 +143,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled();      // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no libcuda link)
-// Tensor map of a row-major [n_rows, dim] fp32 table: boxes of 32 floats x 128 rows, SWIZZLE_128B.
-int make_row_table_map(CUtensorMap* map, const float* table, int64_t n_rows, int dim);
+// Tensor map of a row-major [n_rows, dim] fp32 table: boxes of 32 floats x box_rows rows, SWIZZLE_128B.
+int make_row_table_map(CUtensorMap* map, const float* table, int64_t n_rows, int dim, int box_rows = TC_N);
 // max_i ||I_i||_2 into *out (device float, zeroed by the callee), for the TF32 error margins
 int launch_item_maxnorm(const float* item_table, int64_t n_item, int dim, float* out, void* stream);
 

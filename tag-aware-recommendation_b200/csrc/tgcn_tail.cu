@@ -467,6 +467,29 @@ static int tail_check(int64_t n, int dim, int C, int E) {
     return TAGREC_OK;
 }
 
+namespace tagrec {      // tgcn_tail_tc.cu
+size_t tail_tc_workspace_bytes(int C);
+bool tail_tc_available();
+int tail_fwd_tc(const float* z, const float* wb, const float* xf, const float* wf, const float* bf, int64_t n, int C,
+                int E, float* out, void* workspace, void* stream);
+}  // namespace tagrec
+
+extern "C" size_t tagrec_tgcn_tail_fwd_workspace_bytes(int n_bit_conv) { return tail_tc_workspace_bytes(n_bit_conv); }
+
+extern "C" int tagrec_tgcn_tail_fwd_ex(const float* z, const float* wb, const float* xf, const float* wf,
+                                       const float* bf, int64_t n, int dim, int n_bit_conv, int n_extra, float* out,
+                                       void* workspace, size_t workspace_bytes, int path, void* stream) {
+    TAGREC_REQUIRE(z && wf && bf && out && (wb || n_bit_conv == 0) && (xf || n_extra == 0), "null pointer");
+    TAGREC_REQUIRE(path == TAGREC_EVAL_AUTO || path == TAGREC_EVAL_FP32 || path == TAGREC_EVAL_TF32, "bad path");
+    if (int rc = tail_check(n, dim, n_bit_conv, n_extra)) return rc;
+    const bool tc = path != TAGREC_EVAL_FP32 && workspace && workspace_bytes >= tail_tc_workspace_bytes(n_bit_conv) &&
+                    tail_tc_available();
+    TAGREC_REQUIRE(tc || path != TAGREC_EVAL_TF32, "tensor-core path needs a workspace of tagrec_tgcn_tail_fwd_workspace_bytes");
+    if (!tc) return tagrec_tgcn_tail_fwd(z, wb, xf, wf, bf, n, dim, n_bit_conv, n_extra, out, stream);
+    if (n == 0) return TAGREC_OK;
+    return tail_fwd_tc(z, wb, xf, wf, bf, n, n_bit_conv, n_extra, out, workspace, stream);
+}
+
 extern "C" int tagrec_tgcn_tail_fwd(const float* z, const float* wb, const float* xf, const float* wf, const float* bf,
                                     int64_t n, int dim, int n_bit_conv, int n_extra, float* out, void* stream) {
     TAGREC_REQUIRE(z && wf && bf && out && (wb || n_bit_conv == 0) && (xf || n_extra == 0), "null pointer");

@@ -54,15 +54,20 @@ class NbrAttentionFn(torch.autograd.Function):
 
 class TgcnTailFn(torch.autograd.Function):
     """out = relu([relu(bit_conv(z)) | xf] Wf + bf) on K7 (csrc/tgcn_tail.cu); the [N, 2096] feature matrix of
-    tgcn.py:86-106 is generated and consumed on chip, forward and backward."""
+    tgcn.py:86-106 is generated and consumed on chip, forward and backward.  ``path``: forward on the tensor cores
+    (3xTF32 tcgen05 MMAs, csrc/tgcn_tail_tc.cu; "auto" / "tf32") or on the fp32 FMA kernel ("fp32")."""
+    path = "auto"
 
     @staticmethod
     def forward(ctx, z, wb, xf, wf, bf):
         z, wb, xf, wf, bf = (t.detach().contiguous() for t in (z, wb, xf, wf, bf))
         n, c, e = z.shape[0], wb.shape[0], xf.shape[1]
         out = torch.empty((n, z.shape[2]), dtype=torch.float32, device=z.device)
-        check(lib().tagrec_tgcn_tail_fwd(ptr(z), ptr(wb), ptr(xf), ptr(wf), ptr(bf), n, z.shape[2], c, e, ptr(out),
-                                         stream_ptr(z.device)), "tagrec_tgcn_tail_fwd")
+        nbytes = int(lib().tagrec_tgcn_tail_fwd_workspace_bytes(c))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
+        check(lib().tagrec_tgcn_tail_fwd_ex(ptr(z), ptr(wb), ptr(xf), ptr(wf), ptr(bf), n, z.shape[2], c, e, ptr(out),
+                                            ptr(ws), nbytes, {"auto": 0, "fp32": 1, "tf32": 2}[TgcnTailFn.path],
+                                            stream_ptr(z.device)), "tagrec_tgcn_tail_fwd_ex")
         ctx.save_for_backward(z, wb, xf, wf, out)
         return out
 

@@ -818,12 +818,14 @@ def test_k7a_type_attention_and_vec_conv_vs_torch(n):
         assert relerr(named[k].grad.cpu().numpy(), P[k].grad.numpy()) < TOL, k
 
 
+@pytest.mark.parametrize("path", ["tf32", "fp32"])
 @pytest.mark.parametrize("n", [1, 127, 128, 700])
-def test_k7_tgcn_tail_vs_conv2d(n):
+def test_k7_tgcn_tail_vs_conv2d(n, path, monkeypatch):
     """K7 (bit-level conv + concat + fusion, fused) forward/backward against the reference formulation with real
     Conv2d modules (tgcn.py:86-106) in torch fp64: every input and parameter gradient; tile edges (n = 1, 127, 128)
-    and several tiles per CTA (n = 700 > 4 * 128)."""
-    from tagrec_b200.tgcn import BasicLayer
+    and several tiles per CTA (n = 700 > 4 * 128).  Both forward paths: 3xTF32 tcgen05 MMAs (default) and fp32 FMAs."""
+    from tagrec_b200.tgcn import BasicLayer, TgcnTailFn
+    monkeypatch.setattr(TgcnTailFn, "path", path)
     g = torch.Generator().manual_seed(11 + n)
     layer = BasicLayer(64, 64, 32, 10, 32, 8).to(dev())
     with torch.no_grad():
