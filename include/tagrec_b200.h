@@ -326,6 +326,11 @@ int tagrec_tgcn_tail_bwd(const float* g_out, const float* out, const float* z, c
                          const float* wf, int64_t n, int dim, int n_bit_conv, int n_extra, void* workspace,
                          size_t workspace_bytes, float* g_z, float* g_wb, float* g_xf, float* g_wf, float* g_bf,
                          void* stream);
+/* same with the path of the z-gradient pass chosen explicitly (AUTO = tensor cores, 3xTF32 tcgen05; FP32 = FMA kernel) */
+int tagrec_tgcn_tail_bwd_ex(const float* g_out, const float* out, const float* z, const float* wb, const float* xf,
+                         const float* wf, int64_t n, int dim, int n_bit_conv, int n_extra, void* workspace,
+                         size_t workspace_bytes, float* g_z, float* g_wb, float* g_xf, float* g_wf, float* g_bf,
+                         int path, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K7a TGCN type attention + vector-level conv     replaces model/tgcn.py:78-84 (BasicLayer._atten2) and the

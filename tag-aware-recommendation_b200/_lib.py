@@ -89,6 +89,8 @@ PROTOTYPES = {
     "tagrec_tgcn_tail_fwd_workspace_bytes": (_sz, [_i32]),
     "tagrec_tgcn_tail_fwd_ex": (_i32, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _sz, _i32, _p]),
     "tagrec_tgcn_tail_bwd": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _sz, _p, _p, _p, _p, _p, _p]),
+    "tagrec_tgcn_tail_bwd_ex": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _sz, _p, _p, _p, _p, _p, _i32,
+                                       _p]),
     "tagrec_tgcn_mix_fwd": (_i32, [_p] * 9 + [_i64, _i32, _i32, _i32, _p, _p, _p]),
     "tagrec_tgcn_mix_bwd": (_i32, [_p] * 9 + [_i64, _i32, _i32, _i32] + [_p] * 13 + [_p, _sz, _p]),
     "tagrec_tgcn_mix_workspace_bytes": (_sz, [_i64]),

@@ -455,8 +455,11 @@ static size_t tail_smem_bwd_w() { return ((size_t)2 * T3C * T3H * TW + 2 * T3H *
 
 using namespace tagrec;
 
+namespace tagrec {
+size_t tail_tc_bwd_workspace_bytes(int C);
+}
 extern "C" size_t tagrec_tgcn_tail_workspace_bytes(int64_t n, int n_bit_conv) {
-    return (size_t)(n_bit_conv + 1) * TW * TW * 4 + (size_t)n * TW * 4 + 256;
+    return (size_t)(n_bit_conv + 1) * TW * TW * 4 + (size_t)n * TW * 4 + 256 + tagrec::tail_tc_bwd_workspace_bytes(n_bit_conv);
 }
 
 static int tail_check(int64_t n, int dim, int C, int E) {
@@ -472,6 +475,10 @@ size_t tail_tc_workspace_bytes(int C);
 bool tail_tc_available();
 int tail_fwd_tc(const float* z, const float* wb, const float* xf, const float* wf, const float* bf, int64_t n, int C,
                 int E, float* out, void* workspace, void* stream);
+size_t tail_tc_bwd_workspace_bytes(int C);
+int tail_bwd_z_tc(const float* g_out, const float* out, const float* z, const float* wb, const float* wf, int64_t n,
+                  int C, int E, void* workspace, float* g_pre, float* g_z, float* g_wb, float* g_xf, float* g_bf,
+                  void* stream);
 }  // namespace tagrec
 
 extern "C" size_t tagrec_tgcn_tail_fwd_workspace_bytes(int n_bit_conv) { return tail_tc_workspace_bytes(n_bit_conv); }
@@ -506,10 +513,21 @@ extern "C" int tagrec_tgcn_tail_bwd(const float* g_out, const float* out, const 
                                     const float* xf, const float* wf, int64_t n, int dim, int n_bit_conv, int n_extra,
                                     void* workspace, size_t workspace_bytes, float* g_z, float* g_wb, float* g_xf,
                                     float* g_wf, float* g_bf, void* stream) {
+    return tagrec_tgcn_tail_bwd_ex(g_out, out, z, wb, xf, wf, n, dim, n_bit_conv, n_extra, workspace, workspace_bytes, g_z,
+                                   g_wb, g_xf, g_wf, g_bf, TAGREC_EVAL_AUTO, stream);
+}
+
+extern "C" int tagrec_tgcn_tail_bwd_ex(const float* g_out, const float* out, const float* z, const float* wb,
+                                       const float* xf, const float* wf, int64_t n, int dim, int n_bit_conv,
+                                       int n_extra, void* workspace, size_t workspace_bytes, float* g_z, float* g_wb,
+                                       float* g_xf, float* g_wf, float* g_bf, int path, void* stream) {
     const int C = n_bit_conv, E = n_extra;
     TAGREC_REQUIRE(g_out && out && z && wf && g_z && g_wf && g_bf && ((wb && g_wb) || C == 0) && ((xf && g_xf) || E == 0),
                    "null pointer");
+    TAGREC_REQUIRE(path == TAGREC_EVAL_AUTO || path == TAGREC_EVAL_FP32 || path == TAGREC_EVAL_TF32, "bad path");
     if (int rc = tail_check(n, dim, C, E)) return rc;
+    const bool tc = path != TAGREC_EVAL_FP32 && tail_tc_available();
+    TAGREC_REQUIRE(tc || path != TAGREC_EVAL_TF32, "tensor-core path not available");
     cudaStream_t st = (cudaStream_t)stream;
     const int F = C * TW + E;
     TAGREC_CUDA(cudaMemsetAsync(g_wf, 0, (size_t)F * TW * 4, st));
@@ -521,12 +539,17 @@ extern "C" int tagrec_tgcn_tail_bwd(const float* g_out, const float* out, const 
     const int NC = C + (E > 0 ? 1 : 0);
     float* wft = reinterpret_cast<float*>(workspace);
     float* g_pre = wft + (((size_t)NC * TW * TW + 63) / 64) * 64;
-    TAGREC_LAUNCH(tgcn_tail_transpose_kernel, (unsigned)((NC * TW * TW + 255) / 256), 256, 0, stream, wf, C, E, wft);
+    void* tc_ws = g_pre + (size_t)n * TW;
     const int64_t n_tiles = (n + TM - 1) / TM;
-    const size_t smem_z = tail_smem_bwd_z(C);
-    TAGREC_CUDA(cudaFuncSetAttribute(tgcn_tail_bwd_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z));
-    TAGREC_LAUNCH(tgcn_tail_bwd_z_kernel, (unsigned)std::min<int64_t>(n_tiles, kSMs), 256, smem_z, stream, g_out, out, z, wb,
-                  wft, n, C, E, g_pre, g_z, g_wb, g_xf, g_bf);
+    if (tc) {
+        if (int rc = tail_bwd_z_tc(g_out, out, z, wb, wf, n, C, E, tc_ws, g_pre, g_z, g_wb, g_xf, g_bf, stream)) return rc;
+    } else {
+        TAGREC_LAUNCH(tgcn_tail_transpose_kernel, (unsigned)((NC * TW * TW + 255) / 256), 256, 0, stream, wf, C, E, wft);
+        const size_t smem_z = tail_smem_bwd_z(C);
+        TAGREC_CUDA(cudaFuncSetAttribute(tgcn_tail_bwd_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z));
+        TAGREC_LAUNCH(tgcn_tail_bwd_z_kernel, (unsigned)std::min<int64_t>(n_tiles, kSMs), 256, smem_z, stream, g_out, out, z,
+                      wb, wft, n, C, E, g_pre, g_z, g_wb, g_xf, g_bf);
+    }
     const int groups = (NC + T3C - 1) / T3C;
     const int64_t n_halves = (n + T3H - 1) / T3H;
     int64_t splits = std::max<int64_t>(1, std::min<int64_t>(n_halves, kSMs / groups));

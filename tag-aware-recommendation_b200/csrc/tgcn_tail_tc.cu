@@ -234,6 +234,250 @@ tgcn_tail_fwd_tc_kernel(const __grid_constant__ CUtensorMap wt_map, const float*
     }
 }
 
+// ------------------------------------------------------------------------------------------------ T2 on tcgen05
+// Backward to z of the same layer (tgcn_tail.cu, T2): per 64-feature chunk  G_c = g_pre Wf_c^T  is one fresh
+// 128 x 64 accumulator (24 MMAs: no long accumulation chain), read back by 16 epilogue warps (thread = node x 16
+// feature dims) that apply the recomputed ReLU mask and fold it into g_z, g_wb and (last chunk) g_xf.
+//   A operand: the tile's g_pre = g_out * (out > 0), split hi | lo ONCE per tile into the swizzled layout (K = outputs)
+//   B operand: rows c*64 .. c*64+63 of Wf (feature-major, K = outputs: the parameter's own layout), hi / lo copies by TMA
+constexpr int KZ_NACC = 4;
+constexpr int KZ_THREADS = 64 + 512;
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+
+// ws[h][c][d][o] = hi / lo part of Wf[c*64 + d][o]   (rows past the table: 0)
+__global__ void tgcn_tail_split_rows_kernel(const float* __restrict__ wf, int C, int E, float* __restrict__ ws) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int NC = C + (E > 0 ? 1 : 0);
+    if (idx >= NC * KT_W * KT_W) return;
+    const int c = idx / (KT_W * KT_W), d = (idx / KT_W) % KT_W;
+    const float w = (c < C || d < E) ? __ldg(wf + idx) : 0.f;
+    const float h = kt_hi(w);
+    ws[idx] = h;
+    ws[(size_t)NC * KT_W * KT_W + idx] = kt_lo(w, h);
+}
+
+__global__ void __launch_bounds__(KZ_THREADS, 1)
+tgcn_tail_bwd_z_tc_kernel(const __grid_constant__ CUtensorMap ws_map, const float* __restrict__ g_out,
+                          const float* __restrict__ out, const float* __restrict__ z, const float* __restrict__ wb,
+                          int64_t n, int C, int E, float* __restrict__ g_pre, float* __restrict__ g_z,
+                          float* __restrict__ g_wb, float* __restrict__ g_xf, float* __restrict__ g_bf) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* As = base;                                   // g_pre: hi 32 KB | lo 32 KB
+    unsigned char* Bs = As + 2 * KT_A_TILE;                     // [S] x (hi 16 KB | lo 16 KB)
+    float* WB = reinterpret_cast<float*>(Bs + KT_STAGES * 2 * KT_B_TILE);      // [C][3]
+    float* GWB = WB + ((3 * C + 3) & ~3);                       // [16 warps][C][3] per-warp partial sums of g_wb
+    float* BF = GWB + 16 * ((3 * C + 3) & ~3);                  // [16][64] partial column sums of g_pre
+    uint64_t* bars = reinterpret_cast<uint64_t*>(BF + 16 * KT_W);
+    uint64_t* bfull = bars;                     // [S]    TMA -> MMA
+    uint64_t* sfree = bfull + KT_STAGES;        // [S]    MMA (commit) -> TMA
+    uint64_t* accfull = sfree + KT_STAGES;      // [NACC] MMA -> epilogue
+    uint64_t* accfree = accfull + KZ_NACC;      // [NACC] epilogue -> MMA
+    uint64_t* aready = accfree + KZ_NACC;       // [1]    g_pre tiles written
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n0 = (int64_t)blockIdx.x * KT_M;
+    const int NC = C + (E > 0 ? 1 : 0);
+    const int c3 = (3 * C + 3) & ~3;
+
+    if (tid == 0) {
+        for (int s = 0; s < KT_STAGES; ++s) {
+            mbar_init(smem_u32(bfull + s), 1);
+            mbar_init(smem_u32(sfree + s), 1);
+        }
+        for (int x = 0; x < KZ_NACC; ++x) {
+            mbar_init(smem_u32(accfull + x), 1);
+            mbar_init(smem_u32(accfree + x), 16);
+        }
+        mbar_init(smem_u32(aready), 16);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 3 * C; i += KZ_THREADS) WB[i] = __ldg(wb + i);
+    for (int i = tid; i < 16 * c3; i += KZ_THREADS) GWB[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int c = 0; c < NC; ++c) {
+                const int s = c % KT_STAGES;
+                mbar_wait(smem_u32(sfree + s), ((c / KT_STAGES) & 1) ^ 1);
+                const uint32_t bar = smem_u32(bfull + s);
+                mbar_expect_tx(bar, 2 * KT_B_TILE);
+                const uint32_t dst = smem_u32(Bs + s * 2 * KT_B_TILE);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int row0 = (h * NC + c) * KT_W;
+                    tma_load_2d(dst + h * KT_B_TILE, &ws_map, bar, 0, row0);
+                    tma_load_2d(dst + h * KT_B_TILE + KT_B_KH, &ws_map, bar, 32, row0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(smem_u32(aready), 0);
+            const uint32_t ah = smem_u32(As), al = ah + KT_A_TILE;
+            for (int c = 0; c < NC; ++c) {
+                const int s = c % KT_STAGES, x = c % KZ_NACC;
+                mbar_wait(smem_u32(bfull + s), (c / KT_STAGES) & 1);
+                mbar_wait(smem_u32(accfree + x), ((c / KZ_NACC) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t bh = smem_u32(Bs + s * 2 * KT_B_TILE), bl = bh + KT_B_TILE;
+                const uint32_t d = tmem_acc + (uint32_t)(x * KT_W);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t ao = (uint32_t)((kk >> 2) * TC_KH_BYTES + (kk & 3) * 32);
+                    const uint32_t bo = (uint32_t)((kk >> 2) * KT_B_KH + (kk & 3) * 32);
+                    umma_tf32_ss64(d, umma_desc_sw128(al + ao), umma_desc_sw128(bh + bo), kk != 0);
+                    umma_tf32_ss64(d, umma_desc_sw128(ah + ao), umma_desc_sw128(bl + bo), 1);
+                    umma_tf32_ss64(d, umma_desc_sw128(ah + ao), umma_desc_sw128(bh + bo), 1);
+                }
+                umma_commit(smem_u32(sfree + s));
+                umma_commit(smem_u32(accfull + x));
+            }
+        }
+    } else {
+        const int et = tid - 64, ew = warp - 2;                  // 512 epilogue threads, 16 warps
+        // ---- the tile's g_pre: to global (T3 reads it), to the operand tiles (hi | lo), column sums for g_bf ----
+        {
+            float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);     // this thread's 4 output columns over its 4 nodes
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int idx = et + 512 * it, node = idx >> 4, c16 = idx & 15;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n0 + node < n) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(g_out + (n0 + node) * KT_W) + c16);
+                    const float4 o = __ldg(reinterpret_cast<const float4*>(out + (n0 + node) * KT_W) + c16);
+                    v.x = o.x > 0.f ? g.x : 0.f;
+                    v.y = o.y > 0.f ? g.y : 0.f;
+                    v.z = o.z > 0.f ? g.z : 0.f;
+                    v.w = o.w > 0.f ? g.w : 0.f;
+                    *reinterpret_cast<float4*>(g_pre + (n0 + node) * KT_W + 4 * c16) = v;
+                }
+                colsum.x += v.x; colsum.y += v.y; colsum.z += v.z; colsum.w += v.w;
+                const float4 h = make_float4(kt_hi(v.x), kt_hi(v.y), kt_hi(v.z), kt_hi(v.w));
+                const uint32_t off = sw128_off(node, c16);
+                *reinterpret_cast<float4*>(As + off) = h;
+                *reinterpret_cast<float4*>(As + KT_A_TILE + off) =
+                    make_float4(kt_lo(v.x, h.x), kt_lo(v.y, h.y), kt_lo(v.z, h.z), kt_lo(v.w, h.w));
+            }
+            // lanes l and l + 16 hold the same columns (c16 = et & 15): fold them, one slot per (warp, column)
+            colsum.x += __shfl_xor_sync(0xffffffffu, colsum.x, 16);
+            colsum.y += __shfl_xor_sync(0xffffffffu, colsum.y, 16);
+            colsum.z += __shfl_xor_sync(0xffffffffu, colsum.z, 16);
+            colsum.w += __shfl_xor_sync(0xffffffffu, colsum.w, 16);
+            if (lane < 16) *reinterpret_cast<float4*>(BF + ew * KT_W + 4 * lane) = colsum;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(aready));
+        }
+        // ---- per chunk: thread = (node row, 16 feature dims) ----
+        const int q = warp & 3, cq = ew >> 2;
+        const int node_l = q * 32 + lane;
+        const int64_t node = n0 + node_l;
+        const bool valid = node < n;
+        float zz[3][16], gz[3][16];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) v = __ldg(reinterpret_cast<const float4*>(z + (node * 3 + r) * KT_W + 16 * cq) + j4);
+                zz[r][4 * j4 + 0] = v.x; zz[r][4 * j4 + 1] = v.y; zz[r][4 * j4 + 2] = v.z; zz[r][4 * j4 + 3] = v.w;
+                gz[r][4 * j4 + 0] = gz[r][4 * j4 + 1] = gz[r][4 * j4 + 2] = gz[r][4 * j4 + 3] = 0.f;
+            }
+        float* gwb_w = GWB + ew * c3;
+        for (int c = 0; c < NC; ++c) {
+            const int x = c % KZ_NACC;
+            mbar_wait(smem_u32(accfull + x), (c / KZ_NACC) & 1);
+            tc_fence_after();
+            uint32_t v[16];
+            tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(x * KT_W + 16 * cq), v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(accfree + x));
+            if (c < C) {
+                const float w0 = WB[3 * c], w1 = WB[3 * c + 1], w2 = WB[3 * c + 2];
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    // the SAME expression as bit_pre() of tgcn_tail.cu / the forward's generator
+                    const float pre = fmaf(w2, zz[2][j], fmaf(w1, zz[1][j], w0 * zz[0][j]));
+                    const float g = pre > 0.f ? __uint_as_float(v[j]) : 0.f;
+                    gz[0][j] = fmaf(w0, g, gz[0][j]);
+                    gz[1][j] = fmaf(w1, g, gz[1][j]);
+                    gz[2][j] = fmaf(w2, g, gz[2][j]);
+                    t0 = fmaf(g, zz[0][j], t0);
+                    t1 = fmaf(g, zz[1][j], t1);
+                    t2 = fmaf(g, zz[2][j], t2);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+                    t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+                    t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+                }
+                if (lane == 0) {
+                    gwb_w[3 * c] = t0;
+                    gwb_w[3 * c + 1] = t1;
+                    gwb_w[3 * c + 2] = t2;
+                }
+            } else if (valid && 16 * cq < E) {       // the vector-level chunk: its gradient goes back to the caller
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4)
+                    if (16 * cq + 4 * j4 < E)
+                        *reinterpret_cast<float4*>(g_xf + node * E + 16 * cq + 4 * j4) =
+                            make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                        __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4)
+                    *reinterpret_cast<float4*>(g_z + (node * 3 + r) * KT_W + 16 * cq + 4 * j4) =
+                        make_float4(gz[r][4 * j4], gz[r][4 * j4 + 1], gz[r][4 * j4 + 2], gz[r][4 * j4 + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // per-CTA sums -> one atomic per parameter element
+    for (int i = tid; i < 3 * C; i += KZ_THREADS) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) s += GWB[w * c3 + i];
+        if (s != 0.f) atomicAdd(g_wb + i, s);
+    }
+    if (tid < KT_W) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) s += BF[w * KT_W + tid];
+        if (s != 0.f) atomicAdd(g_bf + tid, s);
+    }
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(256u) : "memory");
+    }
+}
+
 size_t tail_tc_workspace_bytes(int C) { return (size_t)2 * (C + 1) * KT_W * KT_W * 4 + 256; }
 
 bool tail_tc_available() { return encode_tiled() != nullptr; }
@@ -250,6 +494,27 @@ int tail_fwd_tc(const float* z, const float* wb, const float* xf, const float* w
     TAGREC_CUDA(cudaFuncSetAttribute(tgcn_tail_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TAGREC_LAUNCH(tgcn_tail_fwd_tc_kernel, (unsigned)((n + KT_M - 1) / KT_M), KT_THREADS, smem, stream, map, z, wb, xf, bf, n,
                   C, E, out);
+    return TAGREC_OK;
+}
+
+size_t tail_tc_bwd_workspace_bytes(int C) { return (size_t)2 * (C + 1) * KT_W * KT_W * 4 + 256; }
+
+// T2 on the tensor cores; g_wb / g_bf are accumulated into (zeroed by the caller)
+int tail_bwd_z_tc(const float* g_out, const float* out, const float* z, const float* wb, const float* wf, int64_t n,
+                  int C, int E, void* workspace, float* g_pre, float* g_z, float* g_wb, float* g_xf, float* g_bf,
+                  void* stream) {
+    const int NC = C + (E > 0 ? 1 : 0);
+    float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    TAGREC_LAUNCH(tgcn_tail_split_rows_kernel, (unsigned)((NC * KT_W * KT_W + 255) / 256), 256, 0, stream, wf, C, E, ws);
+    CUtensorMap map;
+    if (int rc = make_row_table_map(&map, ws, (int64_t)2 * NC * KT_W, KT_W, KT_W)) return rc;
+    const int c3 = (3 * C + 3) & ~3;
+    const size_t smem = 1024 + (size_t)2 * KT_A_TILE + KT_STAGES * 2 * KT_B_TILE + ((size_t)c3 * 17 + 16 * KT_W) * 4 +
+                        (2 * KT_STAGES + 2 * KZ_NACC + 1) * 8 + 64;
+    TAGREC_REQUIRE(smem <= 227 * 1024, "too many bit-level conv channels for the tensor-core backward");
+    TAGREC_CUDA(cudaFuncSetAttribute(tgcn_tail_bwd_z_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TAGREC_LAUNCH(tgcn_tail_bwd_z_tc_kernel, (unsigned)((n + KT_M - 1) / KT_M), KZ_THREADS, smem, stream, map, g_out, out, z,
+                  wb, n, C, E, g_pre, g_z, g_wb, g_xf, g_bf);
     return TAGREC_OK;
 }
 

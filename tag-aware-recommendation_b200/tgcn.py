@@ -80,9 +80,10 @@ class TgcnTailFn(torch.autograd.Function):
         g_bf = torch.empty(z.shape[2], dtype=torch.float32, device=z.device)
         nbytes = int(lib().tagrec_tgcn_tail_workspace_bytes(n, c))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
-        check(lib().tagrec_tgcn_tail_bwd(ptr(g_out), ptr(out), ptr(z), ptr(wb), ptr(xf), ptr(wf), n, z.shape[2], c, e,
-                                         ptr(ws), nbytes, ptr(g_z), ptr(g_wb), ptr(g_xf), ptr(g_wf), ptr(g_bf),
-                                         stream_ptr(z.device)), "tagrec_tgcn_tail_bwd")
+        check(lib().tagrec_tgcn_tail_bwd_ex(ptr(g_out), ptr(out), ptr(z), ptr(wb), ptr(xf), ptr(wf), n, z.shape[2], c, e,
+                                            ptr(ws), nbytes, ptr(g_z), ptr(g_wb), ptr(g_xf), ptr(g_wf), ptr(g_bf),
+                                            {"auto": 0, "fp32": 1, "tf32": 2}[TgcnTailFn.path], stream_ptr(z.device)),
+              "tagrec_tgcn_tail_bwd_ex")
         return g_z, g_wb, g_xf, g_wf, g_bf
 
 
