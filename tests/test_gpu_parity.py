@@ -857,6 +857,36 @@ def test_k7_tgcn_tail_vs_conv2d(n, path, monkeypatch):
 
 
 
+@pytest.mark.parametrize("path", ["tf32", "fp32"])
+@pytest.mark.parametrize("C,E", [(2, 8), (0, 16), (3, 0), (11, 64)])
+def test_k7_tail_other_widths(C, E, path, monkeypatch):
+    """K7 through TgcnTailFn for conv widths other than the defaults (fewer chunks than partial accumulators, no
+    bit-level chunks, no extra chunk, a full 64-wide extra chunk), against the dense torch formulation in fp64."""
+    from tagrec_b200.tgcn import TgcnTailFn
+    monkeypatch.setattr(TgcnTailFn, "path", path)
+    g = torch.Generator().manual_seed(100 * C + E)
+    n = 300
+    z = torch.randn(n, 3, 64, generator=g)
+    wb = torch.randn(C, 3, generator=g) * 0.5
+    xf = torch.relu(torch.randn(n, E, generator=g))
+    wf = torch.randn(C * 64 + E, 64, generator=g) * 0.1
+    bf = torch.randn(64, generator=g) * 0.1
+    up = torch.randn(n, 64, generator=g)
+    leaves = [t.clone().to(dev()).requires_grad_(True) for t in (z, wb, xf, wf, bf)]
+    out = TgcnTailFn.apply(*leaves)
+    (out * up.to(dev())).sum().backward()
+    ref_leaves = [t.clone().double().requires_grad_(True) for t in (z, wb, xf, wf, bf)]
+    rz, rwb, rxf, rwf, rbf = ref_leaves
+    feat = torch.relu(torch.einsum('cr,nrd->ncd', rwb, rz)).reshape(n, -1)
+    ref = torch.relu(torch.cat([feat, rxf], dim=1) @ rwf + rbf)
+    (ref * up.double()).sum().backward()
+    assert relerr(out.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+    for name, got, want in zip(("z", "wb", "xf", "wf", "bf"), leaves, ref_leaves):
+        if want.grad is None or want.numel() == 0:
+            continue
+        assert relerr(got.grad.cpu().numpy(), want.grad.numpy()) < TOL, name
+
+
 @pytest.mark.parametrize("nu,n_item,dim,scale", [(70, 3000, 64, 1.0), (33, 700, 256, 0.05), (130, 9000, 64, 30.0)])
 def test_k3b_auc_vs_oracle(nu, n_item, dim, scale):
     """Device AUC (csrc/eval_auc.cu) == the oracle's restatement of roc_auc_score (rank-sum with tie averaging) per
