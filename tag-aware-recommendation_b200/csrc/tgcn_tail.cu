@@ -457,9 +457,11 @@ using namespace tagrec;
 
 namespace tagrec {
 size_t tail_tc_bwd_workspace_bytes(int C);
+size_t tail_tc_bwd_w_workspace_bytes(int64_t n);
 }
 extern "C" size_t tagrec_tgcn_tail_workspace_bytes(int64_t n, int n_bit_conv) {
-    return (size_t)(n_bit_conv + 1) * TW * TW * 4 + (size_t)n * TW * 4 + 256 + tagrec::tail_tc_bwd_workspace_bytes(n_bit_conv);
+    return (size_t)(n_bit_conv + 1) * TW * TW * 4 + (size_t)n * TW * 4 + 512 + tagrec::tail_tc_bwd_workspace_bytes(n_bit_conv) +
+           tagrec::tail_tc_bwd_w_workspace_bytes(n);
 }
 
 static int tail_check(int64_t n, int dim, int C, int E) {
@@ -476,6 +478,9 @@ bool tail_tc_available();
 int tail_fwd_tc(const float* z, const float* wb, const float* xf, const float* wf, const float* bf, int64_t n, int C,
                 int E, float* out, void* workspace, void* stream);
 size_t tail_tc_bwd_workspace_bytes(int C);
+size_t tail_tc_bwd_w_workspace_bytes(int64_t n);
+int tail_bwd_w_tc(const float* z, const float* wb, const float* xf, const float* g_pre, int64_t n, int C, int E,
+                  void* workspace, float* g_wf, void* stream);
 int tail_bwd_z_tc(const float* g_out, const float* out, const float* z, const float* wb, const float* wf, int64_t n,
                   int C, int E, void* workspace, float* g_pre, float* g_z, float* g_wb, float* g_xf, float* g_bf,
                   void* stream);
@@ -508,6 +513,11 @@ extern "C" int tagrec_tgcn_tail_fwd(const float* z, const float* wb, const float
                   n_extra, out);
     return TAGREC_OK;
 }
+
+#ifndef TAGREC_TAIL_T3_FMA
+#define TAGREC_TAIL_T3_FMA 0        // 1: keep the weight-gradient pass (T3) on the FFMA2 kernel also on the tensor-core path
+#endif
+static constexpr bool kTailT3Fma = TAGREC_TAIL_T3_FMA != 0;
 
 extern "C" int tagrec_tgcn_tail_bwd(const float* g_out, const float* out, const float* z, const float* wb,
                                     const float* xf, const float* wf, int64_t n, int dim, int n_bit_conv, int n_extra,
@@ -549,6 +559,10 @@ extern "C" int tagrec_tgcn_tail_bwd_ex(const float* g_out, const float* out, con
         TAGREC_CUDA(cudaFuncSetAttribute(tgcn_tail_bwd_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z));
         TAGREC_LAUNCH(tgcn_tail_bwd_z_kernel, (unsigned)std::min<int64_t>(n_tiles, kSMs), 256, smem_z, stream, g_out, out, z,
                       wb, wft, n, C, E, g_pre, g_z, g_wb, g_xf, g_bf);
+    }
+    if (tc && !kTailT3Fma) {
+        void* w_ws = reinterpret_cast<unsigned char*>(tc_ws) + tail_tc_bwd_workspace_bytes(C);
+        return tail_bwd_w_tc(z, wb, xf, g_pre, n, C, E, w_ws, g_wf, stream);
     }
     const int groups = (NC + T3C - 1) / T3C;
     const int64_t n_halves = (n + T3H - 1) / T3H;

@@ -478,6 +478,235 @@ tgcn_tail_bwd_z_tc_kernel(const __grid_constant__ CUtensorMap ws_map, const floa
     }
 }
 
+// ------------------------------------------------------------------------------------------------ T3 on tcgen05
+// Weight gradient of the fusion layer: g_Wf[c*64 + d][o] = sum_node feature(c, d)[node] * g_pre[node][o] — a product
+// whose K dimension is the NODE index, and TF32 operands must be K-major.  So z, xf and g_pre are transposed once per
+// call (node-contiguous rows; g_pre also split hi | lo there), the g_pre^T tiles arrive by TMA, and the generators
+// write features of TWO conv channels (M = 128 rows) for 64 nodes per stage straight into the swizzled A tiles.
+// The tensor core's fp32 accumulation rounds toward zero: after every KW_FLUSH stages (96 MMAs) the accumulator is
+// drained into fp32 registers of four epilogue warps (thread = feature row, 64 output columns).
+constexpr int KW_FLUSH = 4;
+constexpr int KW_NACC = 2;
+constexpr int KW_THREADS = 64 + 256 + 128;
+constexpr int KW_ST = 64;                       // nodes per stage (K = 64)
+
+// zT[r*64 + d][node] = z[node][r][d];  xT[f][node] = xf[node][f] (rows >= E: 0);  gT[h][o][node] = hi / lo of g_pre
+// Classic 32 x 32 tile transpose: grid (node tiles, 10 column tiles: 6 of z, 2 of xf, 2 of g_pre), 128-byte segments
+// on both sides.
+__global__ void __launch_bounds__(256)
+tgcn_tail_transpose_nodes_kernel(const float* __restrict__ z, const float* __restrict__ xf, const float* __restrict__ g_pre,
+                                 int64_t n, int64_t np, int E, float* __restrict__ zT, float* __restrict__ xT,
+                                 float* __restrict__ gT) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t n0 = (int64_t)blockIdx.x * 32;
+    const int ct = blockIdx.y;                                  // column tile
+    const float* src;
+    int width, col0;
+    if (ct < 6) { src = z; width = 192; col0 = 32 * ct; }
+    else if (ct < 8) { src = xf; width = E; col0 = 32 * (ct - 6); }
+    else { src = g_pre; width = 64; col0 = 32 * (ct - 8); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int node = ty + 8 * k;
+        tile[node][tx] = (n0 + node < n && col0 + tx < width) ? __ldg(src + (n0 + node) * width + col0 + tx) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = ty + 8 * k;                               // column of this tile -> output row
+        const float v = tile[tx][c];
+        const size_t o = (size_t)(col0 + c) * np + n0 + tx;
+        if (ct < 6) zT[o] = v;
+        else if (ct < 8) xT[o] = v;
+        else {
+            const float h = kt_hi(v);
+            gT[o] = h;
+            gT[o + (size_t)64 * np] = kt_lo(v, h);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(KW_THREADS, 1)
+tgcn_tail_bwd_w_tc_kernel(const __grid_constant__ CUtensorMap gt_map, const float* __restrict__ zT,
+                          const float* __restrict__ xT, const float* __restrict__ wb, int64_t np, int C, int E,
+                          int64_t stages_per_split, float* __restrict__ g_wf) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* As = base;                                   // [S] x (hi 32 KB | lo 32 KB): 128 feature rows x 64 nodes
+    unsigned char* Bs = As + KT_STAGES * 2 * KT_A_TILE;         // [S] x (hi 16 KB | lo 16 KB): 64 output rows x 64 nodes
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + KT_STAGES * 2 * KT_B_TILE);
+    uint64_t* afull = bars;                     // [S]    generators -> MMA
+    uint64_t* bfull = afull + KT_STAGES;        // [S]    TMA -> MMA
+    uint64_t* sfree = bfull + KT_STAGES;        // [S]    MMA (commit) -> generators, TMA
+    uint64_t* accfull = sfree + KT_STAGES;      // [NACC] MMA -> epilogue
+    uint64_t* accfree = accfull + KW_NACC;      // [NACC] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfree + KW_NACC);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c0 = blockIdx.x * 2;
+    const int64_t n_stages = np / KW_ST;
+    const int64_t st_begin = (int64_t)blockIdx.y * stages_per_split;
+    const int64_t st_end = min(n_stages, st_begin + stages_per_split);
+    const int n_st = (int)max((int64_t)0, st_end - st_begin);
+    const int n_groups = (n_st + KW_FLUSH - 1) / KW_FLUSH;
+
+    if (tid == 0) {
+        for (int s = 0; s < KT_STAGES; ++s) {
+            mbar_init(smem_u32(afull + s), 8);
+            mbar_init(smem_u32(bfull + s), 1);
+            mbar_init(smem_u32(sfree + s), 1);
+        }
+        for (int x = 0; x < KW_NACC; ++x) {
+            mbar_init(smem_u32(accfull + x), 1);
+            mbar_init(smem_u32(accfree + x), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA: g_pre^T tiles, hi rows 0..63, lo rows 64..127 =================
+        if (lane == 0) {
+            for (int i = 0; i < n_st; ++i) {
+                const int s = i % KT_STAGES;
+                mbar_wait(smem_u32(sfree + s), ((i / KT_STAGES) & 1) ^ 1);
+                const uint32_t bar = smem_u32(bfull + s);
+                mbar_expect_tx(bar, 2 * KT_B_TILE);
+                const uint32_t dst = smem_u32(Bs + s * 2 * KT_B_TILE);
+                const int col0 = (int)((st_begin + i) * KW_ST);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    tma_load_2d(dst + h * KT_B_TILE, &gt_map, bar, col0, h * 64);
+                    tma_load_2d(dst + h * KT_B_TILE + KT_B_KH, &gt_map, bar, col0 + 32, h * 64);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            for (int i = 0; i < n_st; ++i) {
+                const int s = i % KT_STAGES, g = i / KW_FLUSH, x = g % KW_NACC;
+                const bool first = (i % KW_FLUSH) == 0;
+                mbar_wait(smem_u32(afull + s), (i / KT_STAGES) & 1);
+                mbar_wait(smem_u32(bfull + s), (i / KT_STAGES) & 1);
+                if (first) mbar_wait(smem_u32(accfree + x), ((g / KW_NACC) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t ah = smem_u32(As + s * 2 * KT_A_TILE), al = ah + KT_A_TILE;
+                const uint32_t bh = smem_u32(Bs + s * 2 * KT_B_TILE), bl = bh + KT_B_TILE;
+                const uint32_t d = tmem_acc + (uint32_t)(x * KT_W);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t ao = (uint32_t)((kk >> 2) * TC_KH_BYTES + (kk & 3) * 32);
+                    const uint32_t bo = (uint32_t)((kk >> 2) * KT_B_KH + (kk & 3) * 32);
+                    umma_tf32_ss64(d, umma_desc_sw128(al + ao), umma_desc_sw128(bh + bo), !(first && kk == 0));
+                    umma_tf32_ss64(d, umma_desc_sw128(ah + ao), umma_desc_sw128(bl + bo), 1);
+                    umma_tf32_ss64(d, umma_desc_sw128(ah + ao), umma_desc_sw128(bh + bo), 1);
+                }
+                umma_commit(smem_u32(sfree + s));
+                if ((i % KW_FLUSH) == KW_FLUSH - 1 || i == n_st - 1) umma_commit(smem_u32(accfull + x));
+            }
+        }
+    } else if (warp < 10) {
+        // ================= generators: thread = 4 x (feature dim d, four consecutive nodes), both channels =================
+        const int gt = tid - 64;
+        float w[2][3];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) w[cc][r] = (c0 + cc < C) ? __ldg(wb + 3 * (c0 + cc) + r) : 0.f;
+        for (int i = 0; i < n_st; ++i) {
+            const int s = i % KT_STAGES;
+            const int64_t node0 = (st_begin + i) * KW_ST;
+            float4 z0[4], z1[4], z2[4], xe[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {                    // loads first, then the wait for the stage
+                const int idx = gt + 256 * it, n4 = idx & 15, d = idx >> 4;
+                const float* zp = zT + (size_t)d * np + node0 + 4 * n4;
+                z0[it] = __ldg(reinterpret_cast<const float4*>(zp));
+                z1[it] = __ldg(reinterpret_cast<const float4*>(zp + (size_t)64 * np));
+                z2[it] = __ldg(reinterpret_cast<const float4*>(zp + (size_t)128 * np));
+                xe[it] = (c0 <= C && C < c0 + 2) ? __ldg(reinterpret_cast<const float4*>(xT + (size_t)d * np + node0 + 4 * n4))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            mbar_wait(smem_u32(sfree + s), ((i / KT_STAGES) & 1) ^ 1);
+            unsigned char* hi = As + s * 2 * KT_A_TILE;
+            unsigned char* lo = hi + KT_A_TILE;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int idx = gt + 256 * it, n4 = idx & 15, d = idx >> 4;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = c0 + cc;
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < C) {        // the SAME expression as bit_pre() of tgcn_tail.cu
+                        f.x = fmaxf(fmaf(w[cc][2], z2[it].x, fmaf(w[cc][1], z1[it].x, w[cc][0] * z0[it].x)), 0.f);
+                        f.y = fmaxf(fmaf(w[cc][2], z2[it].y, fmaf(w[cc][1], z1[it].y, w[cc][0] * z0[it].y)), 0.f);
+                        f.z = fmaxf(fmaf(w[cc][2], z2[it].z, fmaf(w[cc][1], z1[it].z, w[cc][0] * z0[it].z)), 0.f);
+                        f.w = fmaxf(fmaf(w[cc][2], z2[it].w, fmaf(w[cc][1], z1[it].w, w[cc][0] * z0[it].w)), 0.f);
+                    } else if (c == C) {
+                        f = xe[it];     // vector-level features (rows >= E of xT are zero)
+                    }
+                    const float4 h = make_float4(kt_hi(f.x), kt_hi(f.y), kt_hi(f.z), kt_hi(f.w));
+                    const uint32_t off = sw128_off(cc * 64 + d, n4);
+                    *reinterpret_cast<float4*>(hi + off) = h;
+                    *reinterpret_cast<float4*>(lo + off) =
+                        make_float4(kt_lo(f.x, h.x), kt_lo(f.y, h.y), kt_lo(f.z, h.z), kt_lo(f.w, h.w));
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(afull + s));
+        }
+    } else {
+        // ================= epilogue: thread = feature row of the channel pair, 64 output columns =================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        float sum[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) sum[j] = 0.f;
+        for (int g = 0; g < n_groups; ++g) {
+            const int x = g % KW_NACC;
+            mbar_wait(smem_u32(accfull + x), (g / KW_NACC) & 1);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(x * KT_W);
+            tmem_ld32(taddr, v0);
+            tmem_ld32(taddr + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(accfree + x));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                sum[j] += __uint_as_float(v0[j]);
+                sum[32 + j] += __uint_as_float(v1[j]);
+            }
+        }
+        const int grow = (c0 + (row >> 6)) * KT_W + (row & 63);
+        if (grow < C * KT_W + E) {
+#pragma unroll
+            for (int j4 = 0; j4 < 16; ++j4)
+                red_add4(reinterpret_cast<float4*>(g_wf + (size_t)grow * KT_W + 4 * j4),
+                         make_float4(sum[4 * j4], sum[4 * j4 + 1], sum[4 * j4 + 2], sum[4 * j4 + 3]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(128u) : "memory");
+    }
+}
+
 size_t tail_tc_workspace_bytes(int C) { return (size_t)2 * (C + 1) * KT_W * KT_W * 4 + 256; }
 
 bool tail_tc_available() { return encode_tiled() != nullptr; }
@@ -515,6 +744,41 @@ int tail_bwd_z_tc(const float* g_out, const float* out, const float* z, const fl
     TAGREC_CUDA(cudaFuncSetAttribute(tgcn_tail_bwd_z_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TAGREC_LAUNCH(tgcn_tail_bwd_z_tc_kernel, (unsigned)((n + KT_M - 1) / KT_M), KZ_THREADS, smem, stream, map, g_out, out, z,
                   wb, n, C, E, g_pre, g_z, g_wb, g_xf, g_bf);
+    return TAGREC_OK;
+}
+
+static int64_t tail_tc_np(int64_t n) { return ((n + 127) / 128) * 128; }
+size_t tail_tc_bwd_w_workspace_bytes(int64_t n) { return (size_t)tail_tc_np(n) * (192 + 64 + 128) * 4 + 256; }
+
+// T3 on the tensor cores; g_wf is accumulated into (zeroed by the caller)
+int tail_bwd_w_tc(const float* z, const float* wb, const float* xf, const float* g_pre, int64_t n, int C, int E,
+                  void* workspace, float* g_wf, void* stream) {
+    const int NC = C + (E > 0 ? 1 : 0);
+    const int64_t np = tail_tc_np(n);
+    float* zT = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    float* xT = zT + (size_t)192 * np;
+    float* gT = xT + (size_t)64 * np;
+    TAGREC_LAUNCH(tgcn_tail_transpose_nodes_kernel, dim3((unsigned)(np / 32), 10), 256, 0, stream, z, xf, g_pre, n, np, E,
+                  zT, xT, gT);
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(TAGREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver", __FILE__, __LINE__);
+    CUtensorMap map;                                            // [128 rows (hi | lo)][np nodes], boxes of 32 nodes x 64 rows
+    const cuuint64_t gdim[2] = {(cuuint64_t)np, 128};
+    const cuuint64_t gstride[1] = {(cuuint64_t)np * 4};
+    const cuuint32_t box[2] = {32, 64};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, gT, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return fail(TAGREC_ECUDA, "cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+    const int pairs = (NC + 1) / 2;
+    const int64_t n_stages = np / KW_ST;
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>(n_stages, kSMs / pairs));
+    const int64_t sps = (n_stages + splits - 1) / splits;
+    splits = (n_stages + sps - 1) / sps;
+    const size_t smem = 1024 + (size_t)KT_STAGES * 2 * (KT_A_TILE + KT_B_TILE) + (3 * KT_STAGES + 2 * KW_NACC) * 8 + 64;
+    TAGREC_CUDA(cudaFuncSetAttribute(tgcn_tail_bwd_w_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TAGREC_LAUNCH(tgcn_tail_bwd_w_tc_kernel, dim3((unsigned)pairs, (unsigned)splits), KW_THREADS, smem, stream, map, zT, xT, wb,
+                  np, C, E, sps, g_wf);
     return TAGREC_OK;
 }
 
