@@ -1132,6 +1132,38 @@ def test_graphed_step_matches_eager(tiny, model_name):
         assert relerr(b.cpu().numpy(), a.cpu().numpy()) < 2e-4
 
 
+def test_graphed_step_tgcn_matches_eager(tiny, tiny_tgcn):
+    """TGCN inside ONE CUDA graph: K4, K7a, the three tcgen05 passes of K7 (TMA descriptors of per-call workspaces are
+    captured by value) and K8 replay to the same loss trajectory as the eager step."""
+    e = tiny["edge_index_train"]
+    I = nums(tiny)[1]
+    r = np.random.RandomState(7)
+    batches = []
+    for _ in range(6):
+        sel = r.randint(0, len(e), 48)
+        batches.append(torch.tensor(np.stack([e[sel, 0], e[sel, 1], r.randint(0, I, 48)], 1), device=dev()))
+    runs = []
+    for graphed in (False, True):
+        model = _tgcn_model(tiny, tiny_tgcn)
+        model.train()
+        opt = T.FusedAdam(model.parameters(), lr=0.01, capturable=True)
+        losses = []
+        if graphed:
+            step = T.GraphedStep(model, opt, warmup=2)
+            for b in batches:
+                losses.append(float(sum(step.loss(b))))
+            assert step.graph is not None
+        else:
+            for b in batches:
+                lossx = model.loss(b)
+                opt.zero_grad()
+                sum(lossx).backward()
+                opt.step()
+                losses.append(float(sum(lossx)))
+        runs.append(losses)
+    assert np.allclose(runs[0], runs[1], rtol=2e-5, atol=1e-7), runs
+
+
 # ------------------------------------------------------------------------------------------- end-to-end drop-in loops
 class _Args:
     pool = None
