@@ -35,6 +35,10 @@ int tagrec_version(void);
 const char* tagrec_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's "gpu_launches"). */
 uint64_t tagrec_launch_count(void);
+/* sizeof() of the descriptor structs below as THIS library was compiled: a binding (ctypes / cffi / cgo ...) asserts
+ * its own struct layout against these before the first call, so a stale declaration fails at load time instead of
+ * reading past a short struct.  which: 0 = tagrec_csr_t, 1 = tagrec_mirror_t, 2 = tagrec_route_plan_t; other -> 0. */
+size_t tagrec_sizeof_struct(int which);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K0  adjacency -> CSR            replaces model/help/adj.py:7-35 (create_ui_adj / create_uit_adj, lil_matrix

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "tagrec_version": (_i32, []),
     "tagrec_last_error": (C.c_char_p, []),
     "tagrec_launch_count": (_u64, []),
+    "tagrec_sizeof_struct": (_sz, [_i32]),
     "tagrec_csr_workspace_bytes": (_sz, [_i64]),
     "tagrec_csr_build_structure": (_i32, [_p, _p, _i64, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i32, _p, _sz,
                                           _p, _p, _p, _i64, _p, C.POINTER(_i64), _p]),
@@ -124,6 +125,11 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        for which, cls in enumerate((CsrDesc, MirrorDesc, RoutePlan)):
+            want, got = int(handle.tagrec_sizeof_struct(which)), C.sizeof(cls)
+            if want != got:
+                raise TagrecError(f"ctypes layout of {cls.__name__} is {got} bytes but {LIB_PATH} was compiled with "
+                                  f"{want}: _lib.py and include/tagrec_b200.h have drifted (or the .so is stale)")
         _lib = handle
     return _lib
 

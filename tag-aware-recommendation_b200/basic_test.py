@@ -4,7 +4,8 @@
 ``{'recall': [per k], 'precision': [...], 'hr': [...], 'ndcg': [...], 'auc': [x]}`` (or a dict of such dicts keyed
 ``inter<{n}-{count}`` when ``group_k > 1``).  Per user chunk the model's ``eval_topk`` (K3: tcgen05 scoring + mask +
 top-K) produces the masked top-K directly, ``eval_auc`` (K3b) the per-user AUC sums; everything stays on the device
-until the end.  Models without ``eval_topk`` go through ``predict_rating`` + ``torch.topk`` exactly like the reference.
+until the end.  A model must offer ``eval_topk`` / ``eval_auc`` (``eval_ops.EvalMixin``: any model whose ``forward()``
+returns the (user, item) tables that ``predict_rating`` multiplies); there is no host path.
 Multi-GPU (new): users are sharded over the ranks of the default process group, sums are all-reduced.
 
 Documented deviations: (i) ties are ordered by item id (the reference's torch.topk order is arbitrary);
@@ -50,15 +51,6 @@ def user_group_split(test_ui, train_ui, k, method="interaction"):
     return groups
 
 
-def auc_rank_sum(scores_row, test_items):
-    """training/utils.py:37-45 for one user on the host (used only by the predict_rating fallback)."""
-    from sklearn.metrics import roc_auc_score
-    r_all = np.zeros((len(scores_row),))
-    r_all[test_items] = 1
-    keep = scores_row >= 0
-    return roc_auc_score(r_all[keep], scores_row[keep])
-
-
 class Basic_test():
     def __init__(self, data, args=None):
         cfg = config.current()
@@ -97,10 +89,11 @@ class Basic_test():
         rank, world = self._world()
         mine = all_users[rank::world] if (world > 1 and cfg.get('eval_shard', True)) else all_users
         sharded = world > 1 and cfg.get('eval_shard', True)
-        if hasattr(model, "eval_topk"):
-            sums, auc = self._sums_device(model, true_name, true_ui, mine, topks)
-        else:
-            sums, auc = self._sums_dense(model, true_ui, mine, topks)
+        if not hasattr(model, "eval_topk"):
+            raise TypeError(f"{type(model).__name__} offers no eval_topk(): this evaluation loop scores on the device "
+                            "(K3) and has no host path.  Give the model tagrec_b200.eval_ops.EvalMixin — it only needs "
+                            "forward() to return the (user, item) tables predict_rating multiplies")
+        sums, auc = self._sums_device(model, true_name, true_ui, mine, topks)
         if sharded:
             import torch.distributed as dist
             packed = torch.cat([sums.flatten(), auc.flatten()])
@@ -134,41 +127,6 @@ class Basic_test():
             if want_auc:
                 model.eval_auc(ub, train_ptr, train_items, test_ptr, test_items, out=auc)
         return sums, auc
-
-    def _sums_dense(self, model, true_ui, users, topks):
-        """The reference's own procedure (basic_test.py:30-80) for models that only offer predict_rating."""
-        cfg = config.current()
-        max_k = max(topks)
-        tot = {k: np.zeros(len(topks)) for k in ('recall', 'precision', 'hr', 'ndcg')}
-        auc = 0.0
-        with torch.no_grad():
-            for user in minibatch(users, cfg['test_batch']):
-                rating = model.predict_rating(torch.tensor(user, dtype=torch.long, device=cfg['device']))
-                rows, cols = [], []
-                for i, u in enumerate(user):
-                    its = self.pos_ui.get(u, [])
-                    rows.extend([i] * len(its))
-                    cols.extend(its)
-                rating[rows, cols] = -(1 << 10)
-                _, top = torch.topk(rating, k=max_k)
-                top = top.cpu().numpy()
-                rating_h = rating.cpu().numpy()
-                for i, u in enumerate(user):
-                    truth = true_ui[u]
-                    label = np.isin(top[i], truth).astype(np.float64)
-                    auc += auc_rank_sum(rating_h[i], truth)
-                    for q, k in enumerate(topks):
-                        right = label[:k].sum()
-                        tot['precision'][q] += right / k
-                        tot['recall'][q] += right / len(truth)
-                        tot['hr'][q] += right > 0
-                        disc = 1.0 / np.log2(np.arange(2, k + 2))
-                        idcg = disc[:min(k, len(truth))].sum() or 1.0
-                        tot['ndcg'][q] += (label[:k] * disc).sum() / idcg
-        dev = cfg['device']
-        sums = torch.tensor(np.stack([tot['recall'], tot['precision'], tot['hr'], tot['ndcg']]), dtype=torch.float64,
-                            device=dev)
-        return sums, torch.tensor([auc, float(len(users))], dtype=torch.float64, device=dev)
 
     def run(self, model, istest=False, group_k=0):
         cfg = config.current()

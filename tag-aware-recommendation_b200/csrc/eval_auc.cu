@@ -374,14 +374,6 @@ extern "C" int tagrec_eval_auc_ex(const int64_t* users, int64_t nu, const float*
         if (int rc = eval_auc_tc(users, nu, user_table, item_table, n_item, test_ptr, pos_sorted, n_pos, n_test_total,
                                  tc_ws, acc2, stream))
             return rc;
-#if defined(AT_EXPERIMENT) && AT_EXPERIMENT == 4
-        {
-            float h[2];
-            cudaMemcpyAsync(h, tc_ws, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
-            cudaStreamSynchronize((cudaStream_t)stream);
-            printf("AT_EXPERIMENT 4: max |3xTF32 - exact| / (||u|| max||i||) = %.3e (max item norm %.3f)\n", h[1], h[0]);
-        }
-#endif
         TAGREC_LAUNCH(auc_finalize_kernel, (unsigned)((nu + 7) / 8), 256, 0, stream, users, nu, user_table, item_table,
                       n_item, dim, train_ptr, train_items, test_ptr, pos_sorted, n_pos, acc2, out);
         return TAGREC_OK;

@@ -38,15 +38,11 @@ constexpr int AT_PC = 32;                   // positives per row staged in share
 // |3xTF32 score - canonical fp32 score| <= AT_MARGIN * ||u|| * max||i||.  Worst-case terms, all relative to ||u|| ||i||:
 // dropped lo.lo products 2^-20 = 0.95e-6; TF32 truncation of the two lo operands 2 * 2^-20 = 1.9e-6; fp32 accumulation
 // inside the tensor core over 24 instructions ~ 1.4e-6; rounding of the canonical sequential dot itself 64 * 2^-24 =
-// 3.8e-6: sum 8e-6.  Measured maximum over 6e8 scores (AT_EXPERIMENT 4): 0.93e-6.
+// 3.8e-6: sum 8e-6.  Measured maximum over 6e8 scores (tools/probes/eval_tc_experiments.patch, AT_EXPERIMENT 4): 0.93e-6.
 constexpr float AT_MARGIN = 1.0e-5f;
 constexpr int AT_THREADS = 640;             // 20 warps: TMA, MMA, 16 epilogue (4 per scheduler: the searches are latency-bound), 2 converter
 constexpr int AT_STAGE_BYTES = 2 * TC_TILE_BYTES;        // hi tile + lo tile
 constexpr int AT_Q = 256;                                // a warp's queue of in-range scores (of 32 rows x 32 columns)
-#ifndef AT_EXPERIMENT
-#define AT_EXPERIMENT 0      // timing experiments (WRONG results): 1 no exact re-scores, 2 no bisection, 3 no scan at all;
-                             // 4: measure max |3xTF32 score - exact score| / (||u|| max||i||) into item_maxnorm[1]
-#endif
 
 struct AucTcArgs {
     const int64_t* users;
@@ -332,10 +328,6 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
                     r.certain = (unsigned int)(nreal * pm);
                     return r;
                 }
-#if AT_EXPERIMENT == 2
-                r.certain = nreal;
-                return r;
-#endif
                 // 8 columns at a time, step-major: 8 independent probe chains per thread (shared-memory latency is
                 // high while the MMA and the converter stream through the same banks); the first two levels of
                 // the search compare against pivots held in registers.
@@ -373,7 +365,6 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
                 r.certain += n_sure * (unsigned int)pm - off_sum / TC_M;
                 return r;
             };
-#if AT_EXPERIMENT != 3
             // Which columns are in range at all?  For a trained model (AUC 0.9+) it is a few per cent, spread over
             // all rows — so the dense search above (every lane, all its 32 columns) would run for nearly every tile
             // with nearly every result "below all".  Sparse case: the warp's in-range (row, column) pairs go to a
@@ -444,27 +435,7 @@ auc_tc_kernel(const __grid_constant__ CUtensorMap item_map, AucTcArgs a) {
                 r0.certain += racc[lane];
                 r0.um = rum[lane];
             }
-#else
-            const Scan r0{v0[3], 0u};
-#endif
-#if AT_EXPERIMENT == 4
-            if (valid) {
-                float worst = 0.f;
-                for (int j = 0; j < 32; ++j) {
-                    if (j >= nvalid) break;
-                    float sv = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) sv = (j == k) ? __uint_as_float(v0[k]) : sv;
-                    const float ex = at_dot_seq(urow_s, a.item_table + (it0 + j) * TC_D);
-                    worst = fmaxf(worst, fabsf(sv - ex));
-                }
-                atomic_max_float(const_cast<float*>(a.item_maxnorm) + 1, worst / (sqrtf(unorm2) * __ldg(a.item_maxnorm)));
-            }
-#endif
             unsigned int um = r0.um;
-#if AT_EXPERIMENT == 1
-            um = 0;
-#endif
             tot += 2ull * (unsigned long long)r0.certain;
             tc_fence_before();
             __syncwarp();
@@ -521,9 +492,6 @@ int eval_auc_tc(const int64_t* users, int64_t nu, const float* user_table, const
     const int32_t *vr_owner, *vr_part, *nv;
     int64_t nv_max = 0;
     if (int rc = launch_auc_vrows(n_pos, nu, n_test_total, ws, &vr_owner, &vr_part, &nv, &nv_max, stream)) return rc;
-#if AT_EXPERIMENT == 4
-    TAGREC_CUDA(cudaMemsetAsync(maxnorm, 0, 8, (cudaStream_t)stream));
-#endif
     if (int rc = launch_item_maxnorm(item_table, n_item, TC_D, maxnorm, stream)) return rc;
     AucTcArgs a{};
     a.users = users; a.nu = nu; a.user_table = user_table; a.item_table = item_table; a.n_item = n_item;

@@ -66,9 +66,6 @@ struct TcArgs {
 #ifndef TC_INTERLEAVE
 #define TC_INTERLEAVE 0      // 1: issue the two halves' MMAs alternately (independent accumulators back to back)
 #endif
-#ifndef TC_EXPERIMENT
-#define TC_EXPERIMENT 0      // 1 / 2: timing experiments (wrong results), see tools/tune_eval.sh
-#endif
 constexpr int TC_NACC = TC_TS ? 3 : 4;   // accumulator ring (128 TMEM columns each; A takes 128 columns in TS form)
 
 
@@ -102,15 +99,6 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
     const int64_t i_end = min(a.n_item, i_begin + a.items_per_split);
     const int n_tiles = (int)((i_end - i_begin + TC_N - 1) / TC_N);
 
-#if TC_EXPERIMENT == 9
-    __shared__ long long dbg_acc[16][4];        // [warp][wait_full | fast | slow | n_slow_iters]
-    long long d_wait = 0, d_fast = 0, d_slow = 0, d_iters = 0;
-#endif
-#if TC_EXPERIMENT != 0
-    long long dbg_c0 = clock64();
-    unsigned long long dbg_t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
-#endif
     // ---- prologue: barriers, TMEM allocation ----
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -186,9 +174,6 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % S;
                 mbar_wait(smem_u32(bfree + s), ((t / S) & 1) ^ 1);
-#if TC_EXPERIMENT == 4 || TC_EXPERIMENT == 5
-                if (t >= S) continue;                         // timing experiment: no item-tile traffic (pure MMA rate)
-#endif
                 const uint32_t bar = smem_u32(full + s);
                 mbar_expect_tx(bar, TC_TILE_BYTES);
                 const uint32_t dst = smem_u32(Bs + s * TC_TILE_BYTES);
@@ -202,12 +187,9 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
         if (lane == 0) {
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % S;
-#if TC_EXPERIMENT == 4 || TC_EXPERIMENT == 5
-                if (t < S)
-#endif
                 mbar_wait(smem_u32(full + s), (t / S) & 1);
                 const uint32_t b0 = smem_u32(Bs + s * TC_TILE_BYTES);
-#if TC_INTERLEAVE && TC_EXPERIMENT != 5
+#if TC_INTERLEAVE
                 // Consecutive MMAs into the SAME accumulator form a dependent chain (each waits for the previous
                 // accumulate to retire); alternating the two halves' accumulators keeps the tensor pipe busy.
                 {
@@ -242,23 +224,6 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
                     mbar_wait(smem_u32(accfree + r), ((n / TC_NACC) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d = acc_base + (uint32_t)(r * TC_N);
-#if TC_EXPERIMENT == 5      // timing experiment: half as many MMA instructions, each N = 256 (same flops, wrong results)
-                    if (hh == 0) {
-#pragma unroll
-                        for (int kk = 0; kk < 8; ++kk) {
-                            const uint32_t off = (uint32_t)((kk >> 2) * TC_KH_BYTES + (kk & 3) * 32);
-                            const uint32_t idesc256 = (TC_IDESC & ~(0x3Fu << 17)) | ((256u >> 3) << 17);
-                            asm volatile(
-                                "{\n\t.reg .pred p;\n\t"
-                                "setp.ne.b32 p, %4, 0;\n\t"
-                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-                                ::"r"(acc_base), "r"(tmem_base + (uint32_t)(kk * 8)), "l"(umma_desc_sw128(b0 + off)),
-                                  "r"(idesc256), "r"((uint32_t)(kk > 0)) : "memory");
-                        }
-                    }
-                    umma_commit(smem_u32(accfull + r));
-                    continue;
-#endif
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {     // K = 8 per instruction: 4 per 128-byte swizzle row, 2 k-halves
                         const uint32_t off = (uint32_t)((kk >> 2) * TC_KH_BYTES + (kk & 3) * 32);
@@ -298,17 +263,10 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
             const int n = t * NH + h, r = n % TC_NACC;
             const int64_t it0 = i_begin + (int64_t)t * TC_N;
             const unsigned char* brow = Bs + s * TC_TILE_BYTES;
-#if TC_EXPERIMENT == 9
-            long long d_t0 = clock64();
-#endif
             // another split may have raised the bound (a stale read only prunes less); issued before the wait
             const float sh_new = sh_slot ? __ldcg(sh_slot) : -INFINITY;
             mbar_wait(smem_u32(accfull + r), (n / TC_NACC) & 1);
             tc_fence_after();
-#if TC_EXPERIMENT == 9
-            long long d_t1 = clock64();
-            d_wait += d_t1 - d_t0;
-#endif
             const uint32_t taddr = acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * TC_N);
             if (sh_new > thr_sh) {
                 thr_sh = sh_new;
@@ -316,9 +274,6 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
             }
             // ---- fast path: 128 TF32 scores of this row -> a 128-bit candidate mask (usually empty) ----
             uint32_t cm[TC_N / 32];
-#if TC_EXPERIMENT == 1
-            if (t == 8) thr_lo = INFINITY;                    // timing experiment: no candidate work after warm-up
-#endif
             auto scan32 = [&](const uint32_t (&v)[32]) -> uint32_t {
                 float m = __uint_as_float(v[0]);
 #pragma unroll
@@ -332,11 +287,6 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
             };
 #pragma unroll
             for (int c = 0; c < TC_N / 32; c += 2) {      // two 32-column loads in flight per wait
-#if TC_EXPERIMENT == 2
-                if (c >= 2) { cm[c] = cm[c + 1] = 0; continue; }   // timing experiment: drain half of the accumulator
-#elif TC_EXPERIMENT >= 3 && TC_EXPERIMENT <= 5
-                if (t > 0) { cm[c] = cm[c + 1] = 0; continue; }    // timing experiment: no drain (MMA + TMA floor)
-#endif
                 uint32_t v0[32], v1[32];
                 tmem_ld32(taddr + c * 32, v0);
                 tmem_ld32(taddr + (c + 1) * 32, v1);
@@ -348,16 +298,9 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(accfree + r));
-#if TC_EXPERIMENT == 9
-            long long d_t2 = clock64();
-            d_fast += d_t2 - d_t1;
-#endif
             // ---- slow path: all lanes' candidates of this tile in lockstep ----
             uint64_t lo64 = (uint64_t)cm[0] | ((uint64_t)cm[1] << 32), hi64 = (uint64_t)cm[2] | ((uint64_t)cm[3] << 32);
             while (lo64 | hi64) {
-#if TC_EXPERIMENT == 9
-                ++d_iters;
-#endif
                 int il;
                 if (lo64) {
                     il = __ffsll((long long)lo64) - 1;
@@ -426,9 +369,6 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
             }
             // this warp no longer reads B stage `s`
             __syncwarp();
-#if TC_EXPERIMENT == 9
-            d_slow += clock64() - d_t2;
-#endif
             if (lane == 0) mbar_arrive(smem_u32(bfree + s));
         }
         if (valid) {
@@ -441,32 +381,6 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap item_map, TcArgs a) {
     }
     tc_fence_before();
     __syncthreads();
-#if TC_EXPERIMENT == 9
-    {
-        // warp-level maxima over lanes (lanes diverge in the slow path: the slowest lane is the warp's time)
-        long long it_sum = d_iters;
-        for (int o = 16; o > 0; o >>= 1) {
-            d_slow = max(d_slow, __shfl_xor_sync(0xffffffffu, d_slow, o));
-            d_iters = max(d_iters, __shfl_xor_sync(0xffffffffu, d_iters, o));
-            it_sum += __shfl_xor_sync(0xffffffffu, it_sum, o);
-        }
-        if (lane == 0 && warp < 16) { dbg_acc[warp][0] = d_wait; dbg_acc[warp][1] = d_fast; dbg_acc[warp][2] = d_slow; dbg_acc[warp][3] = it_sum; }
-        __syncthreads();
-        if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
-            for (int w = 2; w < 2 + 4 * NH; ++w)
-                printf("  epi warp %d: wait_accfull %lld  fast %lld  slow %lld cycles, lane-events %lld\n", w,
-                       dbg_acc[w][0], dbg_acc[w][1], dbg_acc[w][2], dbg_acc[w][3]);
-    }
-#endif
-#if TC_EXPERIMENT != 0
-    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
-        unsigned long long dbg_t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t1));
-        const long long dc = clock64() - dbg_c0;
-        printf("eval_tc experiment: %lld SM cycles in %llu ns => %.0f MHz, %d tiles, %.1f cycles/tile\n", dc,
-               dbg_t1 - dbg_t0, 1e3 * (double)dc / (double)(dbg_t1 - dbg_t0), n_tiles, (double)dc / n_tiles);
-    }
-#endif
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)

@@ -14,7 +14,7 @@ from .functional import BprLossFn
 from .routing import DgcfPropagateFn
 
 
-class DGCF(nn.Module, EvalMixin):
+class DGCF(EvalMixin, nn.Module):
     def __init__(self, data, args=None):
         super().__init__()
         self._config(config.current())
@@ -79,6 +79,7 @@ class DGCF(nn.Module, EvalMixin):
         return list(self.embed)
 
     def loss(self, batch_data):
+        self._cache = None               # a training step follows: the cached inference table goes stale
         data, cor = batch_data
         ego = torch.cat(list(self.embed), dim=0)
         final = self._final_table(ego)

@@ -33,7 +33,7 @@ class Layer(nn.Module):
         return DisenRouteFn.apply(adj, self.iter_k, fac)
 
 
-class DisenGCN(nn.Module, EvalMixin):
+class DisenGCN(EvalMixin, nn.Module):
     def __init__(self, data, args=None):
         super().__init__()
         self._config(config.current())
@@ -90,6 +90,7 @@ class DisenGCN(nn.Module, EvalMixin):
         return torch.split(self._final_table(), self.num_list, dim=0)
 
     def loss(self, batch_data):
+        self._cache = None               # a training step follows: the cached inference table goes stale
         data, cor = batch_data
         final = self._final_table()
         return BprLossFn.apply(data, self.num_list[0], self.reg, self.loss_func, final, final)

@@ -60,6 +60,14 @@ class EvalMixin:
     """K3 entry points shared by the drop-in models: everything the evaluation loop needs from ``forward()``'s
     (user, item) tables without materialising predict_rating's [B, n_item] matrix."""
 
+    def train(self, mode=True):
+        """The inference tables are cached between user batches of ONE evaluation run (the reference re-propagates
+        for every batch, lightgcn.py:85).  Every mode switch drops the cache: ``Basic_train.run`` calls ``train()`` at
+        each epoch and both evaluation loops call ``eval()`` first, so a table never survives a parameter update even
+        when the optimizer writes through raw pointers (FusedAdam, CUDA-graph replays) and leaves ``_version`` alone."""
+        self._cache = None
+        return super().train(mode)
+
     def _eval_tables(self):
         with torch.no_grad():
             all_users, all_items = self.forward()[:2]

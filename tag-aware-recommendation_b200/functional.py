@@ -223,11 +223,12 @@ class LightGCNLossFn(torch.autograd.Function):
             elif ws.get("pending_nodes") is not None:
                 tns.index_fill_(0, ws["pending_nodes"], 0.0)
         ws["pending_nodes"] = nodes
+        ws["generation"] = ws.get("generation", 0) + 1             # the work tables now belong to THIS forward
         g_final = ws["g_final"]
         g_reg = ws["g_reg"] if model.reg != 0 else None
         loss_out = torch.empty(2, dtype=torch.float32, device=dev)
         bpr_fwd_bwd(batch, model.num_list[0], final, e0, model.reg, model.loss_func, g_final, g_reg, loss_out)
-        ctx.model, ctx.has_reg, ctx.nodes = model, g_reg is not None, nodes
+        ctx.model, ctx.has_reg, ctx.nodes, ctx.generation = model, g_reg is not None, nodes, ws["generation"]
         ctx.sizes = [e.shape[0] for e in embeds]
         return loss_out[0], loss_out[1]
 
@@ -235,6 +236,10 @@ class LightGCNLossFn(torch.autograd.Function):
     def backward(ctx, g_loss, g_regterm):
         model = ctx.model
         ws, graph, nl = model._ws, model.norm_adj, model.num_layer
+        if ws.get("generation") != ctx.generation:
+            raise RuntimeError("LightGCN.loss() was called again before this loss was back-propagated: the saved layer "
+                               "tables and gradient buffers are shared work space and now hold the later call's data "
+                               "(run backward() right after loss(), as training/basic_train.py:18-24 does)")
         g_final = ws["g_final"]
         dev, (n, dim) = g_final.device, g_final.shape
         upstream = torch.stack([g_loss.reshape(()), g_regterm.reshape(())]).to(torch.float32)
@@ -298,14 +303,18 @@ class BprLossFn(torch.autograd.Function):
         loss_out = torch.empty(2, dtype=torch.float32, device=final.device)
         bpr_fwd_bwd(batch, item_offset, final_c, src_c, reg, loss_kind, g_final, g_reg, loss_out)
         ctx.same = same
+        ctx.merged = same and reg != 0
         ctx.save_for_backward(g_final, g_reg if (g_reg is not None and not same) else None)
         return loss_out[0], loss_out[1]
 
     @staticmethod
     def backward(ctx, g_loss, g_regterm):
         g_final, g_reg = ctx.saved_tensors
-        # when the L2 term reads the final table both parts were scattered into one buffer; both upstream
-        # gradients are the same scalar in every caller (sum(lossx).backward()), so one multiply suffices
+        # when the L2 term reads the final table both parts were scattered into ONE buffer, which is only right when
+        # both upstream gradients are the same scalar (sum(lossx).backward(), basic_train.py:18).  A caller that weights
+        # the two parts differently gets NaN gradients instead of silently wrong ones (no host sync for the check).
+        if ctx.merged and g_regterm is not None and g_regterm is not g_loss:
+            g_loss = torch.where(g_loss == g_regterm, g_loss, torch.full_like(g_loss, float("nan")))
         gf = g_final * g_loss
         gr = None if (g_reg is None or ctx.same) else g_reg * g_regterm
         return None, None, None, None, gf, gr

@@ -90,4 +90,11 @@ class GraphedStep:
         for a, b in zip(old, new):
             a.copy_(b)
         self.graph.replay()
+        # the replay rewrote the parameters without going through torch: drop the model's cached inference table and
+        # bump the versions that version-keyed caches look at
+        if hasattr(self.model, "_cache"):
+            self.model._cache = None
+        for g in self.real_opt.param_groups:
+            for p in g["params"]:
+                torch._C._increment_version(p)
         return tuple(x.clone() for x in self.static_out)

@@ -10,7 +10,7 @@ from .eval_ops import EvalMixin
 from .functional import LightGCNLossFn, LightGCNPropagateFn, lightgcn_forward_layers
 
 
-class LightGCN(nn.Module, EvalMixin):
+class LightGCN(EvalMixin, nn.Module):
     def __init__(self, data, args=None):
         super().__init__()
         self._config(config.current())
@@ -104,6 +104,7 @@ class LightGCN(nn.Module, EvalMixin):
         return list(self.embed)
 
     def loss(self, batch_data):
+        self._cache = None               # a training step follows: the cached inference table goes stale
         if self._dropout_active():
             from .functional import BprLossFn
             final = self._final_table()

@@ -18,7 +18,7 @@ from .eval_ops import EvalMixin
 from .functional import BprLossFn, NgcfDenseFn
 
 
-class NGCF(nn.Module, EvalMixin):
+class NGCF(EvalMixin, nn.Module):
     def __init__(self, data, args=None):
         super().__init__()
         self._config(config.current())
@@ -104,6 +104,7 @@ class NGCF(nn.Module, EvalMixin):
         return list(self.embed)
 
     def loss(self, batch_data):
+        self._cache = None               # a training step follows: the cached inference table goes stale
         final = self._final_table()
         return BprLossFn.apply(batch_data, self.num_list[0], self.reg, self.loss_func, final, final)
 

@@ -16,6 +16,10 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, capturable=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, capturable=capturable))
 
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self.__dict__.pop("_dev", None)         # device-side counters are re-seeded from the loaded ``step``
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -38,13 +42,18 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = torch.zeros((), dtype=torch.int64, device=p.device) if cap else 0
                     st["exp_avg"] = torch.zeros_like(p)
                     st["exp_avg_sq"] = torch.zeros_like(p)
+                for key in ("exp_avg", "exp_avg_sq"):          # a state loaded from a checkpoint may live elsewhere
+                    if st[key].device != p.device or st[key].dtype != torch.float32 or not st[key].is_contiguous():
+                        st[key] = st[key].to(device=p.device, dtype=torch.float32).contiguous()
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 if cap:
                     if scal is None:
                         # one device-side counter per group (every tensor of the group steps together)
                         gs = dev_state.setdefault(gi, {})
                         if "step" not in gs:
-                            gs["step"] = torch.zeros((), dtype=torch.int64, device=p.device)
+                            # resume: start from the counter a loaded state_dict carries (torch's Adam stores a
+                            # float tensor, this class an int or an int64 tensor), not from zero
+                            gs["step"] = torch.full((), int(st["step"]), dtype=torch.int64, device=p.device)
                             gs["scal"] = torch.zeros(2, dtype=torch.float32, device=p.device)
                         check(L.tagrec_adam_advance(ptr(gs["step"]), group["lr"], b1, b2, ptr(gs["scal"]),
                                                     stream_ptr(p.device)), "tagrec_adam_advance")
@@ -54,8 +63,10 @@ class FusedAdam(torch.optim.Optimizer):
                                                  b2, group["eps"], group["weight_decay"], ptr(scal), stream_ptr(p.device)),
                           "tagrec_adam_step_dev")
                 else:
-                    st["step"] += 1
+                    st["step"] = int(st["step"]) + 1           # int(): a state loaded from torch's Adam holds a tensor
                     check(L.tagrec_adam_step(ptr(p), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(),
                                              group["lr"], b1, b2, group["eps"], group["weight_decay"], st["step"],
                                              stream_ptr(p.device)), "tagrec_adam_step")
+                # the kernel wrote the parameter through a raw pointer: tell autograd / version-keyed caches
+                torch._C._increment_version(p)
         return loss

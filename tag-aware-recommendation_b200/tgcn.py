@@ -220,7 +220,7 @@ class BasicLayer(nn.Module):
         return torch.split(out, [eu.shape[0], ei.shape[0], et.shape[0]], dim=0)
 
 
-class TGCN(nn.Module, EvalMixin):
+class TGCN(EvalMixin, nn.Module):
     def __init__(self, data):
         super().__init__()
         self._config(config.current())
@@ -314,6 +314,7 @@ class TGCN(nn.Module, EvalMixin):
         return self.embed['user'], self.embed['item'], self.embed['tag']
 
     def loss(self, batch_data):
+        self._cache = None               # a training step follows: the cached inference table goes stale
         all_users, all_items = self.forward()[:2]
         final = torch.cat([all_users, all_items], dim=0)
         return BprLossFn.apply(batch_data, self.num_user, self.reg, self.loss_func, final, final)

@@ -28,6 +28,21 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert sorted(_lib.PROTOTYPES) == names
 
 
+def test_struct_layouts_match_the_compiled_library():
+    """tagrec_sizeof_struct() is what the .so was compiled with; the ctypes mirrors (and the struct INTEGRATION.md
+    shows a maintainer) must agree field for field."""
+    L = _lib.lib()
+    for which, cls in enumerate((_lib.CsrDesc, _lib.MirrorDesc, _lib.RoutePlan)):
+        assert L.tagrec_sizeof_struct(which) == ctypes.sizeof(cls), cls.__name__
+    assert L.tagrec_sizeof_struct(99) == 0
+    # INTEGRATION.md's reference-side stub declares the same fields, in the same order, as _lib.CsrDesc
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index("class Csr(C.Structure)"):]
+    block = block[:block.index("]\n") + 1]
+    fields = re.findall(r'\("([a-z_]+)",', block)
+    assert fields == [f[0] for f in _lib.CsrDesc._fields_], fields
+
+
 def test_version_and_error_text():
     L = _lib.lib()
     assert L.tagrec_version() >= 100

@@ -76,14 +76,35 @@ def test_sharded_forward_world2_gloo(tmp_path):
 
 
 class _FixedScores(torch.nn.Module):
-    """Stand-in model that only offers predict_rating (the reference's own evaluation procedure is then used)."""
+    """Stand-in model for the CPU test of Basic_test's HOST logic (user sharding, chunking, all-reduce, division by
+    the user count): eval_topk / eval_auc — device kernels in the product — are played by the oracle here."""
 
     def __init__(self, scores):
         super().__init__()
-        self.scores = scores
+        self.scores = scores.numpy()
 
-    def predict_rating(self, users):
-        return self.scores[users].clone()
+    def eval_topk(self, users, k, train_ptr, train_items, path="auto"):
+        from oracle import metrics as OM
+        u = users.numpy()
+        ms = OM.mask_train(self.scores[u], u, train_ptr.numpy(), train_items.numpy())
+        return torch.as_tensor(OM.topk_ids(ms, k).astype(np.int32)), None
+
+    def eval_auc(self, users, train_ptr, train_items, test_ptr, test_items, out=None):
+        from oracle import metrics as OM
+        u = users.numpy()
+        ms = OM.mask_train(self.scores[u], u, train_ptr.numpy(), train_items.numpy())
+        tp, ti = test_ptr.numpy(), test_items.numpy()
+        out += torch.tensor([sum(OM.auc_one(ms[r], ti[tp[x]:tp[x + 1]]) for r, x in enumerate(u)), float(len(u))],
+                            dtype=torch.float64)
+        return out
+
+
+def _oracle_metric_sums(users, topk_ids, test_ptr, test_items, ks, out=None):
+    """tagrec_eval_metrics (a device kernel) played by the oracle."""
+    from oracle import metrics as OM
+    r = OM.ranking_metrics(topk_ids.numpy(), users.numpy(), test_ptr.numpy(), test_items.numpy(), list(ks))
+    out += torch.tensor([r["recall"], r["precision"], r["hr"], r["ndcg"]], dtype=torch.float64)
+    return out
 
 
 def _eval_worker(rank, world, port, out):
@@ -102,6 +123,7 @@ def _eval_worker(rank, world, port, out):
     d.num = {"user": U, "item": I}
     d.user_items = {"train": user_lists(g, "train"), "test": user_lists(g, "test")}
     scores = torch.sigmoid(torch.tensor(g["lgcn_fwd_0"]) @ torch.tensor(g["lgcn_fwd_1"]).T)
+    T.basic_test.metric_sums = _oracle_metric_sums
     res = T.Basic_test(d).run(_FixedScores(scores))
     if rank == 0:
         np.save(out, np.array([res[k][j] for k in ("recall", "precision", "hr", "ndcg") for j in range(2)] + res["auc"],
