@@ -1,9 +1,22 @@
-"""Run under torchrun on N >= 2 GPUs: the node-range sharded LightGCN step (K1 on row blocks + NCCL all-gather)
-equals the single-GPU step on the same inputs.  Exit code 0 and 'MULTI_GPU_OK' on success.
+"""Run under torchrun on N >= 2 GPUs: the node-range sharded LightGCN training step equals the single-GPU step on the
+same inputs, for EVERY exchange path the product has:
+
+    nccl          K1 on row blocks + NCCL all-gather of each layer's rows
+    peer-stores   all-gather fused into K1's epilogue through per-peer mappings (TAGREC_MULTICAST=0)
+    multicast     the same through the NVLS multicast address (what bench.py runs on an NVSwitch box)
+    + "rebalanced": the fused path after the measured re-partition bench.py applies
+    + "sharded-adam": owner-sharded FusedAdam (each rank updates its row block and stores the new rows to all ranks)
+
+Checked per mode, against the single-GPU run of the same K steps (SURVEY §4 / §8 e: within 1e-5):
+loss and reg of every step, the gradient and the propagated tables of step 1, the parameters after K Adam steps, and
+that the replicas (gradients, parameters) are BIT-identical across ranks.  Prints one JSON line per mode and
+'MULTI_GPU_OK' / 'MULTI_GPU_FAIL'; exit code 0 only on success.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tests/multi_gpu_check.py
+        tests/multi_gpu_check.py [--out profiles/r2_multi_gpu_parity_n2.jsonl]
 """
+import argparse
+import json
 import os
 import sys
 
@@ -14,52 +27,128 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+STEPS = 3
+TOL = 1e-5
+
 
 def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--users", type=int, default=30000)
+    ap.add_argument("--items", type=int, default=6000)
+    args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     import tagrec_b200 as T
-    from tagrec_b200.distributed import shard_graph
-    U, I = 30000, 6000
+    from tagrec_b200.distributed import rebalance_by_measurement, shard_graph
+    U, I = args.users, args.items
     rng = np.random.RandomState(0)
-    u = np.r_[rng.randint(0, U, 400000), rng.permutation(U)[:9000]]
-    i = np.r_[rng.randint(0, I, 400000), np.zeros(9000, dtype=np.int64)]           # item 0 is a long row
+    ne = 13 * U
+    u = np.r_[rng.randint(0, U, ne), rng.permutation(U)[:9000]]
+    i = np.r_[(rng.zipf(1.3, ne) - 1) % I, np.zeros(9000, dtype=np.int64)]         # item 0 is a long row
     key = np.unique(u.astype(np.int64) * I + i)
     ui = (key // I, key % I)
     T.set_config("lightgcn", use_tag=False, reg=1e-3, dim_layer_list=[64, 64, 64], device=dev, init_device=dev)
     full = T.build_csr(U, I, ui, "bi_norm", dev)
-    batch = torch.tensor(np.stack([ui[0][:2048], ui[1][:2048], rng.randint(0, I, 2048)], 1), device=dev)
+    sel = rng.randint(0, len(key), (STEPS, 2048))
+    batches = [torch.tensor(np.stack([ui[0][s], ui[1][s], rng.randint(0, I, 2048)], 1), device=dev) for s in sel]
 
-    def run(graph):
+    def run(graph, optimizer="torch"):
         class D:
             num = {"user": U, "item": I}
             prebuilt_adj = graph
         torch.manual_seed(5)
         m = T.LightGCN(D)
         m.train()
-        lossx = m.loss(batch)
-        sum(lossx).backward()
-        fw = torch.cat([t.detach() for t in m.forward()])
-        return [x.item() for x in lossx], torch.cat([p.grad for p in m.embed]), fw
+        if optimizer == "sharded":
+            opt = T.ShardedFusedAdam(m, lr=0.01)
+        elif optimizer == "fused":
+            opt = T.FusedAdam(m.parameters(), lr=0.01)
+        else:
+            opt = torch.optim.Adam(m.parameters(), lr=0.01)
+        losses, g1, f1 = [], None, None
+        for s in range(STEPS):
+            lossx = m.loss(batches[s])
+            opt.zero_grad()
+            sum(lossx).backward()
+            if s == 0:
+                g1 = torch.cat([p.grad for p in m.embed]).clone()
+            opt.step()
+            losses.append([x.item() for x in lossx])
+            if s == 0:
+                m.eval()
+                with torch.no_grad():
+                    f1 = torch.cat([t.detach() for t in m.forward()]).clone()
+                m.train()
+        params = torch.cat([p.detach() for p in m.embed]).clone()
+        own = (graph.comm.lo, graph.comm.hi) if (optimizer == "sharded" and graph.comm is not None) else None
+        return np.array(losses), g1, f1, params, own
 
-    l1, g1, f1 = run(full)
-    l2, g2, f2 = run(shard_graph(full, rank, world))
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
-    errs = (abs(l1[0] - l2[0]) / abs(l1[0]), abs(l1[1] - l2[1]) / abs(l1[1]), rel(g2, g1), rel(f2, f1))
-    ok = all(e < 1e-5 for e in errs)
-    # replicas must be bit-identical across ranks (each row is produced by exactly one rank)
-    ref = g2.clone()
-    dist.broadcast(ref, src=0)
-    same = bool(torch.equal(ref, g2))
-    flags = torch.tensor([int(ok), int(same)], device=dev)
-    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    ref = {o: run(full, o) for o in ("torch", "fused")}
+    assert rel(ref["fused"][3], ref["torch"][3]) < 1e-6          # FusedAdam == torch Adam on one GPU
+
+    def sharded(mode):
+        os.environ["TAGREC_MULTICAST"] = "0" if mode == "peer-stores" else "1"
+        g = shard_graph(full, rank, world)
+        kind = "nccl all-gather"
+        if mode != "nccl":
+            g.comm.enable_p2p(dev).table("probe", (8, 64))
+            kind = g.comm.peer.kind
+            if mode in ("rebalanced", "sharded-adam"):
+                g = rebalance_by_measurement(full, g, rank, world)
+        return g, kind
+
+    ok_all, lines = True, []
+    for mode in ("nccl", "peer-stores", "multicast", "rebalanced", "sharded-adam"):
+        if mode == "sharded-adam" and not hasattr(T, "ShardedFusedAdam"):
+            continue
+        g, kind = sharded(mode)
+        optimizer = "sharded" if mode == "sharded-adam" else "torch"
+        want = ref["fused" if optimizer == "sharded" else "torch"]
+        losses, g1, f1, params, own = run(g, optimizer)
+        if own is not None:                 # sharded optimizer: a rank's gradient is defined on its own rows only
+            lo, hi = own
+            g1c, w1c = g1[lo:hi], want[1][lo:hi]
+        else:
+            g1c, w1c = g1, want[1]
+        errs = {"loss": float(np.abs(losses[:, 0] - want[0][:, 0]).max() / np.abs(want[0][:, 0]).max()),
+                "reg": float(np.abs(losses[:, 1] - want[0][:, 1]).max() / np.abs(want[0][:, 1]).max()),
+                "grad": float((g1c - w1c).abs().max() / want[1].abs().max()), "final": rel(f1, want[2]),
+                "params_after_steps": rel(params, want[3])}
+        ok = all(e < TOL for e in errs.values())
+        # replicas must be bit-identical across ranks (each row is produced by exactly one rank)
+        same = True
+        for t in ([params, f1] if own is not None else [params, f1, g1]):
+            r0 = t.clone()
+            dist.broadcast(r0, src=0)
+            same = same and bool(torch.equal(r0, t))
+        flags = torch.tensor([int(ok), int(same)], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        ok_all = ok_all and bool(flags.min().item() == 1)
+        line = {"mode": mode, "exchange": kind, "world": world, "steps": STEPS, "errs_vs_single_gpu": errs,
+                "tolerance": TOL, "within_tolerance_all_ranks": bool(flags[0].item()),
+                "replicas_bit_identical": bool(flags[1].item()), "bounds": g.comm.bounds,
+                "losses": losses[:, 0].tolist(), "graph": {"users": U, "items": I, "nnz": full._nnz(),
+                                                           "long_rows": full.n_long}}
+        lines.append(line)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        del g
+        torch.cuda.synchronize()
+        dist.barrier()
     if rank == 0:
-        print(f"world={world} errs(loss,reg,grad,final)={errs} replicas_identical={bool(flags[1])}")
-        print("MULTI_GPU_OK" if flags.min().item() == 1 else "MULTI_GPU_FAIL")
+        print("MULTI_GPU_OK" if ok_all else "MULTI_GPU_FAIL", flush=True)
+        if args.out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+            with open(args.out, "w") as f:
+                for ln in lines:
+                    f.write(json.dumps(ln) + "\n")
+                f.write(json.dumps({"result": "MULTI_GPU_OK" if ok_all else "MULTI_GPU_FAIL", "world": world}) + "\n")
     dist.destroy_process_group()
-    sys.exit(0 if flags.min().item() == 1 else 1)
+    sys.exit(0 if ok_all else 1)
 
 
 if __name__ == "__main__":

@@ -1041,18 +1041,21 @@ def test_fused_adam_vs_torch():
 
 # ----------------------------------------------------------------------------------------------------- multi-GPU
 def test_multi_gpu_sharded_step_matches_single():
-    """Only on boxes with >= 2 GPUs (gpurun --gpus 2): torchrun tests/multi_gpu_check.py."""
-    import os
+    """Only on boxes with >= 2 GPUs (gpurun --gpus N): torchrun tests/multi_gpu_check.py — NCCL all-gather, fused
+    peer-store and fused NVLS-multicast exchange, the re-partitioned graph and the owner-sharded optimizer, each against
+    the single-GPU run of the same steps (<= 1e-5, replicas bit-identical).  Kept logs: profiles/r2_multi_gpu_parity_*."""
     import subprocess
     import sys
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
-           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multi_gpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    out = os.path.join(root, "gpurun_out", f"multi_gpu_parity_n{n}.jsonl")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multi_gpu_check.py"),
+           "--out", out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
 def test_edge_dropout_and_message_dropout_path(tiny):
@@ -1218,6 +1221,69 @@ def test_end_to_end_training_loop(tiny, tiny_tgcn, name, tmp_path):
     ckpt = os.path.join(str(tmp_path), "model.pth.tar")
     assert os.path.exists(ckpt)
     assert list(torch.load(ckpt, map_location="cpu").keys()) == keys_before
+
+
+@pytest.mark.parametrize("mode", ["fused_adam", "graphed"])
+def test_evaluation_follows_raw_pointer_updates(tiny, mode, tmp_path):
+    """FusedAdam writes the parameters through raw pointers and a GraphedStep replays a CUDA graph: neither bumps
+    ``_version``.  The cached inference table must still be rebuilt — train, evaluate, train, evaluate: the second
+    evaluation must equal a from-scratch evaluation of the current parameters, not the first one."""
+    T.set_config("lightgcn", use_tag=False, reg=1e-4, dim_layer_list=[64, 64, 64], device=dev(), lr=0.05, train_batch=64,
+                 test_batch=16, topks=[5, 20], sampler="device")
+    d = make_data(tiny)
+    args = _Args(str(tmp_path))
+    torch.manual_seed(0)
+    model = T.LightGCN(d).to(dev())
+    opt = T.FusedAdam(model.parameters(), lr=0.05, capturable=(mode == "graphed"))
+    sampler, test = T.BPR_training_data(d, args), T.Basic_test(d, args)
+    if mode == "graphed":
+        step = T.GraphedStep(model, opt, warmup=2)
+        loss_func, o = step.loss, step.opt
+    else:
+        loss_func, o = model.loss, opt
+    model.train()
+    T.basic_train.epoch_training(sampler, loss_func, o)
+    r1 = test.run(model, istest=True)
+    users = torch.arange(8, device=dev())
+    p1 = model.predict_rating(users).clone()          # eval mode: cached table
+    # keep training WITHOUT toggling train()/eval() (a user script may do that): loss() / the replay drop the cache
+    T.basic_train.epoch_training(sampler, loss_func, o)
+    p2 = model.predict_rating(users).clone()
+    assert not torch.equal(p1, p2), "predict_rating served a stale table after raw-pointer parameter updates"
+    r2 = test.run(model, istest=True)
+    fresh = T.LightGCN(d).to(dev())
+    fresh.load_state_dict(model.state_dict())
+    r3 = T.Basic_test(d, args).run(fresh, istest=True)
+    assert r2["recall"] == r3["recall"] and r2["ndcg"] == r3["ndcg"] and r2["auc"] == r3["auc"]
+    assert (r1["recall"], r1["auc"]) != (r2["recall"], r2["auc"])
+    # resume: a FusedAdam restored from its state_dict continues the bias correction where it stopped
+    sd = opt.state_dict()
+    opt2 = T.FusedAdam(model.parameters(), lr=0.05, capturable=(mode == "graphed"))
+    opt2.load_state_dict(sd)
+    before = int(sd["state"][0]["step"])
+    lossx = model.loss(next(iter(sampler.mini_batch())))
+    opt2.zero_grad()
+    sum(lossx).backward()
+    opt2.step()
+    assert int(opt2.state_dict()["state"][0]["step"]) == before + 1 and before > 0
+
+
+def test_fused_adam_loads_torch_adam_state(tiny):
+    """State compatibility the docstring claims: a torch.optim.Adam state_dict (tensor ``step``) loads and steps."""
+    p = torch.nn.Parameter(torch.randn(100, 64, device=dev()))
+    ref = torch.nn.Parameter(p.detach().clone())
+    ta, tb = torch.optim.Adam([ref], lr=0.01), torch.optim.Adam([p], lr=0.01)
+    g = torch.randn_like(p)
+    for o, q in ((ta, ref), (tb, p)):
+        q.grad = g.clone()
+        o.step()
+    fa = T.FusedAdam([p], lr=0.01)
+    fa.load_state_dict(tb.state_dict())
+    g2 = torch.randn_like(p)
+    ref.grad, p.grad = g2.clone(), g2.clone()
+    ta.step()
+    fa.step()
+    assert relerr(p.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-6
 
 
 # ------------------------------------------------------------------------------- large-scale, size-independent properties
