@@ -87,3 +87,57 @@ def epoch_test(masked_scores, users, test_ptr, test_items, ks, with_auc=True):
         tot = sum(auc_one(masked_scores[r], test_items[test_ptr[u]:test_ptr[u + 1]]) for r, u in enumerate(users))
         res["auc"] = [tot / n]
     return res, top
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bench.py's CPU arm: epoch_test AS THE REFERENCE EXECUTES IT (training/basic_test.py:30-80): per user batch a dense
+# sigmoid(U I^T) score matrix, Python lists for the mask, torch.topk, and — the expensive part — a full score row
+# copied out and sklearn.metrics.roc_auc_score per user (training/utils.py:37-45).
+def reference_epoch_test(user_table, item_table, pos_ui, true_ui, topks, test_batch, with_auc=True, max_users=None):
+    """user_table / item_table: torch CPU tensors = model.forward()[:2].  Returns the reference's result dict.
+    ``max_users`` bounds the number of evaluated users (bench.py's bounded sample; metrics are then over that subset)."""
+    import torch
+    from sklearn.metrics import roc_auc_score
+    all_users = list(true_ui.keys())
+    if max_users is not None:
+        all_users = all_users[:max_users]
+    max_k = max(topks)
+    n_item = item_table.shape[0]
+    tot = {k: np.zeros(len(topks)) for k in ("precision", "recall", "hr", "ndcg")}
+    auc = []
+    with torch.no_grad():
+        for s in range(0, len(all_users), test_batch):            # training/utils.py:48-54 (without the empty batch)
+            user = all_users[s:s + test_batch]
+            allpos = [pos_ui[u] if u in pos_ui else [] for u in user]
+            truth = [true_ui[u] for u in user]
+            rating = torch.sigmoid(torch.matmul(user_table[torch.tensor(user, dtype=torch.long)], item_table.t()))
+            rows, cols = [], []
+            for i, item in enumerate(allpos):
+                rows.extend([i] * len(item))
+                cols.extend(item)
+            rating[rows, cols] = -(1 << 10)
+            _, top = torch.topk(rating, k=max_k)
+            top = top.cpu().numpy()
+            if with_auc:
+                for i, t in enumerate(truth):                     # training/utils.py:37-45
+                    all_item_scores = rating[i].detach().cpu().numpy()
+                    r_all = np.zeros((n_item,))
+                    r_all[t] = 1
+                    keep = all_item_scores >= 0
+                    auc.append(roc_auc_score(r_all[keep], all_item_scores[keep]))
+            label = np.array([[float(x in set(t)) for x in row] for row, t in zip(top, truth)])   # training/utils.py:7-13
+            for q, k in enumerate(topks):                         # training/utils.py:15-35
+                right = label[:, :k].sum(1)
+                n_true = np.array([len(t) for t in truth], dtype=np.float64)
+                tot["precision"][q] += right.sum() / k
+                tot["recall"][q] += (right / n_true).sum()
+                tot["hr"][q] += (right > 0).sum()
+                disc = 1.0 / np.log2(np.arange(2, k + 2))
+                idcg = np.array([disc[:int(min(k, m))].sum() for m in n_true])
+                idcg[idcg == 0.0] = 1.0
+                tot["ndcg"][q] += ((label[:, :k] * disc).sum(1) / idcg).sum()
+    n = float(len(all_users))
+    res = {k: list(v / n) for k, v in tot.items()}
+    if with_auc:
+        res["auc"] = [float(np.sum(auc)) / n]
+    return res

@@ -107,3 +107,39 @@ def mini_batches(n_rows, batch_size):
         else:
             out.append((i, i + batch_size))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bench.py's CPU arm: the reference's reset() AS IT EXECUTES (numpy's own generator, Python loop per edge, a pool of
+# forked workers over equal chunks, vstack, shuffle) — train_data/bpr_training_data.py:29-45 + train_data/utils.py:5-28,52-55.
+def _sample_neg_chunk(args):
+    pos_inter, data_dict, num_item = args
+    import numpy as np
+    data = []
+    for u, pos_i in pos_inter:                                    # train_data/utils.py:19-26
+        while True:
+            idx = np.random.randint(0, num_item)
+            if idx not in data_dict[u]:
+                data.append([u, pos_i, idx])
+                break
+    return np.array(data)
+
+
+def reference_reset(pos_inter, train_ui, num_item, cpu_core):
+    """One ``BPR_training_data.reset()`` the reference's way; returns the (E, 3) int64 array.  ``cpu_core`` forked
+    workers (multiprocessing.Pool, like bpr_training_data.py:37-39) or an in-process loop when cpu_core == 1."""
+    import multiprocessing
+
+    import numpy as np
+    size = len(pos_inter) // cpu_core                             # train_data/utils.py:5-16 split_data
+    chunks = [pos_inter[i * size:(len(pos_inter) if i == cpu_core - 1 else (i + 1) * size)] for i in range(cpu_core)]
+    jobs = [(c, train_ui, num_item) for c in chunks]
+    if cpu_core == 1:
+        results = [_sample_neg_chunk(jobs[0])]
+    else:
+        with multiprocessing.get_context("fork").Pool(cpu_core) as pool:
+            results = pool.map(_sample_neg_chunk, jobs)
+    data = np.vstack(results)
+    idx = np.arange(len(data))                                    # train_data/utils.py:52-55 shuffle
+    np.random.shuffle(idx)
+    return data[idx]
