@@ -1,18 +1,34 @@
 #!/usr/bin/env python
-"""bench.py — BPR training throughput of the LightGCN hot path on B200 (BASELINE.json metric) + live roofline.
+"""bench.py — BPR training throughput of the graph-embedding hot path on B200 (BASELINE.json metric) + live roofline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-A "step" = one mini-batch through the reference's training step: full-graph propagation (3 fused SpMM layers),
-fused BPR loss + gradient scatter, backward (1 elementwise + 3 SpMM on A^T) and torch.optim.Adam over the whole
-tables — exactly what training/basic_train.py:14-27 does per batch.  Workload at N=1: the 1 B-edge LightGCN
-configuration (BASELINE.json configs[4]: 10 M users x 2 M items, ~1 B interactions, dim 64, 3 layers, batch 2048),
-which fits one 180 GB B200.
+A "step" = one mini-batch through the reference's training step (training/basic_train.py:14-27): full-graph
+propagation forward, fused BPR loss + gradient scatter, backward, Adam over all parameters.
 
-Prints ONE JSON line (see the task contract): value = triples/s with the batch stream resident in HBM;
-e2e = the same through the public Python API with every batch coming from pinned host memory and the loss read back
-each step; roofline = the dominant kernel (K1 forward SpMM layer) timed live with CUDA events inside the timed
-region; cpu_baseline = the oracle's port of the reference step on the host cores, on a bounded sample graph.
+Workloads (BASELINE.json configs):
+  lightgcn_1b (default, configs[4])  LightGCN 3-layer dim-64 batch 2048 on a synthetic 10 M x 2 M graph, ~1 B
+                                     interactions, built and sampled on the device; fits one 180 GB B200.  N > 1: node-range
+                                     row blocks, strong scaling.  Also lightgcn_100m / lightgcn_10m (same family).
+  lastfm (configs[0])                LightGCN on the LastFM-shaped graph — the reference's own CPU-runnable case.
+  delicious_tags_tgcn (configs[1])   TGCN (k = 25, 2 layers) on the Delicious-tags-shaped tripartite graph.
+  amazon_book_ngcf (configs[2])      NGCF [64,64,64] on the Amazon-book-shaped graph.
+  gowalla_dgcf (configs[3])          DGCF 4 intents x 2 routing iterations on the Gowalla-shaped graph.
+The four named shapes go through the drop-in classes end to end (sampler.reset(), model.loss, optimizer,
+Basic_test.run) and BOTH arms run the FULL configuration.
+
+ONE JSON line: value = triples/s with the batch stream resident in HBM; e2e = the same through the public Python API with
+every batch coming from pinned host memory and the loss read back each step; check = last loss + parameter checksums
+after all steps (comparable across N: every rank count trains the same batches); roofline = the dominant kernel (K1
+forward SpMM layer) timed live with CUDA events inside the timed region; cpu_baseline = the reference's CPU path on the
+box's host cores.  The default line also carries "c1": both arms on the full LastFM-shaped config in the same run.
+
+--impl reference: the reference's CPU implementation of the path on the host cores — the UNMODIFIED reference classes
+when a reference tree is present (baseline/_ref or /root/reference: build container only), else oracle/train_step.py's
+op-for-op torch-CPU port (the GPU box has no reference tree).  Its line reports exactly what ran: `steps` steps of
+`ms_per_step` each on the graph named in cpu_baseline.sample; for lightgcn_* that graph is a bounded sample of the same
+degree profile and `value` is scaled by nnz ("extrapolated": true, "scale") — the reference cannot build the 1 B-edge
+graph at all (scipy lil_matrix).
 """
 import argparse
 import json
@@ -25,16 +41,21 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {
-    # name: users, items, interactions, note
+SCALE_WORKLOADS = {
     "lightgcn_1b": dict(n_user=10_000_000, n_item=2_000_000, n_edge=1_000_000_000),
     "lightgcn_100m": dict(n_user=2_000_000, n_item=400_000, n_edge=100_000_000),
     "lightgcn_10m": dict(n_user=400_000, n_item=80_000, n_edge=10_000_000),
-    "amazon_book": dict(n_user=52_643, n_item=91_599, n_edge=2_984_108),
-    "lastfm": dict(n_user=1_892, n_item=17_632, n_edge=92_834),
+}
+NAMED_WORKLOADS = {
+    # name: (model, shape in tagrec_b200.data.SHAPES, use_tag, sampler, config overrides)
+    "lastfm": ("lightgcn", "lastfm", False, "BPR", {}),
+    "delicious_tags_tgcn": ("tgcn", "delicious_tags", True, "BPR", {"dim_layer_list": [64, 64], "neighbor_k": 25}),
+    "amazon_book_ngcf": ("ngcf", "amazon_book", False, "BPR", {}),
+    "gowalla_dgcf": ("dgcf", "gowalla", False, "DGCF", {}),
 }
 DIM, LAYERS, BATCH = 64, 3, 2048
 METRIC, UNIT = "bpr_train_edges_per_sec", "triples/s"
+LR, REG = 0.001, 1e-4
 
 
 def peaks():
@@ -93,41 +114,208 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------------------------------
-def cpu_reference(shape, steps, warmup, full_nnz, threads=None):
-    """The oracle's port of the reference training step on the host cores, on a bounded sample graph of the same
-    shape family (same mean user / item degree), extrapolated linearly in nnz to the full workload (the step is
-    SpMM-bound: 74-88 % of the reference's CPU step is aten::addmm, SURVEY §3.2)."""
+def _finite(x):
+    """NaN / inf are not JSON: replace them with null."""
+    if isinstance(x, float):
+        return x if x == x and abs(x) != float("inf") else None
+    if isinstance(x, dict):
+        return {k: _finite(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_finite(v) for v in x]
+    return x
+
+
+def workload_text(name):
+    if name in SCALE_WORKLOADS:
+        s = SCALE_WORKLOADS[name]
+        return (f"LightGCN {LAYERS}-layer dim-{DIM} BPR batch {BATCH}, synthetic {s['n_user']} users x {s['n_item']} items, "
+                f"~{s['n_edge']} interactions ({name}); full-graph propagation fwd+bwd + Adam every step (reference semantics)")
+    model, shape, use_tag, _, over = NAMED_WORKLOADS[name]
+    from importlib import import_module  # noqa: F401
+    return (f"{model.upper()} dim-{DIM} BPR batch {BATCH} on the {shape}-shaped synthetic graph ({name}"
+            f"{', tripartite user-tag-item' if use_tag else ''}); full-graph propagation fwd+bwd + Adam every step")
+
+
+def config_of(name):
+    """Identical in both arms (the driver compares the two `config` objects)."""
+    small = name in NAMED_WORKLOADS or SCALE_WORKLOADS[name]["n_edge"] < 10_000_000
+    return {"workload": workload_text(name), "batch": BATCH, "dim": DIM, "lr": LR, "reg": REG,
+            "l2": "L2 flushed between timed steps" if small else "inputs larger than L2 (tables >> 126 MB)"}
+
+
+# ======================================================================================================================
+#  CPU arm: the reference's implementation of the path on the host cores
+# ======================================================================================================================
+def find_reference():
+    for p in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(p, "model")) and os.path.isdir(os.path.join(p, "training")):
+            return p
+    return None
+
+
+def import_reference(path):
+    """SURVEY Appendix C shims (all outside the reference tree); returns the reference's CFG dict."""
+    import collections
+    import collections.abc
+    import types
+
+    import numpy as np
+    collections.Iterable = collections.abc.Iterable
+    np.int = int
+    tb = types.ModuleType("tensorboardX")
+    tb.SummaryWriter = object
+    sys.modules.setdefault("tensorboardX", tb)
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    argv, sys.argv = sys.argv, ["bench", "--model", "lightgcn", "--use_tag", "", "--cpu_core", "1",
+                                "--dim_layer_list", "[64,64,64]", "--topks", "[20]"]
+    cwd = os.getcwd()
+    os.chdir("/tmp")                       # utility/word.py creates run/<model>/... relative to the CWD
+    try:
+        from utility.word import CFG
+    finally:
+        sys.argv = argv
+        os.chdir(cwd)
+    return CFG
+
+
+class CpuArm:
+    """One model of the reference on torch-CPU with all host threads: `.step(batch)`, `.tables()` (propagated user /
+    item tables for evaluation).  kind = "reference" (unmodified classes) or "port" (oracle/train_step.py)."""
+
+    def __init__(self, model, ds, over, threads):
+        import numpy as np
+        import torch
+        torch.set_num_threads(threads)
+        self.model_name, self.ds, self.threads = model, ds, threads
+        ref = find_reference() if os.environ.get("TAGREC_BENCH_PORT") != "1" else None
+        self.kind = "reference" if ref else "port"
+        U, I = ds.num["user"], ds.num["item"]
+        if ref:
+            CFG = import_reference(ref)
+            from utility.config import dict_map
+            CFG.update(dict(train_batch=BATCH, test_batch=512, has_val=False, use_tag=bool(ds.num.get("tag")) and model in
+                            ("tgcn",), topks=[20], lr=LR, reg=REG, cor_reg=0, dim_latent=DIM, dim_layer_list=[DIM] * LAYERS,
+                            message_drop_list=[0., 0., 0.], node_drop=0., seed=2020, cpu_core=threads, split_adj_k=1,
+                            device=torch.device("cpu"), model=model))
+            CFG.update(dict_map[model])
+            CFG.update(over)
+            from utility.utils import init_seed
+            init_seed(2020)
+            import importlib
+            cls = getattr(importlib.import_module(f"model.{model}"), {"lightgcn": "LightGCN", "ngcf": "NGCF", "dgcf": "DGCF",
+                                                                      "tgcn": "TGCN"}[model])
+            with np.errstate(divide="ignore"):
+                self.m = cls(ds)
+            self.m.train()
+            self.opt = torch.optim.Adam(self.m.parameters(), lr=LR)                    # com.py:25
+            self.impl = f"unmodified reference classes from {ref}"
+        else:
+            from oracle import adjacency as OA
+            from oracle import train_step as TS
+            e = ds.edge_index["train"]
+            if model == "tgcn":
+                np.random.seed(2020)
+                tables = ds.get_all_neighbor()
+                self.m = TS.TGCNStep((U, I, ds.num["tag"], ds.num["weight"]), tables, n_layer=len(over.get("dim_layer_list", [64, 64])),
+                                     neighbor_k=over.get("neighbor_k", 25), reg=REG, lr=LR)
+            else:
+                norm = {"lightgcn": "bi_norm", "ngcf": "ngcf", "dgcf": "plain"}[model]
+                csr = OA.creat_adj(U, I, (e[:, 0], e[:, 1]), norm)
+                cls = {"lightgcn": TS.LightGCNStep, "ngcf": TS.NGCFStep, "dgcf": TS.DGCFStep}[model]
+                self.m = cls(U, I, csr, reg=REG, lr=LR)
+            self.impl = "oracle/train_step.py (op-for-op torch-CPU port of the reference step)"
+
+    def step(self, batch):
+        if self.kind == "port":
+            return self.m.step(batch)
+        lossx = self.m.loss((batch, None) if self.model_name == "dgcf" else batch)         # basic_train.py:15-27
+        parts = [x.cpu().item() for x in lossx]
+        loss = sum(lossx)
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return parts, loss.cpu().item()
+
+    def tables(self):
+        import torch
+        with torch.no_grad():
+            return [t.detach() for t in self.m.forward()[:2]]
+
+
+def host_batches(ds, n, seed=0):
+    """n fixed (BATCH, 3) triple batches (positives from the train edges, uniform negatives) for the CPU arm."""
     import numpy as np
     import torch
-    from oracle import adjacency as OA
-    from oracle.train_step import LightGCNStep
-    import tagrec_b200 as T
-
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
-    ds = T.data.synth_bipartite(shape["n_user"], shape["n_item"], shape["n_edge"], seed=2020)
+    rng = np.random.RandomState(seed)
     e = ds.edge_index["train"]
-    U, I = ds.num["user"], ds.num["item"]
-    n, rowptr, col, val = OA.creat_adj(U, I, (e[:, 0], e[:, 1]), "bi_norm")
-    m = LightGCNStep(U, I, (n, rowptr, col, val), DIM, LAYERS, reg=1e-4)
-    rng = np.random.RandomState(0)
-    times = []
-    for s in range(warmup + steps):
+    out = []
+    for _ in range(n):
         sel = rng.randint(0, len(e), BATCH)
-        batch = torch.from_numpy(np.stack([e[sel, 0], e[sel, 1], rng.randint(0, I, BATCH)], 1))
+        out.append(torch.from_numpy(np.stack([e[sel, 0], e[sel, 1], rng.randint(0, ds.num["item"], BATCH)], 1)))
+    return out
+
+
+def cpu_train_leg(arm, ds, steps, warmup, budget_s=150.0):
+    """`warmup` + `steps` steps of the CPU arm; fewer when one step is so slow that the run would not end in minutes
+    (the number actually run is what is reported)."""
+    batches = host_batches(ds, warmup + steps)
+    times = []
+    t_start = time.perf_counter()
+    for s, b in enumerate(batches):
         t0 = time.perf_counter()
-        m.step(batch)
+        arm.step(b)
+        dt = time.perf_counter() - t0
         if s >= warmup:
-            times.append(time.perf_counter() - t0)
-    t_sample = sum(times) / len(times)
-    nnz = int(rowptr[-1])
-    scale = full_nnz / nnz
-    return {"value": BATCH / (t_sample * scale), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"oracle/train_step.py (torch-CPU port of the reference step) on a {U}x{I}, nnz={nnz} graph of "
-                      f"the same degree profile: {t_sample*1e3:.1f} ms/step measured, scaled x{scale:.1f} by nnz to "
-                      f"the full workload",
-            "ms_per_step_sample": t_sample * 1e3}, t_sample * scale
+            times.append(dt)
+        elapsed = time.perf_counter() - t_start
+        if times and elapsed + dt > budget_s:
+            break
+    return times
+
+
+def cpu_named(name, steps, warmup, threads=None, eval_users=512, with_eval=True):
+    """Both the `cpu_baseline` object of our line and the `--impl reference` line of a NAMED workload: the full config."""
+    import numpy as np
+    import tagrec_b200 as T
+    threads = threads or os.cpu_count()
+    model, shape, use_tag, _, over = NAMED_WORKLOADS[name]
+    ds = T.data.synth_named(shape)
+    if model == "tgcn":
+        ds.get_all_neighbor = lambda: T.data.get_all_neighbor(ds, width=over.get("neighbor_k", 25))
+    t0 = time.perf_counter()
+    arm = CpuArm(model, ds, over, threads)
+    setup_s = time.perf_counter() - t0
+    times = cpu_train_leg(arm, ds, steps, warmup)
+    t_step = sum(times) / len(times)
+    out = {"value": BATCH / t_step, "unit": UNIT, "cores": threads, "kind": arm.kind,
+           "sample": f"{arm.impl}; the FULL {name} configuration ({ds.num['user']} x {ds.num['item']}, "
+                     f"{len(ds.edge_index['train'])} train interactions), {len(times)} timed steps after {warmup} warm-up",
+           "ms_per_step": t_step * 1e3, "steps_run": len(times), "setup_s": round(setup_s, 1), "extrapolated": False}
+    if with_eval:
+        from oracle import metrics as OM
+        from oracle import sampler as OS
+        # sampler reset() the reference's way (forked workers over equal chunks, Python loop per edge)
+        np.random.seed(2020)
+        t0 = time.perf_counter()
+        OS.reference_reset(ds.edge_index["train"], ds.user_items["train"], ds.num["item"], min(threads, 8))
+        out["sampler_reset_s"] = time.perf_counter() - t0
+        ut, it = arm.tables()
+        n_eval = min(eval_users, len(ds.user_items["test"]))
+        ev = {}
+        OM.reference_epoch_test(ut, it, ds.user_items["train"], ds.user_items["test"], [20], 512, with_auc=True, max_users=16)
+        for with_auc in (False, True):
+            t0 = time.perf_counter()
+            OM.reference_epoch_test(ut, it, ds.user_items["train"], ds.user_items["test"], [20], 512, with_auc=with_auc,
+                                    max_users=n_eval)
+            dt = time.perf_counter() - t0
+            ev["with_auc" if with_auc else "topk_only"] = {"users_per_s": n_eval / dt, "s": dt}
+        ev["users"] = n_eval
+        ev["note"] = ("oracle/metrics.reference_epoch_test: dense sigmoid(U I^T) per 512-user batch, torch.topk, "
+                      "sklearn roc_auc_score per user (training/basic_test.py:30-80) on the first users of the test dict; "
+                      "excludes the reference's re-propagation per user batch (lightgcn.py:85)")
+        out["eval"] = ev
+    return out, t_step
 
 
 def sample_shape(shape, target_edges=3_000_000):
@@ -136,35 +324,196 @@ def sample_shape(shape, target_edges=3_000_000):
                 n_edge=int(shape["n_edge"] * f))
 
 
+def cpu_scale(name, steps, warmup, full_nnz, threads=None):
+    """lightgcn_* workloads: the CPU arm on a bounded sample graph of the same family (same mean user / item degree),
+    `value` scaled linearly in nnz to the full workload (the step is SpMM-bound: 74-88 % of the reference's CPU step is
+    aten::addmm, SURVEY §3.2).  Every reported step was actually run, on the sample."""
+    import tagrec_b200 as T
+    threads = threads or os.cpu_count()
+    shape = sample_shape(SCALE_WORKLOADS[name])
+    ds = T.data.synth_bipartite(shape["n_user"], shape["n_item"], shape["n_edge"], seed=2020)
+    t0 = time.perf_counter()
+    arm = CpuArm("lightgcn", ds, {}, threads)
+    setup_s = time.perf_counter() - t0
+    times = cpu_train_leg(arm, ds, steps, warmup)
+    t_sample = sum(times) / len(times)
+    nnz = 2 * len(ds.edge_index["train"])
+    scale = full_nnz / nnz
+    return {"value": BATCH / (t_sample * scale), "unit": UNIT, "cores": threads, "kind": arm.kind,
+            "sample": f"{arm.impl} on a {ds.num['user']} x {ds.num['item']}, nnz={nnz} graph of the same degree profile: "
+                      f"{len(times)} steps of {t_sample * 1e3:.1f} ms measured; value = sample triples/s / {scale:.1f} "
+                      f"(linear in nnz) for the full workload",
+            "ms_per_step": t_sample * 1e3, "sample_value": BATCH / t_sample, "steps_run": len(times), "extrapolated": True,
+            "scale": scale, "setup_s": round(setup_s, 1)}, t_sample
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is Python
-    and /root/reference is not on the GPU box) — rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference (rank 0 only; the other ranks exit 0 without work)."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    shape = WORKLOADS[args.workload]
-    full_nnz = 2 * int(shape["n_edge"] * 0.97)   # expected after per-user de-duplication
-    cb, t_full = cpu_reference(sample_shape(shape), max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)), full_nnz)
+    name = args.workload
+    if name in NAMED_WORKLOADS:
+        cb, t_step = cpu_named(name, args.steps, args.warmup)
+    else:
+        shape = SCALE_WORKLOADS[name]
+        cb, t_step = cpu_scale(name, args.steps, args.warmup, 2 * int(shape["n_edge"] * 0.94))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config_of(args, shape), optimizer="torch.optim.Adam (com.py:25, as the reference composes it)"),
+            "steps": cb["steps_run"], "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(name),
+            "extrapolated": cb["extrapolated"], "scale": cb.get("scale", 1.0), "steps_requested": args.steps,
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(_finite(line)))
 
 
-def config_of(args, shape):
-    return {"optimizer": "tagrec_b200.FusedAdam" if getattr(args, "optimizer", "fused") == "fused" else "torch.optim.Adam",
-            "workload": f"LightGCN {LAYERS}-layer dim-{DIM} BPR batch {BATCH}, synthetic {shape['n_user']} users x "
-                        f"{shape['n_item']} items, ~{shape['n_edge']} interactions ({args.workload}); full-graph "
-                        f"propagation fwd+bwd + Adam every step (reference semantics)",
-            "batch": BATCH, "dim": DIM, "layers": LAYERS, "l2": "inputs larger than L2 (tables >> 126 MB)"
-            if shape["n_edge"] >= 10_000_000 else "L2 flushed between timed steps"}
+# ======================================================================================================================
+#  our arm, named shapes (C1-C4): the drop-in classes end to end
+# ======================================================================================================================
+def build_named(T, name, dev):
+    import torch
+    model_name, shape, use_tag, sampler, over = NAMED_WORKLOADS[name]
+    ds = T.data.synth_named(shape)
+    cfg = dict(use_tag=use_tag, reg=REG, dim_latent=DIM, dim_layer_list=[DIM] * LAYERS, train_batch=BATCH, device=dev,
+               lr=LR, sampler="device", topks=[20], test_batch=512, has_val=False)
+    cfg.update(over)
+    T.set_config(model_name, **cfg)
+    torch.manual_seed(2020)
+    if model_name == "tgcn":
+        ds.get_all_neighbor = lambda ds=ds: T.data.get_all_neighbor(ds, width=over.get("neighbor_k", 25))
+    cls = {"lightgcn": T.LightGCN, "ngcf": T.NGCF, "dgcf": T.DGCF, "tgcn": T.TGCN}[model_name]
+    model = cls(ds).to(dev)
+    data = (T.DGCF_training_data if sampler == "DGCF" else T.BPR_training_data)(ds, None)
+    return ds, model, data
 
 
-# ----------------------------------------------------------------------------------------------------------------
-def run_ours(args):
+def named_ours(T, name, dev, steps, warmup, flush):
+    """Train steps (eager + CUDA-graph), e2e, sampler reset(), Basic_test.run with / without AUC on a named shape."""
+    import torch
+    t0 = time.time()
+    ds, model, data = build_named(T, name, dev)
+    opt = T.FusedAdam(model.parameters(), lr=LR)
+    test = T.Basic_test(ds, None)
+    setup_s = time.time() - t0
+    # sampler reset() (train_data/bpr_training_data.py:29-45) — one full re-sample of every positive edge
+    data.reset()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    data.reset()
+    torch.cuda.synchronize()
+    reset_s = time.perf_counter() - t1
+    batches = []
+    while len(batches) < warmup + steps:
+        for b in data.mini_batch():
+            batches.append(b)
+            if len(batches) >= warmup + steps:
+                break
+    model.train()
+
+    def step(b):
+        lossx = model.loss(b)
+        opt.zero_grad()
+        sum(lossx).backward()
+        opt.step()
+        return lossx
+
+    for b in batches[:warmup]:
+        step(b)
+    launches0 = T.launch_count()
+    evs = []
+    for b in batches[warmup:]:
+        flush.zero_()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(b); e.record()
+        evs.append((a, e))
+    torch.cuda.synchronize()
+    launches = T.launch_count() - launches0
+    ms = sum(a.elapsed_time(e) for a, e in evs)
+    # e2e: batches from pinned host memory, loss read back every step
+    host = [(tuple(t.cpu().pin_memory() if torch.is_tensor(t) else t for t in b) if isinstance(b, (tuple, list))
+             else b.cpu().pin_memory()) for b in batches[warmup:]]
+    h2d = sum(t.numel() * t.element_size() for t in (host[0] if isinstance(host[0], tuple) else (host[0],)) if torch.is_tensor(t))
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    last = None
+    for hb in host:
+        flush.zero_()
+        b = tuple(t.to(dev, non_blocking=True) if torch.is_tensor(t) else t for t in hb) if isinstance(hb, tuple) \
+            else hb.to(dev, non_blocking=True)
+        last = [x.cpu().item() for x in step(b)]
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t1
+    # one CUDA graph per step (T.GraphedStep): the launch-bound small graphs
+    graphed = None
+    try:
+        gopt = T.FusedAdam(model.parameters(), lr=LR, capturable=True)
+        gs = T.GraphedStep(model, gopt, warmup=2)
+        for b in batches[:3]:
+            gs.loss(b)
+        gevs = []
+        for b in batches[warmup:]:
+            flush.zero_()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); gs.loss(b); e.record()
+            gevs.append((a, e))
+        torch.cuda.synchronize()
+        gms = sum(a.elapsed_time(e) for a, e in gevs) / len(gevs)
+        graphed = {"ms_per_step": gms, "value": BATCH / (gms / 1e3)}
+    except Exception as ex:                                   # reported, not hidden
+        graphed = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+    # evaluation through the drop-in loop (training/basic_test.py:94-111), all test users
+    n_test = len(ds.user_items["test"])
+    ev = {"users": n_test, "items": ds.num["item"]}
+    for with_auc in (False, True):
+        T.CFG["eval_auc"] = with_auc
+        test.run(model, istest=True)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        res = test.run(model, istest=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t1
+        ev["with_auc" if with_auc else "topk_only"] = {"users_per_s": n_test / dt, "s": dt}
+    ev["result"] = {k: [float(x) for x in v] for k, v in res.items()}
+    ev["note"] = "T.Basic_test(ds).run(model, istest=True): forward() + K3 top-20 + metric sums (+ K3b AUC), wall clock"
+    params = torch.cat([p.detach().flatten() for p in model.parameters()]).double()
+    return {"ms_per_step": ms / steps, "value": BATCH * steps / (ms / 1e3), "gpu_launches": launches,
+            "e2e": {"value": BATCH * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
+            "check": {"last_loss": last, "param_abs_sum": float(params.abs().sum()), "param_sq_sum": float((params * params).sum())},
+            "graphed_step": graphed, "sampler_reset_s": reset_s, "eval": ev, "setup_s": round(setup_s, 1),
+            "nnz": model.norm_adj._nnz() if hasattr(model, "norm_adj") and hasattr(model.norm_adj, "_nnz") else None,
+            "nodes": sum(model.num_list)}
+
+
+def run_named(args):
+    import torch
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if int(os.environ.get("RANK", "0")) != 0:
+            return                       # these graphs are a few MB: replicas only (DESIGN §5); rank 0 reports
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import __graft_entry__ as G
+    G.build()
+    import tagrec_b200 as T
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    with ClockSampler(local) as clocks:
+        r = named_ours(T, args.workload, dev, args.steps, args.warmup, flush)
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "check": r["check"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(args.workload),
+            "run": {"optimizer": "tagrec_b200.FusedAdam", "parallelism": "single", "nnz": r["nnz"], "nodes": r["nodes"]},
+            "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": clocks.summary(), "graphed_step": r["graphed_step"],
+            "sampler_reset_s": r["sampler_reset_s"], "eval": r["eval"], "setup_s": r["setup_s"],
+            "roofline": None}
+    if not args.no_cpu_baseline:
+        cb, _ = cpu_named(args.workload, 3, 1)
+        line["cpu_baseline"] = cb
+    print(json.dumps(_finite(line)))
+
+
+# ======================================================================================================================
+#  our arm, lightgcn_* (C5 family): device-built graph, single GPU or node-range row blocks
+# ======================================================================================================================
+def run_scale(args):
     import torch
     import torch.distributed as dist
 
@@ -180,18 +529,18 @@ def run_ours(args):
     import tagrec_b200 as T
     from tagrec_b200 import functional as Fn
 
-    shape = WORKLOADS[args.workload]
+    shape = SCALE_WORKLOADS[args.workload]
     small = shape["n_edge"] < 10_000_000
     t0 = time.time()
-    T.set_config("lightgcn", use_tag=False, reg=1e-4, dim_latent=DIM, dim_layer_list=[DIM] * LAYERS, train_batch=BATCH,
-                 device=dev, init_device=dev, lr=0.001, sampler="device")
+    T.set_config("lightgcn", use_tag=False, reg=REG, dim_latent=DIM, dim_layer_list=[DIM] * LAYERS, train_batch=BATCH,
+                 device=dev, init_device=dev, lr=LR, sampler="device")
+    W, K = args.warmup, args.steps
+    need = BATCH * (K + W)
     if world > 1:
         from tagrec_b200 import distributed as D
-        model, triples, info = D.build_sharded_lightgcn(shape, dev, rank, world, BATCH * (args.steps + args.warmup),
-                                                        eval_users_per_rank=args.eval_users)
+        model, triples, info = D.build_sharded_lightgcn(shape, dev, rank, world, need, eval_users_per_rank=args.eval_users)
     else:
-        ui_row, ui_col = T.data.synth_bipartite_device(shape["n_user"], shape["n_item"], int(shape["n_edge"]),
-                                                       dev, seed=2020)
+        ui_row, ui_col = T.data.synth_bipartite_device(shape["n_user"], shape["n_item"], int(shape["n_edge"]), dev, seed=2020)
         n_train = ui_row.numel()
         graph = T.build_csr(shape["n_user"], shape["n_item"], (ui_row, ui_col), "bi_norm", dev)
 
@@ -201,7 +550,6 @@ def run_ours(args):
         torch.manual_seed(2020)
         model = T.LightGCN(Data)
         # batch stream: device sampler over a random subset of the positive edges (all steps' triples)
-        need = BATCH * (args.steps + args.warmup)
         g = torch.Generator(device=dev); g.manual_seed(1)
         idx = torch.randint(0, n_train, (need,), device=dev, generator=g)
         edges = torch.stack([ui_row[idx], ui_col[idx]], 1).contiguous()
@@ -215,8 +563,12 @@ def run_ours(args):
         del edges, train_items
         info = {"nnz": graph._nnz(), "n": graph.n, "n_long_rows": graph.n_long, "parallelism": "single"}
     # com.py:25 composes optim.Adam(model.parameters(), lr); FusedAdam is this package's drop-in for it (same update
-    # rule, one kernel per tensor).  --optimizer torch runs the reference's own choice.
-    opt = (T.FusedAdam if args.optimizer == "fused" else torch.optim.Adam)(model.parameters(), lr=0.001)
+    # rule, one kernel per tensor; on a sharded graph each rank updates the rows it owns).  --optimizer torch runs the
+    # reference's own choice.
+    if args.optimizer == "fused":
+        opt = T.make_optimizer(model, lr=LR) if hasattr(T, "make_optimizer") else T.FusedAdam(model.parameters(), lr=LR)
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=LR)
     model.train()
     torch.cuda.synchronize()
     setup_s = time.time() - t0
@@ -235,7 +587,6 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    W, K = args.warmup, args.steps
     for s in range(W):
         step(triples[s * BATCH:(s + 1) * BATCH])
     # ---- timed region A: inputs resident in HBM -> "value" ----
@@ -291,8 +642,14 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": BATCH * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 8, "d2h_bytes_per_step": 8,
-           "last_loss": last}
+    e2e = {"value": BATCH * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 8, "d2h_bytes_per_step": 8}
+    # the same W + 2K batches are trained at every N: loss and parameter checksums are comparable across rank counts
+    if hasattr(opt, "consolidate"):
+        opt.consolidate()
+    pflat = torch.cat([p.detach() for p in model.embed]).double()
+    check = {"last_loss": last, "param_abs_sum": float(pflat.abs().sum()), "param_sq_sum": float((pflat * pflat).sum()),
+             "steps_trained": W + 2 * K}
+    del pflat
 
     eval_sharded = None
     if world > 1 and args.eval_users > 0 and info.get("eval_mask") is not None:
@@ -301,7 +658,7 @@ def run_ours(args):
     if world > 1:
         mine = {"rank": rank, "fwd_ms": timer.mean_ms("spmm_fwd"), "bwd_ms": timer.mean_ms("spmm_bwd"),
                 "all_gather_ms": timer.mean_ms("all_gather"), "all_gathers_per_step": timer.count("all_gather") // K,
-                "barrier_ms": timer.mean_ms("barrier"),
+                "barrier_ms": timer.mean_ms("barrier"), "adam_ms": timer.mean_ms("adam"),
                 "nnz": info["nnz"], "rows": info["n"]}
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
@@ -326,41 +683,42 @@ def run_ours(args):
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "ms_per_launch": fwd_ms, "launches_timed": timer.count("spmm_fwd"),
                 "bwd_layer_ms": bwd_ms, "bwd_layer_gbs": bytes_per_launch / (bwd_ms * 1e-3) / 1e9,
-                "bpr_ms": timer.mean_ms("bpr"), "bwd_elementwise_ms": timer.mean_ms("bwd_elementwise"),
+                "bpr_ms": timer.mean_ms("bpr"), "bwd_first_ms": timer.mean_ms("bwd_first"),
                 # the backward launches of the last timed step, in order: G_{L-1} (source non-zero on the batch rows
                 # only), G_{L-2} (batch rows + neighbours), ..., dE0 (dense source); zero source rows are skipped
                 "bwd_launch_ms": [round(x.elapsed_time(y), 3) for x, y in timer.pairs.get("spmm_bwd", [])[-LAYERS:]],
-                "row_mask_ms": timer.mean_ms("row_mask")}
+                "adam_ms": timer.mean_ms("adam")}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(config_of(args, shape), parallelism=info["parallelism"],
-                                                nnz=info["nnz"], nodes=info["n"], long_rows=info["n_long_rows"]),
+            "ms_per_step": ms / K, "check": check, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_of(args.workload),
+            "run": {"optimizer": type(opt).__name__, "parallelism": info["parallelism"], "nnz": info["nnz"],
+                    "nodes": info["n"], "long_rows": info["n_long_rows"], "plan": info.get("plan")},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline,
             "setup_s": round(setup_s, 1)}
     if per_rank:
         line["per_rank"] = per_rank
         line["partition"] = {k: info.get(k) for k in ("bounds", "type_weight_s_per_nnz", "balance_feedback")}
     if world == 1 and not args.no_cpu_baseline:
-        cb, _ = cpu_reference(sample_shape(shape), 3, 1, info["nnz"])
+        cb, _ = cpu_scale(args.workload, 3, 1, info["nnz"])
         line["cpu_baseline"] = cb
     if args.eval_users > 0 and world == 1:
         line["eval"] = eval_leg(T, model, shape, dev, args.eval_users)
     if eval_sharded is not None:
         line["eval"] = eval_sharded
+    if world == 1 and not args.no_c1 and not small:
+        # BASELINE configs[0] — "the reference's own CPU-runnable case" — both arms on the FULL config in the same run
+        del model, opt, triples
+        torch.cuda.empty_cache()
+        fl = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ours = named_ours(T, "lastfm", dev, 20, 5, fl)
+        c1 = {"config": config_of("lastfm"), "ours": ours}
+        if not args.no_cpu_baseline:
+            cpu, _ = cpu_named("lastfm", 10, 2)
+            c1["cpu"] = cpu
+        line["c1"] = c1
     print(json.dumps(_finite(line)))
     if world > 1:
         dist.destroy_process_group()
-
-
-def _finite(x):
-    """NaN / inf are not JSON: replace them with null."""
-    if isinstance(x, float):
-        return x if x == x and abs(x) != float("inf") else None
-    if isinstance(x, dict):
-        return {k: _finite(v) for k, v in x.items()}
-    if isinstance(x, (list, tuple)):
-        return [_finite(v) for v in x]
-    return x
 
 
 def eval_leg_sharded(T, model, shape, dev, eval_mask, world, dist):
@@ -395,9 +753,11 @@ def eval_leg_sharded(T, model, shape, dev, eval_mask, world, dist):
 
 
 def eval_leg(T, model, shape, dev, n_users):
-    """Secondary metric of BASELINE.json: full-rank eval users/s (K3: scoring + mask + top-20 + metric sums).
-    Both scoring paths are timed: the tcgen05 TF32-filter path (default for dim 64) and the exact-fp32 CUDA-core
-    path; they return identical lists (checked here on the benchmark inputs)."""
+    """Secondary metric of BASELINE.json: full-rank eval users/s (K3: scoring + mask + top-20 + metric sums) on the
+    benchmark graph.  The drop-in Basic_test takes the reference's dict-of-lists data object, which cannot hold 10 M
+    users; this leg calls the same kernels Basic_test._sums_device calls, on device CSR masks ("c1" in the line times
+    Basic_test.run itself).  Both scoring paths are timed: the tcgen05 TF32-filter path (default for dim 64) and the
+    exact-fp32 CUDA-core path; they return identical lists (checked here on the benchmark inputs)."""
     import torch
     from tagrec_b200.eval_ops import metric_sums, topk_scores
     graph = model.norm_adj
@@ -466,8 +826,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="lightgcn_1b", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="lightgcn_1b", choices=sorted(SCALE_WORKLOADS) + sorted(NAMED_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c1", action="store_true", help="skip the LastFM-shaped (configs[0]) sub-benchmark of the default line")
     ap.add_argument("--eval-users", type=int, default=16384)
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"])
     args = ap.parse_args()
@@ -475,8 +836,10 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in NAMED_WORKLOADS:
+        run_named(args)
     else:
-        run_ours(args)
+        run_scale(args)
 
 
 if __name__ == "__main__":

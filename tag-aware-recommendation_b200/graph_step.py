@@ -96,5 +96,5 @@ class GraphedStep:
             self.model._cache = None
         for g in self.real_opt.param_groups:
             for p in g["params"]:
-                torch._C._increment_version(p)
+                torch._C._increment_version([p])
         return tuple(x.clone() for x in self.static_out)

@@ -68,5 +68,5 @@ class FusedAdam(torch.optim.Optimizer):
                                              group["lr"], b1, b2, group["eps"], group["weight_decay"], st["step"],
                                              stream_ptr(p.device)), "tagrec_adam_step")
                 # the kernel wrote the parameter through a raw pointer: tell autograd / version-keyed caches
-                torch._C._increment_version(p)
+                torch._C._increment_version([p])
         return loss

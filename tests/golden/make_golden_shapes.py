@@ -75,7 +75,39 @@ def table_entry(out, key, arr, rng):
         out[key + "_full"] = arr.copy()
 
 
-def run_model(ds, name, cls, use_tag, tag, extra=None, tuple_batch=False, after_build=None):
+def truth64(m, bt, tuple_batch, out):
+    """The SAME reference model (same float32 parameter values, same adjacency values) run once more in float64:
+    the yardstick for gradients that are long float32 reductions on both sides (weight gradients summed over 1e5
+    nodes, scatter-added embedding gradients).  Stored for the rows / tensors the float32 golden stores."""
+    import copy
+    t0 = time.time()
+    torch.set_default_dtype(torch.float64)
+    try:
+        m64 = copy.deepcopy(m).double()
+        if hasattr(m64, "norm_adj") and torch.is_tensor(m64.norm_adj):
+            m64.norm_adj = m64.norm_adj.double()
+        m64.train()
+        m64.zero_grad()
+        lossx = m64.loss((bt, None)) if tuple_batch else m64.loss(bt)
+        out["loss64"] = np.array([x.item() for x in lossx], dtype=np.float64)
+        sum(lossx).backward()
+        for k, p in m64.named_parameters():
+            g = (p.grad if p.grad is not None else torch.zeros_like(p)).detach().numpy()
+            if f"grad_{k}_rows" in out:
+                out[f"grad64_{k}_vals"] = g[out[f"grad_{k}_rows"]].copy()
+            else:
+                out[f"grad64_{k}_full"] = g.copy()
+            ref32 = out.get(f"grad_{k}_vals", out.get(f"grad_{k}_full"))
+            g64 = out.get(f"grad64_{k}_vals", out.get(f"grad64_{k}_full"))
+            scale = np.abs(g64).max()
+            if scale > 0:
+                print(f"    {k}: reference fp32 vs fp64 {np.abs(ref32 - g64).max() / scale:.2e}", flush=True)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    print(f"  float64 pass {time.time() - t0:.1f} s", flush=True)
+
+
+def run_model(ds, name, cls, use_tag, tag, extra=None, tuple_batch=False, with64=False):
     """loss / grads / propagated tables / top-20 of 512 users from the reference class at its seeded initial state."""
     t0 = time.time()
     set_cfg(name, use_tag=use_tag, reg=1e-4, train_batch=BATCH, test_batch=512, topks=[20], **(extra or {}))
@@ -100,6 +132,8 @@ def run_model(ds, name, cls, use_tag, tag, extra=None, tuple_batch=False, after_
     for k, p in m.named_parameters():
         g = p.grad if p.grad is not None else torch.zeros_like(p)
         table_entry(out, f"grad_{k}", g.detach().numpy(), rng)
+    if with64:
+        truth64(m, bt, tuple_batch, out)
     # top-20 of 512 users (dict-key order prefix of the test users), masked like basic_test.py:37-47, (-score, id) order
     m.eval()
     users = list(ds.user_items["test"].keys())[:512]
@@ -238,12 +272,13 @@ def main():
                 np.random.seed(2020)
                 return DATA.get_all_neighbor(ds, width=25)
             ds.get_all_neighbor = tables
-            out, m = run_model(ds, "tgcn", TGCN, True, "c2_tgcn", extra=dict(dim_layer_list=[64, 64], neighbor_k=25))
+            out, m = run_model(ds, "tgcn", TGCN, True, "c2_tgcn", extra=dict(dim_layer_list=[64, 64], neighbor_k=25),
+                               with64=True)
             save("c2_tgcn", out)
     if "c3" in which:
         print("C3 amazon_book / NGCF", flush=True)
         ds = DATA.synth_named("amazon_book")
-        out, m = run_model(ds, "ngcf", NGCF, False, "c3")
+        out, m = run_model(ds, "ngcf", NGCF, False, "c3", with64=True)
         save("c3_ngcf", out)
     if "c4" in which:
         print("C4 gowalla / DGCF", flush=True)
