@@ -480,7 +480,7 @@ def named_ours(T, name, dev, steps, warmup, flush):
             "check": {"last_loss": last, "param_abs_sum": float(params.abs().sum()), "param_sq_sum": float((params * params).sum())},
             "graphed_step": graphed, "sampler_reset_s": reset_s, "eval": ev, "setup_s": round(setup_s, 1),
             "nnz": model.norm_adj._nnz() if hasattr(model, "norm_adj") and hasattr(model.norm_adj, "_nnz") else None,
-            "nodes": sum(model.num_list)}
+            "nodes": int(sum(ds.num[k] for k in (("user", "item", "tag") if NAMED_WORKLOADS[name][2] else ("user", "item"))))}
 
 
 def run_named(args):

@@ -1254,7 +1254,8 @@ def test_evaluation_follows_raw_pointer_updates(tiny, mode, tmp_path):
     fresh = T.LightGCN(d).to(dev())
     fresh.load_state_dict(model.state_dict())
     r3 = T.Basic_test(d, args).run(fresh, istest=True)
-    assert r2["recall"] == r3["recall"] and r2["ndcg"] == r3["ndcg"] and r2["auc"] == r3["auc"]
+    for key in ("recall", "ndcg", "auc"):            # long rows meet through atomics: equal up to summation order
+        assert np.allclose(np.asarray(r2[key], dtype=np.float64), np.asarray(r3[key], dtype=np.float64), rtol=0, atol=1e-6), (key, r2[key], r3[key])
     assert (r1["recall"], r1["auc"]) != (r2["recall"], r2["auc"])
     # resume: a FusedAdam restored from its state_dict continues the bias correction where it stopped
     sd = opt.state_dict()
