@@ -561,7 +561,8 @@ def run_scale(args):
                                                            T._lib.ptr(train_items), shape["n_item"], 2020, 0,
                                                            T._lib.ptr(triples), T._lib.stream_ptr(dev)), "sampler")
         del edges, train_items
-        info = {"nnz": graph._nnz(), "n": graph.n, "n_long_rows": graph.n_long, "parallelism": "single"}
+        info = {"nnz": graph._nnz(), "n": graph.n, "n_long_rows": graph.n_long, "parallelism": "single",
+                "plan": graph.col_block}
     # com.py:25 composes optim.Adam(model.parameters(), lr); FusedAdam is this package's drop-in for it (same update
     # rule, one kernel per tensor; on a sharded graph each rank updates the rows it owns).  --optimizer torch runs the
     # reference's own choice.

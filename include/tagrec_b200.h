@@ -75,6 +75,12 @@ int tagrec_csr_build_structure(const int64_t* ui_row, const int64_t* ui_col, int
 int tagrec_csr_normalise(const int64_t* rowptr, const int32_t* col, const float* weight, const float* dpow,
                          int64_t n, int mode, int self_loops, float* val, void* stream);
 
+/* Plan builder of the column-blocked K1 (no reference equivalent): bounds[w * n_sel + i] = index of the first stored
+ * entry of row rows[i] (local row ids, ascending columns per row) whose column id is >= w * window, for w = 0 .. n_win
+ * — i.e. where each L2-sized window of the gathered table starts inside each selected row. */
+int tagrec_csr_window_bounds(const int64_t* rowptr, const int32_t* col, const int32_t* rows, int64_t n_sel,
+                             int64_t window, int n_win, int64_t* bounds, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K1  CSR SpMM with fused epilogues      replaces model/help/adj.py:158-167 (split_mm = torch.sparse.mm) and
  *                                        its autograd transpose, plus model/lightgcn.py:54-60.
@@ -103,6 +109,16 @@ typedef struct {
     int32_t* long_counter;
     int32_t long_row;           /* rows with more entries than this are "long"; 0 = TAGREC_LONG_ROW */
     int32_t long_chunk;         /* entries per chunk of a long row;             0 = TAGREC_LONG_CHUNK */
+    /* Column-blocked plans (L2-windowed gathers).  A chunk may be ANY [begin, end) piece of its row:
+     * the plan cuts the rows that gather from a table far larger than the L2 at column-window boundaries and lists
+     * the pieces window-major, so that the chunks in flight at any time gather from one L2-sized window of the source
+     * table.  long_nchunks[slot] = number of pieces of that row (NULL: ceil(degree / long_chunk), the plain plan).
+     * Rows with local index >= blocked_row_begin are "long" already above blocked_min_deg entries (0: long_row).
+     * chunk_lanes = 0: one warp per chunk; 1: one sub-warp (dim/4 lanes) per chunk — short pieces. */
+    const int32_t* long_nchunks;
+    int64_t blocked_row_begin;
+    int32_t blocked_min_deg;
+    int32_t chunk_lanes;
 } tagrec_csr_t;
 
 /* Fused compute + collective (multi-GPU, no reference equivalent — the reference is single-device): where an
@@ -152,6 +168,17 @@ int tagrec_lightgcn_bwd_layer_ex(const tagrec_csr_t* a, const float* g_next, con
                                  float* g_out, int dim, const tagrec_mirror_t* out_mirror, void* stream);
 /* nz[r] = (row r of the [n, dim] table has a non-zero element). */
 int tagrec_row_nonzero(const float* table, int64_t n, int dim, uint8_t* nz, void* stream);
+
+/* Sparse form of the FIRST backward table of a BPR step (same closed form as tagrec_lightgcn_bwd_layer with
+ * g_next == NULL, restricted to the listed rows): dL/dF is non-zero on the batch's nodes only, hence so is
+ * G_L = nb(g_final * upstream[0] * inv_layers, e_k).  nodes[n_nodes] = GLOBAL row ids (duplicates allowed).  Rows in
+ * [row_lo, row_hi) are written to g_out — a table the caller keeps all-zero otherwise — and every listed row is flagged
+ * in nz (the byte map tagrec_lightgcn_bwd_layer_ex takes as g_next_nz; may be NULL).  tagrec_rows_zero restores the
+ * all-zero state (table and / or map) for the same list afterwards: O(batch) instead of O(N) work per step. */
+int tagrec_lightgcn_bwd_first_sparse(const int64_t* nodes, int64_t n_nodes, int64_t row_lo, int64_t row_hi,
+                                     const float* e_k, const float* g_final, const float* upstream, float inv_layers,
+                                     float* g_out, uint8_t* nz, int dim, void* stream);
+int tagrec_rows_zero(const int64_t* nodes, int64_t n_nodes, float* table, uint8_t* nz, int dim, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K2  fused BPR step            replaces model/lightgcn.py:68-82 / model/ngcf.py:95-105 (3 gathers, mul_loss,
@@ -386,6 +413,14 @@ int tagrec_sample_bpr_device(const int64_t* edges, int64_t e, const int64_t* tra
 /* Fused dense Adam (torch.optim.Adam semantics, com.py:25): one pass over param/grad/m/v. */
 int tagrec_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int64_t step, void* stream);
+/* Owner-sharded form (multi-GPU): the same step on a contiguous, 16-byte aligned segment (n % 4 == 0) of a parameter
+ * table this rank owns; the new values are stored through `param_mirror` (bases point at the segment's first element in
+ * every rank's replica, or one NVLS multicast address) so each row of the replicated table is updated by its owner
+ * only; exp_avg / exp_avg_sq stay local.  The caller separates this launch from the next reader with a cross-rank
+ * barrier. */
+int tagrec_adam_step_mirror(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                            float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                            const tagrec_mirror_t* param_mirror, void* stream);
 
 /* CUDA-graph-capturable form: the step counter and this step's bias corrections live in device memory.
  * tagrec_adam_advance: *step_dev += 1; scal_dev[0] = lr / (1 - beta1^step), scal_dev[1] = 1 / sqrt(1 - beta2^step)

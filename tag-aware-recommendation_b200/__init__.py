@@ -24,6 +24,6 @@ from .bpr_training_data import (Abstract_training_data, BPR_training_data, DGCF_
 from .basic_train import Basic_train, epoch_training           # noqa: F401
 from .basic_test import Basic_test                             # noqa: F401
 from .early_stop import Early_stop                             # noqa: F401
-from .optim import FusedAdam                                   # noqa: F401
+from .optim import FusedAdam, ShardedFusedAdam, make_optimizer   # noqa: F401
 from .graph_step import GraphedStep                            # noqa: F401
 from . import data, distributed                                # noqa: F401

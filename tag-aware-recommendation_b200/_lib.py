@@ -28,7 +28,8 @@ class CsrDesc(C.Structure):
     """tagrec_csr_t"""
     _fields_ = [("rowptr", _p), ("col", _p), ("val", _p), ("n_rows", _i64), ("row_offset", _i64), ("long_rows", _p), ("item_slot", _p),
                 ("item_begin", _p), ("item_end", _p), ("n_long", _i64), ("n_items", _i64), ("long_scratch", _p),
-                ("long_counter", _p), ("long_row", C.c_int32), ("long_chunk", C.c_int32)]
+                ("long_counter", _p), ("long_row", C.c_int32), ("long_chunk", C.c_int32), ("long_nchunks", _p),
+                ("blocked_row_begin", _i64), ("blocked_min_deg", C.c_int32), ("chunk_lanes", C.c_int32)]
 
 
 class RoutePlan(C.Structure):
@@ -52,6 +53,9 @@ PROTOTYPES = {
     "tagrec_csr_build_structure": (_i32, [_p, _p, _i64, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i32, _p, _sz,
                                           _p, _p, _p, _i64, _p, C.POINTER(_i64), _p]),
     "tagrec_csr_normalise": (_i32, [_p, _p, _p, _p, _i64, _i32, _i32, _p, _p]),
+    "tagrec_lightgcn_bwd_first_sparse": (_i32, [_p, _i64, _i64, _i64, _p, _p, _p, _f32, _p, _p, _i32, _p]),
+    "tagrec_rows_zero": (_i32, [_p, _i64, _p, _p, _i32, _p]),
+    "tagrec_csr_window_bounds": (_i32, [_p, _p, _p, _i64, _i64, _i32, _p, _p]),
     "tagrec_spmm": (_i32, [C.POINTER(CsrDesc), _p, _p, _i32, _f32, _p]),
     "tagrec_lightgcn_fwd_layer": (_i32, [C.POINTER(CsrDesc), _p, _p, _p, _i32, _i32, _i32, _f32, _p]),
     "tagrec_lightgcn_bwd_layer": (_i32, [C.POINTER(CsrDesc), _p, _p, _p, _p, _p, _f32, _p, _i32, _p]),
@@ -102,6 +106,7 @@ PROTOTYPES = {
     "tagrec_sample_neg_tail_host": (_i32, [_p, _p, _i64, _p, _p, _i64, _p]),
     "tagrec_sample_bpr_device": (_i32, [_p, _i64, _p, _p, _i64, _u64, _u64, _p, _p]),
     "tagrec_adam_step": (_i32, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _p]),
+    "tagrec_adam_step_mirror": (_i32, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i64, C.POINTER(MirrorDesc), _p]),
     "tagrec_adam_advance": (_i32, [_p, _f32, _f32, _f32, _p, _p]),
     "tagrec_adam_step_dev": (_i32, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _p, _p]),
 }

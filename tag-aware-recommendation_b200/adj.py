@@ -48,34 +48,112 @@ class CsrGraph:
     def _values(self):
         return self.val
 
+    # ---- the launch plan of K1 -------------------------------------------------------------------------------
+    COLBLOCK_MIN_TABLE_BYTES = 1 << 30      # block only rows that gather from a table far larger than the 126 MB L2
+
+    def _column_block_spec(self):
+        """(first local row, min degree, window rows) of the column-blocked region, or None.
+
+        Rows of the non-user node types (items, tags) gather rows of the USER table; when that table is far larger than
+        the L2 (1 B-edge graph: 2.56 GB) every such gather is a DRAM access — the item-row half of a layer then runs
+        at the HBM roofline of a gather formulation (profiles/r1_spmm_l2_probe.md).  The plan cuts those rows at
+        boundaries of L2-sized column windows and orders the pieces window-major, so that the pieces in flight at any
+        time gather from ONE window of the table and each of its rows is fetched from DRAM once per launch instead of
+        once per use.  TAGREC_COLBLOCK=0 switches it off; _MB / _MIN_DEG tune window and the shortest blocked row."""
+        import os
+        if os.environ.get("TAGREC_COLBLOCK", "1") == "0" or len(self.num_list) < 2:
+            return None
+        n_user = int(self.num_list[0])
+        force = os.environ.get("TAGREC_COLBLOCK_FORCE") == "1"           # tests: block graphs of any size
+        if n_user * 256 < self.COLBLOCK_MIN_TABLE_BYTES and not force:
+            return None
+        begin = min(max(n_user - self.row_offset, 0), self.n_rows)
+        if begin >= self.n_rows:
+            return None
+        window = int(float(os.environ.get("TAGREC_COLBLOCK_MB", "48")) * (1 << 20)) // 256
+        min_deg = int(os.environ.get("TAGREC_COLBLOCK_MIN_DEG", "384"))
+        return begin, min_deg, max(window, 64)
+
     def _build_plan(self):
         """Rows above ``long_row`` nnz are cut into ``long_chunk`` pieces (see csrc/spmm.cu).  The thresholds are the
         tuned 4096 / 2048 on big graphs; a small graph is only a few waves of rows, where one sub-warp walking a
-        2000-entry hub row IS the launch time, so it is planned with 256 / 256."""
+        2000-entry hub row IS the launch time, so it is planned with 256 / 256.  Rows of the column-blocked region
+        (``_column_block_spec``) are cut at column-window boundaries instead and listed window-major."""
         small = self._nnz() < _lib.SMALL_GRAPH_NNZ
         self.long_row = _lib.SMALL_LONG_ROW if small else _lib.LONG_ROW
         self.long_chunk = _lib.SMALL_LONG_CHUNK if small else _lib.LONG_CHUNK
         LONG_ROW, LONG_CHUNK = self.long_row, self.long_chunk
         dev = self.device
         deg = self.rowptr[1:] - self.rowptr[:-1]
-        long_rows = torch.nonzero(deg > LONG_ROW).flatten()
+        import os
+        spec = None if (small and os.environ.get("TAGREC_COLBLOCK_FORCE") != "1") else self._column_block_spec()
+        self.col_block = None
+        self.blocked_row_begin, self.blocked_min_deg, self.chunk_lanes = 0, 0, 0
+        self.long_nchunks = None
+        self._scratch = {}
+        is_long = deg > LONG_ROW
+        if spec is not None:
+            begin_row, min_deg, window = spec
+            blocked = torch.zeros_like(is_long)
+            blocked[begin_row:] = deg[begin_row:] > min_deg
+            is_long = is_long | blocked
+        long_rows = torch.nonzero(is_long).flatten()
         self.n_long = int(long_rows.numel())
         if self.n_long == 0:
             self.long_rows = self.item_slot = self.item_begin = self.item_end = None
             self.n_items = 0
-            self._scratch = {}
             return
-        nchunks = (deg[long_rows] + LONG_CHUNK - 1) // LONG_CHUNK
-        slot = torch.repeat_interleave(torch.arange(self.n_long, device=dev), nchunks)
-        first = torch.cumsum(nchunks, 0) - nchunks
-        k = torch.arange(slot.numel(), device=dev) - first[slot]
-        begin = self.rowptr[long_rows][slot] + k * LONG_CHUNK
-        end = torch.minimum(begin + LONG_CHUNK, self.rowptr[long_rows + 1][slot])
+        slot_of = torch.arange(self.n_long, device=dev)
+        slots, begins, ends = [], [], []
+        counts = torch.zeros(self.n_long, dtype=torch.int64, device=dev)
+        if spec is not None:
+            sel = blocked[long_rows]                                  # long rows that are column-blocked
+            b_slots = slot_of[sel]
+            b_rows = long_rows[sel].to(torch.int32).contiguous()
+            nb = int(b_rows.numel())
+            if nb:
+                n_win = (self.n + window - 1) // window
+                bounds = torch.empty((n_win + 1, nb), dtype=torch.int64, device=dev)
+                check(lib().tagrec_csr_window_bounds(ptr(self.rowptr), ptr(self.col), ptr(b_rows), nb, window, n_win,
+                                                     ptr(bounds), stream_ptr(dev)), "tagrec_csr_window_bounds")
+                seg_b, seg_e = bounds[:-1].reshape(-1), bounds[1:].reshape(-1)       # window-major [n_win * nb]
+                pieces = (seg_e - seg_b + LONG_CHUNK - 1) // LONG_CHUNK
+                counts[b_slots] = pieces.reshape(n_win, nb).sum(0)
+                keep = torch.nonzero(pieces > 0).flatten()
+                seg_b, seg_e, pieces = seg_b[keep], seg_e[keep], pieces[keep]
+                seg_slot = b_slots[keep % nb]
+                del keep, bounds
+                if int(pieces.max()) == 1:
+                    slots.append(seg_slot); begins.append(seg_b); ends.append(seg_e)
+                else:
+                    rep = torch.repeat_interleave(torch.arange(pieces.numel(), device=dev), pieces)
+                    first = torch.cumsum(pieces, 0) - pieces
+                    k = torch.arange(rep.numel(), device=dev) - first[rep]
+                    pb = seg_b[rep] + k * LONG_CHUNK
+                    slots.append(seg_slot[rep]); begins.append(pb); ends.append(torch.minimum(pb + LONG_CHUNK, seg_e[rep]))
+                    del rep, first, k, pb
+                self.col_block = {"rows": nb, "window_rows": window, "windows": int(n_win), "min_deg": min_deg,
+                                  "pieces": int(sum(x.numel() for x in slots))}
+                self.blocked_row_begin, self.blocked_min_deg, self.chunk_lanes = int(begin_row), int(min_deg), 1
+            plain = ~sel
+        else:
+            plain = torch.ones(self.n_long, dtype=torch.bool, device=dev)
+        p_slots = slot_of[plain]
+        if p_slots.numel():                                           # plain long rows: equal-count pieces
+            rows_p = long_rows[plain]
+            nchunks = (deg[rows_p] + LONG_CHUNK - 1) // LONG_CHUNK
+            counts[p_slots] = nchunks
+            rep = torch.repeat_interleave(torch.arange(p_slots.numel(), device=dev), nchunks)
+            first = torch.cumsum(nchunks, 0) - nchunks
+            k = torch.arange(rep.numel(), device=dev) - first[rep]
+            pb = self.rowptr[rows_p][rep] + k * LONG_CHUNK
+            slots.append(p_slots[rep]); begins.append(pb)
+            ends.append(torch.minimum(pb + LONG_CHUNK, self.rowptr[rows_p + 1][rep]))
         self.long_rows = long_rows.to(torch.int32)
-        self.item_slot = slot.to(torch.int32)
-        self.item_begin, self.item_end = begin.contiguous(), end.contiguous()
-        self.n_items = int(slot.numel())
-        self._scratch = {}
+        self.item_slot = torch.cat(slots).to(torch.int32).contiguous()
+        self.item_begin, self.item_end = torch.cat(begins).contiguous(), torch.cat(ends).contiguous()
+        self.n_items = int(self.item_slot.numel())
+        self.long_nchunks = counts.to(torch.int32).contiguous()
 
     def desc(self, dim, transposed=False):
         """tagrec_csr_t for a launch at feature width ``dim`` (scratch rows are dim floats wide)."""
@@ -86,7 +164,9 @@ class CsrGraph:
         d.row_offset = self.row_offset
         d.n_long, d.n_items = self.n_long, self.n_items
         d.long_row, d.long_chunk = self.long_row, self.long_chunk
+        d.blocked_row_begin, d.blocked_min_deg, d.chunk_lanes = self.blocked_row_begin, self.blocked_min_deg, self.chunk_lanes
         if self.n_long:
+            d.long_nchunks = ptr(self.long_nchunks)
             if dim not in self._scratch:
                 self._scratch[dim] = (torch.zeros(self.n_long, dim, dtype=torch.float32, device=self.device),
                                       torch.zeros(self.n_long, dtype=torch.int32, device=self.device))

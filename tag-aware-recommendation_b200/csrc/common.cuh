@@ -93,4 +93,35 @@ __device__ __forceinline__ void red_add4(float4* addr, const float4& v) {
                  : "memory");
 }
 
+// Where an output row is stored.  n == 0: the local table only.  n >= 1: the same table on n ranks of one NVSwitch
+// domain — base[r] is rank r's copy mapped into this process (peer memory over NVLink 5), or a single NVLS
+// multicast address (n == 1) that the switch replicates to every rank.  This is the all-gather of the sharded path,
+// fused into the SpMM epilogue: rows cross NVLink while the next rows are still being gathered from HBM.
+struct Mirror {
+    int n;
+    float* base[TAGREC_MAX_PEERS];
+};
+
+__device__ __forceinline__ void store_row(float* local, const Mirror& m, int64_t o, const float4& v) {
+    if (m.n == 0) {
+        reinterpret_cast<float4*>(local)[o] = v;
+        return;
+    }
+#pragma unroll
+    for (int p = 0; p < TAGREC_MAX_PEERS; ++p)
+        if (p < m.n) reinterpret_cast<float4*>(m.base[p])[o] = v;
+}
+
+inline int set_mirror(Mirror& m, const tagrec_mirror_t* src) {
+    m.n = 0;
+    if (!src || src->n == 0) return TAGREC_OK;
+    TAGREC_REQUIRE(src->n >= 1 && src->n <= TAGREC_MAX_PEERS, "mirror: bad rank count");
+    m.n = src->n;
+    for (int p = 0; p < src->n; ++p) {
+        TAGREC_REQUIRE(src->base[p], "mirror: null base pointer");
+        m.base[p] = static_cast<float*>(src->base[p]);
+    }
+    return TAGREC_OK;
+}
+
 }  // namespace tagrec

@@ -217,3 +217,37 @@ extern "C" int tagrec_csr_normalise(const int64_t* rowptr, const int32_t* col, c
     TAGREC_LAUNCH(normalise_kernel, kSMs * 8, 256, 0, stream, rowptr, col, weight, dpow, n, mode, self_loops, val);
     return TAGREC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column-window bounds of selected rows (plan builder of the column-blocked K1, adj.py): bounds[w * n_sel + i] = index
+// of the first stored entry of row rows[i] whose column id is >= w * window  (w = 0 .. n_win; ascending columns per
+// row make it a lower bound).  One thread per (row, boundary).
+namespace tagrec {
+__global__ void __launch_bounds__(256)
+window_bounds_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ rows,
+                     int64_t n_sel, int64_t window, int n_win, int64_t* __restrict__ bounds) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_sel * (n_win + 1)) return;
+    const int64_t w = idx / n_sel, i = idx - w * n_sel;
+    const int64_t r = rows[i];
+    int64_t lo = __ldg(rowptr + r), hi = __ldg(rowptr + r + 1);
+    const int64_t key = w * window;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(col + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    bounds[idx] = lo;
+}
+}  // namespace tagrec
+
+extern "C" int tagrec_csr_window_bounds(const int64_t* rowptr, const int32_t* col, const int32_t* rows, int64_t n_sel,
+                                        int64_t window, int n_win, int64_t* bounds, void* stream) {
+    TAGREC_REQUIRE(rowptr && col && rows && bounds, "null pointer");
+    TAGREC_REQUIRE(window > 0 && n_win >= 1 && n_sel >= 0, "bad window / count");
+    if (n_sel == 0) return TAGREC_OK;
+    const int64_t total = n_sel * (n_win + 1);
+    const int64_t grid = (total + 255) / 256;
+    TAGREC_REQUIRE(grid < (1ll << 31), "grid too large");
+    TAGREC_LAUNCH(tagrec::window_bounds_kernel, (unsigned)grid, 256, 0, stream, rowptr, col, rows, n_sel, window, n_win, bounds);
+    return TAGREC_OK;
+}

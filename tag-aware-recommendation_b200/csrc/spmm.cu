@@ -22,25 +22,6 @@ namespace tagrec {
 
 enum { EPI_PLAIN = 0, EPI_FWD = 1, EPI_BWD = 2, EPI_BWD0 = 3 };
 
-// Where an output row is stored.  n == 0: the local table only.  n >= 1: the same table on n ranks of one NVSwitch
-// domain — base[r] is rank r's copy mapped into this process (peer memory over NVLink 5), or a single NVLS
-// multicast address (n == 1) that the switch replicates to every rank.  This is the all-gather of the sharded path,
-// fused into the SpMM epilogue: rows cross NVLink while the next rows are still being gathered from HBM.
-struct Mirror {
-    int n;
-    float* base[TAGREC_MAX_PEERS];
-};
-
-__device__ __forceinline__ void store_row(float* local, const Mirror& m, int64_t o, const float4& v) {
-    if (m.n == 0) {
-        reinterpret_cast<float4*>(local)[o] = v;
-        return;
-    }
-#pragma unroll
-    for (int p = 0; p < TAGREC_MAX_PEERS; ++p)
-        if (p < m.n) reinterpret_cast<float4*>(m.base[p])[o] = v;
-}
-
 struct Epi {
     Mirror my, macc;        // mirrors of y / acc (n == 0: local only)
     float* y;               // output rows (plain / fwd: raw layer, bwd: g_out)
@@ -231,29 +212,47 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
     const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
 
     if ((int)blockIdx.x < n_long_blocks) {
-        // ---- one chunk of a long row per warp ----
-        const int64_t item = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+        // ---- chunks of long / column-blocked rows: partial sums meet in the row's scratch row ----
+        const bool per_sub = a.chunk_lanes != 0 && RPW > 1;      // one sub-warp per chunk (short, column-window pieces)
+        const int64_t unit = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+        const int64_t item = per_sub ? unit * RPW + sub : unit;
         if (item >= a.n_items) return;
         const int slot = __ldg(a.item_slot + item);
         const int64_t b = __ldg(a.item_begin + item), e = __ldg(a.item_end + item);
-        float4 p = gather_rows<LPR, MASKED>(a.col, a.val, x4, b, e, sub, RPW, sl, mask, ep.src_nz);
-        p = combine_subs<LPR>(p);
+        float4 p;
+        if (per_sub) {
+            p = gather_rows<LPR, MASKED>(a.col, a.val, x4, b, e, 0, 1, sl, mask, ep.src_nz);
+        } else {
+            p = gather_rows<LPR, MASKED>(a.col, a.val, x4, b, e, sub, RPW, sl, mask, ep.src_nz);
+            p = combine_subs<LPR>(p);
+        }
+        const bool writer = per_sub || sub == 0;
         float4* scr = reinterpret_cast<float4*>(a.long_scratch) + (int64_t)slot * LPR + sl;
-        if (sub == 0) red_add4(scr, p);
+        if (writer) red_add4(scr, p);
         __threadfence();
-        __syncwarp();
+        __syncwarp(per_sub ? mask : 0xffffffffu);
         const int64_t r = __ldg(a.long_rows + slot);
-        const int64_t deg = __ldg(a.rowptr + r + 1) - __ldg(a.rowptr + r);
-        const int nchunks = (int)((deg + a.long_chunk - 1) / a.long_chunk);
+        int nchunks;
+        if (a.long_nchunks) {
+            nchunks = __ldg(a.long_nchunks + slot);
+        } else {
+            const int64_t deg = __ldg(a.rowptr + r + 1) - __ldg(a.rowptr + r);
+            nchunks = (int)((deg + a.long_chunk - 1) / a.long_chunk);
+        }
         int ticket = 0;
-        if (lane == 0) ticket = atomicAdd(a.long_counter + slot, 1);
-        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (per_sub) {
+            if (sl == 0) ticket = atomicAdd(a.long_counter + slot, 1);
+            ticket = __shfl_sync(mask, ticket, 0, LPR);
+        } else {
+            if (lane == 0) ticket = atomicAdd(a.long_counter + slot, 1);
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        }
         if (ticket != nchunks - 1) return;
         __threadfence();
-        if (sub == 0) {  // last piece: complete row sits in the scratch row; run the fused epilogue, leave it zeroed
+        if (writer) {  // last piece: complete row sits in the scratch row; run the fused epilogue, leave it zeroed
             const float4 tot = __ldcg(scr);
             __stcg(scr, make_float4(0.f, 0.f, 0.f, 0.f));
-            if (lane == 0) a.long_counter[slot] = 0;
+            if (sl == 0) a.long_counter[slot] = 0;
             epilogue<LPR, EPI>(ep, r + a.row_offset, tot, sl, mask);
         }
         return;
@@ -269,7 +268,8 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
         s = __ldg(a.rowptr + r);
         e = __ldg(a.rowptr + r + 1);
     }
-    const bool is_long = gather && (e - s) > a.long_row;
+    const int64_t long_thr = (r >= a.blocked_row_begin && a.blocked_min_deg > 0) ? a.blocked_min_deg : a.long_row;
+    const bool is_long = gather && (e - s) > long_thr;
     if (is_long || !gather) e = s;  // long rows are produced by the chunk blocks above
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -313,7 +313,8 @@ static int launch(const tagrec_csr_t* a, const float* x, const Epi& ep, int dim,
         TAGREC_REQUIRE(a->long_rows && a->item_slot && a->item_begin && a->item_end && a->long_scratch &&
                            a->long_counter, "long-row plan arrays missing");
     const int lpr = dim / 4, rpw = 32 / lpr;
-    const int64_t long_blocks = (n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int64_t chunks_per_block = (int64_t)kWarpsPerBlock * ((a->chunk_lanes != 0 && rpw > 1) ? rpw : 1);
+    const int64_t long_blocks = (n_items + chunks_per_block - 1) / chunks_per_block;
     const int64_t row_blocks = (a->n_rows + (int64_t)rpw * kWarpsPerBlock - 1) / ((int64_t)rpw * kWarpsPerBlock);
     const int64_t grid = long_blocks + row_blocks;
     TAGREC_REQUIRE(grid < (1ll << 31), "grid too large");
@@ -321,6 +322,7 @@ static int launch(const tagrec_csr_t* a, const float* x, const Epi& ep, int dim,
     d.n_items = n_items;
     if (d.long_row <= 0) d.long_row = TAGREC_LONG_ROW;
     if (d.long_chunk <= 0) d.long_chunk = TAGREC_LONG_CHUNK;
+    if (d.blocked_min_deg <= 0) d.blocked_row_begin = INT64_MAX;
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const dim3 block(kWarpsPerBlock * 32);
     if (lpr == 16 && ep.src_nz && gather && (EPI == EPI_BWD || EPI == EPI_BWD0)) {
@@ -345,18 +347,6 @@ extern "C" int tagrec_spmm(const tagrec_csr_t* a, const float* x, float* y, int 
     ep.y = y;
     ep.scale = beta;
     return launch<EPI_PLAIN>(a, x, ep, dim, 1, stream);
-}
-
-static int set_mirror(Mirror& m, const tagrec_mirror_t* src) {
-    m.n = 0;
-    if (!src || src->n == 0) return TAGREC_OK;
-    TAGREC_REQUIRE(src->n >= 1 && src->n <= TAGREC_MAX_PEERS, "mirror: bad rank count");
-    m.n = src->n;
-    for (int p = 0; p < src->n; ++p) {
-        TAGREC_REQUIRE(src->base[p], "mirror: null base pointer");
-        m.base[p] = static_cast<float*>(src->base[p]);
-    }
-    return TAGREC_OK;
 }
 
 extern "C" int tagrec_lightgcn_fwd_layer(const tagrec_csr_t* a, const float* x, float* y, float* acc, int dim,
@@ -440,5 +430,88 @@ extern "C" int tagrec_row_nonzero(const float* table, int64_t n, int dim, uint8_
     if (lpr == 16) { TAGREC_LAUNCH((row_nonzero_kernel<16>), grid, 256, 0, stream, t4, n, nz); }
     else if (lpr == 8) { TAGREC_LAUNCH((row_nonzero_kernel<8>), grid, 256, 0, stream, t4, n, nz); }
     else { TAGREC_LAUNCH((row_nonzero_kernel<32>), grid, 256, 0, stream, t4, n, nz); }
+    return TAGREC_OK;
+}
+
+namespace tagrec {
+// First backward table of a BPR step, sparse form.  dL/dF is non-zero on the batch's nodes only, so
+// G_L = nb(gY, E^L) is too: instead of an elementwise pass over all N rows (3 tables x N x dim floats), only the listed
+// rows are produced — into a table that is all-zero otherwise — and flagged in the byte map the masked K1 launch reads.
+// Duplicate nodes write identical values.  Rows outside [row_lo, row_hi) (another rank's block) are flagged, not written.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+bwd_first_sparse_kernel(const int64_t* __restrict__ nodes, int64_t n_nodes, int64_t row_lo, int64_t row_hi,
+                        const float4* __restrict__ e_k, const float4* __restrict__ g_final,
+                        const float* __restrict__ upstream, float inv_layers, float4* __restrict__ g_out,
+                        uint8_t* __restrict__ nz) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = t / LPR;
+    const int sl = (int)(t % LPR);
+    const int lane = threadIdx.x & 31;
+    const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((lane / LPR) * LPR));
+    if (i >= n_nodes) return;
+    const int64_t v = __ldg(nodes + i);
+    if (nz && sl == 0) nz[v] = 1;
+    if (v < row_lo || v >= row_hi) return;
+    const float s = inv_layers * (upstream ? __ldg(upstream) : 1.f);
+    const int64_t o = v * LPR + sl;
+    float4 g = __ldg(g_final + o);
+    g.x *= s; g.y *= s; g.z *= s; g.w *= s;
+    const float4 e = __ldg(e_k + o);
+    const float ss = sub_sum<LPR>(dot4(e, e), mask);
+    const float dt = sub_sum<LPR>(dot4(e, g), mask);
+    const float nrm = sqrtf(ss);
+    float4 out;
+    if (nrm >= 1e-12f) {
+        const float proj = dt / nrm;
+        out.x = (g.x - (e.x / nrm) * proj) / nrm;
+        out.y = (g.y - (e.y / nrm) * proj) / nrm;
+        out.z = (g.z - (e.z / nrm) * proj) / nrm;
+        out.w = (g.w - (e.w / nrm) * proj) / nrm;
+    } else {
+        out.x = g.x / 1e-12f; out.y = g.y / 1e-12f; out.z = g.z / 1e-12f; out.w = g.w / 1e-12f;
+    }
+    g_out[o] = out;
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+rows_zero_kernel(const int64_t* __restrict__ nodes, int64_t n_nodes, float4* __restrict__ table, uint8_t* __restrict__ nz) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = t / LPR;
+    if (i >= n_nodes) return;
+    const int64_t v = __ldg(nodes + i);
+    if (table) table[v * LPR + (t % LPR)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nz && t % LPR == 0) nz[v] = 0;
+}
+}  // namespace tagrec
+
+extern "C" int tagrec_lightgcn_bwd_first_sparse(const int64_t* nodes, int64_t n_nodes, int64_t row_lo, int64_t row_hi,
+                                                const float* e_k, const float* g_final, const float* upstream,
+                                                float inv_layers, float* g_out, uint8_t* nz, int dim, void* stream) {
+    TAGREC_REQUIRE(nodes && e_k && g_final && g_out, "null pointer");
+    TAGREC_REQUIRE(dim == 32 || dim == 64 || dim == 128, "dim must be 32, 64 or 128");
+    if (n_nodes == 0) return TAGREC_OK;
+    const int lpr = dim / 4;
+    const unsigned grid = (unsigned)((n_nodes * lpr + 255) / 256);
+    const float4* e4 = reinterpret_cast<const float4*>(e_k);
+    const float4* g4 = reinterpret_cast<const float4*>(g_final);
+    float4* o4 = reinterpret_cast<float4*>(g_out);
+    if (lpr == 16) { TAGREC_LAUNCH((bwd_first_sparse_kernel<16>), grid, 256, 0, stream, nodes, n_nodes, row_lo, row_hi, e4, g4, upstream, inv_layers, o4, nz); }
+    else if (lpr == 8) { TAGREC_LAUNCH((bwd_first_sparse_kernel<8>), grid, 256, 0, stream, nodes, n_nodes, row_lo, row_hi, e4, g4, upstream, inv_layers, o4, nz); }
+    else { TAGREC_LAUNCH((bwd_first_sparse_kernel<32>), grid, 256, 0, stream, nodes, n_nodes, row_lo, row_hi, e4, g4, upstream, inv_layers, o4, nz); }
+    return TAGREC_OK;
+}
+
+extern "C" int tagrec_rows_zero(const int64_t* nodes, int64_t n_nodes, float* table, uint8_t* nz, int dim, void* stream) {
+    TAGREC_REQUIRE(nodes && (table || nz), "null pointer");
+    TAGREC_REQUIRE(dim == 32 || dim == 64 || dim == 128, "dim must be 32, 64 or 128");
+    if (n_nodes == 0) return TAGREC_OK;
+    const int lpr = dim / 4;
+    const unsigned grid = (unsigned)((n_nodes * lpr + 255) / 256);
+    float4* t4 = reinterpret_cast<float4*>(table);
+    if (lpr == 16) { TAGREC_LAUNCH((rows_zero_kernel<16>), grid, 256, 0, stream, nodes, n_nodes, t4, nz); }
+    else if (lpr == 8) { TAGREC_LAUNCH((rows_zero_kernel<8>), grid, 256, 0, stream, nodes, n_nodes, t4, nz); }
+    else { TAGREC_LAUNCH((rows_zero_kernel<32>), grid, 256, 0, stream, nodes, n_nodes, t4, nz); }
     return TAGREC_OK;
 }

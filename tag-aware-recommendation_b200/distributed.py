@@ -199,53 +199,127 @@ def shard_graph(full: CsrGraph, rank, world, group=None, calibrate=True, weights
     return g
 
 
-def rebalance_by_measurement(full, graph, rank, world, dim=64, n_layer=3):
-    """One feedback step: time the REAL fused forward layer (mirrored epilogue stores included) on the current row
-    blocks, scale each block's modelled cost by measured/mean, and cut again.  Collective."""
-    dev = full.device
-    n = full.n
+def row_costs(full, type_bounds=None, type_weight=None, row_cost=3.0):
+    """Modelled cost of every row (see partition_rows) as a float64 device vector — the state the measured
+    re-partitioning below refines."""
+    rp = full.rowptr
+    deg = (rp[1:] - rp[:-1]).to(torch.float64)
+    if type_weight is None:
+        return deg + row_cost
+    w = torch.empty(deg.numel(), dtype=torch.float64, device=rp.device)
+    for t, wt in enumerate(type_weight):
+        w[type_bounds[t]:type_bounds[t + 1]] = float(wt)
+    return deg * w + row_cost * float(min(type_weight))
+
+
+def cut_by_cost(cost, world):
+    """world + 1 row indices splitting ``cost`` into contiguous ranges of (almost) equal total."""
+    n = cost.numel()
+    cum = torch.cat([torch.zeros(1, dtype=torch.float64, device=cost.device), torch.cumsum(cost, 0)])
+    total = float(cum[-1])
+    targets = torch.tensor([total * p / world for p in range(1, world)], dtype=torch.float64, device=cost.device)
+    cuts = torch.searchsorted(cum, targets, right=False).clamp_(0, n).tolist() if world > 1 else []
+    bounds = [0] + [int(c) for c in cuts] + [n]
+    for i in range(1, len(bounds)):
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds
+
+
+def shard_with_bounds(full, bounds, rank, world, group=None, peer=None):
+    comm = RowComm(bounds, rank, world, group)
+    comm.peer = peer
+    lo, hi = comm.lo, comm.hi
+    rp, col, val = slice_csr(full.rowptr, full.col, full.val, lo, hi)
+    val_t = None
+    if full.val_t is not full.val:
+        a, b = int(full.rowptr[lo]), int(full.rowptr[hi])
+        val_t = full.val_t[a:b].clone()
+    return CsrGraph(full.n, rp, col, val, val_t, None, full.norm_type, full.num_list, row_offset=lo, comm=comm)
+
+
+def measured_step_ms(model, batch, reps=2):
+    """Per-rank K1 time of one real training step (forward layers + backward gather launches, CUDA events around every
+    launch, mirrored stores and sparse first table included; no optimizer) — what the partition must equalise."""
+    from . import functional as Fn
+    model.train()
+    out = []
+    for it in range(reps + 1):
+        timer = Fn.KernelTimer()
+        Fn.KERNEL_TIMER = timer if it > 0 else None
+        lossx = model.loss(batch)
+        sum(lossx).backward()
+        for p in model.parameters():
+            p.grad = None
+        torch.cuda.synchronize()
+        Fn.KERNEL_TIMER = None
+        if it > 0:
+            out.append(sum(a.elapsed_time(b) for name in ("spmm_fwd", "spmm_bwd") for a, b in timer.pairs.get(name, [])))
+    return min(out)
+
+
+def rebalance_by_measurement(full, graph, rank, world, make_model=None, batch=None, rounds=2, tol=0.03):
+    """Measured feedback on the partition (collective).  Each round times one REAL training step per rank (forward and
+    backward K1 launches: the backward of a user-row block costs more than its forward, so balancing the forward alone
+    leaves ranks 20 % apart), scales the modelled cost of every rank's rows by measured / mean and cuts again.
+    ``make_model(graph)`` builds the model on a candidate partition; without it one forward layer is timed (the
+    round-1 behaviour, kept for callers that have no model yet)."""
     comm = graph.comm
-    names = [f"raw{k}" for k in range(n_layer - 1)] + ["final"]
-    mirrors = None
-    tabs = {}
-    if comm.peer is not None:
-        mirrors = {}
-        for nm in names:
-            t, m = comm.peer.table(nm, (n, dim))
-            tabs[nm] = t
-            mirrors[id(t)] = m
-            mirrors["name", id(t)] = nm
-    else:
-        for nm in names:
-            tabs[nm] = torch.empty((n, dim), device=dev)
-    raw = [tabs[f"raw{k}"] for k in range(n_layer - 1)] + [torch.empty((n, dim), device=dev)]
-    e0 = torch.randn(n, dim, device=dev) * 0.1
-    d = graph.desc(dim)
+    cost = row_costs(full, getattr(graph, "type_bounds", None), getattr(graph, "type_weight", None))
+    history = []
+    for rnd in range(rounds):
+        if make_model is not None:
+            model = make_model(graph)
+            mine_ms = measured_step_ms(model, batch)
+            del model
+        else:
+            mine_ms = _forward_layer_ms(graph)
+        mine = torch.tensor([mine_ms], dtype=torch.float64, device=full.device)
+        allt = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allt, mine, group=comm.group)
+        tms = [float(x.item()) for x in allt]
+        mean = sum(tms) / world
+        history.append({"bounds": list(comm.bounds), "k1_ms_per_step": [round(x, 3) for x in tms]})
+        if max(tms) / mean - 1.0 < tol:
+            break
+        for p in range(world):
+            cost[comm.bounds[p]:comm.bounds[p + 1]] *= tms[p] / mean
+        bounds = cut_by_cost(cost, world)
+        peer, tb, tw = comm.peer, getattr(graph, "type_bounds", None), getattr(graph, "type_weight", None)
+        del graph
+        torch.cuda.empty_cache()
+        graph = shard_with_bounds(full, bounds, rank, world, comm.group, peer)
+        graph.type_bounds, graph.type_weight = tb, tw
+        comm = graph.comm
+    graph.balance_feedback = history
+    return graph
+
+
+def _forward_layer_ms(graph, dim=64):
+    """One fused forward layer on this rank's block (mirrored stores included), best of 2 after a warm-up."""
     from ._lib import check, lib, ptr, stream_ptr
     import ctypes as C
+    dev, n, comm = graph.device, graph.n, graph.comm
+    m = None
+    if comm.peer is not None:
+        raw0, m = comm.peer.table("raw0", (n, dim))
+        final, _ = comm.peer.table("final", (n, dim))
+    else:
+        raw0, final = torch.empty((n, dim), device=dev), torch.empty((n, dim), device=dev)
+    e0 = torch.randn(n, dim, device=dev) * 0.1
+    d = graph.desc(dim)
     times = []
     for it in range(3):
         torch.cuda.synchronize()
-        dist.barrier()
+        dist.barrier(group=comm.group)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        m = mirrors.get(id(raw[0])) if mirrors else None
-        check(lib().tagrec_lightgcn_fwd_layer_p2p(C.byref(d), ptr(e0), ptr(raw[0]), ptr(tabs["final"]), dim, 1, 0, 0.25,
+        check(lib().tagrec_lightgcn_fwd_layer_p2p(C.byref(d), ptr(e0), ptr(raw0), ptr(final), dim, 1, 0, 0.25,
                                                   C.byref(m) if m is not None else None, None, stream_ptr(dev)),
               "calibration layer")
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
-    mine = torch.tensor([min(times[1:])], dtype=torch.float64, device=dev)
-    allt = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(allt, mine)
-    tms = [float(x.item()) for x in allt]
-    mean = sum(tms) / world
-    fac = [tm / mean for tm in tms]
-    new = shard_graph(full, rank, world, comm.group, weights=(graph.type_bounds, graph.type_weight),
-                      range_scale=(comm.bounds, fac), peer=comm.peer)
-    new.balance_feedback = {"ms_before": tms}
-    return new
+    return min(times[1:])
 
 
 def build_sharded_lightgcn(shape, dev, rank, world, n_triples, seed=2020, eval_users_per_rank=0):
@@ -286,8 +360,16 @@ def build_sharded_lightgcn(shape, dev, rank, world, n_triples, seed=2020, eval_u
             print(f"[tagrec_b200] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-gather",
                   flush=True)
             graph.comm.peer = None
+    def make_model(g):
+        class Data:
+            num = {"user": shape["n_user"], "item": shape["n_item"]}
+            prebuilt_adj = g
+        torch.manual_seed(seed)
+        return T.LightGCN(Data)
+
     if os.environ.get("TAGREC_REBALANCE", "1") != "0":
-        graph = rebalance_by_measurement(full, graph, rank, world)
+        graph = rebalance_by_measurement(full, graph, rank, world, make_model=make_model, batch=triples[:2048],
+                                         rounds=int(os.environ.get("TAGREC_REBALANCE_ROUNDS", "3")))
     nnz_full, n_long_full = full._nnz(), full.n_long
     del full
     torch.cuda.empty_cache()
@@ -300,5 +382,6 @@ def build_sharded_lightgcn(shape, dev, rank, world, n_triples, seed=2020, eval_u
     info = {"nnz": graph._nnz(), "n": graph.n_rows, "n_long_rows": graph.n_long, "nnz_global": nnz_full,
             "parallelism": f"node-range row blocks x{world}, {mode}, replicated parameters",
             "rows_local": graph.n_rows, "bounds": graph.comm.bounds, "type_weight_s_per_nnz": graph.type_weight,
-            "balance_feedback": getattr(graph, "balance_feedback", None), "eval_mask": eval_mask}
+            "balance_feedback": getattr(graph, "balance_feedback", None), "eval_mask": eval_mask,
+            "plan": graph.col_block}
     return model, triples, info

@@ -90,77 +90,106 @@ def lightgcn_forward_layers(graph, e0, n_layer, raw, final, mirrors=None):
 
 
 def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad=None, upstream=None, mirrors=None,
-                             sparse_rows=None, g_first=None, mask_depth=0):
-    """Closed-form backward of the above: one elementwise launch (layer L) + L launches of K1 on
-    A^T with the normalise-Jacobian epilogue.  ``bufs`` = two scratch tables, ``g_out`` receives dL/dE0.
-    Sharded + ``mirrors``: outputs are stored to every rank by the kernels; the first table G_L is non-zero only on
-    ``sparse_rows`` (the batch's nodes), so only those rows are exchanged (``g_first``: a table that is zero outside
-    this rank's block and outside ``sparse_rows``)."""
+                             batch_nodes=None, mask_depth=0, local_out=False):
+    """Closed-form backward of the above: the first table G_L (no gather) + L launches of K1 on A^T with
+    the normalise-Jacobian epilogue.  ``bufs`` = two scratch tables, ``g_out`` receives dL/dE0.
+
+    ``batch_nodes`` (int64 global row ids of the batch's users and items): dL/dF — hence G_L — is non-zero on those rows
+    only, so G_L is produced by the O(batch) sparse kernel into a table this graph keeps all-zero, flagged in a byte
+    map, consumed by the masked K1 launch (the 256 B gathers of all-zero rows are never issued) and cleared again.
+    Without it (a generic upstream gradient) G_L is an elementwise pass over all rows.
+    Sharded graphs: ``mirrors`` selects the fused peer-store exchange (outputs stored to every rank by the kernels);
+    G_L's few rows are summed across ranks (each row is non-zero on its owner only).  ``local_out``: dL/dE0 is needed on
+    this rank's rows only (owner-sharded optimizer) — the last launch is not exchanged at all."""
     L, st, dim = lib(), stream_ptr(g_final.device), g_final.shape[1]
     d = graph.desc(dim, transposed=True)
     comm = graph.comm
     inv = 1.0 / (n_layer + 1)
-    g_next = None
     t = KERNEL_TIMER
-    # The upstream gradient touches only the batch's 3*B rows, so G_L is non-zero on those rows only and G_{L-1} on
-    # them and their neighbours: the first ``mask_depth`` gather launches get a byte map of the non-zero source rows and
-    # never issue the 256 B gathers of all-zero rows (tagrec_lightgcn_bwd_layer_ex).
-    gathers = 0
-
-    def nz_mask(table):
-        nonlocal gathers
-        gathers += 1
-        if table is None or gathers > mask_depth:
-            return None
-        mk = _buf(graph_ws, "nz_mask", (table.shape[0],), table.device, torch.uint8)
+    ws = graph.__dict__.setdefault("_bwd_ws", {})
+    n = g_final.shape[0]
+    sparse = batch_nodes is not None
+    mk = None
+    if sparse:
+        g_next = _zero_buf(ws, "g_sparse", (n, dim), g_final.device)
+        mk = _zero_buf(ws, "nz_mask", (n,), g_final.device, torch.uint8) if mask_depth > 0 else None
+        lo, hi = (comm.lo, comm.hi) if comm is not None else (0, n)
         if t:
-            t.start("row_mask")
-        check(L.tagrec_row_nonzero(ptr(table), table.shape[0], dim, ptr(mk), st), "tagrec_row_nonzero")
+            t.start("bwd_first")
+        check(L.tagrec_lightgcn_bwd_first_sparse(ptr(batch_nodes), batch_nodes.numel(), lo, hi, ptr(raw[n_layer - 1]),
+                                                 ptr(g_final), ptr(upstream), inv, ptr(g_next), ptr(mk), dim, st),
+              "tagrec_lightgcn_bwd_first_sparse")
+        if comm is not None and comm.world > 1:
+            rows = g_next.index_select(0, batch_nodes)            # zero where another rank owns the node
+            torch.distributed.all_reduce(rows, group=comm.group)
+            g_next.index_copy_(0, batch_nodes, rows)
         if t:
-            t.stop("row_mask")
-        return mk
-
-    graph_ws = graph.__dict__.setdefault("_bwd_ws", {})
-    for k in range(n_layer, 0, -1):
-        first = g_next is None
-        sparse = first and mirrors is not None and sparse_rows is not None and g_first is not None
-        out = g_first if sparse else bufs[k % 2]
-        m = mirrors.get(id(out)) if (mirrors and not sparse) else None
-        name = "bwd_elementwise" if first else "spmm_bwd"
-        mk = None if first else nz_mask(g_next)
+            t.stop("bwd_first")
+    else:
+        g_next = bufs[n_layer % 2]
+        m = mirrors.get(id(g_next)) if mirrors else None
         if t:
-            t.start(name)
-        check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d), ptr(g_next), ptr(mk), ptr(raw[k - 1]), ptr(g_final), None,
-                                             ptr(upstream), inv, ptr(out), dim, _mref(m), st),
+            t.start("bwd_first")
+        check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d), None, None, ptr(raw[n_layer - 1]), ptr(g_final), None,
+                                             ptr(upstream), inv, ptr(g_next), dim, _mref(m), st),
               "tagrec_lightgcn_bwd_layer")
         if t:
-            t.stop(name)
+            t.stop("bwd_first")
+        if comm is not None:
+            if mirrors:
+                comm.peer.barrier(mirrors["name", id(g_next)])
+            else:
+                comm.all_gather_rows(g_next)
+
+    def clear_sparse():
+        check(L.tagrec_rows_zero(ptr(batch_nodes), batch_nodes.numel(), ptr(ws["g_sparse"]), ptr(mk), dim, st),
+              "tagrec_rows_zero")
+
+    first_gather = True
+    for k in range(n_layer - 1, 0, -1):
+        out = bufs[k % 2]
+        m = mirrors.get(id(out)) if mirrors else None
+        if t:
+            t.start("spmm_bwd")
+        check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d), ptr(g_next), ptr(mk) if first_gather else None, ptr(raw[k - 1]),
+                                             ptr(g_final), None, ptr(upstream), inv, ptr(out), dim, _mref(m), st),
+              "tagrec_lightgcn_bwd_layer")
+        if t:
+            t.stop("spmm_bwd")
+        if first_gather and sparse:
+            clear_sparse()
+        first_gather = False
         g_next = out
         if comm is not None:
-            if sparse:
-                rows = out.index_select(0, sparse_rows)          # zero where another rank owns the node
-                torch.distributed.all_reduce(rows, group=comm.group)
-                out.index_copy_(0, sparse_rows, rows)
-            elif mirrors:
+            if mirrors:
                 comm.peer.barrier(mirrors["name", id(out)])
             else:
                 comm.all_gather_rows(g_next)
-    m = mirrors.get(id(g_out)) if mirrors else None
-    mk = nz_mask(g_next)
+    m = mirrors.get(id(g_out)) if (mirrors and not local_out) else None
     if t:
         t.start("spmm_bwd")
-    check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d), ptr(g_next), ptr(mk), None, ptr(g_final), ptr(reg_grad), ptr(upstream),
-                                         inv, ptr(g_out), dim, _mref(m), st), "tagrec_lightgcn_bwd_layer")
+    check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d), ptr(g_next), ptr(mk) if first_gather else None, None, ptr(g_final),
+                                         ptr(reg_grad), ptr(upstream), inv, ptr(g_out), dim, _mref(m), st),
+          "tagrec_lightgcn_bwd_layer")
     if t:
         t.stop("spmm_bwd")
-    if comm is not None:
+    if first_gather and sparse:
+        clear_sparse()
+    if comm is not None and not local_out:
         if mirrors:
             comm.peer.barrier(mirrors["name", id(g_out)])
         else:
             comm.all_gather_rows(g_out)
-    if comm is not None and mirrors is not None and sparse_rows is not None and g_first is not None:
-        g_first.index_fill_(0, sparse_rows, 0.0)                # keep the invariant for the next step
     return g_out
+
+
+def _zero_buf(ws, name, shape, device, dtype=torch.float32):
+    """A persistent table that is all-zero between uses (its users restore that state themselves)."""
+    tns = ws.get(name)
+    if tns is None or tns.shape != torch.Size(shape) or tns.device != device or tns.dtype != dtype:
+        tns = torch.zeros(shape, dtype=dtype, device=device)
+        ws[name] = tns
+    return tns
 
 
 def bpr_fwd_bwd(batch, item_offset, final, reg_src, reg, loss_kind, g_final, g_reg, loss_out):
@@ -245,17 +274,15 @@ class LightGCNLossFn(torch.autograd.Function):
         upstream = torch.stack([g_loss.reshape(()), g_regterm.reshape(())]).to(torch.float32)
         raw = ws["raw_list"]
         p2p = graph.comm is not None and graph.comm.peer is not None
-        tabs, mirrors = _tables(model, [("gbuf0", True), ("gbuf1", True)] + ([("g_e0", True)] if p2p else []), n, dim,
-                                dev)
-        g_e0 = tabs["g_e0"] if p2p else torch.empty((n, dim), dtype=torch.float32, device=dev)
-        g_first = None
-        if p2p:
-            g_first = ws.get("g_first")
-            if g_first is None or g_first.shape != (n, dim):
-                g_first = ws["g_first"] = torch.zeros((n, dim), dtype=torch.float32, device=dev)
+        local_out = bool(ws.get("local_grad_only")) and graph.comm is not None
+        tabs, mirrors = _tables(model, [("gbuf0", True), ("gbuf1", True)] + ([("g_e0", True)] if p2p and not local_out else []),
+                                n, dim, dev)
+        # single GPU / NCCL: a fresh table per step (the parameters' .grad are views of it and may outlive the step);
+        # fused exchange: the symmetric-memory table other ranks store into
+        g_e0 = tabs["g_e0"] if (p2p and not local_out) else torch.empty((n, dim), dtype=torch.float32, device=dev)
         lightgcn_backward_layers(graph, raw, g_final, nl, [tabs["gbuf0"], tabs["gbuf1"]], g_e0,
                                  ws["g_reg"] if ctx.has_reg else None, upstream, mirrors,
-                                 ctx.nodes if p2p else None, g_first, mask_depth=MASK_DEPTH)
+                                 batch_nodes=ctx.nodes, mask_depth=MASK_DEPTH, local_out=local_out)
         g_final.index_fill_(0, ctx.nodes, 0.0)
         if ctx.has_reg:
             ws["g_reg"].index_fill_(0, ctx.nodes, 0.0)

@@ -70,3 +70,105 @@ class FusedAdam(torch.optim.Optimizer):
                 # the kernel wrote the parameter through a raw pointer: tell autograd / version-keyed caches
                 torch._C._increment_version([p])
         return loss
+
+
+class ShardedFusedAdam(torch.optim.Optimizer):
+    """Owner-sharded Adam for a LightGCN on a node-range sharded graph with the fused exchange (multi-GPU only; no
+    reference equivalent — the reference is single-device).
+
+    The embedding tables stay REPLICATED (``model.state_dict()`` is full-size on every rank, SURVEY §8 e), but each row
+    is updated by the rank that owns it: rank p runs the Adam step on rows [lo_p, hi_p) only and the kernel stores the
+    new parameter rows into every rank's replica (tagrec_adam_step_mirror: NVLS multicast / peer stores), followed by
+    one device-side barrier.  Per step this replaces 7 x N x dim x 4 bytes of replicated optimizer traffic on every
+    GPU by 1/P of it, and the last backward launch no longer has to exchange dL/dE0 at all — a rank only needs the
+    gradient rows it owns (``model._ws['local_grad_only']``; ``p.grad`` is defined on the owned rows only).
+    ``exp_avg`` / ``exp_avg_sq`` are full-size tensors whose owned rows are live; ``consolidate()`` all-gathers them so
+    that ``state_dict()`` is complete on every rank before a checkpoint."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        params = list(model.parameters())
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        graph = model.norm_adj
+        comm = getattr(graph, "comm", None)
+        if comm is None or comm.peer is None or comm.world < 2:
+            raise ValueError("ShardedFusedAdam needs a model on a sharded graph with the fused exchange enabled "
+                             "(graph.comm.enable_p2p); use FusedAdam otherwise")
+        if [id(p) for p in model.parameters()] != [id(p) for p in model.embed]:
+            raise ValueError("ShardedFusedAdam shards row tables only (LightGCN)")
+        self.model, self.comm = model, comm
+        flat = model._flat_params()
+        n, dim = flat.shape
+        table, mirror = comm.peer.table("e0", (n, dim))          # the parameters move into symmetric memory
+        table.copy_(flat)
+        off = 0
+        for p in model.embed:
+            p.data = table[off:off + p.shape[0]]
+            off += p.shape[0]
+        model._ws["flat"] = table
+        model._ws["local_grad_only"] = True
+        self._mirror = mirror
+        self._m = torch.zeros((n, dim), dtype=torch.float32, device=flat.device)
+        self._v = torch.zeros((n, dim), dtype=torch.float32, device=flat.device)
+        self._step = 0
+        off = 0
+        for p in model.embed:
+            self.state[p] = {"step": 0, "exp_avg": self._m[off:off + p.shape[0]], "exp_avg_sq": self._v[off:off + p.shape[0]]}
+            off += p.shape[0]
+        comm.peer.barrier("e0")
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        import ctypes as C
+        from . import functional as Fn
+        from ._lib import MirrorDesc
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        L, comm, model = lib(), self.comm, self.model
+        group = self.param_groups[0]
+        b1, b2 = group["betas"]
+        self._step += 1
+        table = model._ws["flat"]
+        dim = table.shape[1]
+        t = Fn.KERNEL_TIMER
+        if t:
+            t.start("adam")
+        off = 0
+        for p in model.embed:
+            lo, hi = max(comm.lo, off), min(comm.hi, off + p.shape[0])       # owned rows of this parameter
+            if hi > lo and p.grad is not None:
+                g = p.grad
+                if not (g.is_contiguous() and g.dtype == torch.float32):
+                    raise RuntimeError("ShardedFusedAdam needs contiguous float32 gradients")
+                a, cnt = lo - off, (hi - lo) * dim
+                seg = MirrorDesc()
+                seg.n, seg.self = self._mirror.n, self._mirror.self
+                for r in range(self._mirror.n):
+                    seg.base[r] = self._mirror.base[r] + lo * dim * 4
+                check(L.tagrec_adam_step_mirror(ptr(p[a:]), ptr(g[a:]), ptr(self._m[lo:]), ptr(self._v[lo:]), cnt,
+                                                group["lr"], b1, b2, group["eps"], group["weight_decay"], self._step,
+                                                C.byref(seg), stream_ptr(p.device)), "tagrec_adam_step_mirror")
+            self.state[p]["step"] = self._step
+            torch._C._increment_version([p])
+            off += p.shape[0]
+        comm.peer.barrier("e0")                  # every rank's replica is complete before the next forward gathers it
+        if t:
+            t.stop("adam")
+        return loss
+
+    def consolidate(self):
+        """All-gather the optimizer state row blocks (collective) — call before ``state_dict()`` / a checkpoint."""
+        self.comm.all_gather_rows(self._m)
+        self.comm.all_gather_rows(self._v)
+
+
+def make_optimizer(model, lr=1e-3, **kw):
+    """FusedAdam over ``model.parameters()``, or the owner-sharded form when the model sits on a sharded graph with the
+    fused exchange (and TAGREC_SHARDED_ADAM != 0)."""
+    import os
+    comm = getattr(getattr(model, "norm_adj", None), "comm", None)
+    if (comm is not None and comm.peer is not None and comm.world > 1 and hasattr(model, "embed")
+            and [id(p) for p in model.parameters()] == [id(p) for p in model.embed] and os.environ.get("TAGREC_SHARDED_ADAM", "1") != "0"):
+        return ShardedFusedAdam(model, lr=lr, **kw)
+    return FusedAdam(model.parameters(), lr=lr, **kw)

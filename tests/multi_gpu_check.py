@@ -107,7 +107,14 @@ def main():
             g.comm.enable_p2p(dev).table("probe", (8, 64))
             kind = g.comm.peer.kind
             if mode in ("rebalanced", "sharded-adam"):
-                g = rebalance_by_measurement(full, g, rank, world)
+                def make_model(gr):
+                    class D:
+                        num = {"user": U, "item": I}
+                        prebuilt_adj = gr
+                    torch.manual_seed(5)
+                    return T.LightGCN(D)
+                g = rebalance_by_measurement(full, g, rank, world, make_model=make_model, batch=batches[0], rounds=2,
+                                             tol=0.0)
         return g, kind
 
     ok_all, lines = True, []

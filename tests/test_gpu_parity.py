@@ -181,6 +181,56 @@ def test_lightgcn_long_rows_and_upstream_scale():
     assert abs(lossx[0].item() - loss.item()) < TOL and abs(lossx[1].item() - reg.item()) < TOL * reg.item()
 
 
+@pytest.mark.parametrize("window_mb,min_deg", [("0.0625", "4"), ("0.25", "40"), ("4", "4")])
+def test_lightgcn_column_blocked_plan_vs_oracle(monkeypatch, window_mb, min_deg):
+    """The column-blocked K1 plan (rows of the item block cut at column-window boundaries, pieces listed window-major,
+    one sub-warp per piece, per-row piece counts) forced onto a small graph: forward tables, loss and gradient equal the
+    fp64 oracle exactly like the plain plan; hubs produce multi-piece windows, most rows single-piece windows, rows below
+    the degree threshold stay whole."""
+    monkeypatch.setenv("TAGREC_COLBLOCK_FORCE", "1")
+    monkeypatch.setenv("TAGREC_COLBLOCK_MB", window_mb)
+    monkeypatch.setenv("TAGREC_COLBLOCK_MIN_DEG", min_deg)
+    U, I = 9000, 700
+    ui = random_graph(U, I, 60000, 3, hub=8000)
+    T.set_config("lightgcn", use_tag=False, reg=1e-2, dim_layer_list=[64, 64, 64], device=dev())
+
+    class D:
+        num = {"user": U, "item": I}
+    import scipy.sparse as sp
+    D.ui_adj = sp.coo_matrix((np.ones(len(ui[0])), ui), dtype=np.float32, shape=(U, I))
+    torch.manual_seed(1)
+    model = T.LightGCN(D).to(dev())
+    g = model.norm_adj
+    assert g.col_block is not None and g.col_block["rows"] > 0 and g.chunk_lanes == 1
+    assert int(g.long_nchunks.sum()) == g.n_items
+    # every stored entry of a blocked row is covered exactly once by its pieces
+    cover = torch.zeros(g._nnz() + 1, dtype=torch.int64, device=dev())
+    cover.index_add_(0, g.item_begin, torch.ones_like(g.item_begin))
+    cover.index_add_(0, g.item_end, -torch.ones_like(g.item_end))
+    cover = torch.cumsum(cover, 0)[:-1]
+    deg = g.rowptr[1:] - g.rowptr[:-1]
+    in_long = torch.zeros(g.n_rows, dtype=torch.bool, device=dev())
+    in_long[g.long_rows.long()] = True
+    assert torch.equal(cover, torch.repeat_interleave(in_long.long(), deg))
+    rng = np.random.RandomState(0)
+    batch = np.stack([ui[0][:512], ui[1][:512], rng.randint(0, I, 512)], 1).astype(np.int64)
+    batch[:64, 1] = 0
+    lossx = model.loss(torch.tensor(batch, device=dev()))
+    (2.0 * lossx[0] + 3.0 * lossx[1]).backward()
+    csr = (g.rowptr.cpu().numpy(), g.col.cpu().numpy(), g.val.cpu().numpy())
+    e0 = torch.cat([p.detach().cpu().double() for p in model.embed])
+    final, raw = OP.lightgcn_forward(csr, e0, 3)
+    loss, reg, gf, ge = OP.bpr_forward_backward(final, e0, batch, U, 1e-2, "softplus")
+    g0 = OP.lightgcn_backward(csr, raw, 2.0 * gf, 3) + 3.0 * ge
+    got = torch.cat([p.grad.cpu().double() for p in model.embed])
+    assert relerr(got.numpy(), g0.numpy()) < TOL
+    assert abs(lossx[0].item() - loss.item()) < TOL and abs(lossx[1].item() - reg.item()) < TOL * reg.item()
+    model.eval()
+    with torch.no_grad():
+        fw = torch.cat([t for t in model.forward()]).cpu().double()
+    assert relerr(fw.numpy(), final.numpy()) < TOL
+
+
 def test_training_trajectory_vs_reference(tiny):
     """3+1 Adam steps through Basic_train's epoch_training on the reference's fixed triple file: same per-step
     losses and same parameters afterwards (incl. the tail batch being trained twice)."""
