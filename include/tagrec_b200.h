@@ -127,6 +127,23 @@ typedef struct {
  * included.  A single NVLS multicast address is expressed as n == 1.  The row block's all-gather then happens
  * inside the SpMM epilogue (stores over NVLink 5 overlap the gathers from HBM); the caller places a cross-rank
  * barrier between this launch and the first launch that reads the table. */
+/* MULTI-GPU CONTRACT (replaces the tagrec_comm_* wrappers SURVEY §8(b) sketched; decided against them on purpose).
+ * The library owns NO communicator and does NO rendezvous: it never calls NCCL, never opens IPC handles and keeps no
+ * cross-rank state.  One process per GPU; the CALLER
+ *   1. allocates every table other ranks store into ([N, dim] fp32: layer tables, mean table, gradient ping-pong
+ *      tables, dL/dE0, the parameter table for tagrec_adam_step_mirror) as symmetric / peer-mapped memory — cuMemCreate
+ *      + cuMemExportToShareableHandle / cuMemMap, cudaIpc*, NVSHMEM, or torch.distributed._symmetric_memory (what
+ *      tag-aware-recommendation_b200/distributed.py::PeerTables uses) — and passes the mapped addresses here:
+ *      base[r] = rank r's copy of the SAME table as seen from this process (base[self] = the local copy), or n == 1
+ *      with base[0] = an NVLS multicast address bound to all replicas (cuMulticastCreate / BindMem);
+ *   2. passes `row_offset` / `n_rows` of its contiguous row block in tagrec_csr_t (global column ids are kept);
+ *   3. places a cross-rank barrier ON THE SAME STREAM between a launch that stores through a mirror and the first
+ *      launch (on any rank) that reads that table — a device-side signal exchange (symmetric-memory barrier) or a
+ *      1-element NCCL all-reduce; stores through a mirror are plain st.global and are visible after that barrier;
+ *   4. runs its own small collectives (the 3*B-row all-reduce of the first backward table, metric sums of the sharded
+ *      evaluation) with whatever library it uses; the kernels only need the result in device memory.
+ * Without mirrors (NULL / n == 0) every kernel writes its local table only and the caller all-gathers row blocks
+ * (ncclAllGather over [row_offset, row_offset + n_rows)) — the baseline path, also supported. */
 #define TAGREC_MAX_PEERS 8
 typedef struct {
     int32_t n;

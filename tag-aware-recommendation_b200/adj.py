@@ -33,6 +33,14 @@ class CsrGraph:
         self.shape = (self.n, self.n)
         self.device = rowptr.device
         self._build_plan()
+        # the masked backward launch (source rows mostly all-zero: their gathers are skipped) is bound by instruction
+        # issue, not by DRAM — it keeps the PLAIN plan; a second, plain plan is built only when the main one is blocked
+        self._plain_plan = None
+        if self.col_block is not None:
+            main = self._plan_state()
+            self._build_plan(allow_block=False)
+            self._plain_plan = self._plan_state()
+            self._set_plan_state(main)
 
     # --- torch-sparse-like accessors the reference's models use (dgcf.py:50, disengcn.py:27) ---
     def _nnz(self):
@@ -74,7 +82,17 @@ class CsrGraph:
         min_deg = int(os.environ.get("TAGREC_COLBLOCK_MIN_DEG", "384"))
         return begin, min_deg, max(window, 64)
 
-    def _build_plan(self):
+    _PLAN_KEYS = ("long_row", "long_chunk", "col_block", "blocked_row_begin", "blocked_min_deg", "chunk_lanes",
+                  "long_nchunks", "_scratch", "n_long", "long_rows", "item_slot", "item_begin", "item_end", "n_items")
+
+    def _plan_state(self):
+        return {k: getattr(self, k) for k in self._PLAN_KEYS}
+
+    def _set_plan_state(self, st):
+        for k, v in st.items():
+            setattr(self, k, v)
+
+    def _build_plan(self, allow_block=True):
         """Rows above ``long_row`` nnz are cut into ``long_chunk`` pieces (see csrc/spmm.cu).  The thresholds are the
         tuned 4096 / 2048 on big graphs; a small graph is only a few waves of rows, where one sub-warp walking a
         2000-entry hub row IS the launch time, so it is planned with 256 / 256.  Rows of the column-blocked region
@@ -86,7 +104,8 @@ class CsrGraph:
         dev = self.device
         deg = self.rowptr[1:] - self.rowptr[:-1]
         import os
-        spec = None if (small and os.environ.get("TAGREC_COLBLOCK_FORCE") != "1") else self._column_block_spec()
+        spec = None if (not allow_block or (small and os.environ.get("TAGREC_COLBLOCK_FORCE") != "1")) \
+            else self._column_block_spec()
         self.col_block = None
         self.blocked_row_begin, self.blocked_min_deg, self.chunk_lanes = 0, 0, 0
         self.long_nchunks = None
@@ -155,8 +174,17 @@ class CsrGraph:
         self.n_items = int(self.item_slot.numel())
         self.long_nchunks = counts.to(torch.int32).contiguous()
 
-    def desc(self, dim, transposed=False):
-        """tagrec_csr_t for a launch at feature width ``dim`` (scratch rows are dim floats wide)."""
+    def desc(self, dim, transposed=False, plain=False):
+        """tagrec_csr_t for a launch at feature width ``dim`` (scratch rows are dim floats wide).  ``plain``: the plan
+        without column blocking (used by the masked backward launch)."""
+        if plain and self._plain_plan is not None:
+            main = self._plan_state()
+            self._set_plan_state(self._plain_plan)
+            try:
+                return self.desc(dim, transposed)
+            finally:
+                self._plain_plan = self._plan_state()        # keeps the scratch tables created on first use
+                self._set_plan_state(main)
         d = CsrDesc()
         d.rowptr, d.col = ptr(self.rowptr), ptr(self.col)
         d.val = ptr(self.val_t if transposed else self.val)

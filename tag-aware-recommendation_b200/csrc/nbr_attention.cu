@@ -22,7 +22,8 @@ namespace tagrec {
 
 constexpr int AD = 32;        // dim_atten
 constexpr int ED = 64;        // embedding dim
-constexpr int MAXW = 64;      // weight ids staged in smem by the backward
+constexpr int MAXW = 64;      // weight ids staged in smem by the backward (edge multiplicities are small integers; larger
+                              // ids — a user who applied one tag more than 64 times — add straight to global memory)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -113,7 +114,8 @@ nbr_attention_bwd_kernel(const float* __restrict__ g_out, const float* __restric
                          float* __restrict__ g_ej, float* __restrict__ g_v) {
     __shared__ float s_ww[MAXW * AD];
     __shared__ float s_v[AD];
-    for (int i = threadIdx.x; i < n_w * AD; i += blockDim.x) s_ww[i] = 0.f;
+    const int n_stage = n_w < MAXW ? n_w : MAXW;
+    for (int i = threadIdx.x; i < n_stage * AD; i += blockDim.x) s_ww[i] = 0.f;
     if (threadIdx.x < AD) s_v[threadIdx.x] = 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -156,14 +158,17 @@ nbr_attention_bwd_kernel(const float* __restrict__ g_out, const float* __restric
             gv = fmaf(gxs, fmaxf(h, 0.f), gv);
             const float gh = h > 0.f ? gxs * vd : 0.f;
             gpv += gh;
-            if (w > 0) atomicAdd(&s_ww[(w - 1) * AD + lane], gh);
+            if (w > 0) {
+                if (w <= MAXW) atomicAdd(&s_ww[(w - 1) * AD + lane], gh);
+                else atomicAdd(g_ww + (w - 1) * AD + lane, gh);
+            }
             if (j > 0) atomicAdd(g_pj + (j - 1) * AD + lane, gh);
         }
         g_pv[v * AD + lane] = gpv;
         atomicAdd(&s_v[lane], gv);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_w * AD; i += blockDim.x)
+    for (int i = threadIdx.x; i < n_stage * AD; i += blockDim.x)
         if (s_ww[i] != 0.f) atomicAdd(g_ww + i, s_ww[i]);
     if (threadIdx.x < AD) atomicAdd(g_v + threadIdx.x, s_v[threadIdx.x]);
 }
@@ -193,7 +198,7 @@ extern "C" int tagrec_nbr_attention_bwd(const float* g_out, const float* att, co
                    "null pointer");
     TAGREC_REQUIRE(dim == ED && dim_atten == AD, "neighbour attention is built for dim 64 / dim_atten 32");
     TAGREC_REQUIRE(k >= 1 && k <= 32 && ld >= k, "neighbor_k must be in 1..32");
-    TAGREC_REQUIRE(n_w >= 1 && n_w <= MAXW, "at most 64 distinct edge-weight ids");
+    TAGREC_REQUIRE(n_w >= 1, "n_w (rows of the edge-weight embedding table) must be positive");
     if (n == 0) return TAGREC_OK;
     TAGREC_LAUNCH(nbr_attention_bwd_kernel, (unsigned)((n + 7) / 8), 256, 0, stream, g_out, att, pv, ww, pj, ej, v, nbr,
                   nbw, n, k, ld, n_w, g_pv, g_ww, g_pj, g_ej, g_v);

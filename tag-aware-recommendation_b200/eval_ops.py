@@ -71,6 +71,11 @@ class EvalMixin:
     def _eval_tables(self):
         with torch.no_grad():
             all_users, all_items = self.forward()[:2]
+        pad = (-all_users.shape[1]) % 32
+        if pad:      # K3 tiles the embedding dimension in 32s (176-d tables of the default [64, 32, 16] widths): zero
+            # columns leave every dot product unchanged
+            all_users = torch.nn.functional.pad(all_users, (0, pad))
+            all_items = torch.nn.functional.pad(all_items, (0, pad))
         return all_users.contiguous(), all_items.contiguous()
 
     def eval_topk(self, users, k, train_ptr, train_items, path="auto"):

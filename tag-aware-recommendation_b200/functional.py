@@ -103,6 +103,7 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
     this rank's rows only (owner-sharded optimizer) — the last launch is not exchanged at all."""
     L, st, dim = lib(), stream_ptr(g_final.device), g_final.shape[1]
     d = graph.desc(dim, transposed=True)
+    d_masked = graph.desc(dim, transposed=True, plain=True)      # the masked launch keeps the plain plan (issue-bound)
     comm = graph.comm
     inv = 1.0 / (n_layer + 1)
     t = KERNEL_TIMER
@@ -151,7 +152,8 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
         m = mirrors.get(id(out)) if mirrors else None
         if t:
             t.start("spmm_bwd")
-        check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d), ptr(g_next), ptr(mk) if first_gather else None, ptr(raw[k - 1]),
+        use_mask = first_gather and mk is not None
+        check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d_masked if use_mask else d), ptr(g_next), ptr(mk) if use_mask else None, ptr(raw[k - 1]),
                                              ptr(g_final), None, ptr(upstream), inv, ptr(out), dim, _mref(m), st),
               "tagrec_lightgcn_bwd_layer")
         if t:
@@ -168,7 +170,8 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
     m = mirrors.get(id(g_out)) if (mirrors and not local_out) else None
     if t:
         t.start("spmm_bwd")
-    check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d), ptr(g_next), ptr(mk) if first_gather else None, None, ptr(g_final),
+    use_mask = first_gather and mk is not None
+    check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d_masked if use_mask else d), ptr(g_next), ptr(mk) if use_mask else None, None, ptr(g_final),
                                          ptr(reg_grad), ptr(upstream), inv, ptr(g_out), dim, _mref(m), st),
           "tagrec_lightgcn_bwd_layer")
     if t:

@@ -130,6 +130,19 @@ class Attention1(nn.Module):
         self.b = nn.Parameter(torch.empty(1, atten_dim))
         self.v = nn.Parameter(torch.empty(1, atten_dim))
 
+    def forward_torch(self, ev, ej, ew, v_jw):
+        """tgcn.py:20-37 composed from torch ops — layer widths K4 is not built for (anything but 64-d rows with a
+        32-d attention space): index 0 of a table entry is the zero padding row, padding slots take part in the softmax."""
+        v_j, v_w = v_jw
+        ej0 = torch.cat([ej.new_zeros((1, ej.shape[1])), ej])
+        ew0 = torch.cat([ew.new_zeros((1, ew.shape[1])), ew])
+        e_nj, e_nw = ej0[v_j], ew0[v_w]
+        d = self.in_features
+        av = (torch.matmul(ev, self.W_1[:d]) + self.b).unsqueeze(1) + torch.matmul(e_nw, self.W_1[d:]) \
+            + torch.matmul(e_nj, self.W_2)
+        a = torch.softmax(torch.matmul(F.relu(av), self.v.T), dim=1)
+        return torch.sum(a * e_nj, dim=1)
+
     def forward(self, ev, ej, ew, v_jw, pj=None):
         """tgcn.py:20-37.  ``pj`` = ej @ W_2 may be passed in when two calls share the neighbour type."""
         v_j, v_w = v_jw
@@ -145,6 +158,8 @@ class BasicLayer(nn.Module):
     def __init__(self, in_features, out_features, atten_dim, weight_dim, num_bit_conv, num_vector_conv):
         super().__init__()
         self._in_dim = in_features
+        self._out_dim = out_features
+        self._atten_dim = atten_dim
         self._num_vector_conv = num_vector_conv
         self._num_bit_conv = num_bit_conv
         self.atten1 = nn.ModuleDict()
@@ -200,7 +215,29 @@ class BasicLayer(nn.Module):
             cache[key] = (torch.cat([a[0], b[0]], 0).contiguous(), torch.cat([a[1], b[1]], 0).contiguous())
         return cache[key]
 
+    def _tail_torch(self, z, xf):
+        """tgcn.py:86-91,100-106 from torch ops (fusion widths K7 is not built for): rectified bit-level features
+        relu(wb[c, :] . z[v, :, d]) channel-major, the vector-level features appended, then the fusion layer."""
+        wb = self.conv["bit_level"].weight[:, 0, :, 0]                       # [C, 3]
+        bit = F.relu(torch.einsum("cs,nsd->ncd", wb, z)).reshape(z.shape[0], -1)
+        return F.relu(torch.matmul(torch.cat([bit, xf], dim=1), self.Wf) + self.bf)
+
+    def _forward_torch(self, eu, ei, et, ew, u_iw, u_tw, i_uw, i_tw, t_uw, t_iw):
+        """The whole layer in the reference's own formulation (tgcn.py:107-137) for input widths other than 64."""
+        a_u, a_i, a_t = self.atten1["user"], self.atten1["item"], self.atten1["tag"]
+        eu_iN, eu_tN = a_i.forward_torch(eu, ei, ew, u_iw), a_t.forward_torch(eu, et, ew, u_tw)
+        ei_uN, ei_tN = a_u.forward_torch(ei, eu, ew, i_uw), a_t.forward_torch(ei, et, ew, i_tw)
+        et_uN, et_iN = a_u.forward_torch(et, eu, ew, t_uw), a_i.forward_torch(et, ei, ew, t_iw)
+        outs = []
+        for trip in ((eu, eu_iN, eu_tN), (ei_uN, ei, ei_tN), (et_uN, et_iN, et)):
+            z = self._atten2(*trip)
+            outs.append(self._tail_torch(z, self._vec_conv(z)))
+        return tuple(outs)
+
     def forward(self, eu, ei, et, ew, u_iw, u_tw, i_uw, i_tw, t_uw, t_iw):
+        if self._in_dim != 64 or self._atten_dim != 32 or u_iw[0].shape[1] > 32 or self._num_vector_conv not in (4, 8) \
+                or self._num_bit_conv > 256:
+            return self._forward_torch(eu, ei, et, ew, u_iw, u_tw, i_uw, i_tw, t_uw, t_iw)
         a_u, a_i, a_t = self.atten1["user"], self.atten1["item"], self.atten1["tag"]
         pj_u, pj_i, pj_t = skinny_mm(eu, a_u.W_2), skinny_mm(ei, a_i.W_2), skinny_mm(et, a_t.W_2)
         # Each Attention1 module serves two node types (e.g. "item" neighbours of users and of tags): one K4 pass over
@@ -215,8 +252,11 @@ class BasicLayer(nn.Module):
             m.weight.reshape(m.weight.shape[0], -1) for m in self.conv["vec_level"].values())
         z, xf = TgcnMixFn.apply(torch.cat([eu, ei_uN, et_uN], 0), torch.cat([eu_iN, ei, et_iN], 0),
                                 torch.cat([eu_tN, ei_tN, et], 0), *par)
-        wb = self.conv["bit_level"].weight[:, 0, :, 0]                       # [32, 3]
-        out = TgcnTailFn.apply(z, wb, xf, self.Wf, self.bf.reshape(-1))
+        if self._out_dim != 64:          # K7 fuses a 64-wide fusion layer; other output widths: same maths from torch ops
+            out = self._tail_torch(z, xf)
+        else:
+            wb = self.conv["bit_level"].weight[:, 0, :, 0]                   # [32, 3]
+            out = TgcnTailFn.apply(z, wb, xf, self.Wf, self.bf.reshape(-1))
         return torch.split(out, [eu.shape[0], ei.shape[0], et.shape[0]], dim=0)
 
 
@@ -251,12 +291,10 @@ class TGCN(EvalMixin, nn.Module):
         self.transtag_reg = cfg['transtag_reg']
         self.loss_func = cfg['mul_loss_func']
         self.margin = cfg['margin']
-        if any(d != 64 for d in self.dim_layer_list) or self.dim_atten != 32 or self.neighbor_k > 32:
-            raise NotImplementedError("K4 is built for 64-d layers, dim_atten 32 and neighbor_k <= 32 "
-                                      "(utility/config.py:41-51 defaults: 64 / 32 / 25)")
-        if self.num_vec_conv not in (4, 8) or self.num_bit_conv > 256:
-            raise NotImplementedError("K7 is built for num_vec_conv in (4, 8) and num_bit_conv <= 256 "
-                                      "(utility/config.py defaults: 8 / 32)")
+        # The kernels (K4 / K7a / K7) are built for the reference's tgcn overlay (utility/config.py:41-51: 64-d rows,
+        # dim_atten 32, neighbor_k 25, 32 bit-level and 8 vector-level channels) with 64-wide layers; every other
+        # configuration — e.g. the argparse default dim_layer_list [64, 32, 16] (utility/utils.py:39) — runs the same
+        # maths layer by layer from torch ops on the device (BasicLayer._forward_torch / _tail_torch).
 
     def _init_weight(self):
         self.embed = nn.ParameterDict({

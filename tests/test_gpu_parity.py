@@ -774,6 +774,107 @@ def test_tgcn_forward_loss_grad_vs_reference(tiny, tiny_tgcn):
     assert not bad, bad
 
 
+# ------------------------------------------------------------------------- reference-default layer widths [64, 32, 16]
+@pytest.fixture(scope="module")
+def tiny_widths():
+    return dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_widths.npz")))
+
+
+@pytest.mark.parametrize("name", ["ngcf", "tgcn"])
+def test_default_layer_widths_vs_reference(tiny, tiny_widths, name, tmp_path):
+    """dim_layer_list = [64, 32, 16] — the reference's argparse default (utility/utils.py:39) and this package's own:
+    the 176-d concatenated tables, loss and every gradient equal the unmodified reference (tests/golden/
+    make_golden_widths.py); K1 / K2 run natively at these widths, the dense halves of the narrower layers run the same
+    maths from torch ops on the device; K3 pads the 176-d tables to 192; the drop-in loops run end to end."""
+    g, tag = tiny_widths, f"{name}_w"
+    cfg = dict(use_tag=True, reg=1e-3, dim_layer_list=[64, 32, 16], device=dev(), test_batch=16, topks=[5, 20],
+               train_batch=64, lr=0.01, epochs=1, test_interval=1, sampler="device")
+    if name == "tgcn":
+        cfg["neighbor_k"] = 5
+    T.set_config(name, **cfg)
+    d = make_data(tiny, tags=True)
+    d.uit_data = tiny["uit_data"]
+    if name == "tgcn":
+        names = ["ui", "ut", "iu", "it", "tu", "ti"]
+        d.get_all_neighbor = lambda: [(g[f"{tag}_nbr_{n}"], g[f"{tag}_nbw_{n}"]) for n in names]
+        model = T.TGCN(d).to(dev())
+    else:
+        model = T.NGCF(d).to(dev())
+    sd = model.state_dict()
+    assert sorted(sd.keys()) == sorted(k[len(tag) + 7:] for k in g if k.startswith(f"{tag}_param_"))
+    with torch.no_grad():
+        for k in sd:
+            assert tuple(sd[k].shape) == g[f"{tag}_param_{k}"].shape, k
+            sd[k].copy_(torch.tensor(g[f"{tag}_param_{k}"]))
+    model.train()
+    fw = model.forward()
+    for k in range(3):
+        assert fw[k].shape[1] == 176
+        assert relerr(fw[k].detach().cpu().numpy(), g[f"{tag}_fwd_{k}"]) < TOL
+    lossx = model.loss(torch.tensor(g[f"{tag}_batch"], device=dev()))
+    for j in range(2):
+        assert abs(lossx[j].item() - g[f"{tag}_loss"][j]) < TOL * abs(g[f"{tag}_loss"][j])
+    sum(lossx).backward()
+    gmax = max(float(np.abs(g[f"{tag}_grad_{n}"]).max()) for n, _ in model.named_parameters())
+    for n, p in model.named_parameters():
+        want = g[f"{tag}_grad_{n}"]
+        got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(want)
+        # tensors whose whole gradient is below 1e-7 of the model's largest gradient entry are float32 noise on both sides
+        assert relerr(got, want) < 2 * TOL or float(np.abs(got - want).max()) < 1e-7 * gmax, (n, relerr(got, want))
+    model.eval()
+    with torch.no_grad():
+        r = model.predict_rating(torch.tensor(g[f"{tag}_pred_users"], device=dev()))
+    assert relerr(r.cpu().numpy(), g[f"{tag}_pred"]) < TOL
+    # K3 on the padded table == (-score, id) order of the reference's own predict_rating rows
+    U = int(d.num["user"])
+    ptr_, items = T.bpr_training_data.user_items_to_csr(d.user_items["train"], U)
+    users = g[f"{tag}_pred_users"]
+    ids, _ = model.eval_topk(torch.tensor(users, device=dev()), 10, torch.tensor(ptr_, device=dev()),
+                             torch.tensor(items, device=dev()).int())
+    ms = OM.mask_train(g[f"{tag}_pred"].astype(np.float64), users, ptr_, items)
+    ref = OM.topk_ids(ms, 10)
+    for r_ in range(len(users)):
+        assert near_tie_ok(ms[r_], ids[r_].cpu().numpy(), ref[r_], 10)
+    # the drop-in loops on the default configuration
+    args = _Args(str(tmp_path))
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    train = T.Basic_train([T.BPR_training_data(d, args)], [model.loss], [opt], T.Basic_test(d, args), args)
+    train.run(model)
+    res = T.Basic_test(d, args).run(model, istest=True)
+    assert set(res) == {"recall", "precision", "hr", "ndcg", "auc"} and 0.0 <= res["auc"][0] <= 1.0
+
+
+def test_k4_backward_with_more_than_64_weight_ids():
+    """num['weight'] is the largest adjacency entry (data/tgcn_load.py:23) — a user who applied one tag 200 times gives a
+    200-row edge-weight table.  The backward stages the first 64 ids in shared memory and adds the rest straight to
+    global memory: same gradients as the torch formulation."""
+    from tagrec_b200.tgcn import Attention1
+    g = torch.Generator().manual_seed(3)
+    nv, nj, nw, k = 300, 50, 200, 9
+    att = Attention1(64, 32, 10).to(dev())
+    with torch.no_grad():
+        for p in att.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+    ev, ej, ew = torch.randn(nv, 64, generator=g), torch.randn(nj, 64, generator=g), torch.randn(nw, 10, generator=g)
+    rng = np.random.RandomState(4)
+    v_j = rng.randint(0, nj + 1, (nv, k))
+    v_w = rng.randint(1, nw + 1, (nv, k)) * (v_j > 0)
+    up = torch.randn(nv, 64, generator=g)
+    a = [t.clone().to(dev()).requires_grad_(True) for t in (ev, ej, ew)]
+    b = [t.clone().double().to(dev()).requires_grad_(True) for t in (ev, ej, ew)]
+    tj, tw = torch.tensor(v_j, device=dev()), torch.tensor(v_w, device=dev())
+    (att(a[0], a[1], a[2], (tj, tw)) * up.to(dev())).sum().backward()
+    got = {n: p.grad.clone() for n, p in att.named_parameters()}
+    att.zero_grad()
+    att64 = Attention1(64, 32, 10).to(dev()).double()
+    att64.load_state_dict({k_: v.double() for k_, v in att.state_dict().items()})
+    (att64.forward_torch(b[0], b[1], b[2], (tj, tw)) * up.double().to(dev())).sum().backward()
+    for x, y in zip(a, b):
+        assert relerr(x.grad.cpu().numpy(), y.grad.cpu().numpy()) < TOL
+    for n, p in att64.named_parameters():
+        assert relerr(got[n].cpu().numpy(), p.grad.cpu().numpy()) < TOL, n
+
+
 def test_k4_neighbour_attention_vs_torch():
     """K4 forward/backward against the reference formulation (tgcn.py:20-37) in torch fp64: padding slots (index 0)
     take part in the softmax, duplicate neighbours and shared weight ids collide in the scatter."""

@@ -107,7 +107,7 @@ def check_params(g, model):
 def check_topk(model, ds, users, ids_ref, scores_ref, k=20):
     """Our masked top-k vs the reference's (-score, id) order.  The reference ranks fp32 sigmoid(dot); the kernel ranks
     the exact fp32 dot, so a list may differ only where the reference's own scores tie / nearly tie at the boundary."""
-    U = model.num_list[0]
+    U = int(ds.num["user"])
     ptr_, items = T.bpr_training_data.user_items_to_csr(ds.user_items["train"], U)
     got, _ = model.eval_topk(torch.tensor(users, device=dev()), k, torch.tensor(ptr_, device=dev()),
                              torch.tensor(items, device=dev()).int())
