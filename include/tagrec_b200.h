@@ -427,6 +427,17 @@ int tagrec_sample_neg_tail_host(const uint32_t* state, const int64_t* group, int
 int tagrec_sample_bpr_device(const int64_t* edges, int64_t e, const int64_t* train_ptr, const int32_t* train_items,
                              int64_t num_item, uint64_t seed, uint64_t epoch, int64_t* triples_out, void* stream);
 
+/* TGCN neighbour tables on the device — replaces data/utils.py:87-106 (all_neighbor_sample) and
+ * data/tgcn_load.py:41-53 (a Python loop over every row with matrix[i].toarray() + np.random.choice).
+ * One relation per call: rows [row_begin, row_begin + n_rows) of the tripartite CSR (integer multiplicities in
+ * `weight`), restricted to columns [col_lo, col_hi).  ids[i * width + s] = (neighbour column - col_lo) + 1, 0 = padding
+ * (only in empty rows); rows shorter than `width` are filled by sampling WITH replacement, longer rows contribute a
+ * uniformly random width-subset in random order; wts = the matching integer edge weights.  width <= 64.  Philox
+ * keyed by (seed, relation, row): the reference's distribution, not numpy's stream. */
+int tagrec_neighbor_table(const int64_t* rowptr, const int32_t* col, const float* weight, int64_t row_begin,
+                          int64_t n_rows, int32_t col_lo, int32_t col_hi, int width, uint64_t seed, uint32_t relation,
+                          int64_t* ids, int64_t* wts, void* stream);
+
 /* Fused dense Adam (torch.optim.Adam semantics, com.py:25): one pass over param/grad/m/v. */
 int tagrec_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int64_t step, void* stream);

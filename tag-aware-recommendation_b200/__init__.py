@@ -4,7 +4,7 @@ chenzheng5555/tag-aware-recommendation, behind the reference's own Python interf
 Public surface (same names / call conventions as the reference):
     CFG / set_config / bind            utility/word.py CFG
     creat_adj, split_mm, CsrGraph      model/help/adj.py
-    LightGCN, NGCF                     model/lightgcn.py, model/ngcf.py
+    LightGCN, NGCF, TGCN, DGCF, DisenGCN, KGAT    model/*.py
     BPR_training_data                  train_data/bpr_training_data.py
     Basic_train, Basic_test, Early_stop   training/*.py
 All device work goes through libtagrec_b200.so (include/tagrec_b200.h); there is no CPU fallback.
@@ -18,6 +18,7 @@ from .ngcf import NGCF                                         # noqa: F401
 from .dgcf import DGCF                                         # noqa: F401
 from .disengcn import DisenGCN                                 # noqa: F401
 from .tgcn import TGCN                                         # noqa: F401
+from .kgat import KGAT, KGAT_training_data                     # noqa: F401
 from . import routing                                          # noqa: F401
 from .bpr_training_data import (Abstract_training_data, BPR_training_data, DGCF_training_data,   # noqa: F401
                                 TransTag_training_data)

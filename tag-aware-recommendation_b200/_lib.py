@@ -105,6 +105,7 @@ PROTOTYPES = {
     "tagrec_sample_bpr_host": (_i32, [_p, _p, _i64, _p, _p, _i64, _p]),
     "tagrec_sample_neg_tail_host": (_i32, [_p, _p, _i64, _p, _p, _i64, _p]),
     "tagrec_sample_bpr_device": (_i32, [_p, _i64, _p, _p, _i64, _u64, _u64, _p, _p]),
+    "tagrec_neighbor_table": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i32, _u64, _u32, _p, _p, _p]),
     "tagrec_adam_step": (_i32, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _p]),
     "tagrec_adam_step_mirror": (_i32, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i64, C.POINTER(MirrorDesc), _p]),
     "tagrec_adam_advance": (_i32, [_p, _f32, _f32, _f32, _p, _p]),

@@ -26,6 +26,8 @@ MODEL_OVERLAY = {
     "lightgcn": {"mul_loss_func": "softplus", "norm_type": "bi_norm", "cor_batch": 100},
     "dgcf": {"mul_loss_func": "softplus", "norm_type": "plain", "factor_k": 4, "iterate_k": 2, "cor_batch": 100},
     "disengcn": {"mul_loss_func": "softplus", "norm_type": "plain", "factor_k": 4, "iterate_k": 2, "cor_batch": 100},
+    "kgat": {"dim_relation": 64, "transe_reg": 0.0001, "transe_batch": 1024, "agg_type": "bi_agg",
+             "mul_loss_func": "softplus"},
     "tgcn": {"dim_weight": 10, "dim_atten": 32, "num_bit_conv": 32, "num_vec_conv": 8, "margin": 1,
              "transtag_batch": 512, "neighbor_k": 25, "transtag_reg": 0.0001, "mul_loss_func": "logsigmoid"},
 }

@@ -214,3 +214,90 @@ extern "C" int tagrec_sample_bpr_device(const int64_t* edges, int64_t e, const i
                   (uint32_t)num_item, seed, epoch, h, triples_out);
     return TAGREC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// TGCN neighbour tables on the device.  Replaces data/utils.py:87-106 (all_neighbor_sample) + data/tgcn_load.py:41-53:
+// a Python loop over every row with ``matrix[i].toarray()`` and np.random.choice.  One thread per row of one relation
+// (row type a -> column type b = the stored entries of the row whose column id lies in [col_lo, col_hi) of the
+// tripartite CSR): `width` neighbour ids (+1; 0 = padding, only in empty rows) drawn WITH replacement when the row has
+// fewer than `width` entries, a uniformly random `width`-subset in random order otherwise (Floyd's algorithm + a
+// Fisher-Yates pass), and the matching integer edge weights.  Philox4x32-10 keyed by (seed, relation, row):
+// statistically the reference's tables, not numpy's stream (the host builder in data.py keeps the stream-identical form).
+namespace tagrec {
+constexpr int kMaxNbrWidth = 64;
+
+__device__ __forceinline__ uint32_t bounded_u32(uint32_t r, uint32_t n) {       // uniform in [0, n), n < 2^31
+    return (uint32_t)(((uint64_t)r * (uint64_t)n) >> 32);
+}
+
+__global__ void __launch_bounds__(128)
+neighbor_table_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ weight,
+                      int64_t row_begin, int64_t n_rows, int32_t col_lo, int32_t col_hi, int width, uint64_t seed,
+                      uint32_t relation, int64_t* __restrict__ ids, int64_t* __restrict__ wts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const int64_t r = row_begin + i;
+    int64_t lo = __ldg(rowptr + r), hi = __ldg(rowptr + r + 1);
+    {   // the row's entries with column in [col_lo, col_hi): two lower bounds over the ascending columns
+        int64_t a = lo, b = hi;
+        while (a < b) { const int64_t m = (a + b) >> 1; if (__ldg(col + m) < col_lo) a = m + 1; else b = m; }
+        const int64_t s = a;
+        b = hi;
+        while (a < b) { const int64_t m = (a + b) >> 1; if (__ldg(col + m) < col_hi) a = m + 1; else b = m; }
+        lo = s; hi = a;
+    }
+    const int64_t x = hi - lo;
+    int64_t* out_i = ids + i * width;
+    int64_t* out_w = wts + i * width;
+    if (x == 0) {
+        for (int s = 0; s < width; ++s) { out_i[s] = 0; out_w[s] = 0; }
+        return;
+    }
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t blk = 0;
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    int have = 0;
+    auto next = [&]() -> uint32_t {
+        if (have == 0) {
+            rnd = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)(r >> 32), relation, blk++), key);
+            have = 4;
+        }
+        const uint32_t v = have == 4 ? rnd.x : have == 3 ? rnd.y : have == 2 ? rnd.z : rnd.w;
+        --have;
+        return v;
+    };
+    int32_t pick[kMaxNbrWidth];
+    if (x < width) {                                    // with replacement (np.random.choice(ids, max_deg))
+        for (int s = 0; s < width; ++s) pick[s] = (int32_t)bounded_u32(next(), (uint32_t)x);
+    } else {                                            // without replacement: Floyd, then shuffle the order
+        int cnt = 0;
+        for (int64_t j = x - width; j < x; ++j) {
+            int32_t t = (int32_t)bounded_u32(next(), (uint32_t)(j + 1));
+            bool seen = false;
+            for (int q = 0; q < cnt; ++q) seen |= (pick[q] == t);
+            pick[cnt++] = seen ? (int32_t)j : t;
+        }
+        for (int s = width - 1; s > 0; --s) {
+            const int t = (int)bounded_u32(next(), (uint32_t)(s + 1));
+            const int32_t tmp = pick[s]; pick[s] = pick[t]; pick[t] = tmp;
+        }
+    }
+    for (int s = 0; s < width; ++s) {
+        const int64_t e = lo + pick[s];
+        out_i[s] = (int64_t)(__ldg(col + e) - col_lo) + 1;
+        out_w[s] = (int64_t)llrintf(__ldg(weight + e));
+    }
+}
+}  // namespace tagrec
+
+extern "C" int tagrec_neighbor_table(const int64_t* rowptr, const int32_t* col, const float* weight, int64_t row_begin,
+                                     int64_t n_rows, int32_t col_lo, int32_t col_hi, int width, uint64_t seed,
+                                     uint32_t relation, int64_t* ids, int64_t* wts, void* stream) {
+    TAGREC_REQUIRE(rowptr && col && weight && ids && wts, "null pointer");
+    TAGREC_REQUIRE(width >= 1 && width <= tagrec::kMaxNbrWidth, "table width must be in 1..64");
+    TAGREC_REQUIRE(col_hi >= col_lo && row_begin >= 0 && n_rows >= 0, "bad row / column range");
+    if (n_rows == 0) return TAGREC_OK;
+    TAGREC_LAUNCH(tagrec::neighbor_table_kernel, (unsigned)((n_rows + 127) / 128), 128, 0, stream, rowptr, col, weight,
+                  row_begin, n_rows, col_lo, col_hi, width, seed, relation, ids, wts);
+    return TAGREC_OK;
+}

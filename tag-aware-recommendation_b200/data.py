@@ -20,6 +20,23 @@ class Dataset:
         self.ui_adj = self.ut_adj = self.it_adj = None
         self.uit_data = None
 
+    def create_edge(self):
+        return create_edge(self)
+
+
+def create_edge(ds):
+    """data/tgcn_load.py:55-70 TGCN_load.create_edge: the six directed relations (ui iu ut tu it ti) as [2, E] arrays of
+    global node ids (users, then items, then tags) — the layout KGAT_training_data expects."""
+    U, I = int(ds.num["user"]), int(ds.num["item"])
+    edge = {}
+    user, item = ds.ui_adj.row, ds.ui_adj.col + U
+    edge[0], edge[1] = np.stack([user, item]), np.stack([item, user])
+    user, tag = ds.ut_adj.row, ds.ut_adj.col + I + U
+    edge[2], edge[3] = np.stack([user, tag]), np.stack([tag, user])
+    item, tag = ds.it_adj.row + U, ds.it_adj.col + I + U
+    edge[4], edge[5] = np.stack([item, tag]), np.stack([tag, item])
+    return edge
+
 
 def _coo(rows, cols, shape):
     # data/utils.py:50-53 to_sparse_adj
@@ -203,4 +220,30 @@ def get_all_neighbor(ds, fork_semantics=True, width=None):
     out = [all_neighbor_sample(a, d) for a, d in zip(mats, max_deg)]
     if saved is not None:
         np.random.set_state(saved)
+    return out
+
+
+def get_all_neighbor_device(ds, width, device, seed=2020):
+    """The six neighbour tables (ui, ut, iu, it, tu, ti) of data/tgcn_load.py:41-53 built on the device
+    (``tagrec_neighbor_table``): K0 builds the weighted tripartite CSR from the (u, i) / (u, i, t) lists, then one launch
+    per relation samples ``width`` (= neighbor_k, the columns TGCN reads, tgcn.py:199) neighbours per row.  Returns a
+    list of ``(ids, weights)`` int64 device tensors [n_rows, width] — same contract as ``get_all_neighbor`` (ids + 1,
+    0 = padding in empty rows only), same distribution, a Philox stream instead of numpy's.  No per-row host loop:
+    112 K rows x 6 relations take microseconds instead of the reference's minutes."""
+    from . import adj
+    from ._lib import check, lib, ptr, stream_ptr
+    U, I, Tn = int(ds.num["user"]), int(ds.num["item"]), int(ds.num["tag"])
+    g = adj.build_csr(U, I, (ds.ui_adj.row, ds.ui_adj.col), "plain", device, Tn,
+                      (ds.ut_adj.row, ds.ut_adj.col), (ds.it_adj.row, ds.it_adj.col))
+    off = [0, U, U + I, U + I + Tn]
+    rel = [(0, 1), (0, 2), (1, 0), (1, 2), (2, 0), (2, 1)]                  # (row type, column type): ui ut iu it tu ti
+    out = []
+    for k, (a, b) in enumerate(rel):
+        n = off[a + 1] - off[a]
+        ids = torch.empty((n, width), dtype=torch.int64, device=device)
+        wts = torch.empty((n, width), dtype=torch.int64, device=device)
+        check(lib().tagrec_neighbor_table(ptr(g.rowptr), ptr(g.col), ptr(g.val), off[a], n, off[b], off[b + 1], int(width),
+                                          int(seed), k, ptr(ids), ptr(wts), stream_ptr(torch.device(device))),
+              "tagrec_neighbor_table")
+        out.append((ids, wts))
     return out

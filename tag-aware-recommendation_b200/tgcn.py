@@ -316,12 +316,15 @@ class TGCN(EvalMixin, nn.Module):
         ``neighbor_k`` columns; the shuffle still advances numpy's global generator once per relation, which the
         parity-mode samplers read — so the draw is reproduced, the tables are uploaded once."""
         for adj_w in self.all_sample:
-            np.random.shuffle(np.arange(np.asarray(adj_w[0]).shape[1]))
+            np.random.shuffle(np.arange(int((adj_w[0] if torch.is_tensor(adj_w[0]) else np.asarray(adj_w[0])).shape[1])))
         if self._nbr_dev is None or self._nbr_dev[0][0].device != self.embed["user"].device:
             dev = self.embed["user"].device
-            self._nbr_dev = [tuple(torch.as_tensor(np.ascontiguousarray(np.asarray(x)[:, :self.neighbor_k]),
-                                                   dtype=torch.long, device=dev) for x in adj_w)
-                             for adj_w in self.all_sample]
+
+            def up(x):       # host tables (numpy, the reference's contract) or device tables (get_all_neighbor_device)
+                if torch.is_tensor(x):
+                    return x[:, :self.neighbor_k].to(device=dev, dtype=torch.long).contiguous()
+                return torch.as_tensor(np.ascontiguousarray(np.asarray(x)[:, :self.neighbor_k]), dtype=torch.long, device=dev)
+            self._nbr_dev = [tuple(up(x) for x in adj_w) for adj_w in self.all_sample]
         return self._nbr_dev
 
     def _propagate(self):

@@ -774,6 +774,95 @@ def test_tgcn_forward_loss_grad_vs_reference(tiny, tiny_tgcn):
     assert not bad, bad
 
 
+# ------------------------------------------------------------------------------------------------------- KGAT (f-4)
+@pytest.fixture(scope="module")
+def tiny_kgat():
+    return dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_kgat.npz")))
+
+
+def _kgat_model(tiny, g, tag, agg_type, edges_e2):
+    T.set_config("kgat", use_tag=True, reg=1e-3, cor_reg=1e-3, agg_type=agg_type, dim_layer_list=[64, 64, 64],
+                 transe_batch=32, device=dev())
+    d = make_data(tiny, tags=True)
+    import scipy.sparse as sp
+    uit = tiny["uit_data"].astype(np.int64)
+    U, I, Tg, W = nums(tiny)
+    d.ut_adj = sp.coo_matrix((np.ones(len(uit)), (uit[:, 0], uit[:, 2])), dtype=np.float32, shape=(U, Tg))
+    d.it_adj = sp.coo_matrix((np.ones(len(uit)), (uit[:, 1], uit[:, 2])), dtype=np.float32, shape=(I, Tg))
+    stock = lambda: T.data.create_edge(d)                                         # noqa: E731
+    d.create_edge = (lambda: {k: np.ascontiguousarray(v.T) for k, v in stock().items()}) if edges_e2 else stock
+    model = T.KGAT(d).to(dev())
+    sd = model.state_dict()
+    assert sorted(sd.keys()) == sorted(k[len(tag) + 7:] for k in g if k.startswith(f"{tag}_param_"))
+    with torch.no_grad():
+        for k in sd:
+            sd[k].copy_(torch.tensor(g[f"{tag}_param_{k}"]))
+    return d, model
+
+
+@pytest.mark.parametrize("tag,agg_type,edges_e2,width", [("kgat_stock", "bi_agg", False, 64), ("kgat_inter", "bi_inter", True, 256)])
+def test_kgat_forward_loss_grad_vs_reference(tiny, tiny_kgat, tag, agg_type, edges_e2, width):
+    """T.KGAT == model/kgat.py: the stock overlay (ego tables; unused attention) and the intended bi_inter model
+    (relation-aware attention -> row softmax -> K1 propagation with value gradients -> K6 dense layers): tables, loss
+    tuple and the gradient of EVERY parameter, the attention parameters included."""
+    g = tiny_kgat
+    d, model = _kgat_model(tiny, g, tag, agg_type, edges_e2)
+    model.train()
+    fw = model.forward()
+    for k in range(2):
+        assert fw[k].shape[1] == width
+        assert relerr(fw[k].detach().cpu().numpy(), g[f"{tag}_fwd_{k}"]) < TOL
+    lossx = model.loss(torch.tensor(g[f"{tag}_batch"], device=dev()))
+    for j in range(2):
+        assert abs(lossx[j].item() - g[f"{tag}_loss"][j]) < TOL * abs(g[f"{tag}_loss"][j])
+    sum(lossx).backward()
+    gmax = max(float(np.abs(g[f"{tag}_grad_{n}"]).max()) for n, _ in model.named_parameters())
+    for n, p in model.named_parameters():
+        want = g[f"{tag}_grad_{n}"]
+        got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(want)
+        assert relerr(got, want) < 2 * TOL or float(np.abs(got - want).max()) < 1e-7 * gmax, (n, relerr(got, want))
+    if edges_e2:
+        return
+    # second phase (com.py:80-83): KGAT_training_data's stream and transe_loss
+    np.random.seed(2020)
+    td = T.KGAT_training_data(d, None)
+    assert td.tot_inter == int(g[f"{tag}_kg_tot_inter"][0])
+    for i, b in enumerate(td.mini_batch()):
+        assert np.array_equal(b.cpu().numpy(), g[f"{tag}_kg_batches"][i])
+        if i == 2:
+            break
+    model.zero_grad()
+    lossx = model.transe_loss(torch.tensor(g[f"{tag}_kg_batches"][0], device=dev()))
+    for j in range(2):
+        assert abs(lossx[j].item() - g[f"{tag}_transe_loss"][j]) < TOL * abs(g[f"{tag}_transe_loss"][j])
+    sum(lossx).backward()
+    for n, p in model.named_parameters():
+        want = g[f"{tag}_transe_grad_{n}"]
+        got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(want)
+        assert relerr(got, want) < 2 * TOL or np.abs(want).max() == 0, (n, relerr(got, want))
+
+
+def test_kgat_end_to_end_loop(tiny, tmp_path):
+    """kgat_comp (com.py:77-86) with the drop-in classes: BPR phase + TransE phase sharing one Adam, evaluation on K3."""
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_kgat.npz")))
+    d, model = _kgat_model(tiny, g, "kgat_inter", "bi_inter", True)
+    T.CFG.update(train_batch=64, test_batch=16, topks=[5, 20], epochs=2, test_interval=1, patient_epoch=5, lr=0.01,
+                 sampler="device")
+    args = _Args(str(tmp_path))
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    stock = lambda: T.data.create_edge(d)                                         # noqa: E731
+    d2 = type("D2", (), {"num": d.num, "create_edge": staticmethod(stock)})
+    train_data = [T.BPR_training_data(d, args), T.KGAT_training_data(d2, args)]
+    train_data[1].tot_inter = 3                                                   # keep the TransE phase short
+    test = T.Basic_test(d, args)
+    first = T.epoch_training(train_data[0], model.loss, opt)
+    T.Basic_train(train_data, [model.loss, model.transe_loss], [opt, opt], test, args).run(model)
+    last = T.epoch_training(train_data[0], model.loss, opt)
+    assert np.isfinite(last).all() and np.mean(last) < np.mean(first)
+    res = test.run(model, istest=True)
+    assert set(res) == {"recall", "precision", "hr", "ndcg", "auc"} and 0.0 <= res["auc"][0] <= 1.0
+
+
 # ------------------------------------------------------------------------- reference-default layer widths [64, 32, 16]
 @pytest.fixture(scope="module")
 def tiny_widths():
@@ -873,6 +962,63 @@ def test_k4_backward_with_more_than_64_weight_ids():
         assert relerr(x.grad.cpu().numpy(), y.grad.cpu().numpy()) < TOL
     for n, p in att64.named_parameters():
         assert relerr(got[n].cpu().numpy(), p.grad.cpu().numpy()) < TOL, n
+
+
+def test_device_neighbour_tables_properties_and_training(tiny):
+    """tagrec_neighbor_table (device form of data/utils.py:87-106): every entry is a real neighbour with its stored
+    multiplicity, empty rows are all padding, rows shorter than the table are filled with replacement, longer rows give
+    distinct neighbours, the draw is close to uniform — and TGCN trains on the device-built tables."""
+    d = make_data(tiny, tags=True)
+    d.uit_data = tiny["uit_data"]
+    import scipy.sparse as sp
+    uit = tiny["uit_data"].astype(np.int64)
+    U, I, Tg, W = nums(tiny)
+    # the loaders keep duplicate (u, t) / (i, t) pairs (multiplicities), data/utils.py:50-53
+    d.ut_adj = sp.coo_matrix((np.ones(len(uit)), (uit[:, 0], uit[:, 2])), dtype=np.float32, shape=(U, Tg))
+    d.it_adj = sp.coo_matrix((np.ones(len(uit)), (uit[:, 1], uit[:, 2])), dtype=np.float32, shape=(I, Tg))
+    width = 6
+    tabs = T.data.get_all_neighbor_device(d, width, dev(), seed=11)
+    mats = [d.ui_adj, d.ut_adj, d.ui_adj.T, d.it_adj, d.ut_adj.T, d.it_adj.T]
+    for (ids, wts), m in zip(tabs, mats):
+        m = sp.csr_matrix(m)
+        m.sum_duplicates()
+        ids, wts = ids.cpu().numpy(), wts.cpu().numpy()
+        assert ids.shape == (m.shape[0], width)
+        for r in range(m.shape[0]):
+            nb = m.indices[m.indptr[r]:m.indptr[r + 1]]
+            if len(nb) == 0:
+                assert (ids[r] == 0).all() and (wts[r] == 0).all()
+                continue
+            assert (ids[r] >= 1).all() and set(ids[r] - 1) <= set(nb)
+            assert all(wts[r, s] == int(m[r, ids[r, s] - 1]) for s in range(width))
+            if len(nb) >= width:
+                assert len(set(ids[r])) == width                  # without replacement
+    # uniformity: a row with 3 neighbours sampled 6 x 4000 times (different seeds) -> each ~ 1/3
+    r = int(np.argmax(np.asarray((sp.csr_matrix(d.ui_adj) != 0).sum(1)).ravel() == 3))
+    cnt = {}
+    for seed in range(200):
+        ids = T.data.get_all_neighbor_device(d, width, dev(), seed=seed)[0][0][r].cpu().numpy()
+        for x in ids:
+            cnt[int(x)] = cnt.get(int(x), 0) + 1
+    assert len(cnt) == 3 and max(cnt.values()) / min(cnt.values()) < 1.35, cnt
+    # a different seed gives different tables; the same seed the same tables
+    a = T.data.get_all_neighbor_device(d, width, dev(), seed=1)[2][0]
+    b = T.data.get_all_neighbor_device(d, width, dev(), seed=1)[2][0]
+    c = T.data.get_all_neighbor_device(d, width, dev(), seed=2)[2][0]
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    # TGCN on device-built tables: loss goes down
+    T.set_config("tgcn", use_tag=True, reg=1e-4, dim_layer_list=[64, 64], neighbor_k=width, device=dev(), lr=0.01,
+                 train_batch=64, sampler="device")
+    d.get_all_neighbor = lambda: T.data.get_all_neighbor_device(d, width, dev(), seed=2020)
+    torch.manual_seed(0)
+    model = T.TGCN(d).to(dev())
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    sampler = T.BPR_training_data(d, None)
+    model.train()
+    first = T.epoch_training(sampler, model.loss, opt)
+    for _ in range(3):
+        last = T.epoch_training(sampler, model.loss, opt)
+    assert np.isfinite(last).all() and np.mean(last) < np.mean(first)
 
 
 def test_k4_neighbour_attention_vs_torch():
