@@ -753,6 +753,29 @@ def eval_leg_sharded(T, model, shape, dev, eval_mask, world, dist):
             "kernel": "eval_tc_kernel (tcgen05.mma kind::tf32 filter + exact fp32 re-score), users sharded over ranks"}
 
 
+def measure_tf32_peak(dev, n=8192, reps=10):
+    """Measured dense TF32 throughput of this GPU: cuBLAS fp32 GEMM with TF32 tensor cores allowed, 8192^3, best of
+    `reps` (CUDA events) — the denominator for the K3-TC tensor fraction (the driver's MEASURED_PEAKS.json has bf16 only)."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        torch.matmul(a, b)
+        best = float("inf")
+        for _ in range(reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); torch.matmul(a, b); e.record()
+            torch.cuda.synchronize()
+            best = min(best, s.elapsed_time(e))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def eval_leg(T, model, shape, dev, n_users):
     """Secondary metric of BASELINE.json: full-rank eval users/s (K3: scoring + mask + top-20 + metric sums) on the
     benchmark graph.  The drop-in Basic_test takes the reference's dict-of-lists data object, which cannot hold 10 M
@@ -813,10 +836,13 @@ def eval_leg(T, model, shape, dev, n_users):
                "mean_auc": _finite(float(auc["tf32"][1][0] / max(auc["tf32"][1][1], 1.0))),
                "kernel": "auc_tc_kernel (3xTF32 tcgen05.mma + exact band, canonical fp32 re-scores)",
                "fp32_cuda_core_path_ms": auc["fp32"][0], "sums_identical": auc_same}
-    tf32_peak = 1100.0      # nominal dense TF32 TFLOP/s (B200_PROFILING.md); no measured TF32 figure in MEASURED_PEAKS
+    tf32_peak = 1100.0      # nominal dense TF32 TFLOP/s (B200_PROFILING.md); MEASURED_PEAKS.json only has bf16
+    measured_tf32 = measure_tf32_peak(dev)
     return {"users_per_s": out["tf32"]["users_per_s"], "users": n_users, "items": shape["n_item"], "k": 20,
             "ms": out["tf32"]["ms"], "tflops": out["tf32"]["tflops"],
             "tensor_frac_of_nominal_tf32": out["tf32"]["tflops"] / tf32_peak,
+            "tf32_peak_measured_tflops": measured_tf32,
+            "tensor_frac_of_measured_tf32": out["tf32"]["tflops"] / measured_tf32 if measured_tf32 else None,
             "kernel": "eval_tc_kernel (tcgen05.mma kind::tf32 filter + exact fp32 re-score)",
             "fp32_cuda_core_path": out["fp32"], "paths_identical": same, "auc": auc_out}
 

@@ -57,14 +57,33 @@ __device__ __forceinline__ float sub_sum(float v, unsigned mask) {
 #define SPMM_MINB 16
 #endif
 
-// acc = sum_{j in [begin,end), chunk(j) == part (mod nparts)} val[j] * x[col[j]]   for this lane's float4 slice.
-template <int LPR, bool MASKED = false>
-__device__ __forceinline__ float4 gather_rows(const int32_t* __restrict__ col, const float* __restrict__ val,
-                                              const float4* __restrict__ x4, int64_t begin, int64_t end, int part,
-                                              int nparts, int sl, unsigned mask,
-                                              const uint8_t* __restrict__ src_nz = nullptr) {
-    constexpr int U = SPMM_U < LPR ? SPMM_U : LPR;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+// A lane's slice of a table row: V float4 (row = LPR * V float4; lane sl owns float4 sl, sl + LPR, ...: every one of its
+// V loads is part of a coalesced LPR * 16-byte segment).  V = 1: 16 lanes per 64-float row (the round-1 mapping).
+// V = 2: 8 lanes per 64-float row, four rows per warp — half the warp-instructions per stored entry (the index
+// broadcast, address arithmetic and loop control are shared by two 128-bit loads and eight FMAs instead of one and four).
+template <int V>
+struct Slice {
+    float4 v[V];
+};
+
+template <int V>
+__device__ __forceinline__ Slice<V> zero_slice() {
+    Slice<V> z;
+#pragma unroll
+    for (int i = 0; i < V; ++i) z.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return z;
+}
+
+// acc = sum_{j in [begin,end), chunk(j) == part (mod nparts)} val[j] * x[col[j]]   for this lane's slice.
+template <int LPR, int V, bool MASKED = false>
+__device__ __forceinline__ Slice<V> gather_rows(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                                const float4* __restrict__ x4, int64_t begin, int64_t end, int part,
+                                                int nparts, int sl, unsigned mask,
+                                                const uint8_t* __restrict__ src_nz = nullptr) {
+    constexpr int U0 = SPMM_U / V < 1 ? 1 : SPMM_U / V;      // entries in flight per lane (U0 * V 128-bit loads)
+    constexpr int U = U0 < LPR ? U0 : LPR;
+    constexpr int ROW4 = LPR * V;                            // float4 per table row
+    Slice<V> acc = zero_slice<V>();
     const int32_t* __restrict__ colp = col + begin;
     const float* __restrict__ valp = val + begin;
     const int len = (int)(end - begin);          // a row (or chunk) never exceeds 2^31 entries
@@ -74,7 +93,7 @@ __device__ __forceinline__ float4 gather_rows(const int32_t* __restrict__ col, c
     float v = 0.f;
     // Zero-row skipping (backward tables that are non-zero only near the batch): the lane that loaded a column id
     // also looks its row up in the byte map and parks the answer in the id's sign bit, so the broadcast below needs no
-    // extra shuffle and the 256 B gather of an all-zero row is never issued.
+    // extra shuffle and the gather of an all-zero row is never issued.
     if (base + sl < len) {
         c = __ldcs(colp + base + sl);
         v = __ldcs(valp + base + sl);
@@ -94,14 +113,21 @@ __device__ __forceinline__ float4 gather_rows(const int32_t* __restrict__ col, c
 #pragma unroll
         for (int j0 = 0; j0 < LPR; j0 += U) {
             if (j0 < cnt) {
-                float4 xv[U];
+                float4 xv[U][V];
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
                     const int cj = __shfl_sync(mask, c, j0 + j, LPR);
-                    xv[j] = (j0 + j < cnt && (!MASKED || cj >= 0)) ? ldg4(xs + (int64_t)cj * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const bool live = j0 + j < cnt && (!MASKED || cj >= 0);
+                    const float4* __restrict__ src = xs + (int64_t)cj * ROW4;
+#pragma unroll
+                    for (int q = 0; q < V; ++q) xv[j][q] = live ? ldg4(src + q * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int j = 0; j < U; ++j) fma4(acc, __shfl_sync(mask, v, j0 + j, LPR), xv[j]);
+                for (int j = 0; j < U; ++j) {
+                    const float vj = __shfl_sync(mask, v, j0 + j, LPR);
+#pragma unroll
+                    for (int q = 0; q < V; ++q) fma4(acc.v[q], vj, xv[j][q]);
+                }
             }
         }
         c = cn;
@@ -111,97 +137,130 @@ __device__ __forceinline__ float4 gather_rows(const int32_t* __restrict__ col, c
     return acc;
 }
 
-template <int LPR, int EPI>
-__device__ __forceinline__ void epilogue(const Epi& ep, int64_t r, float4 acc, int sl, unsigned mask) {
-    const int64_t o = r * LPR + sl;
+template <int LPR, int V>
+__device__ __forceinline__ float slice_dot(const Slice<V>& a, const Slice<V>& b) {
+    float d = dot4(a.v[0], b.v[0]);
+#pragma unroll
+    for (int q = 1; q < V; ++q) d += dot4(a.v[q], b.v[q]);
+    return d;
+}
+
+template <int LPR, int V, int EPI>
+__device__ __forceinline__ void epilogue(const Epi& ep, int64_t r, Slice<V> acc, int sl, unsigned mask) {
+    const int64_t o0 = r * (LPR * V) + sl;           // float4 index of this lane's first slice element; + q * LPR
     if (EPI == EPI_PLAIN) {
         float4* y4 = reinterpret_cast<float4*>(ep.y);
-        if (ep.scale != 0.f) {
-            const float4 old = y4[o];
-            acc.x = fmaf(ep.scale, old.x, acc.x);
-            acc.y = fmaf(ep.scale, old.y, acc.y);
-            acc.z = fmaf(ep.scale, old.z, acc.z);
-            acc.w = fmaf(ep.scale, old.w, acc.w);
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            float4 a = acc.v[q];
+            if (ep.scale != 0.f) {
+                const float4 old = y4[o0 + q * LPR];
+                a.x = fmaf(ep.scale, old.x, a.x);
+                a.y = fmaf(ep.scale, old.y, a.y);
+                a.z = fmaf(ep.scale, old.z, a.z);
+                a.w = fmaf(ep.scale, old.w, a.w);
+            }
+            y4[o0 + q * LPR] = a;
         }
-        y4[o] = acc;
     } else if (EPI == EPI_FWD) {
         // lightgcn.py:55-60: raw layer propagates, normalised copy joins the mean
-        const float ss = sub_sum<LPR>(dot4(acc, acc), mask);
+        const float ss = sub_sum<LPR>(slice_dot<LPR, V>(acc, acc), mask);
         const float nrm = fmaxf(sqrtf(ss), 1e-12f);
-        store_row(ep.y, ep.my, o, acc);
         float4* a4 = reinterpret_cast<float4*>(ep.acc);
-        float4 a = ep.first ? __ldg(reinterpret_cast<const float4*>(ep.x0) + o) : a4[o];
-        a.x += acc.x / nrm;
-        a.y += acc.y / nrm;
-        a.z += acc.z / nrm;
-        a.w += acc.w / nrm;
-        if (ep.last) {
-            a.x *= ep.scale;
-            a.y *= ep.scale;
-            a.z *= ep.scale;
-            a.w *= ep.scale;
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            const int64_t o = o0 + q * LPR;
+            store_row(ep.y, ep.my, o, acc.v[q]);
+            float4 a = ep.first ? __ldg(reinterpret_cast<const float4*>(ep.x0) + o) : a4[o];
+            a.x += acc.v[q].x / nrm;
+            a.y += acc.v[q].y / nrm;
+            a.z += acc.v[q].z / nrm;
+            a.w += acc.v[q].w / nrm;
+            if (ep.last) {
+                a.x *= ep.scale;
+                a.y *= ep.scale;
+                a.z *= ep.scale;
+                a.w *= ep.scale;
+            }
+            store_row(ep.acc, ep.macc, o, a);
         }
-        store_row(ep.acc, ep.macc, o, a);
     } else {
         const float up0 = ep.upstream ? __ldg(ep.upstream) : 1.f;
         const float s = ep.scale * up0;
-        float4 g = __ldg(reinterpret_cast<const float4*>(ep.g_final) + o);
-        g.x *= s;
-        g.y *= s;
-        g.z *= s;
-        g.w *= s;
-        float4 out;
+        Slice<V> g;
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            g.v[q] = __ldg(reinterpret_cast<const float4*>(ep.g_final) + o0 + q * LPR);
+            g.v[q].x *= s;
+            g.v[q].y *= s;
+            g.v[q].z *= s;
+            g.v[q].w *= s;
+        }
         if (EPI == EPI_BWD) {
             // Jacobian of e / max(||e||, eps) applied to g
-            const float4 e = __ldg(reinterpret_cast<const float4*>(ep.e_k) + o);
-            const float ss = sub_sum<LPR>(dot4(e, e), mask);
-            const float dt = sub_sum<LPR>(dot4(e, g), mask);
+            Slice<V> e;
+#pragma unroll
+            for (int q = 0; q < V; ++q) e.v[q] = __ldg(reinterpret_cast<const float4*>(ep.e_k) + o0 + q * LPR);
+            const float ss = sub_sum<LPR>(slice_dot<LPR, V>(e, e), mask);
+            const float dt = sub_sum<LPR>(slice_dot<LPR, V>(e, g), mask);
             const float nrm = sqrtf(ss);
-            if (nrm >= 1e-12f) {
-                const float proj = dt / nrm;
-                out.x = (g.x - (e.x / nrm) * proj) / nrm + acc.x;
-                out.y = (g.y - (e.y / nrm) * proj) / nrm + acc.y;
-                out.z = (g.z - (e.z / nrm) * proj) / nrm + acc.z;
-                out.w = (g.w - (e.w / nrm) * proj) / nrm + acc.w;
-            } else {
-                out.x = g.x / 1e-12f + acc.x;
-                out.y = g.y / 1e-12f + acc.y;
-                out.z = g.z / 1e-12f + acc.z;
-                out.w = g.w / 1e-12f + acc.w;
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                float4 out;
+                if (nrm >= 1e-12f) {
+                    const float proj = dt / nrm;
+                    out.x = (g.v[q].x - (e.v[q].x / nrm) * proj) / nrm + acc.v[q].x;
+                    out.y = (g.v[q].y - (e.v[q].y / nrm) * proj) / nrm + acc.v[q].y;
+                    out.z = (g.v[q].z - (e.v[q].z / nrm) * proj) / nrm + acc.v[q].z;
+                    out.w = (g.v[q].w - (e.v[q].w / nrm) * proj) / nrm + acc.v[q].w;
+                } else {
+                    out.x = g.v[q].x / 1e-12f + acc.v[q].x;
+                    out.y = g.v[q].y / 1e-12f + acc.v[q].y;
+                    out.z = g.v[q].z / 1e-12f + acc.v[q].z;
+                    out.w = g.v[q].w / 1e-12f + acc.v[q].w;
+                }
+                store_row(ep.y, ep.my, o0 + q * LPR, out);
             }
         } else {
-            out.x = g.x + acc.x;
-            out.y = g.y + acc.y;
-            out.z = g.z + acc.z;
-            out.w = g.w + acc.w;
-            if (ep.reg_grad) {
-                const float up1 = ep.upstream ? __ldg(ep.upstream + 1) : 1.f;
-                const float4 rg = reinterpret_cast<const float4*>(ep.reg_grad)[o];
-                out.x = fmaf(up1, rg.x, out.x);
-                out.y = fmaf(up1, rg.y, out.y);
-                out.z = fmaf(up1, rg.z, out.z);
-                out.w = fmaf(up1, rg.w, out.w);
+            const float up1 = (ep.reg_grad && ep.upstream) ? __ldg(ep.upstream + 1) : 1.f;
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                float4 out;
+                out.x = g.v[q].x + acc.v[q].x;
+                out.y = g.v[q].y + acc.v[q].y;
+                out.z = g.v[q].z + acc.v[q].z;
+                out.w = g.v[q].w + acc.v[q].w;
+                if (ep.reg_grad) {
+                    const float4 rg = reinterpret_cast<const float4*>(ep.reg_grad)[o0 + q * LPR];
+                    out.x = fmaf(up1, rg.x, out.x);
+                    out.y = fmaf(up1, rg.y, out.y);
+                    out.z = fmaf(up1, rg.z, out.z);
+                    out.w = fmaf(up1, rg.w, out.w);
+                }
+                store_row(ep.y, ep.my, o0 + q * LPR, out);
             }
         }
-        store_row(ep.y, ep.my, o, out);
     }
 }
 
-template <int LPR>
-__device__ __forceinline__ float4 combine_subs(float4 p) {
+template <int LPR, int V>
+__device__ __forceinline__ Slice<V> combine_subs(Slice<V> p) {
 #pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {
-        p.x += __shfl_xor_sync(0xffffffffu, p.x, o);
-        p.y += __shfl_xor_sync(0xffffffffu, p.y, o);
-        p.z += __shfl_xor_sync(0xffffffffu, p.z, o);
-        p.w += __shfl_xor_sync(0xffffffffu, p.w, o);
+    for (int q = 0; q < V; ++q) {
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+            p.v[q].x += __shfl_xor_sync(0xffffffffu, p.v[q].x, o);
+            p.v[q].y += __shfl_xor_sync(0xffffffffu, p.v[q].y, o);
+            p.v[q].z += __shfl_xor_sync(0xffffffffu, p.v[q].z, o);
+            p.v[q].w += __shfl_xor_sync(0xffffffffu, p.v[q].w, o);
+        }
     }
     return p;
 }
 
 constexpr int kWarpsPerBlock = SPMM_WPB;
 
-template <int LPR, int EPI, bool MASKED = false>
+template <int LPR, int V, int EPI, bool MASKED = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, SPMM_MINB)
 spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_blocks, int gather) {
     constexpr int RPW = 32 / LPR;
@@ -219,16 +278,19 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
         if (item >= a.n_items) return;
         const int slot = __ldg(a.item_slot + item);
         const int64_t b = __ldg(a.item_begin + item), e = __ldg(a.item_end + item);
-        float4 p;
+        Slice<V> p;
         if (per_sub) {
-            p = gather_rows<LPR, MASKED>(a.col, a.val, x4, b, e, 0, 1, sl, mask, ep.src_nz);
+            p = gather_rows<LPR, V, MASKED>(a.col, a.val, x4, b, e, 0, 1, sl, mask, ep.src_nz);
         } else {
-            p = gather_rows<LPR, MASKED>(a.col, a.val, x4, b, e, sub, RPW, sl, mask, ep.src_nz);
-            p = combine_subs<LPR>(p);
+            p = gather_rows<LPR, V, MASKED>(a.col, a.val, x4, b, e, sub, RPW, sl, mask, ep.src_nz);
+            p = combine_subs<LPR, V>(p);
         }
         const bool writer = per_sub || sub == 0;
-        float4* scr = reinterpret_cast<float4*>(a.long_scratch) + (int64_t)slot * LPR + sl;
-        if (writer) red_add4(scr, p);
+        float4* scr = reinterpret_cast<float4*>(a.long_scratch) + (int64_t)slot * (LPR * V) + sl;
+        if (writer) {
+#pragma unroll
+            for (int q = 0; q < V; ++q) red_add4(scr + q * LPR, p.v[q]);
+        }
         __threadfence();
         __syncwarp(per_sub ? mask : 0xffffffffu);
         const int64_t r = __ldg(a.long_rows + slot);
@@ -250,10 +312,14 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
         if (ticket != nchunks - 1) return;
         __threadfence();
         if (writer) {  // last piece: complete row sits in the scratch row; run the fused epilogue, leave it zeroed
-            const float4 tot = __ldcg(scr);
-            __stcg(scr, make_float4(0.f, 0.f, 0.f, 0.f));
+            Slice<V> tot;
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                tot.v[q] = __ldcg(scr + q * LPR);
+                __stcg(scr + q * LPR, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
             if (sl == 0) a.long_counter[slot] = 0;
-            epilogue<LPR, EPI>(ep, r + a.row_offset, tot, sl, mask);
+            epilogue<LPR, V, EPI>(ep, r + a.row_offset, tot, sl, mask);
         }
         return;
     }
@@ -272,7 +338,7 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
     const bool is_long = gather && (e - s) > long_thr;
     if (is_long || !gather) e = s;  // long rows are produced by the chunk blocks above
 
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    Slice<V> acc = zero_slice<V>();
     if (gather) {
         bool side_by_side = true;
         if (RPW > 1) {
@@ -287,20 +353,25 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
             side_by_side = par <= seq;
         }
         if (side_by_side) {
-            acc = gather_rows<LPR, MASKED>(a.col, a.val, x4, s, e, 0, 1, sl, mask, ep.src_nz);
+            acc = gather_rows<LPR, V, MASKED>(a.col, a.val, x4, s, e, 0, 1, sl, mask, ep.src_nz);
         } else {
 #pragma unroll
             for (int i = 0; i < RPW; ++i) {
                 const int64_t si = __shfl_sync(0xffffffffu, s, i * LPR);
                 const int64_t ei = __shfl_sync(0xffffffffu, e, i * LPR);
-                float4 p = gather_rows<LPR, MASKED>(a.col, a.val, x4, si, ei, sub, RPW, sl, mask, ep.src_nz);
-                p = combine_subs<LPR>(p);
+                Slice<V> p = gather_rows<LPR, V, MASKED>(a.col, a.val, x4, si, ei, sub, RPW, sl, mask, ep.src_nz);
+                p = combine_subs<LPR, V>(p);
                 if (sub == i) acc = p;
             }
         }
     }
-    if (valid && !is_long) epilogue<LPR, EPI>(ep, r + a.row_offset, acc, sl, mask);
+    if (valid && !is_long) epilogue<LPR, V, EPI>(ep, r + a.row_offset, acc, sl, mask);
 }
+
+// dim 64: lanes per row.  16 = one float4 per lane (round 1); 8 = two float4 per lane, four rows per warp.
+#ifndef SPMM_LANES64
+#define SPMM_LANES64 16
+#endif
 
 template <int EPI>
 static int launch(const tagrec_csr_t* a, const float* x, const Epi& ep, int dim, int gather, void* stream) {
@@ -312,7 +383,7 @@ static int launch(const tagrec_csr_t* a, const float* x, const Epi& ep, int dim,
     if (n_items > 0)
         TAGREC_REQUIRE(a->long_rows && a->item_slot && a->item_begin && a->item_end && a->long_scratch &&
                            a->long_counter, "long-row plan arrays missing");
-    const int lpr = dim / 4, rpw = 32 / lpr;
+    const int lpr = dim == 64 ? SPMM_LANES64 : dim / 4, rpw = 32 / lpr;
     const int64_t chunks_per_block = (int64_t)kWarpsPerBlock * ((a->chunk_lanes != 0 && rpw > 1) ? rpw : 1);
     const int64_t long_blocks = (n_items + chunks_per_block - 1) / chunks_per_block;
     const int64_t row_blocks = (a->n_rows + (int64_t)rpw * kWarpsPerBlock - 1) / ((int64_t)rpw * kWarpsPerBlock);
@@ -325,14 +396,16 @@ static int launch(const tagrec_csr_t* a, const float* x, const Epi& ep, int dim,
     if (d.blocked_min_deg <= 0) d.blocked_row_begin = INT64_MAX;
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const dim3 block(kWarpsPerBlock * 32);
-    if (lpr == 16 && ep.src_nz && gather && (EPI == EPI_BWD || EPI == EPI_BWD0)) {
-        TAGREC_LAUNCH((spmm_kernel<16, EPI, true>), (unsigned)grid, block, 0, stream, d, x4, ep, (int)long_blocks, gather);
-    } else if (lpr == 16) {
-        TAGREC_LAUNCH((spmm_kernel<16, EPI>), (unsigned)grid, block, 0, stream, d, x4, ep, (int)long_blocks, gather);
-    } else if (lpr == 8) {
-        TAGREC_LAUNCH((spmm_kernel<8, EPI>), (unsigned)grid, block, 0, stream, d, x4, ep, (int)long_blocks, gather);
+    constexpr int L64 = SPMM_LANES64, V64 = 16 / SPMM_LANES64;
+    static_assert(L64 == 16 || L64 == 8, "SPMM_LANES64 must be 16 or 8");
+    if (dim == 64 && ep.src_nz && gather && (EPI == EPI_BWD || EPI == EPI_BWD0)) {
+        TAGREC_LAUNCH((spmm_kernel<L64, V64, EPI, true>), (unsigned)grid, block, 0, stream, d, x4, ep, (int)long_blocks, gather);
+    } else if (dim == 64) {
+        TAGREC_LAUNCH((spmm_kernel<L64, V64, EPI>), (unsigned)grid, block, 0, stream, d, x4, ep, (int)long_blocks, gather);
+    } else if (dim == 32) {
+        TAGREC_LAUNCH((spmm_kernel<8, 1, EPI>), (unsigned)grid, block, 0, stream, d, x4, ep, (int)long_blocks, gather);
     } else {
-        TAGREC_LAUNCH((spmm_kernel<32, EPI>), (unsigned)grid, block, 0, stream, d, x4, ep, (int)long_blocks, gather);
+        TAGREC_LAUNCH((spmm_kernel<32, 1, EPI>), (unsigned)grid, block, 0, stream, d, x4, ep, (int)long_blocks, gather);
     }
     return TAGREC_OK;
 }
