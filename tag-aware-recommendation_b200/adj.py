@@ -78,7 +78,7 @@ class CsrGraph:
         begin = min(max(n_user - self.row_offset, 0), self.n_rows)
         if begin >= self.n_rows:
             return None
-        window = int(float(os.environ.get("TAGREC_COLBLOCK_MB", "48")) * (1 << 20)) // 256
+        window = int(float(os.environ.get("TAGREC_COLBLOCK_MB", "96")) * (1 << 20)) // 256
         min_deg = int(os.environ.get("TAGREC_COLBLOCK_MIN_DEG", "384"))
         return begin, min_deg, max(window, 64)
 

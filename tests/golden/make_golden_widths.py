@@ -46,6 +46,26 @@ def run(d, name, cls, tag, extra):
     out[f"{tag}_pred_users"] = users.numpy()
     with torch.no_grad():
         out[f"{tag}_pred"] = m.predict_rating(users).numpy().copy()
+    # float64 truth: the same reference class, same parameters and batch, run in double.  The weight / bias gradients
+    # are float32 sums over every node on both sides; the parity bar for them is stated against this truth.
+    torch.set_default_dtype(torch.float64)
+    try:
+        import copy
+        m64 = copy.deepcopy(m).double()
+        if hasattr(m64, "norm_adj") and torch.is_tensor(m64.norm_adj):
+            m64.norm_adj = m64.norm_adj.double()
+        m64.zero_grad()
+        m64.train()
+        lossx = m64.loss(torch.tensor(batch, dtype=torch.long))
+        out[f"{tag}_loss64"] = np.array([x.item() for x in lossx], dtype=np.float64)
+        sum(lossx).backward()
+        for k, p in m64.named_parameters():
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            out[f"{tag}_grad64_{k}"] = g.detach().numpy().copy()
+            e = np.abs(out[f"{tag}_grad_{k}"].astype(np.float64) - out[f"{tag}_grad64_{k}"]).max()
+            print(f"{tag} {k}: max|g| {np.abs(out[f'{tag}_grad64_{k}']).max():.3e}  reference fp32 vs fp64 {e / max(np.abs(out[f'{tag}_grad64_{k}']).max(), 1e-300):.2e}")
+    finally:
+        torch.set_default_dtype(torch.float32)
     return out
 
 

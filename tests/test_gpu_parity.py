@@ -789,6 +789,9 @@ def _kgat_model(tiny, g, tag, agg_type, edges_e2):
     U, I, Tg, W = nums(tiny)
     d.ut_adj = sp.coo_matrix((np.ones(len(uit)), (uit[:, 0], uit[:, 2])), dtype=np.float32, shape=(U, Tg))
     d.it_adj = sp.coo_matrix((np.ones(len(uit)), (uit[:, 1], uit[:, 2])), dtype=np.float32, shape=(I, Tg))
+    # the golden generator's ui_adj is in canonical (row, col) order: make_golden.make_dataset calls ui_adj.max(), which
+    # sum_duplicates()-sorts a scipy COO matrix in place; create_edge (and so the TransE batch stream) follows that order
+    d.ui_adj.sum_duplicates()
     stock = lambda: T.data.create_edge(d)                                         # noqa: E731
     d.create_edge = (lambda: {k: np.ascontiguousarray(v.T) for k, v in stock().items()}) if edges_e2 else stock
     model = T.KGAT(d).to(dev())
@@ -908,8 +911,17 @@ def test_default_layer_widths_vs_reference(tiny, tiny_widths, name, tmp_path):
     for n, p in model.named_parameters():
         want = g[f"{tag}_grad_{n}"]
         got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(want)
-        # tensors whose whole gradient is below 1e-7 of the model's largest gradient entry are float32 noise on both sides
-        assert relerr(got, want) < 2 * TOL or float(np.abs(got - want).max()) < 1e-7 * gmax, (n, relerr(got, want))
+        # The bar is the float64 run of the same reference model (make_golden_widths.py): bias / weight gradients are
+        # float32 sums over every node on both sides, and the reference's own float32 result is 1e-5 .. 5e-4 away from
+        # that truth for them (two runs of the reference differ by as much).  This path must sit within 1e-5 of the band
+        # the reference itself occupies: e_mine <= max(1e-5 + e_ref, 2 e_ref).  Tensors whose whole gradient is below
+        # 1e-7 of the model's largest gradient entry are float32 noise on both sides.
+        truth = g[f"{tag}_grad64_{n}"]
+        scale = float(np.abs(truth).max())
+        e_ref = float(np.abs(want.astype(np.float64) - truth).max() / scale) if scale > 0 else 0.0
+        e_mine = float(np.abs(got.astype(np.float64) - truth).max() / scale) if scale > 0 else float(np.abs(got).max())
+        ok = e_mine <= max(TOL + e_ref, 2.0 * e_ref) or float(np.abs(got - truth).max()) < 1e-7 * gmax
+        assert ok, (n, "vs float64", e_mine, "reference's own float32 error", e_ref)
     model.eval()
     with torch.no_grad():
         r = model.predict_rating(torch.tensor(g[f"{tag}_pred_users"], device=dev()))
