@@ -33,24 +33,6 @@
 namespace tagrec {
 
 
-struct TcArgs {
-    const int64_t* users;
-    int64_t nu;
-    const float* user_table;
-    const float* item_table;
-    int64_t n_item;
-    const int64_t* train_ptr;
-    const int32_t* train_items;
-    const float* item_maxnorm;   // device scalar: max_i ||I_i||_2
-    float* shared_thr;           // [nu] or NULL: per-user lower bound of the final K-th best score, shared by the item
-                                 // splits of that user (max over splits of their own exact K-th best)
-    int k;
-    int splits;
-    int stages;
-    int64_t items_per_split;     // multiple of TC_N
-    float* part_scores;          // [nu, splits, k]  raw exact dot products, -inf when absent
-    int32_t* part_ids;           // [nu, splits, k]  -1 when absent
-};
 
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -732,6 +714,15 @@ static size_t tc_smem_wide(int stages, int k) {
     return 1024 + (size_t)stages * TC_TILE_BYTES + (size_t)2 * k * TC_M * 4 + 256;
 }
 
+// TAGREC_EVAL_CG2=0 keeps the single-CTA kernel for every shape (A/B timing); =force runs the pair kernel for every
+// 64-d shape its shared-memory budget allows (tests: partial tiles, tiny tables, many splits).
+static int cg2_mode() {
+    const char* e = getenv("TAGREC_EVAL_CG2");
+    if (e && e[0] == '0') return 0;
+    if (e && e[0] == 'f') return 2;
+    return 1;
+}
+
 TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
     TcPlan p{};
     p.ok = false;
@@ -761,6 +752,30 @@ TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
             if (p.nh == 1) return p;
         }
         p.smem = tc_smem(p.nh, p.stages, k);
+        // CTA pairs (eval_tc2_kernel): whenever two 128-user halves per CTA would be used and the K-lists leave room for
+        // at least 3 stages of the pair kernel's ring.
+        const int mode = cg2_mode();
+        if ((p.nh == 2 && mode == 1) || mode == 2) {
+            int st = TC_MAX_STAGES;
+            while (st >= 3 && tc2_smem(st, k) > budget) --st;
+            if (st >= 3 && (item_tiles >= 16 || mode == 2)) {
+                p.cg2 = 1;
+                p.stages = st;
+                p.smem = tc2_smem(st, k);
+            }
+        }
+    }
+    if (p.cg2) {
+        const int64_t pairs = (nu + 2 * TC_M - 1) / (2 * TC_M);
+        const int64_t tiles256 = (n_item + 255) / 256;
+        int64_t best_s = std::max<int64_t>(1, (kSMs / 2) / pairs);
+        best_s = std::min<int64_t>(best_s, std::max<int64_t>(1, std::min<int64_t>(TC_MAX_SPLITS / 2, tiles256 / 8)));
+        p.splits = (int)best_s;
+        p.items_per_split = ((tiles256 + p.splits - 1) / p.splits) * 256;
+        p.splits = (int)((n_item + p.items_per_split - 1) / p.items_per_split);
+        p.lists = 2 * p.splits;
+        p.ok = true;
+        return p;
     }
     const int64_t user_tiles = (nu + TC_M * p.nh - 1) / (TC_M * p.nh);
     int64_t best_s = user_tiles >= kSMs ? 1 : kSMs / user_tiles;
@@ -768,6 +783,7 @@ TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
     p.splits = (int)best_s;
     p.items_per_split = ((item_tiles + p.splits - 1) / p.splits) * TC_N;
     p.splits = (int)((n_item + p.items_per_split - 1) / p.items_per_split);
+    p.lists = p.splits;
     p.ok = true;
     return p;
 }
@@ -811,15 +827,17 @@ int eval_topk_tc(const int64_t* users, int64_t nu, const float* user_table, cons
     float* maxnorm = reinterpret_cast<float*>(workspace);
     a.item_maxnorm = maxnorm;
     a.part_scores = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
-    a.part_ids = reinterpret_cast<int32_t*>(a.part_scores + (size_t)nu * p.splits * k);
+    a.part_ids = reinterpret_cast<int32_t*>(a.part_scores + (size_t)nu * p.lists * k);
     // (the max over splits of their own K-th best is no tighter than one's own bound when two splits advance in
     // lockstep; it pays with many short splits, where late starters inherit the early ones' bounds)
-    a.shared_thr = p.splits > 2 ? reinterpret_cast<float*>(a.part_ids + (size_t)nu * p.splits * k) : nullptr;
+    a.shared_thr = p.lists > 2 ? reinterpret_cast<float*>(a.part_ids + (size_t)nu * p.lists * k) : nullptr;
     if (a.shared_thr)
         TAGREC_LAUNCH(fill_f32_kernel, (unsigned)((nu + 255) / 256), 256, 0, stream, a.shared_thr, nu, -INFINITY);
     if (int rc = launch_item_maxnorm(item_table, n_item, dim, maxnorm, stream)) return rc;
     const dim3 grid((unsigned)((nu + TC_M * p.nh - 1) / (TC_M * p.nh)), (unsigned)p.splits);
-    if (p.kb > 1) {
+    if (p.cg2) {
+        if (int rc = launch_eval_tc2(&map, a, p.smem, stream)) return rc;
+    } else if (p.kb > 1) {
         TAGREC_CUDA(cudaFuncSetAttribute(eval_tc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
         TAGREC_LAUNCH(eval_tc_wide_kernel, grid, 64 + 128, p.smem, stream, map, a, p.kb);
     } else if (p.nh == 2) {
@@ -830,12 +848,12 @@ int eval_topk_tc(const int64_t* users, int64_t nu, const float* user_table, cons
         TAGREC_LAUNCH(eval_tc_kernel<1>, grid, 64 + 128, p.smem, stream, map, a);
     }
     TAGREC_LAUNCH(eval_tc_merge_kernel, (unsigned)((nu + 7) / 8), 256, 0, stream, a.part_scores, a.part_ids, users, nu,
-                  p.splits, k, train_ptr, train_items, topk_ids, topk_scores);
+                  p.lists, k, train_ptr, train_items, topk_ids, topk_scores);
     return TAGREC_OK;
 }
 
 size_t eval_tc_workspace_bytes(int64_t nu, const TcPlan& p, int k) {
-    return 256 + (size_t)nu * p.splits * k * 8 + (size_t)nu * 4;
+    return 256 + (size_t)nu * p.lists * k * 8 + (size_t)nu * 4;
 }
 
 }  // namespace tagrec

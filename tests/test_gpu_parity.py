@@ -386,12 +386,16 @@ def _random_eval_case(nu, n_item, k, seed, scale=1.0, heavy=False, n_tables=None
 
 @pytest.mark.parametrize("nu,n_item,k,scale,heavy", [
     (1, 50, 20, 1.0, False), (64, 129, 5, 1.0, False), (130, 5000, 20, 1.0, True), (300, 40000, 20, 0.1, True),
-    (129, 1025, 64, 1.0, False), (257, 3000, 100, 1.0, False), (700, 20000, 10, 3.0, False)])
-def test_k3_tensor_core_path_equals_fp32_path(nu, n_item, k, scale, heavy):
-    """tcgen05 TF32 filter + exact fp32 re-score (csrc/eval_tc.cu) returns the SAME ids and scores as the exact
-    fp32 CUDA-core path — bit-exact, including item-id tie-breaks, partial tiles, several item splits, users with
-    very long train rows and both CTA shapes (1 / 2 user halves)."""
+    (129, 1025, 64, 1.0, False), (257, 3000, 100, 1.0, False), (700, 20000, 10, 3.0, False),
+    (1500, 70000, 20, 0.3, True), (2100, 16000, 32, 1.0, False)])
+@pytest.mark.parametrize("cg2", ["0", "auto", "force"])
+def test_k3_tensor_core_path_equals_fp32_path(nu, n_item, k, scale, heavy, cg2, monkeypatch):
+    """tcgen05 TF32 filter + exact fp32 re-score (csrc/eval_tc.cu, eval_tc2.cu) returns the SAME ids and scores as the
+    exact fp32 CUDA-core path — bit-exact, including item-id tie-breaks, partial tiles, several item splits, users with
+    very long train rows, both single-CTA shapes (1 / 2 user halves) and the CTA-pair kernel (cta_group::2 M256 x N256;
+    "force" runs it on every shape whose K-lists fit its shared memory, "0" never)."""
     from tagrec_b200.eval_ops import topk_scores
+    monkeypatch.setenv("TAGREC_EVAL_CG2", cg2)
     users, ut, it, ptr_, items = _random_eval_case(nu, n_item, k, 1000 + nu + n_item, scale, heavy)
     ids_a, sc_a = topk_scores(users, ut, it, ptr_, items, k, path="fp32")
     ids_b, sc_b = topk_scores(users, ut, it, ptr_, items, k, path="tf32")
@@ -424,9 +428,11 @@ def test_k3_tensor_core_wide_tables_equal_fp32_path(nu, n_item, dim, k):
     assert torch.equal(sc_a, sc_b)
 
 
-def test_k3_tensor_core_ties_and_masked_tail():
+@pytest.mark.parametrize("cg2", ["0", "force"])
+def test_k3_tensor_core_ties_and_masked_tail(cg2, monkeypatch):
     """Duplicate item rows (exact score ties -> lower id first) and a user with fewer than k un-masked items."""
     from tagrec_b200.eval_ops import topk_scores
+    monkeypatch.setenv("TAGREC_EVAL_CG2", cg2)
     I = 1000
     g = torch.Generator().manual_seed(5)
     it = torch.randn(I, 64, generator=g) * 0.1

@@ -22,7 +22,7 @@ def main():
         agg[k][0] += 1
         agg[k][1] += us
         tot += us
-    own = sum(t for k, (c, t) in agg.items() if k.startswith("tagrec::"))
+    own = sum(t for k, (c, t) in agg.items() if "tagrec::" in k)
     print(f"{sum(c for c, _ in agg.values()) / steps:.0f} launches / step, {tot / steps / 1000:.2f} ms kernel time / step, "
           f"tagrec:: share {100 * own / tot:.0f} %")
     print("| kernel | launches / step | µs / step | share |\n|---|---:|---:|---:|")

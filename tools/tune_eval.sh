@@ -12,7 +12,7 @@
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p build/variants
-SRC="api.cu spmm.cu bpr.cu csr_build.cu eval_topk.cu eval_tc.cu eval_auc.cu eval_auc_tc.cu ngcf_dense.cu routing.cu nbr_attention.cu tgcn_tail.cu tgcn_tail_tc.cu tgcn_mix.cu xty.cu sampler.cu adam.cu"
+SRC="api.cu spmm.cu bpr.cu csr_build.cu eval_topk.cu eval_tc.cu eval_tc2.cu eval_auc.cu eval_auc_tc.cu ngcf_dense.cu routing.cu nbr_attention.cu tgcn_tail.cu tgcn_tail_tc.cu tgcn_mix.cu xty.cu sampler.cu adam.cu"
 rm -rf build/variants/csrc && cp -r tag-aware-recommendation_b200/csrc build/variants/csrc
 mkdir -p build/variants/include && cp include/tagrec_b200.h build/variants/include/
 sed -i 's#../../include/tagrec_b200.h#../include/tagrec_b200.h#' build/variants/csrc/common.cuh
