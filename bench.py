@@ -689,6 +689,14 @@ def run_scale(args):
                 # only), G_{L-2} (batch rows + neighbours), ..., dE0 (dense source); zero source rows are skipped
                 "bwd_launch_ms": [round(x.elapsed_time(y), 3) for x, y in timer.pairs.get("spmm_bwd", [])[-LAYERS:]],
                 "adam_ms": timer.mean_ms("adam")}
+    if traffic:
+        # `achieved` counts ALGORITHMIC bytes (every gathered 256-byte row, SURVEY §8 d); with the column-blocked plan most
+        # of the item-row half's gathers are served by L2, so it exceeds the DRAM peak.  The DRAM-side figure, from the
+        # ncu-measured bytes of the same launch (profiles/spmm_traffic.json) and the live launch time:
+        roofline["dram_achieved"] = traffic / (fwd_ms * 1e-3) / 1e9
+        roofline["dram_frac"] = roofline["dram_achieved"] / peak
+        roofline["note"] = ("frac > 1: algorithmic bytes / time against the DRAM copy peak; the launch moves `traffic` DRAM bytes "
+                            "(ncu), i.e. dram_frac of the peak; ncu: 69 % of stalls long-scoreboard, no unit saturated")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "check": check, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_of(args.workload),
@@ -836,6 +844,8 @@ def eval_leg(T, model, shape, dev, n_users):
                "mean_auc": _finite(float(auc["tf32"][1][0] / max(auc["tf32"][1][1], 1.0))),
                "kernel": "auc_tc_kernel (3xTF32 tcgen05.mma + exact band, canonical fp32 re-scores)",
                "fp32_cuda_core_path_ms": auc["fp32"][0], "sums_identical": auc_same}
+    from tagrec_b200.eval_ops import eval_plan
+    plan = eval_plan(n_users, shape["n_item"], DIM, 20)
     tf32_peak = 1100.0      # nominal dense TF32 TFLOP/s (B200_PROFILING.md); MEASURED_PEAKS.json only has bf16
     measured_tf32 = measure_tf32_peak(dev)
     return {"users_per_s": out["tf32"]["users_per_s"], "users": n_users, "items": shape["n_item"], "k": 20,
@@ -843,7 +853,9 @@ def eval_leg(T, model, shape, dev, n_users):
             "tensor_frac_of_nominal_tf32": out["tf32"]["tflops"] / tf32_peak,
             "tf32_peak_measured_tflops": measured_tf32,
             "tensor_frac_of_measured_tf32": out["tf32"]["tflops"] / measured_tf32 if measured_tf32 else None,
-            "kernel": "eval_tc_kernel (tcgen05.mma kind::tf32 filter + exact fp32 re-score)",
+            "kernel": ("eval_tc2_kernel (CTA pairs: tcgen05.mma.cta_group::2 M256xN256xK8 kind::tf32 filter + exact fp32 re-score)"
+                       if plan["cta_pairs"] else "eval_tc_kernel (tcgen05.mma kind::tf32 filter + exact fp32 re-score)"),
+            "plan": plan,
             "fp32_cuda_core_path": out["fp32"], "paths_identical": same, "auc": auc_out}
 
 

@@ -227,7 +227,8 @@ size_t tagrec_eval_workspace_bytes(int64_t nu, int64_t n_item, int k);
  *   TAGREC_EVAL_FP32  CUDA-core fp32 tiles (any dim % 32 == 0);
  *   TAGREC_EVAL_TF32  dim in {64, 128, 192, 256}: tcgen05.mma kind::tf32 (accumulators and user rows in TMEM, item
  *                     tiles by TMA) as a filter with a proven error margin, every candidate re-scored in exact fp32
- *                     (csrc/eval_tc.cu);
+ *                     (csrc/eval_tc.cu); 64-d tables with >= 256-user batches run on CTA pairs (tcgen05.mma
+ *                     cta_group::2, M256 x N256 x K8; csrc/eval_tc2.cu);
  *   TAGREC_EVAL_AUTO  TF32 when the dim allows it, else FP32 (what tagrec_eval_topk does). */
 #define TAGREC_EVAL_AUTO 0
 #define TAGREC_EVAL_FP32 1
@@ -236,6 +237,10 @@ int tagrec_eval_topk_ex(const int64_t* users, int64_t nu, const float* user_tabl
                         int64_t n_item, int dim, const int64_t* train_ptr, const int32_t* train_items, int k,
                         int32_t* topk_ids, float* topk_scores, void* workspace, size_t workspace_bytes, int path,
                         void* stream);
+/* The launch shape tagrec_eval_topk[_ex] would use for the tensor-core path (reporting / tests; no GPU needed):
+ * plan[0] = 1 if the shape runs on tensor cores, [1] = 1 for the CTA-pair kernel (cta_group::2), [2] = 128-user halves
+ * per CTA, [3] = item splits, [4] = TMA stages, [5] = K-lists per user handed to the merge kernel. */
+int tagrec_eval_plan(int64_t nu, int64_t n_item, int dim, int k, int32_t* plan);
 
 /* Per-user AUC (training/utils.py:37-45 roc_auc_score over the un-masked items of one user, basic_test.py:52-53),
  * summed over `users`: out[0] += sum of AUC_u, out[1] += number of users that have both classes (the reference raises

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "tagrec_bpr_fwd_bwd": (_i32, [_p, _i64, _i64, _p, _p, _i32, _f32, _i32, _p, _p, _p, _p]),
     "tagrec_eval_topk": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "tagrec_eval_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "tagrec_eval_plan": (_i32, [_i64, _i64, _i32, _i32, _p]),
     "tagrec_eval_topk_ex": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _sz, _i32, _p]),
     "tagrec_eval_auc_workspace_bytes": (_sz, [_i64, _i64]),
     "tagrec_eval_auc": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _sz, _p, _p]),

@@ -331,6 +331,18 @@ extern "C" size_t tagrec_eval_workspace_bytes(int64_t nu, int64_t n_item, int k)
     return need;
 }
 
+extern "C" int tagrec_eval_plan(int64_t nu, int64_t n_item, int dim, int k, int32_t* plan) {
+    TAGREC_REQUIRE(plan, "plan is null");
+    const TcPlan p = tc_plan(nu, n_item, dim, k);
+    plan[0] = p.ok ? 1 : 0;
+    plan[1] = p.ok ? p.cg2 : 0;
+    plan[2] = p.ok ? p.nh : 0;
+    plan[3] = p.ok ? p.splits : 0;
+    plan[4] = p.ok ? p.stages : 0;
+    plan[5] = p.ok ? p.lists : 0;
+    return TAGREC_OK;
+}
+
 extern "C" int tagrec_eval_topk(const int64_t* users, int64_t nu, const float* user_table, const float* item_table,
                                 int64_t n_item, int dim, const int64_t* train_ptr, const int32_t* train_items, int k,
                                 int32_t* topk_ids, float* topk_scores, void* workspace, size_t workspace_bytes,

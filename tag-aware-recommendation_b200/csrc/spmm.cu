@@ -75,6 +75,10 @@ __device__ __forceinline__ Slice<V> zero_slice() {
 }
 
 // acc = sum_{j in [begin,end), chunk(j) == part (mod nparts)} val[j] * x[col[j]]   for this lane's slice.
+// The gathers go out SPMM_U at a time and are then consumed in order.  A software-pipelined form (groups of 4, the next
+// group's loads in flight while one is accumulated) was measured on the column-blocked 1 B-edge launch, where 69 % of the
+// stalls are long-scoreboard: 76 ms per layer instead of 50 (fewer loads in flight, spills at the 64-register cap);
+// not kept (profiles/r2_spmm_1b_ncu.md).
 template <int LPR, int V, bool MASKED = false>
 __device__ __forceinline__ Slice<V> gather_rows(const int32_t* __restrict__ col, const float* __restrict__ val,
                                                 const float4* __restrict__ x4, int64_t begin, int64_t end, int part,

@@ -26,6 +26,16 @@ def topk_scores(users, user_table, item_table, train_ptr, train_items, k, path="
     return ids, scores
 
 
+def eval_plan(nu, n_item, dim, k):
+    """Launch shape of the tensor-core top-K path for this problem size (host only): dict with tensor_core, cta_pairs
+    (eval_tc2_kernel, tcgen05.mma.cta_group::2), halves, splits, stages, lists."""
+    import ctypes as C
+    plan = (C.c_int32 * 6)()
+    check(lib().tagrec_eval_plan(int(nu), int(n_item), int(dim), int(k), plan), "tagrec_eval_plan")
+    keys = ("tensor_core", "cta_pairs", "halves", "splits", "stages", "lists")
+    return {k_: int(v) for k_, v in zip(keys, plan)}
+
+
 def metric_sums(users, topk_ids, test_ptr, test_items, ks, out=None):
     """training/utils.py:15-35 summed over ``users``: returns float64 [4, len(ks)] = recall|precision|hr|ndcg."""
     dev = topk_ids.device

@@ -207,3 +207,21 @@ def test_neighbour_tables_bit_exact_vs_reference(tiny, tiny_tgcn):
         assert np.array_equal(ids, tiny_tgcn[f"tgcn_nbr_{name}"]), name
         assert np.array_equal(w, tiny_tgcn[f"tgcn_nbw_{name}"]), name
     assert np.array_equal(before, np.random.get_state()[1])
+
+
+def test_eval_plan_picks_the_pair_kernel(monkeypatch):
+    """tagrec_eval_plan (host only): the benchmark shape of the evaluation leg runs on CTA pairs (eval_tc2_kernel,
+    tcgen05.mma.cta_group::2 M256 x N256), small user batches and wide tables on the single-CTA kernels, K-lists too
+    large for the pair kernel's shared memory fall back; TAGREC_EVAL_CG2=0 switches the pair kernel off."""
+    from tagrec_b200.eval_ops import eval_plan
+    monkeypatch.delenv("TAGREC_EVAL_CG2", raising=False)
+    p = eval_plan(16384, 2_000_000, 64, 20)
+    assert p["tensor_core"] == 1 and p["cta_pairs"] == 1 and p["lists"] == 2 * p["splits"] and p["stages"] >= 3
+    assert eval_plan(512, 2_000_000, 64, 20)["cta_pairs"] == 0           # few users: one 128-user half per CTA, many splits
+    assert eval_plan(16384, 500_000, 256, 20)["cta_pairs"] == 0          # wide tables: eval_tc_wide_kernel
+    assert eval_plan(16384, 2_000_000, 64, 100)["cta_pairs"] == 0        # 2 x 100 x 256 list entries do not fit beside the stages
+    assert eval_plan(16384, 2_000_000, 48, 20)["tensor_core"] == 0       # fp32 tiles
+    monkeypatch.setenv("TAGREC_EVAL_CG2", "0")
+    assert eval_plan(16384, 2_000_000, 64, 20)["cta_pairs"] == 0
+    monkeypatch.setenv("TAGREC_EVAL_CG2", "force")
+    assert eval_plan(130, 5000, 64, 20)["cta_pairs"] == 1
