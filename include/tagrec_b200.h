@@ -37,7 +37,7 @@ const char* tagrec_last_error(void);
 uint64_t tagrec_launch_count(void);
 /* sizeof() of the descriptor structs below as THIS library was compiled: a binding (ctypes / cffi / cgo ...) asserts
  * its own struct layout against these before the first call, so a stale declaration fails at load time instead of
- * reading past a short struct.  which: 0 = tagrec_csr_t, 1 = tagrec_mirror_t, 2 = tagrec_route_plan_t; other -> 0. */
+ * reading past a short struct.  which: 0 = tagrec_csr_t, 1 = tagrec_mirror_t, 2 = tagrec_route_plan_t, 3 = tagrec_adam_t; other -> 0. */
 size_t tagrec_sizeof_struct(int which);
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -183,6 +183,26 @@ int tagrec_lightgcn_bwd_layer_p2p(const tagrec_csr_t* a, const float* g_next, co
 int tagrec_lightgcn_bwd_layer_ex(const tagrec_csr_t* a, const float* g_next, const uint8_t* g_next_nz, const float* e_k,
                                  const float* g_final, const float* reg_grad, const float* upstream, float inv_layers,
                                  float* g_out, int dim, const tagrec_mirror_t* out_mirror, void* stream);
+/* The LAST backward launch of a step with the optimizer folded into its epilogue (owner-sharded Adam, multi-GPU; also
+ * valid on one GPU): the launch produces rows of dL/dE0 — the gradient of the embedding table itself — and each row is
+ * consumed where it is produced: exp_avg / exp_avg_sq / param rows are updated with the same arithmetic as
+ * tagrec_adam_step (torch.optim.Adam, amsgrad = False) and the NEW parameter row is stored through param_mirror into
+ * every rank's replica, so the 3 GB parameter exchange of a step rides under the gathers of this launch instead of
+ * following it (measured at 8 GPUs: 4.2 ms per step for the separate tagrec_adam_step_mirror pass, NVLink-ingest bound).
+ * param / exp_avg / exp_avg_sq are FULL-size [n, dim] tables indexed by global row; g_out (optional, may be NULL)
+ * still receives the gradient rows locally.  Nothing in this launch reads `param` besides the row being updated. */
+typedef struct tagrec_adam_t {
+    float* param;
+    float* exp_avg;
+    float* exp_avg_sq;
+    float lr, beta1, beta2, eps, weight_decay;
+    int32_t reserved;
+    int64_t step;                   /* the step being taken, counts from 1 (bias corrections) */
+    tagrec_mirror_t param_mirror;   /* n == 0: local table only */
+} tagrec_adam_t;
+int tagrec_lightgcn_bwd_layer_adam(const tagrec_csr_t* a, const float* g_next, const uint8_t* g_next_nz,
+                                   const float* g_final, const float* reg_grad, const float* upstream,
+                                   float inv_layers, float* g_out, int dim, const tagrec_adam_t* adam, void* stream);
 /* nz[r] = (row r of the [n, dim] table has a non-zero element). */
 int tagrec_row_nonzero(const float* table, int64_t n, int dim, uint8_t* nz, void* stream);
 

@@ -43,6 +43,13 @@ class MirrorDesc(C.Structure):
     _fields_ = [("n", C.c_int32), ("self", C.c_int32), ("base", _p * 8)]
 
 
+class AdamDesc(C.Structure):
+    """tagrec_adam_t"""
+    _fields_ = [("param", _p), ("exp_avg", _p), ("exp_avg_sq", _p), ("lr", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float), ("reserved", C.c_int32),
+                ("step", C.c_int64), ("param_mirror", MirrorDesc)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/tagrec_b200.h (tests/test_abi.py checks that)
 PROTOTYPES = {
     "tagrec_version": (_i32, []),
@@ -65,6 +72,7 @@ PROTOTYPES = {
                                              C.POINTER(MirrorDesc), _p]),
     "tagrec_lightgcn_bwd_layer_ex": (_i32, [C.POINTER(CsrDesc), _p, _p, _p, _p, _p, _p, _f32, _p, _i32,
                                             C.POINTER(MirrorDesc), _p]),
+    "tagrec_lightgcn_bwd_layer_adam": (_i32, [_p, _p, _p, _p, _p, _p, _f32, _p, _i32, _p, _p]),
     "tagrec_row_nonzero": (_i32, [_p, _i64, _i32, _p, _p]),
     "tagrec_bpr_fwd_bwd": (_i32, [_p, _i64, _i64, _p, _p, _i32, _f32, _i32, _p, _p, _p, _p]),
     "tagrec_eval_topk": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p]),
@@ -132,7 +140,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        for which, cls in enumerate((CsrDesc, MirrorDesc, RoutePlan)):
+        for which, cls in enumerate((CsrDesc, MirrorDesc, RoutePlan, AdamDesc)):
             want, got = int(handle.tagrec_sizeof_struct(which)), C.sizeof(cls)
             if want != got:
                 raise TagrecError(f"ctypes layout of {cls.__name__} is {got} bytes but {LIB_PATH} was compiled with "

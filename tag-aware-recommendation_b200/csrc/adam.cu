@@ -15,11 +15,7 @@ adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __rest
         inv_sqrt_bc2 = __ldg(scal + 1);
     }
     auto upd = [&](float& pp, float gg, float& mm, float& vv) {
-        if (wd != 0.f) gg = fmaf(wd, pp, gg);
-        mm = mm + (gg - mm) * (1.f - b1);
-        vv = b2 * vv + (1.f - b2) * gg * gg;
-        const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
-        pp = pp - step_size * (mm / denom);
+        adam_update(pp, gg, mm, vv, b1, b2, eps, wd, step_size, inv_sqrt_bc2);
     };
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {

@@ -14,6 +14,7 @@ extern "C" size_t tagrec_sizeof_struct(int which) {
         case 0: return sizeof(tagrec_csr_t);
         case 1: return sizeof(tagrec_mirror_t);
         case 2: return sizeof(tagrec_route_plan_t);
+        case 3: return sizeof(tagrec_adam_t);
         default: return 0;
     }
 }

@@ -112,6 +112,17 @@ __device__ __forceinline__ void store_row(float* local, const Mirror& m, int64_t
         if (p < m.n) reinterpret_cast<float4*>(m.base[p])[o] = v;
 }
 
+// One element of torch.optim.Adam's single-tensor update (amsgrad = False, maximize = False); shared by adam.cu and the
+// optimizer epilogue of K1's last backward launch so that both produce the same bits.
+__device__ __forceinline__ void adam_update(float& pp, float gg, float& mm, float& vv, float b1, float b2, float eps,
+                                            float wd, float step_size, float inv_sqrt_bc2) {
+    if (wd != 0.f) gg = fmaf(wd, pp, gg);
+    mm = mm + (gg - mm) * (1.f - b1);
+    vv = b2 * vv + (1.f - b2) * gg * gg;
+    const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+    pp = pp - step_size * (mm / denom);
+}
+
 inline int set_mirror(Mirror& m, const tagrec_mirror_t* src) {
     m.n = 0;
     if (!src || src->n == 0) return TAGREC_OK;

@@ -34,6 +34,12 @@ struct Epi {
     const uint8_t* src_nz;  // optional byte per SOURCE row: 0 = the row of x is all-zero, its gather is skipped
     float scale;            // plain: beta | fwd: final_scale | bwd: 1/(L+1)
     int first, last;
+    // bwd0 only, optional: the optimizer folded into the epilogue (tagrec_lightgcn_bwd_layer_adam)
+    float* adam_p;          // parameter table the output rows are the gradient of (NULL: plain gradient output)
+    float* adam_m;
+    float* adam_v;
+    Mirror mp;              // mirrors of adam_p
+    float b1, b2, eps, wd, step_size, inv_sqrt_bc2;
 };
 
 template <int LPR>
@@ -240,6 +246,22 @@ __device__ __forceinline__ void epilogue(const Epi& ep, int64_t r, Slice<V> acc,
                     out.y = fmaf(up1, rg.y, out.y);
                     out.z = fmaf(up1, rg.z, out.z);
                     out.w = fmaf(up1, rg.w, out.w);
+                }
+                if (ep.adam_p) {
+                    // the gradient row is consumed where it is produced: Adam on this row, new parameters to every rank
+                    const int64_t o = o0 + q * LPR;
+                    float4 pp = reinterpret_cast<const float4*>(ep.adam_p)[o];
+                    float4 mm = reinterpret_cast<const float4*>(ep.adam_m)[o];
+                    float4 vv = reinterpret_cast<const float4*>(ep.adam_v)[o];
+                    adam_update(pp.x, out.x, mm.x, vv.x, ep.b1, ep.b2, ep.eps, ep.wd, ep.step_size, ep.inv_sqrt_bc2);
+                    adam_update(pp.y, out.y, mm.y, vv.y, ep.b1, ep.b2, ep.eps, ep.wd, ep.step_size, ep.inv_sqrt_bc2);
+                    adam_update(pp.z, out.z, mm.z, vv.z, ep.b1, ep.b2, ep.eps, ep.wd, ep.step_size, ep.inv_sqrt_bc2);
+                    adam_update(pp.w, out.w, mm.w, vv.w, ep.b1, ep.b2, ep.eps, ep.wd, ep.step_size, ep.inv_sqrt_bc2);
+                    store_row(ep.adam_p, ep.mp, o, pp);
+                    reinterpret_cast<float4*>(ep.adam_m)[o] = mm;
+                    reinterpret_cast<float4*>(ep.adam_v)[o] = vv;
+                    if (ep.y) reinterpret_cast<float4*>(ep.y)[o] = out;
+                    continue;
                 }
                 store_row(ep.y, ep.my, o0 + q * LPR, out);
             }
@@ -479,6 +501,37 @@ extern "C" int tagrec_lightgcn_bwd_layer_ex(const tagrec_csr_t* a, const float* 
     const int gather = g_next != nullptr;
     if (e_k) return launch<EPI_BWD>(a, g_next, ep, dim, gather, stream);
     return launch<EPI_BWD0>(a, g_next, ep, dim, gather, stream);
+}
+
+extern "C" int tagrec_lightgcn_bwd_layer_adam(const tagrec_csr_t* a, const float* g_next, const uint8_t* g_next_nz,
+                                              const float* g_final, const float* reg_grad, const float* upstream,
+                                              float inv_layers, float* g_out, int dim, const tagrec_adam_t* adam,
+                                              void* stream) {
+    TAGREC_REQUIRE(g_final && adam, "g_final/adam is null");
+    TAGREC_REQUIRE(adam->param && adam->exp_avg && adam->exp_avg_sq, "adam: null table");
+    TAGREC_REQUIRE(adam->step >= 1, "adam: step counts from 1");
+    TAGREC_REQUIRE((((uintptr_t)adam->param | (uintptr_t)adam->exp_avg | (uintptr_t)adam->exp_avg_sq) & 15) == 0,
+                   "adam: tables must be 16-byte aligned");
+    Epi ep{};
+    if (int rc = set_mirror(ep.mp, &adam->param_mirror)) return rc;
+    ep.y = g_out;
+    ep.g_final = g_final;
+    ep.reg_grad = reg_grad;
+    ep.upstream = upstream;
+    ep.scale = inv_layers;
+    ep.src_nz = (g_next && dim == 64) ? g_next_nz : nullptr;
+    ep.adam_p = adam->param;
+    ep.adam_m = adam->exp_avg;
+    ep.adam_v = adam->exp_avg_sq;
+    ep.b1 = adam->beta1;
+    ep.b2 = adam->beta2;
+    ep.eps = adam->eps;
+    ep.wd = adam->weight_decay;
+    const double bc1 = 1.0 - pow((double)adam->beta1, (double)adam->step);      // same host arithmetic as tagrec_adam_step
+    const double bc2 = 1.0 - pow((double)adam->beta2, (double)adam->step);
+    ep.step_size = (float)((double)adam->lr / bc1);
+    ep.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    return launch<EPI_BWD0>(a, g_next, ep, dim, g_next != nullptr, stream);
 }
 
 namespace tagrec {

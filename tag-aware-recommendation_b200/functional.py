@@ -90,7 +90,7 @@ def lightgcn_forward_layers(graph, e0, n_layer, raw, final, mirrors=None):
 
 
 def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad=None, upstream=None, mirrors=None,
-                             batch_nodes=None, mask_depth=0, local_out=False):
+                             batch_nodes=None, mask_depth=0, local_out=False, adam=None):
     """Closed-form backward of the above: the first table G_L (no gather) + L launches of K1 on A^T with
     the normalise-Jacobian epilogue.  ``bufs`` = two scratch tables, ``g_out`` receives dL/dE0.
 
@@ -100,7 +100,10 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
     Without it (a generic upstream gradient) G_L is an elementwise pass over all rows.
     Sharded graphs: ``mirrors`` selects the fused peer-store exchange (outputs stored to every rank by the kernels);
     G_L's few rows are summed across ranks (each row is non-zero on its owner only).  ``local_out``: dL/dE0 is needed on
-    this rank's rows only (owner-sharded optimizer) — the last launch is not exchanged at all."""
+    this rank's rows only (owner-sharded optimizer) — the last launch is not exchanged at all.  ``adam`` (an
+    ``_lib.AdamDesc``): the optimizer step runs in the epilogue of the last launch (tagrec_lightgcn_bwd_layer_adam): the
+    gradient rows are consumed where they are produced and the new parameter rows go to every rank; ``g_out`` may then
+    be None."""
     L, st, dim = lib(), stream_ptr(g_final.device), g_final.shape[1]
     d = graph.desc(dim, transposed=True)
     d_masked = graph.desc(dim, transposed=True, plain=True)      # the masked launch keeps the plain plan (issue-bound)
@@ -171,9 +174,14 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
     if t:
         t.start("spmm_bwd")
     use_mask = first_gather and mk is not None
-    check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d_masked if use_mask else d), ptr(g_next), ptr(mk) if use_mask else None, None, ptr(g_final),
-                                         ptr(reg_grad), ptr(upstream), inv, ptr(g_out), dim, _mref(m), st),
-          "tagrec_lightgcn_bwd_layer")
+    if adam is not None:
+        check(L.tagrec_lightgcn_bwd_layer_adam(C.byref(d_masked if use_mask else d), ptr(g_next), ptr(mk) if use_mask else None,
+                                               ptr(g_final), ptr(reg_grad), ptr(upstream), inv, ptr(g_out), dim,
+                                               C.byref(adam), st), "tagrec_lightgcn_bwd_layer_adam")
+    else:
+        check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d_masked if use_mask else d), ptr(g_next), ptr(mk) if use_mask else None, None, ptr(g_final),
+                                             ptr(reg_grad), ptr(upstream), inv, ptr(g_out), dim, _mref(m), st),
+              "tagrec_lightgcn_bwd_layer")
     if t:
         t.stop("spmm_bwd")
     if first_gather and sparse:
@@ -282,14 +290,22 @@ class LightGCNLossFn(torch.autograd.Function):
                                 n, dim, dev)
         # single GPU / NCCL: a fresh table per step (the parameters' .grad are views of it and may outlive the step);
         # fused exchange: the symmetric-memory table other ranks store into
-        g_e0 = tabs["g_e0"] if (p2p and not local_out) else torch.empty((n, dim), dtype=torch.float32, device=dev)
+        # optimizer folded into the last launch (optim.ShardedFusedAdam(fused_backward=True)): no gradient table at all
+        hook = ws.get("adam_epilogue")
+        adam = hook.begin_fused_step() if hook is not None else None
+        if adam is not None:
+            g_e0 = None
+        else:
+            g_e0 = tabs["g_e0"] if (p2p and not local_out) else torch.empty((n, dim), dtype=torch.float32, device=dev)
         lightgcn_backward_layers(graph, raw, g_final, nl, [tabs["gbuf0"], tabs["gbuf1"]], g_e0,
                                  ws["g_reg"] if ctx.has_reg else None, upstream, mirrors,
-                                 batch_nodes=ctx.nodes, mask_depth=MASK_DEPTH, local_out=local_out)
+                                 batch_nodes=ctx.nodes, mask_depth=MASK_DEPTH, local_out=local_out, adam=adam)
         g_final.index_fill_(0, ctx.nodes, 0.0)
         if ctx.has_reg:
             ws["g_reg"].index_fill_(0, ctx.nodes, 0.0)
         ws["pending_nodes"] = None
+        if adam is not None:
+            return (None, None) + (None,) * len(ctx.sizes)          # the parameters were updated in place; no .grad
         return (None, None) + tuple(torch.split(g_e0, ctx.sizes, dim=0))
 
 

@@ -83,9 +83,16 @@ class ShardedFusedAdam(torch.optim.Optimizer):
     GPU by 1/P of it, and the last backward launch no longer has to exchange dL/dE0 at all — a rank only needs the
     gradient rows it owns (``model._ws['local_grad_only']``; ``p.grad`` is defined on the owned rows only).
     ``exp_avg`` / ``exp_avg_sq`` are full-size tensors whose owned rows are live; ``consolidate()`` all-gathers them so
-    that ``state_dict()`` is complete on every rank before a checkpoint."""
+    that ``state_dict()`` is complete on every rank before a checkpoint.
 
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    ``fused_backward`` (default; TAGREC_ADAM_EPILOGUE=0 switches it off): the update runs in the EPILOGUE of the last
+    backward launch (tagrec_lightgcn_bwd_layer_adam) — each dL/dE0 row is consumed where K1 produces it and the new
+    parameter row is stored to every rank from there, so the parameter exchange (N x dim x 4 bytes into every GPU per
+    step: 4 ms of exposed NVLink time at 8 GPUs as a separate pass) overlaps the gathers of that launch.  ``backward()``
+    then applies step t + 1 and ``step()`` only closes it (counter, barrier); ``p.grad`` stays None.  One ``backward()``
+    per ``step()`` — a second one raises."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, fused_backward=None):
         params = list(model.parameters())
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         graph = model.norm_adj
@@ -110,11 +117,32 @@ class ShardedFusedAdam(torch.optim.Optimizer):
         self._m = torch.zeros((n, dim), dtype=torch.float32, device=flat.device)
         self._v = torch.zeros((n, dim), dtype=torch.float32, device=flat.device)
         self._step = 0
+        import os
+        if fused_backward is None:
+            fused_backward = os.environ.get("TAGREC_ADAM_EPILOGUE", "1") != "0"
+        self._applied = False                    # backward() already applied the update of the step being taken
+        if fused_backward:
+            model._ws["adam_epilogue"] = self
         off = 0
         for p in model.embed:
             self.state[p] = {"step": 0, "exp_avg": self._m[off:off + p.shape[0]], "exp_avg_sq": self._v[off:off + p.shape[0]]}
             off += p.shape[0]
         comm.peer.barrier("e0")
+
+    def begin_fused_step(self):
+        """Called by LightGCNLossFn.backward: the tagrec_adam_t of step t + 1 for the epilogue of its last launch."""
+        from ._lib import AdamDesc
+        if self._applied:
+            raise RuntimeError("ShardedFusedAdam(fused_backward=True) applies the update inside backward(): call step() "
+                               "after every backward() (gradient accumulation needs fused_backward=False)")
+        group = self.param_groups[0]
+        d = AdamDesc()
+        d.param, d.exp_avg, d.exp_avg_sq = ptr(self.model._ws["flat"]), ptr(self._m), ptr(self._v)
+        d.lr, (d.beta1, d.beta2), d.eps, d.weight_decay = group["lr"], group["betas"], group["eps"], group["weight_decay"]
+        d.step = self._step + 1
+        d.param_mirror = self._mirror
+        self._applied = True
+        return d
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -129,6 +157,18 @@ class ShardedFusedAdam(torch.optim.Optimizer):
         group = self.param_groups[0]
         b1, b2 = group["betas"]
         self._step += 1
+        if self._applied:                        # the epilogue of the last backward launch did the arithmetic
+            self._applied = False
+            t = Fn.KERNEL_TIMER
+            if t:
+                t.start("adam")
+            for p in model.embed:
+                self.state[p]["step"] = self._step
+                torch._C._increment_version([p])
+            comm.peer.barrier("e0")              # every rank's replica is complete before the next forward gathers it
+            if t:
+                t.stop("adam")
+            return loss
         table = model._ws["flat"]
         dim = table.shape[1]
         t = Fn.KERNEL_TIMER

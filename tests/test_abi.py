@@ -32,7 +32,7 @@ def test_struct_layouts_match_the_compiled_library():
     """tagrec_sizeof_struct() is what the .so was compiled with; the ctypes mirrors (and the struct INTEGRATION.md
     shows a maintainer) must agree field for field."""
     L = _lib.lib()
-    for which, cls in enumerate((_lib.CsrDesc, _lib.MirrorDesc, _lib.RoutePlan)):
+    for which, cls in enumerate((_lib.CsrDesc, _lib.MirrorDesc, _lib.RoutePlan, _lib.AdamDesc)):
         assert L.tagrec_sizeof_struct(which) == ctypes.sizeof(cls), cls.__name__
     assert L.tagrec_sizeof_struct(99) == 0
     # INTEGRATION.md's reference-side stub declares the same fields, in the same order, as _lib.CsrDesc

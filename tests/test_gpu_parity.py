@@ -1354,11 +1354,51 @@ def test_fused_adam_vs_torch():
     assert relerr(p.cpu().numpy(), ref.detach().cpu().numpy()) < 1e-6
 
 
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_adam_in_the_last_backward_epilogue_equals_separate_passes(wd):
+    """tagrec_lightgcn_bwd_layer_adam (the optimizer folded into the epilogue of K1's last backward launch) == the same
+    launch writing the gradient table followed by tagrec_adam_step, bit for bit: parameters, exp_avg, exp_avg_sq and the
+    optional local gradient output, over two steps (rows short enough that no atomics are involved)."""
+    import ctypes as C
+    from tagrec_b200._lib import AdamDesc, check, lib, ptr, stream_ptr
+    rng = np.random.RandomState(3)
+    U, I = 300, 200
+    e = np.unique(rng.randint(0, U, 4000).astype(np.int64) * I + rng.randint(0, I, 4000))
+    g = T.build_csr(U, I, (e // I, e % I), "bi_norm", dev())
+    n, dim = g.n, 64
+    gen = torch.Generator(device=dev()).manual_seed(1)
+    rnd = lambda: torch.randn(n, dim, device=dev(), generator=gen)         # noqa: E731
+    p0, g_final, reg_grad, g_next = rnd() * 0.1, rnd() * 1e-3, rnd() * 1e-4, rnd() * 1e-3
+    upstream = torch.tensor([1.0, 1.0], device=dev())
+    d = g.desc(dim, transposed=True)
+    pa, ma, va = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)     # separate passes
+    pb, mb, vb = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)     # epilogue form
+    for step in (1, 2):
+        grad = torch.empty_like(p0)
+        check(lib().tagrec_lightgcn_bwd_layer_ex(C.byref(d), ptr(g_next), None, None, ptr(g_final), ptr(reg_grad),
+                                                 ptr(upstream), 0.25, ptr(grad), dim, None, stream_ptr()), "bwd")
+        check(lib().tagrec_adam_step(ptr(pa), ptr(grad), ptr(ma), ptr(va), pa.numel(), 0.01, 0.9, 0.999, 1e-8, wd, step,
+                                     stream_ptr()), "adam")
+        ad = AdamDesc()
+        ad.param, ad.exp_avg, ad.exp_avg_sq = ptr(pb), ptr(mb), ptr(vb)
+        ad.lr, ad.beta1, ad.beta2, ad.eps, ad.weight_decay, ad.step = 0.01, 0.9, 0.999, 1e-8, wd, step
+        grad_b = torch.empty_like(p0)
+        check(lib().tagrec_lightgcn_bwd_layer_adam(C.byref(d), ptr(g_next), None, ptr(g_final), ptr(reg_grad),
+                                                   ptr(upstream), 0.25, ptr(grad_b) if step == 1 else None, dim,
+                                                   C.byref(ad), stream_ptr()), "bwd+adam")
+        torch.cuda.synchronize()
+        if step == 1:
+            assert torch.equal(grad, grad_b)
+        assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
+        g_next = rnd() * 1e-3
+    assert not torch.equal(pa, p0)
+
+
 # ----------------------------------------------------------------------------------------------------- multi-GPU
 def test_multi_gpu_sharded_step_matches_single():
     """Only on boxes with >= 2 GPUs (gpurun --gpus N): torchrun tests/multi_gpu_check.py — NCCL all-gather, fused
-    peer-store and fused NVLS-multicast exchange, the re-partitioned graph and the owner-sharded optimizer, each against
-    the single-GPU run of the same steps (<= 1e-5, replicas bit-identical).  Kept logs: profiles/r2_multi_gpu_parity_*."""
+    peer-store and fused NVLS-multicast exchange, the re-partitioned graph and the owner-sharded optimizer (as a separate
+    pass and folded into the last backward launch), each against the single-GPU run of the same steps (<= 1e-5, replicas bit-identical).  Kept logs: profiles/r2_multi_gpu_parity_*."""
     import subprocess
     import sys
     n = torch.cuda.device_count()
