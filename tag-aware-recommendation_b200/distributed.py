@@ -173,6 +173,94 @@ class RowComm:
         return table
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+#  Autograd building blocks for models composed from split_mm + row-wise layers (NGCF) on a row-sharded graph.
+#
+#  Every [N, d] activation is REPLICATED in value; a rank computes the rows it owns and the owners' rows are
+#  all-gathered.  Gradient convention: on rank p the gradient of a replicated activation is correct on p's own rows
+#  (other rows are not used) — row-wise layers need nothing else, the SpMM backward all-gathers the upstream gradient
+#  first (A^T needs every row of it), row-table parameters all-gather their gradient rows at the end, and DENSE
+#  parameters (NGCF's W1 / W2 / biases: partial sums over the local rows) are all-reduced.
+# ----------------------------------------------------------------------------------------------------------------------
+class ShardedSpMMFn(torch.autograd.Function):
+    """rows R_p of A @ x from the replicated x.  Returns a full-size table of which only this rank's rows are filled
+    (the row-wise layer that follows reads only those).  Backward: all-gather the upstream gradient rows, then
+    rows R_p of A^T @ g with K1 on the transposed values of the row block."""
+
+    @staticmethod
+    def forward(ctx, graph, x):
+        from .adj import spmm_raw
+        ctx.graph = graph
+        out = torch.zeros_like(x)
+        spmm_raw(graph, x.detach().contiguous(), out=out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from .adj import spmm_raw
+        graph = ctx.graph
+        g = g.contiguous().clone()
+        graph.comm.all_gather_rows(g)
+        gx = torch.zeros_like(g)
+        spmm_raw(graph, g, out=gx, transposed=True)
+        return None, gx
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """[n_local, d] rows computed by this rank -> the replicated [N, d] table (all-gather).  Backward: this rank's rows
+    of the incoming gradient (correct by the convention above), no communication."""
+
+    @staticmethod
+    def forward(ctx, comm, n, local):
+        ctx.lo, ctx.hi = comm.lo, comm.hi
+        full = torch.empty((n, local.shape[1]), dtype=local.dtype, device=local.device)
+        full[comm.lo:comm.hi] = local
+        comm.all_gather_rows(full)
+        return full
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, None, g[ctx.lo:ctx.hi].contiguous()
+
+
+class RowOwnedParamFn(torch.autograd.Function):
+    """Identity on a replicated row table built from parameters; backward all-gathers the gradient rows from their
+    owners so that every replica of the parameters receives the full gradient (replicated optimizer)."""
+
+    @staticmethod
+    def forward(ctx, comm, x):
+        ctx.comm = comm
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        ctx.comm.all_gather_rows(g)
+        return None, g
+
+
+class AllReduceGradFn(torch.autograd.Function):
+    """Identity on a dense (replicated) parameter; backward sums the partial gradients of the ranks — the all-reduce of
+    dense gradients of the node-range design."""
+
+    @staticmethod
+    def forward(ctx, comm, w):
+        ctx.comm = comm
+        return w.view_as(w)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.comm.group)
+        ctx.comm.bytes_moved += g.numel() * g.element_size()
+        return None, g
+
+
+def is_sharded(graph):
+    comm = getattr(graph, "comm", None)
+    return comm is not None and comm.world > 1
+
+
 def shard_graph(full: CsrGraph, rank, world, group=None, calibrate=True, weights=None, range_scale=None, peer=None):
     """Row block of ``full`` for this rank (plus the communicator that reassembles tables).  With ``calibrate`` the
     cut points equalise MEASURED cost (see partition_rows), otherwise nnz."""

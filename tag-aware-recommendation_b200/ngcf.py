@@ -68,8 +68,42 @@ class NGCF(EvalMixin, nn.Module):
     def _fused_ok(self):
         return all(d == 64 for d in self.dim_layer_list)
 
+    def _bi_inter_embed_sharded(self, all_embed):
+        """The same layers on a node-range sharded graph (distributed.shard_graph; multi-GPU, no reference equivalent):
+        rank p computes rows R_p of every layer — K1 on its row block of A, K6 on those rows — and the layer outputs are
+        all-gathered; in backward the dense weight gradients (partial sums over R_p) are all-reduced, the SpMM backward
+        all-gathers the upstream gradient rows, and the embedding gradient rows are all-gathered at the end, so every
+        replica sees exactly the single-GPU gradients."""
+        from . import distributed as D
+        graph = self.norm_adj
+        comm, n = graph.comm, all_embed.shape[0]
+        lo, hi = comm.lo, comm.hi
+        all_embed = D.RowOwnedParamFn.apply(comm, all_embed)
+        all_embed_list = [all_embed]
+        for k in range(self.num_layer):
+            nei = D.ShardedSpMMFn.apply(graph, all_embed)                      # rows [lo, hi) filled
+            nei_l, e_l = nei[lo:hi], all_embed[lo:hi]
+            w = {name: D.AllReduceGradFn.apply(comm, self.mat[f'{name}_{k}']) for name in ("W1", "b1", "W2", "b2")}
+            p = self.message_drop_list[k] if self.training else 0.0
+            if self._fused_ok() and p == 0.0:
+                out_l, nrm_l = NgcfDenseFn.apply(nei_l, e_l, w["W1"], w["b1"], w["W2"], w["b2"])
+            else:
+                if p != 0.0:
+                    raise NotImplementedError("message dropout on a sharded graph (the ranks would have to share the mask)")
+                sum_embed = F.leaky_relu(torch.matmul(nei_l + e_l, w["W1"] + w["b1"]), 0.2)
+                bi_embed = F.leaky_relu(torch.matmul(nei_l * e_l, w["W2"] + w["b2"]), 0.2)
+                out_l = sum_embed + bi_embed
+                nrm_l = F.normalize(out_l, p=2, dim=1)
+            if k + 1 < self.num_layer:                                         # the last raw layer feeds nothing
+                all_embed = D.GatherRowsFn.apply(comm, n, out_l)
+            all_embed_list += [D.GatherRowsFn.apply(comm, n, nrm_l)]
+        return torch.cat(all_embed_list, dim=1)
+
     def bi_inter_embed(self, all_embed):
         """ngcf.py:73-90."""
+        from .distributed import is_sharded
+        if is_sharded(self.norm_adj):
+            return self._bi_inter_embed_sharded(all_embed)
         all_embed_list = [all_embed]
         for k in range(self.num_layer):
             nei_embed = utils.split_mm(self.norm_adj, all_embed)

@@ -148,3 +148,97 @@ def test_sharded_evaluation_world2_gloo(tmp_path):
     g = dict(np.load(GOLDEN))
     want = np.r_[[g[f"eval_{k}"][j] for k in ("recall", "precision", "hr", "ndcg") for j in range(2)], g["eval_auc"]]
     assert np.allclose(outs[0], want, atol=1e-6), (outs[0], want)
+
+
+class _CpuGraph:
+    """A row block of the normalised adjacency on the CPU: the fields distributed.* / NGCF touch, with K1 (a device
+    kernel in the product) played by a dense-index torch reference below."""
+
+    def __init__(self, n, rowptr, col, val, val_t, row_offset, comm, num_list):
+        self.n, self.rowptr, self.col, self.val, self.val_t = n, rowptr, col, val, val_t
+        self.row_offset, self.comm, self.num_list, self.n_rows = row_offset, comm, num_list, rowptr.numel() - 1
+
+
+def _oracle_spmm_raw(graph, x, out=None, transposed=False, beta=0.0):
+    """tagrec_spmm on a row block: out[row_offset + r] = sum_j val[j] x[col[j]] (other rows untouched)."""
+    if out is None:
+        out = torch.empty_like(x)
+    deg = graph.rowptr[1:] - graph.rowptr[:-1]
+    rows = torch.repeat_interleave(torch.arange(graph.n_rows), deg)
+    v = (graph.val_t if transposed else graph.val).to(x.dtype)
+    y = torch.zeros((graph.n_rows, x.shape[1]), dtype=x.dtype)
+    y.index_add_(0, rows, v[:, None] * x[graph.col.long()])
+    out[graph.row_offset:graph.row_offset + graph.n_rows] = y
+    return out
+
+
+def _ngcf_worker(rank, world, port, out):
+    if world > 1:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    import tagrec_b200 as T
+    from tagrec_b200 import adj as A
+    from tagrec_b200.distributed import RowComm, partition_rows, slice_csr
+    A.spmm_raw = _oracle_spmm_raw
+    g = dict(np.load(GOLDEN))
+    U, I, _, _ = nums(g)
+    n, rowptr, col, val = OA.creat_adj(U, I, blocks(g)[0], "ngcf")
+    # the 'ngcf' normalisation is not symmetric: values of A^T through the transposed CSR
+    import scipy.sparse as sp
+    at = sp.csr_matrix((val, col, rowptr), shape=(n, n)).T.tocsr()
+    at.sort_indices()
+    assert np.array_equal(at.indptr, rowptr) and np.array_equal(at.indices, col)
+    rp, c, v, vt = (torch.tensor(np.asarray(x)) for x in (rowptr, col, val, at.data.astype(np.float32)))
+    bounds = partition_rows(rp, world)
+    comm = RowComm(bounds, rank, world) if world > 1 else None
+    lo, hi = (comm.lo, comm.hi) if comm else (0, n)
+    rpl, cl, vl = slice_csr(rp, c, v, lo, hi)
+    vtl = vt[int(rp[lo]):int(rp[hi])].clone()
+    graph = _CpuGraph(n, rpl, cl, vl, vtl, lo, comm, [U, I])
+    T.set_config("ngcf", use_tag=False, reg=1e-3, dim_layer_list=[32, 16], device=torch.device("cpu"))
+
+    class D:
+        num = {"user": U, "item": I}
+        prebuilt_adj = graph
+    torch.manual_seed(11)
+    m = T.NGCF(D).double()
+    m.train()
+    final = m._final_table()
+    rng = np.random.RandomState(3)
+    bu, bi, bj = rng.randint(0, U, 64), rng.randint(0, I, 64), rng.randint(0, I, 64)
+    fu, fi, fj = final[bu], final[U + bi], final[U + bj]
+    loss = torch.nn.functional.softplus(-((fu * fi).sum(1) - (fu * fj).sum(1))).mean() + 1e-3 * (fu.pow(2).sum() + fi.pow(2).sum())
+    loss.backward()
+    if rank == 0:
+        np.savez(out, loss=loss.item(), final=final.detach().numpy(),
+                 **{f"g_{k}": p.grad.numpy() for k, p in m.named_parameters()})
+    if world > 1:
+        # replicas bit-identical: every gradient row / dense gradient is produced once and shared
+        for k, p in m.named_parameters():
+            r0 = p.grad.clone()
+            dist.broadcast(r0, src=0)
+            assert torch.equal(r0, p.grad), k
+        dist.destroy_process_group()
+
+
+def test_sharded_ngcf_world2_gloo(tmp_path):
+    """NGCF on a node-range sharded graph (distributed.ShardedSpMMFn / GatherRowsFn / RowOwnedParamFn /
+    AllReduceGradFn: K1 on row blocks, all-gather of layer outputs, all-gather of embedding-gradient rows, ALL-REDUCE
+    of the dense weight gradients) == the unsharded model: propagated table, loss and the gradient of every parameter;
+    replicas bit-identical.  K1 is played by a torch reference on the CPU (GPU: tests/multi_gpu_check.py)."""
+    res = []
+    for world in (1, 2):
+        out = str(tmp_path / f"ngcf{world}.npz")
+        port = 33500 + os.getpid() % 2000 + world
+        if world == 1:
+            _ngcf_worker(0, 1, port, out)
+        else:
+            mp.spawn(_ngcf_worker, args=(world, port, out), nprocs=world, join=True)
+        res.append(dict(np.load(out)))
+    a, b = res
+    assert abs(a["loss"] - b["loss"]) < 1e-12 * abs(a["loss"])
+    assert np.abs(a["final"] - b["final"]).max() < 1e-12
+    for k in a:
+        if k.startswith("g_"):
+            assert np.abs(a[k] - b[k]).max() <= 1e-10 * max(np.abs(a[k]).max(), 1e-300), k
+    assert any(k.startswith("g_mat.W1") for k in a) and np.abs(a["g_mat.W1_0"]).max() > 0
