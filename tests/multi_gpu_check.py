@@ -185,12 +185,23 @@ def main():
         return [x.item() for x in lossx], {k: p.grad.clone() for k, p in m.named_parameters()}, fin
 
     l1, g1n, f1n = run_ngcf(full_n)
+    _, g1b, _ = run_ngcf(full_n)                           # the same single-GPU step again: its own run-to-run noise
     gs = shard_graph(full_n, rank, world)
     l2, g2n, f2n = run_ngcf(gs)
     gmax = max(float(v.abs().max()) for v in g1n.values())
+    terr = lambda a, b, k: float((a[k] - b[k]).abs().max()) / max(float(b[k].abs().max()), 1e-7 * gmax)   # noqa: E731
+    emb = [k for k in g1n if k.startswith("embed.")]
+    dense = [k for k in g1n if not k.startswith("embed.")]
+    # Embedding-gradient rows are produced by the same kernels in the same order on one rank: 1e-5.  The DENSE weight /
+    # bias gradients are float32 sums over all N rows whose order differs by construction (partial sums per rank, then an
+    # all-reduce; on one GPU per block, then atomics — two single-GPU runs already differ): their bar is 1e-4 of the
+    # tensor's largest entry, reported next to the single-GPU run-to-run figure.  (In float64 the sharded and the
+    # unsharded gradients agree to 1e-10: tests/test_distributed_cpu.py::test_sharded_ngcf_world2_gloo.)
+    DENSE_TOL = 1e-4
     errs = {"loss": abs(l2[0] - l1[0]) / abs(l1[0]), "reg": abs(l2[1] - l1[1]) / abs(l1[1]), "final": rel(f2n, f1n),
-            "grad_max": max(float((g2n[k] - g1n[k]).abs().max()) / max(float(g1n[k].abs().max()), 1e-7 * gmax) for k in g1n)}
-    ok = all(v < TOL for v in errs.values())
+            "grad_embed": max(terr(g2n, g1n, k) for k in emb), "grad_dense": max(terr(g2n, g1n, k) for k in dense)}
+    noise = {"grad_embed": max(terr(g1b, g1n, k) for k in emb), "grad_dense": max(terr(g1b, g1n, k) for k in dense)}
+    ok = all(v < (DENSE_TOL if k == "grad_dense" else TOL) for k, v in errs.items())
     same = True
     for t in list(g2n.values()) + [f2n]:
         r0 = t.clone()
@@ -200,8 +211,8 @@ def main():
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     ok_all = ok_all and bool(flags.min().item() == 1)
     line = {"mode": "ngcf-sharded", "exchange": "nccl all-gather of layer rows + all-reduce of dense weight gradients",
-            "world": world, "errs_vs_single_gpu": errs, "tolerance": TOL,
-            "within_tolerance_all_ranks": bool(flags[0].item()), "replicas_bit_identical": bool(flags[1].item()),
+            "world": world, "errs_vs_single_gpu": errs, "tolerance": TOL, "dense_grad_tolerance": DENSE_TOL,
+            "single_gpu_run_to_run": noise, "within_tolerance_all_ranks": bool(flags[0].item()), "replicas_bit_identical": bool(flags[1].item()),
             "bytes_moved_per_step": gs.comm.bytes_moved, "params": sorted(g1n)}
     lines.append(line)
     if rank == 0:
