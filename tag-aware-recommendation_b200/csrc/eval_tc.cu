@@ -768,8 +768,16 @@ TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
     if (p.cg2) {
         const int64_t pairs = (nu + 2 * TC_M - 1) / (2 * TC_M);
         const int64_t tiles256 = (n_item + 255) / 256;
+        // Item splits: only as many as it takes to fill the 74 SM pairs.  More, shorter splits would even out the last
+        // wave (64 user tiles: 0.875 of the one-split makespan with 8 splits on paper), but every (user tile, split)
+        // unit pays the threshold start-up of its K-lists again: measured 8.3 / 8.6 / 9.4 / 10.4 / 14.5 ms for
+        // 1 / 2 / 4 / 8 / 15 splits at 16 384 x 2 M (profiles/r2_eval_tc2.md).
         int64_t best_s = std::max<int64_t>(1, (kSMs / 2) / pairs);
         best_s = std::min<int64_t>(best_s, std::max<int64_t>(1, std::min<int64_t>(TC_MAX_SPLITS / 2, tiles256 / 8)));
+        if (const char* e = getenv("TAGREC_EVAL_SPLITS")) {      // tuning override
+            const int64_t v = atoll(e);
+            if (v >= 1 && v <= TC_MAX_SPLITS / 2) best_s = std::min<int64_t>(v, std::max<int64_t>(1, tiles256));
+        }
         p.splits = (int)best_s;
         p.items_per_split = ((tiles256 + p.splits - 1) / p.splits) * 256;
         p.splits = (int)((n_item + p.items_per_split - 1) / p.items_per_split);
