@@ -755,7 +755,10 @@ TcPlan tc_plan(int64_t nu, int64_t n_item, int dim, int k) {
         // CTA pairs (eval_tc2_kernel): whenever two 128-user halves per CTA would be used and the K-lists leave room for
         // at least 3 stages of the pair kernel's ring.
         const int mode = cg2_mode();
-        if ((p.nh == 2 && mode == 1) || mode == 2) {
+        // (below ~3 000 users the pair kernel's extra splits cost more than its instruction shape gains: measured
+        // 2.51 vs 2.27 ms at 1 024 users, 2.42 vs 2.38 at 2 048, 3.24 vs 3.44 at 4 096, 4.94 vs 6.27 at 8 192)
+        const int64_t pairs_avail = (nu + 2 * TC_M - 1) / (2 * TC_M);
+        if ((p.nh == 2 && mode == 1 && pairs_avail >= 12) || mode == 2) {
             int st = TC_MAX_STAGES;
             while (st >= 3 && tc2_smem(st, k) > budget) --st;
             if (st >= 3 && (item_tiles >= 16 || mode == 2)) {
