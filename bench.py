@@ -706,7 +706,7 @@ def run_scale(args):
             "setup_s": round(setup_s, 1)}
     if per_rank:
         line["per_rank"] = per_rank
-        line["partition"] = {k: info.get(k) for k in ("bounds", "type_weight_s_per_nnz", "balance_feedback")}
+        line["partition"] = {k: info.get(k) for k in ("bounds", "bounds_bwd", "type_weight_s_per_nnz", "balance_feedback")}
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_scale(args.workload, 3, 1, info["nnz"])
         line["cpu_baseline"] = cb

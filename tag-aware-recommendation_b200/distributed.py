@@ -345,6 +345,73 @@ def measured_step_ms(model, batch, reps=2):
     return min(out)
 
 
+def measured_fwd_bwd_ms(model, batch, reps=2):
+    """(forward, backward) K1 time of one real training step on this rank, separately (see measured_step_ms)."""
+    from . import functional as Fn
+    model.train()
+    best = None
+    for it in range(reps + 1):
+        timer = Fn.KernelTimer()
+        Fn.KERNEL_TIMER = timer if it > 0 else None
+        lossx = model.loss(batch)
+        sum(lossx).backward()
+        for p in model.parameters():
+            p.grad = None
+        torch.cuda.synchronize()
+        Fn.KERNEL_TIMER = None
+        if it > 0:
+            f = sum(a.elapsed_time(b) for a, b in timer.pairs.get("spmm_fwd", []))
+            b_ = sum(a.elapsed_time(b) for a, b in timer.pairs.get("spmm_bwd", []))
+            best = (f, b_) if best is None else (min(best[0], f), min(best[1], b_))
+    return best
+
+
+def split_partition_by_measurement(full, graph, rank, world, make_model, batch, rounds=2, tol=0.02):
+    """Separate row partitions for the forward and the backward launches (collective).  Every exchanged table is
+    full-size on every rank, so a launch may cut the rows any way it likes — and a row block does not cost the same in
+    both directions: on the 1 B-edge graph a user-row block is the cheaper one forward and the dearer one backward
+    (8 GPUs, one partition balanced on the sum: forward 6.4-7.3 ms, backward 6.6-5.9 ms per launch; every launch ends in
+    a barrier, so a step pays the MAXIMUM of each).  Starting from ``graph`` (both directions on its bounds), each round
+    times a real step per rank, scales the modelled cost of every rank's forward rows by its forward time / mean and
+    of its backward rows by its backward time / mean, and cuts both again.  Returns the forward graph with
+    ``.bwd_graph`` set (functional.lightgcn_backward_layers and optim.ShardedFusedAdam pick it up)."""
+    comm = graph.comm
+    tb, tw = getattr(graph, "type_bounds", None), getattr(graph, "type_weight", None)
+    cost_f = row_costs(full, tb, tw)
+    cost_b = cost_f.clone()
+    gf, gbk = graph, graph
+    history = []
+    for rnd in range(rounds):
+        gf.bwd_graph = gbk if gbk is not gf else None
+        model = make_model(gf)
+        f_ms, b_ms = measured_fwd_bwd_ms(model, batch)
+        del model
+        mine = torch.tensor([f_ms, b_ms], dtype=torch.float64, device=full.device)
+        allt = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allt, mine, group=comm.group)
+        tf, tbw = [float(x[0]) for x in allt], [float(x[1]) for x in allt]
+        mf, mb = sum(tf) / world, sum(tbw) / world
+        history.append({"bounds_fwd": list(gf.comm.bounds), "bounds_bwd": list(gbk.comm.bounds),
+                        "fwd_ms": [round(x, 3) for x in tf], "bwd_ms": [round(x, 3) for x in tbw]})
+        if max(tf) / mf - 1.0 < tol and max(tbw) / mb - 1.0 < tol:
+            break
+        for p in range(world):
+            cost_f[gf.comm.bounds[p]:gf.comm.bounds[p + 1]] *= tf[p] / mf
+            cost_b[gbk.comm.bounds[p]:gbk.comm.bounds[p + 1]] *= tbw[p] / mb
+        bf, bb = cut_by_cost(cost_f, world), cut_by_cost(cost_b, world)
+        peer = comm.peer
+        gf.bwd_graph = None
+        del gf, gbk
+        torch.cuda.empty_cache()
+        gf = shard_with_bounds(full, bf, rank, world, comm.group, peer)
+        gbk = shard_with_bounds(full, bb, rank, world, comm.group, peer)
+        gf.type_bounds, gf.type_weight = tb, tw
+        comm = gf.comm
+    gf.bwd_graph = gbk if gbk is not gf else None
+    gf.balance_feedback = (getattr(graph, "balance_feedback", None) or []) + history
+    return gf
+
+
 def rebalance_by_measurement(full, graph, rank, world, make_model=None, batch=None, rounds=2, tol=0.03):
     """Measured feedback on the partition (collective).  Each round times one REAL training step per rank (forward and
     backward K1 launches: the backward of a user-row block costs more than its forward, so balancing the forward alone
@@ -458,6 +525,9 @@ def build_sharded_lightgcn(shape, dev, rank, world, n_triples, seed=2020, eval_u
     if os.environ.get("TAGREC_REBALANCE", "1") != "0":
         graph = rebalance_by_measurement(full, graph, rank, world, make_model=make_model, batch=triples[:2048],
                                          rounds=int(os.environ.get("TAGREC_REBALANCE_ROUNDS", "3")))
+    if os.environ.get("TAGREC_SPLIT_PARTITION", "1") != "0" and graph.comm.peer is not None:
+        graph = split_partition_by_measurement(full, graph, rank, world, make_model, triples[:2048],
+                                               rounds=int(os.environ.get("TAGREC_SPLIT_ROUNDS", "3")))
     nnz_full, n_long_full = full._nnz(), full.n_long
     del full
     torch.cuda.empty_cache()
@@ -469,7 +539,9 @@ def build_sharded_lightgcn(shape, dev, rank, world, n_triples, seed=2020, eval_u
     model = T.LightGCN(Data)
     info = {"nnz": graph._nnz(), "n": graph.n_rows, "n_long_rows": graph.n_long, "nnz_global": nnz_full,
             "parallelism": f"node-range row blocks x{world}, {mode}, replicated parameters",
-            "rows_local": graph.n_rows, "bounds": graph.comm.bounds, "type_weight_s_per_nnz": graph.type_weight,
+            "rows_local": graph.n_rows, "bounds": graph.comm.bounds,
+            "bounds_bwd": graph.bwd_graph.comm.bounds if getattr(graph, "bwd_graph", None) is not None else None,
+            "type_weight_s_per_nnz": graph.type_weight,
             "balance_feedback": getattr(graph, "balance_feedback", None), "eval_mask": eval_mask,
             "plan": graph.col_block}
     return model, triples, info

@@ -105,9 +105,14 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
     gradient rows are consumed where they are produced and the new parameter rows go to every rank; ``g_out`` may then
     be None."""
     L, st, dim = lib(), stream_ptr(g_final.device), g_final.shape[1]
-    d = graph.desc(dim, transposed=True)
-    d_masked = graph.desc(dim, transposed=True, plain=True)      # the masked launch keeps the plain plan (issue-bound)
-    comm = graph.comm
+    # Sharded graphs may carry a SECOND row block for the backward launches (graph.bwd_graph, see
+    # distributed.split_partition_by_measurement): every table is full-size on every rank, so each launch may cut the
+    # rows its own way, and forward and backward launches of a row block do not cost the same.  The first (sparse)
+    # table stays with the forward owner: it reads the last raw layer, which is not exchanged.
+    gb = getattr(graph, "bwd_graph", None) or graph
+    d = gb.desc(dim, transposed=True)
+    d_masked = gb.desc(dim, transposed=True, plain=True)         # the masked launch keeps the plain plan (issue-bound)
+    comm, comm_b = graph.comm, gb.comm
     inv = 1.0 / (n_layer + 1)
     t = KERNEL_TIMER
     ws = graph.__dict__.setdefault("_bwd_ws", {})
@@ -134,7 +139,8 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
         m = mirrors.get(id(g_next)) if mirrors else None
         if t:
             t.start("bwd_first")
-        check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d), None, None, ptr(raw[n_layer - 1]), ptr(g_final), None,
+        d_first = graph.desc(dim, transposed=True)               # forward owner's rows (see above)
+        check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d_first), None, None, ptr(raw[n_layer - 1]), ptr(g_final), None,
                                              ptr(upstream), inv, ptr(g_next), dim, _mref(m), st),
               "tagrec_lightgcn_bwd_layer")
         if t:
@@ -169,7 +175,7 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
             if mirrors:
                 comm.peer.barrier(mirrors["name", id(out)])
             else:
-                comm.all_gather_rows(g_next)
+                comm_b.all_gather_rows(g_next)
     m = mirrors.get(id(g_out)) if (mirrors and not local_out) else None
     if t:
         t.start("spmm_bwd")
@@ -190,7 +196,7 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
         if mirrors:
             comm.peer.barrier(mirrors["name", id(g_out)])
         else:
-            comm.all_gather_rows(g_out)
+            comm_b.all_gather_rows(g_out)
     return g_out
 
 

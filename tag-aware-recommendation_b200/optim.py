@@ -96,6 +96,7 @@ class ShardedFusedAdam(torch.optim.Optimizer):
         params = list(model.parameters())
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         graph = model.norm_adj
+        graph = getattr(graph, "bwd_graph", None) or graph       # rows are owned by the rank whose BACKWARD produces them
         comm = getattr(graph, "comm", None)
         if comm is None or comm.peer is None or comm.world < 2:
             raise ValueError("ShardedFusedAdam needs a model on a sharded graph with the fused exchange enabled "

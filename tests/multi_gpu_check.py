@@ -8,6 +8,8 @@ same inputs, for EVERY exchange path the product has:
     + "sharded-adam": owner-sharded FusedAdam (each rank updates its row block and stores the new rows to all ranks)
     + "sharded-adam-epilogue": the same update inside the epilogue of the last backward launch
       (tagrec_lightgcn_bwd_layer_adam): losses of every step and the parameters after K steps
+    + "split-partition[-epilogue]": forward and backward launches on DIFFERENT row blocks (graph.bwd_graph), with the
+      replicated torch optimizer and with the owner-sharded Adam epilogue
     + "ngcf-sharded": NGCF (K1 row blocks + K6 on the local rows, layer outputs all-gathered, DENSE weight gradients
       all-reduced): loss, propagated tables and the gradient of every parameter vs the single-GPU model
 
@@ -88,7 +90,8 @@ def main():
         if optimizer == "sharded-epilogue":
             assert all(p.grad is None for p in m.embed)
         params = torch.cat([p.detach() for p in m.embed]).clone()
-        own = (graph.comm.lo, graph.comm.hi) if (optimizer.startswith("sharded") and graph.comm is not None) else None
+        og = getattr(graph, "bwd_graph", None) or graph
+        own = (og.comm.lo, og.comm.hi) if (optimizer.startswith("sharded") and graph.comm is not None) else None
         return np.array(losses), g1, f1, params, own
 
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
@@ -112,6 +115,12 @@ def main():
         if mode != "nccl":
             g.comm.enable_p2p(dev).table("probe", (8, 64))
             kind = g.comm.peer.kind
+            if mode.startswith("split-partition"):
+                # forward rows on the calibrated cut, backward rows on the plain nnz cut: two different row blocks
+                from tagrec_b200.distributed import partition_rows, shard_with_bounds
+                gb = shard_with_bounds(full, partition_rows(full.rowptr, world), rank, world, g.comm.group, g.comm.peer)
+                assert gb.comm.bounds != g.comm.bounds, "the two cuts coincide: the mode would test nothing"
+                g.bwd_graph = gb
             if mode in ("rebalanced", "sharded-adam", "sharded-adam-epilogue"):
                 def make_model(gr):
                     class D:
@@ -124,9 +133,11 @@ def main():
         return g, kind
 
     ok_all, lines = True, []
-    for mode in ("nccl", "peer-stores", "multicast", "rebalanced", "sharded-adam", "sharded-adam-epilogue"):
+    for mode in ("nccl", "peer-stores", "multicast", "rebalanced", "sharded-adam", "sharded-adam-epilogue",
+                 "split-partition", "split-partition-epilogue"):
         g, kind = sharded(mode)
-        optimizer = {"sharded-adam": "sharded", "sharded-adam-epilogue": "sharded-epilogue"}.get(mode, "torch")
+        optimizer = {"sharded-adam": "sharded", "sharded-adam-epilogue": "sharded-epilogue",
+                     "split-partition-epilogue": "sharded-epilogue"}.get(mode, "torch")
         want = ref["fused" if optimizer.startswith("sharded") else "torch"]
         losses, g1, f1, params, own = run(g, optimizer)
         errs = {"loss": float(np.abs(losses[:, 0] - want[0][:, 0]).max() / np.abs(want[0][:, 0]).max()),

@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
     tests/multi_gpu_check.py --out gpurun_out/r2_multi_gpu_parity_n8.jsonl > gpurun_out/n8_parity.log 2>&1
 echo "parity rc=$?"; tail -3 gpurun_out/n8_parity.log | cut -c1-300
-for n in 8 4; do
+for n in ${NS:-8 4}; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n \
       bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/r2_scale_n$n.json 2> gpurun_out/r2_scale_n$n.err
   echo "bench n=$n rc=$?"
