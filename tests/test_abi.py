@@ -75,6 +75,24 @@ def test_argument_validation_of_the_dense_kernels_needs_no_gpu():
         (lambda: L.tagrec_nbr_attention_fwd(one, one, one, one, one, one, one, 10, 40, 40, 64, 32, one, one, None),
          b"neighbor_k"),
     ]
+    # the optimizer epilogue of K1's last backward launch (round 2)
+    csr = _lib.CsrDesc()
+    csr.rowptr, csr.col, csr.val, csr.n_rows = 16, 16, 16, 4
+    ad = _lib.AdamDesc()
+    ad.param, ad.exp_avg, ad.exp_avg_sq, ad.step = 16, 16, 16, 0
+    cases.append((lambda: L.tagrec_lightgcn_bwd_layer_adam(ctypes.byref(csr), one, None, one, None, None, 0.25, None, 64,
+                                                           ctypes.byref(ad), None), b"step counts from 1"))
+    ad2 = _lib.AdamDesc()
+    ad2.param, ad2.exp_avg, ad2.exp_avg_sq, ad2.step = 16, 0, 16, 1
+    cases.append((lambda: L.tagrec_lightgcn_bwd_layer_adam(ctypes.byref(csr), one, None, one, None, None, 0.25, None, 64,
+                                                           ctypes.byref(ad2), None), b"null table"))
+    ad3 = _lib.AdamDesc()
+    ad3.param, ad3.exp_avg, ad3.exp_avg_sq, ad3.step = 20, 16, 16, 1
+    cases.append((lambda: L.tagrec_lightgcn_bwd_layer_adam(ctypes.byref(csr), one, None, one, None, None, 0.25, None, 64,
+                                                           ctypes.byref(ad3), None), b"16-byte aligned"))
+    cases.append((lambda: L.tagrec_lightgcn_bwd_layer_adam(ctypes.byref(csr), one, None, one, None, None, 0.25, None, 64,
+                                                           None, None), b"adam is null"))
+    cases.append((lambda: L.tagrec_eval_plan(10, 10, 64, 5, None), b"plan is null"))
     for call, text in cases:
         assert call() == -1
         assert text in L.tagrec_last_error(), (text, L.tagrec_last_error())
