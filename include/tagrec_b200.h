@@ -203,6 +203,19 @@ typedef struct tagrec_adam_t {
 int tagrec_lightgcn_bwd_layer_adam(const tagrec_csr_t* a, const float* g_next, const uint8_t* g_next_nz,
                                    const float* g_final, const float* reg_grad, const float* upstream,
                                    float inv_layers, float* g_out, int dim, const tagrec_adam_t* adam, void* stream);
+/* Push form for SPARSE sources (round 2).  When the source table of a backward launch is non-zero on a handful of
+ * rows only — the item-row half of the first backward launch of a BPR step sums over USER sources, and only the batch's
+ * <= B users carry a gradient — gathering means scanning every stored entry of those rows to find the few that count.
+ * tagrec_spmm_push_rows goes the other way: for each listed source row r (keep[i] == 0 skips a duplicate) it adds
+ * val[j] * x[r] into y_acc[col[j]] for the entries j of CSR row r (for out = A^T g this is row r of A itself; y_acc is a
+ * full-size table the caller keeps all-zero otherwise).  tagrec_lightgcn_bwd_layer_acc then runs the fused backward
+ * epilogue of tagrec_lightgcn_bwd_layer (with e_k) on the rows of `a` WITHOUT a gather, taking each row's sum from
+ * acc_in and zeroing the rows it consumed. */
+int tagrec_spmm_push_rows(const int64_t* rowptr, const int32_t* col, const float* val, const int64_t* rows,
+                          const uint8_t* keep, int64_t n_rows, const float* x, float* y_acc, int dim, void* stream);
+int tagrec_lightgcn_bwd_layer_acc(const tagrec_csr_t* a, float* acc_in, const float* e_k, const float* g_final,
+                                  const float* upstream, float inv_layers, float* g_out, int dim,
+                                  const tagrec_mirror_t* out_mirror, void* stream);
 /* nz[r] = (row r of the [n, dim] table has a non-zero element). */
 int tagrec_row_nonzero(const float* table, int64_t n, int dim, uint8_t* nz, void* stream);
 

@@ -73,6 +73,8 @@ PROTOTYPES = {
     "tagrec_lightgcn_bwd_layer_ex": (_i32, [C.POINTER(CsrDesc), _p, _p, _p, _p, _p, _p, _f32, _p, _i32,
                                             C.POINTER(MirrorDesc), _p]),
     "tagrec_lightgcn_bwd_layer_adam": (_i32, [_p, _p, _p, _p, _p, _p, _f32, _p, _i32, _p, _p]),
+    "tagrec_spmm_push_rows": (_i32, [_p, _p, _p, _p, _p, _i64, _p, _p, _i32, _p]),
+    "tagrec_lightgcn_bwd_layer_acc": (_i32, [_p, _p, _p, _p, _p, _f32, _p, _i32, _p, _p]),
     "tagrec_row_nonzero": (_i32, [_p, _i64, _i32, _p, _p]),
     "tagrec_bpr_fwd_bwd": (_i32, [_p, _i64, _i64, _p, _p, _i32, _f32, _i32, _p, _p, _p, _p]),
     "tagrec_eval_topk": (_i32, [_p, _i64, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p]),

@@ -204,6 +204,25 @@ class CsrGraph:
             d.long_scratch, d.long_counter = ptr(scr), ptr(cnt)
         return d
 
+    def halves(self):
+        """(user-row block, item-row block) of an unsharded bipartite graph as CsrGraph views with their own launch
+        plans (user rows come first in the CSR: the user block is made of views, the item block of a re-based rowptr).
+        Used by the first backward launch of a BPR step, whose two halves see very different sources (see
+        functional.lightgcn_backward_layers).  None for sharded / tripartite graphs."""
+        if self.comm is not None or self.row_offset != 0 or len(self.num_list) != 2 or self.n_rows != self.n:
+            return None
+        h = self.__dict__.get("_halves")
+        if h is None:
+            U = int(self.num_list[0])
+            cut = int(self.rowptr[U])
+            sym = self.val_t is self.val
+            ub = CsrGraph(self.n, self.rowptr[:U + 1], self.col[:cut], self.val[:cut], None if sym else self.val_t[:cut],
+                          None, self.norm_type, self.num_list, row_offset=0)
+            ib = CsrGraph(self.n, (self.rowptr[U:] - cut).contiguous(), self.col[cut:], self.val[cut:],
+                          None if sym else self.val_t[cut:], None, self.norm_type, self.num_list, row_offset=U)
+            h = self._halves = (ub, ib)
+        return h
+
     def row_slabs(self, k):
         """adj.py:114-130 split_sp_mat row folds (kept for API parity; K1 always runs on the whole CSR)."""
         f = self.n // k

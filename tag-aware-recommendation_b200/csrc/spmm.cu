@@ -32,6 +32,8 @@ struct Epi {
     const float* reg_grad;  // bwd0: optional regulariser gradient (may alias y)
     const float* upstream;  // bwd: optional 2 floats {d/dloss, d/dreg} on device
     const uint8_t* src_nz;  // optional byte per SOURCE row: 0 = the row of x is all-zero, its gather is skipped
+    float* acc_in;          // optional, launches without a gather: the row's sum was accumulated HERE beforehand
+                            // (tagrec_spmm_push_rows) — full-size table, global rows; consumed rows are zeroed again
     float scale;            // plain: beta | fwd: final_scale | bwd: 1/(L+1)
     int first, last;
     // bwd0 only, optional: the optimizer folded into the epilogue (tagrec_lightgcn_bwd_layer_adam)
@@ -365,6 +367,20 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
     if (is_long || !gather) e = s;  // long rows are produced by the chunk blocks above
 
     Slice<V> acc = zero_slice<V>();
+    if (!gather && ep.acc_in && valid) {
+        // the sum of this row was pushed into the accumulation table by its (few) non-zero sources
+        float4* in4 = reinterpret_cast<float4*>(ep.acc_in) + (r + a.row_offset) * (LPR * V) + sl;
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            acc.v[q] = in4[q * LPR];
+            any = any || acc.v[q].x != 0.f || acc.v[q].y != 0.f || acc.v[q].z != 0.f || acc.v[q].w != 0.f;
+        }
+        if (any) {
+#pragma unroll
+            for (int q = 0; q < V; ++q) in4[q * LPR] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     if (gather) {
         bool side_by_side = true;
         if (RPW > 1) {
@@ -532,6 +548,61 @@ extern "C" int tagrec_lightgcn_bwd_layer_adam(const tagrec_csr_t* a, const float
     ep.step_size = (float)((double)adam->lr / bc1);
     ep.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     return launch<EPI_BWD0>(a, g_next, ep, dim, g_next != nullptr, stream);
+}
+
+extern "C" int tagrec_lightgcn_bwd_layer_acc(const tagrec_csr_t* a, float* acc_in, const float* e_k, const float* g_final,
+                                             const float* upstream, float inv_layers, float* g_out, int dim,
+                                             const tagrec_mirror_t* out_mirror, void* stream) {
+    TAGREC_REQUIRE(acc_in && e_k && g_final && g_out, "null pointer");
+    Epi ep{};
+    if (int rc = set_mirror(ep.my, out_mirror)) return rc;
+    ep.y = g_out;
+    ep.e_k = e_k;
+    ep.g_final = g_final;
+    ep.upstream = upstream;
+    ep.scale = inv_layers;
+    ep.acc_in = acc_in;
+    return launch<EPI_BWD>(a, nullptr, ep, dim, 0, stream);
+}
+
+namespace tagrec {
+// y[col[j]] += val[j] * x[r] for every stored entry j of the listed rows r (a sub-warp of dim/4 lanes per listed row; the
+// row of x in registers, one red.global.add.v4.f32 per lane and entry).  keep[i] == 0 skips a listed row (duplicates).
+template <int LPR>
+__global__ void __launch_bounds__(256)
+spmm_push_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+                      const int64_t* __restrict__ rows, const uint8_t* __restrict__ keep, int64_t n_rows,
+                      const float4* __restrict__ x4, float4* __restrict__ y4) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = t / LPR;
+    const int sl = (int)(t % LPR);
+    if (i >= n_rows) return;
+    if (keep && !__ldg(keep + i)) return;
+    const int64_t r = __ldg(rows + i);
+    const float4 xv = __ldg(x4 + r * LPR + sl);
+    const int64_t b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+    for (int64_t j = b; j < e; ++j) {
+        const int64_t c = __ldg(col + j);
+        const float v = __ldg(val + j);
+        red_add4(y4 + c * LPR + sl, make_float4(v * xv.x, v * xv.y, v * xv.z, v * xv.w));
+    }
+}
+}  // namespace tagrec
+
+extern "C" int tagrec_spmm_push_rows(const int64_t* rowptr, const int32_t* col, const float* val, const int64_t* rows,
+                                     const uint8_t* keep, int64_t n_rows, const float* x, float* y_acc, int dim,
+                                     void* stream) {
+    TAGREC_REQUIRE(rowptr && col && val && rows && x && y_acc, "null pointer");
+    TAGREC_REQUIRE(dim == 32 || dim == 64 || dim == 128, "dim must be 32, 64 or 128");
+    if (n_rows == 0) return TAGREC_OK;
+    const int lpr = dim / 4;
+    const unsigned grid = (unsigned)((n_rows * lpr + 255) / 256);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y_acc);
+    if (lpr == 16) { TAGREC_LAUNCH((spmm_push_rows_kernel<16>), grid, 256, 0, stream, rowptr, col, val, rows, keep, n_rows, x4, y4); }
+    else if (lpr == 8) { TAGREC_LAUNCH((spmm_push_rows_kernel<8>), grid, 256, 0, stream, rowptr, col, val, rows, keep, n_rows, x4, y4); }
+    else { TAGREC_LAUNCH((spmm_push_rows_kernel<32>), grid, 256, 0, stream, rowptr, col, val, rows, keep, n_rows, x4, y4); }
+    return TAGREC_OK;
 }
 
 namespace tagrec {

@@ -11,6 +11,8 @@ from ._lib import check, lib, ptr, stream_ptr
 
 LOSS_KIND = {"softplus": 0, "logsigmoid": 1}
 MASK_DEPTH = 1           # backward gather launches that skip all-zero source rows (see lightgcn_backward_layers)
+import os as _os
+PUSH_FIRST_BACKWARD = _os.environ.get("TAGREC_PUSH_BWD", "1") != "0"     # item-row half of the first backward launch: push
 
 
 class KernelTimer:
@@ -155,6 +157,12 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
         check(L.tagrec_rows_zero(ptr(batch_nodes), batch_nodes.numel(), ptr(ws["g_sparse"]), ptr(mk), dim, st),
               "tagrec_rows_zero")
 
+    # Unsharded bipartite graph, first gather launch of a BPR step: its source table is non-zero on the batch's rows
+    # only.  The USER-row half sums over item sources — the batch's items, popular ones among them — and stays a masked
+    # gather (on the user-row block); the ITEM-row half sums over USER sources, of which only the batch's <= B users
+    # count: instead of scanning every stored entry of the item rows for them (half of the launch), those users PUSH
+    # their rows into an accumulation table (B x ~100 entries) and the item rows run the epilogue alone.
+    halves = graph.halves() if (sparse and mk is not None and comm is None and PUSH_FIRST_BACKWARD) else None
     first_gather = True
     for k in range(n_layer - 1, 0, -1):
         out = bufs[k % 2]
@@ -162,9 +170,25 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
         if t:
             t.start("spmm_bwd")
         use_mask = first_gather and mk is not None
-        check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d_masked if use_mask else d), ptr(g_next), ptr(mk) if use_mask else None, ptr(raw[k - 1]),
-                                             ptr(g_final), None, ptr(upstream), inv, ptr(out), dim, _mref(m), st),
-              "tagrec_lightgcn_bwd_layer")
+        if use_mask and halves is not None:
+            ub, ib = halves
+            nb = batch_nodes.numel() // 3
+            users_sorted = torch.sort(batch_nodes[:nb]).values
+            keep = torch.ones(nb, dtype=torch.uint8, device=users_sorted.device)
+            keep[1:] = users_sorted[1:] != users_sorted[:-1]                  # a user that occurs twice pushes once
+            acc_tab = _zero_buf(ws, "push_acc", (n, dim), g_final.device)
+            check(L.tagrec_spmm_push_rows(ptr(graph.rowptr), ptr(graph.col), ptr(graph.val), ptr(users_sorted), ptr(keep),
+                                          nb, ptr(g_next), ptr(acc_tab), dim, st), "tagrec_spmm_push_rows")
+            du = ub.desc(dim, transposed=True, plain=True)
+            check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(du), ptr(g_next), ptr(mk), ptr(raw[k - 1]), ptr(g_final), None,
+                                                 ptr(upstream), inv, ptr(out), dim, None, st), "tagrec_lightgcn_bwd_layer")
+            di = ib.desc(dim, transposed=True)
+            check(L.tagrec_lightgcn_bwd_layer_acc(C.byref(di), ptr(acc_tab), ptr(raw[k - 1]), ptr(g_final), ptr(upstream),
+                                                  inv, ptr(out), dim, None, st), "tagrec_lightgcn_bwd_layer_acc")
+        else:
+            check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(d_masked if use_mask else d), ptr(g_next), ptr(mk) if use_mask else None, ptr(raw[k - 1]),
+                                                 ptr(g_final), None, ptr(upstream), inv, ptr(out), dim, _mref(m), st),
+                  "tagrec_lightgcn_bwd_layer")
         if t:
             t.stop("spmm_bwd")
         if first_gather and sparse:
