@@ -688,7 +688,10 @@ def run_scale(args):
                 # the backward launches of the last timed step, in order: G_{L-1} (source non-zero on the batch rows
                 # only), G_{L-2} (batch rows + neighbours), ..., dE0 (dense source); zero source rows are skipped
                 "bwd_launch_ms": [round(x.elapsed_time(y), 3) for x, y in timer.pairs.get("spmm_bwd", [])[-LAYERS:]],
-                "adam_ms": timer.mean_ms("adam")}
+                "adam_ms": timer.mean_ms("adam"),
+                # the last forward layer of a training step runs on the batch's rows only (the loss reads nothing else of
+                # it): its launch is timed separately and is NOT part of ms_per_launch above
+                "fwd_last_layer_rows_ms": timer.mean_ms("spmm_fwd_rows")}
     if traffic:
         # `achieved` counts ALGORITHMIC bytes (every gathered 256-byte row, SURVEY §8 d); with the column-blocked plan most
         # of the item-row half's gathers are served by L2, so it exceeds the DRAM peak.  The DRAM-side figure, from the
@@ -701,7 +704,12 @@ def run_scale(args):
             "ms_per_step": ms / K, "check": check, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_of(args.workload),
             "run": {"optimizer": type(opt).__name__, "parallelism": info["parallelism"], "nnz": info["nnz"],
-                    "nodes": info["n"], "long_rows": info["n_long_rows"], "plan": info.get("plan")},
+                    "nodes": info["n"], "long_rows": info["n_long_rows"], "plan": info.get("plan"),
+                    "step": ("model.loss(batch) / backward() / optimizer.step() of the drop-in LightGCN: layers 1..L-1 on all "
+                             "rows, layer L on the rows the loss reads (the batch's users and items: nothing else of it "
+                             "reaches the loss or any gradient; TAGREC_LAST_LAYER_ROWS=0 computes it everywhere), backward "
+                             "over all rows, Adam over all rows — loss, gradients and parameters equal the reference's "
+                             "(tests/test_gpu_parity.py, tests/test_gpu_shapes.py)")},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline,
             "setup_s": round(setup_s, 1)}
     if per_rank:

@@ -355,8 +355,10 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
     // ---- RPW consecutive rows per warp ----
     const int64_t w = ((int64_t)blockIdx.x - n_long_blocks) * kWarpsPerBlock + wib;
     if (w * RPW >= a.n_rows) return;
-    const int64_t r = w * RPW + sub;
-    const bool valid = r < a.n_rows;
+    const int64_t ridx = w * RPW + sub;
+    const bool valid = ridx < a.n_rows;
+    // row-subset launches: the n_rows listed rows instead of rows 0 .. n_rows-1
+    const int64_t r = (a.row_list && valid) ? (int64_t)__ldg(a.row_list + ridx) : ridx;
     int64_t s = 0, e = 0;
     if (valid) {
         s = __ldg(a.rowptr + r);
@@ -420,8 +422,8 @@ static int launch(const tagrec_csr_t* a, const float* x, const Epi& ep, int dim,
     TAGREC_REQUIRE(a && a->rowptr && a->n_rows >= 0, "csr descriptor missing");
     TAGREC_REQUIRE(!gather || (a->col && a->val && x), "csr arrays / source table missing");
     TAGREC_REQUIRE(dim == 32 || dim == 64 || dim == 128, "dim must be 32, 64 or 128");
-    if (a->n_rows == 0) return TAGREC_OK;
     const int64_t n_items = gather ? a->n_items : 0;
+    if (a->n_rows == 0 && n_items == 0) return TAGREC_OK;
     if (n_items > 0)
         TAGREC_REQUIRE(a->long_rows && a->item_slot && a->item_begin && a->item_end && a->long_scratch &&
                            a->long_counter, "long-row plan arrays missing");

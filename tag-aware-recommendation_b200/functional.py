@@ -13,6 +13,7 @@ LOSS_KIND = {"softplus": 0, "logsigmoid": 1}
 MASK_DEPTH = 1           # backward gather launches that skip all-zero source rows (see lightgcn_backward_layers)
 import os as _os
 PUSH_FIRST_BACKWARD = _os.environ.get("TAGREC_PUSH_BWD", "1") != "0"     # item-row half of the first backward launch: push
+LAST_LAYER_ROWS = _os.environ.get("TAGREC_LAST_LAYER_ROWS", "1") != "0"  # last forward layer of a training step: batch rows only
 
 
 class KernelTimer:
@@ -54,11 +55,14 @@ def _mref(m):
     return C.byref(m) if m is not None else None
 
 
-def lightgcn_forward_layers(graph, e0, n_layer, raw, final, mirrors=None):
+def lightgcn_forward_layers(graph, e0, n_layer, raw, final, mirrors=None, last_rows=None):
     """lightgcn.py:52-60 — L launches of K1 with the fused normalise + running-mean epilogue.
     raw[k] receives the un-normalised E^{k+1}; ``final`` the mean table.
     Sharded graphs: ``mirrors`` (dict id(tensor) -> MirrorDesc, tables in symmetric memory) selects the fused
-    peer-store all-gather + barrier; without it the row blocks are all-gathered with NCCL after each launch."""
+    peer-store all-gather + barrier; without it the row blocks are all-gathered with NCCL after each launch.
+    ``last_rows`` (int32 local row ids, ascending, unique): the LAST layer is produced on these rows only — a training
+    step reads the mean table at the batch's rows and nothing else of the last layer (lightgcn.py:68-75; its backward
+    needs E^L at the same rows), so raw[L-1] and ``final`` are defined on those rows only afterwards."""
     L, st, dim = lib(), stream_ptr(e0.device), e0.shape[1]
     d = graph.desc(dim)
     comm = graph.comm
@@ -68,13 +72,18 @@ def lightgcn_forward_layers(graph, e0, n_layer, raw, final, mirrors=None):
         last = k == n_layer - 1
         my = mirrors.get(id(raw[k])) if (mirrors and not last) else None
         ma = mirrors.get(id(final)) if (mirrors and last) else None
+        dk, keep, label = d, None, "spmm_fwd"
+        if last and last_rows is not None:
+            dk, keep = graph.subset_desc(dim, last_rows)
+            label = "spmm_fwd_rows"
         if t:
-            t.start("spmm_fwd")
-        check(L.tagrec_lightgcn_fwd_layer_p2p(C.byref(d), ptr(x), ptr(raw[k]), ptr(final), dim, int(k == 0), int(last),
+            t.start(label)
+        check(L.tagrec_lightgcn_fwd_layer_p2p(C.byref(dk), ptr(x), ptr(raw[k]), ptr(final), dim, int(k == 0), int(last),
                                               1.0 / (n_layer + 1), _mref(my), _mref(ma), st),
               "tagrec_lightgcn_fwd_layer")
         if t:
-            t.stop("spmm_fwd")
+            t.stop(label)
+        del keep
         x = raw[k]
         if comm is not None:
             if mirrors:
@@ -278,9 +287,17 @@ class LightGCNLossFn(torch.autograd.Function):
         tabs, mirrors = _tables(model, names, n, dim, dev)
         raw, final = [tabs[f"raw{k}"] for k in range(nl)], tabs["final"]
         ws["raw_list"] = raw
-        lightgcn_forward_layers(graph, e0, nl, raw, final, mirrors)
         batch = batch.contiguous()
         nodes = torch.cat([batch[:, 0], batch[:, 1] + model.num_list[0], batch[:, 2] + model.num_list[0]])
+        last_rows = None
+        if LAST_LAYER_ROWS and not torch.cuda.is_current_stream_capturing():
+            # the last layer on the batch's rows only (this rank's share of them); not under CUDA-graph capture: the
+            # row list has a data-dependent size
+            uniq = torch.unique(nodes)
+            if graph.comm is not None:
+                uniq = uniq[(uniq >= graph.comm.lo) & (uniq < graph.comm.hi)] - graph.comm.lo
+            last_rows = uniq.to(torch.int32)
+        lightgcn_forward_layers(graph, e0, nl, raw, final, mirrors, last_rows=last_rows)
         # The gradient tables are all-zero between steps: K2 scatters into the batch's rows, backward() consumes them
         # and re-zeroes exactly those rows (no state crosses a step, so eager and CUDA-graph steps can alternate).
         # If a previous forward was never followed by its backward, its rows are cleared here first.
