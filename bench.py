@@ -657,7 +657,8 @@ def run_scale(args):
         eval_sharded = eval_leg_sharded(T, model, shape, dev, info["eval_mask"], world, dist)
     per_rank = None
     if world > 1:
-        mine = {"rank": rank, "fwd_ms": timer.mean_ms("spmm_fwd"), "bwd_ms": timer.mean_ms("spmm_bwd"),
+        mine = {"rank": rank, "fwd_ms": timer.mean_ms("spmm_fwd"), "fwd_last_layer_rows_ms": timer.mean_ms("spmm_fwd_rows"),
+                "bwd_ms": timer.mean_ms("spmm_bwd"),
                 "all_gather_ms": timer.mean_ms("all_gather"), "all_gathers_per_step": timer.count("all_gather") // K,
                 "barrier_ms": timer.mean_ms("barrier"), "adam_ms": timer.mean_ms("adam"),
                 "nnz": info["nnz"], "rows": info["n"]}
