@@ -120,11 +120,15 @@ typedef struct {
     int32_t blocked_min_deg;
     int32_t chunk_lanes;
     /* Row-subset launches (round 2).  row_list != NULL: the launch produces the n_rows LISTED rows only
-     * (row_list[i] = local row id, any order, no duplicates; rowptr still covers the whole block) instead of rows
-     * 0 .. n_rows-1; listed rows that are long are produced by the items the caller lists for them (n_rows == 0 with
-     * n_items > 0 is valid).  The last LightGCN layer of a training step is needed on the batch's rows only
+     * (row_list[i] = local row id, any order, no duplicates, negative entries skipped; rowptr still covers the whole
+     * block) instead of rows
+     * 0 .. n_rows-1; listed rows that are long are produced by their chunks in the item list (see row_sel; n_rows == 0
+     * with n_items > 0 is valid).  The last LightGCN layer of a training step is needed on the batch's rows only
      * (model/lightgcn.py:59-60 feeds the mean table to the loss, which reads 3 x batch rows of it). */
     const int32_t* row_list;
+    const uint8_t* row_sel;     /* with row_list: one byte per LOCAL row, non-zero = listed.  The chunk blocks of a long row
+                                   that is not listed exit at once, so the caller may pass the plan's whole chunk list
+                                   (no per-call list of the listed long rows' chunks has to be built) */
 } tagrec_csr_t;
 
 /* Fused compute + collective (multi-GPU, no reference equivalent — the reference is single-device): where an

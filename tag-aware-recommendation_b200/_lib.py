@@ -29,7 +29,7 @@ class CsrDesc(C.Structure):
     _fields_ = [("rowptr", _p), ("col", _p), ("val", _p), ("n_rows", _i64), ("row_offset", _i64), ("long_rows", _p), ("item_slot", _p),
                 ("item_begin", _p), ("item_end", _p), ("n_long", _i64), ("n_items", _i64), ("long_scratch", _p),
                 ("long_counter", _p), ("long_row", C.c_int32), ("long_chunk", C.c_int32), ("long_nchunks", _p),
-                ("blocked_row_begin", _i64), ("blocked_min_deg", C.c_int32), ("chunk_lanes", C.c_int32), ("row_list", _p)]
+                ("blocked_row_begin", _i64), ("blocked_min_deg", C.c_int32), ("chunk_lanes", C.c_int32), ("row_list", _p), ("row_sel", _p)]
 
 
 class RoutePlan(C.Structure):

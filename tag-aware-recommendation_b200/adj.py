@@ -83,8 +83,7 @@ class CsrGraph:
         return begin, min_deg, max(window, 64)
 
     _PLAN_KEYS = ("long_row", "long_chunk", "col_block", "blocked_row_begin", "blocked_min_deg", "chunk_lanes",
-                  "long_nchunks", "_scratch", "n_long", "long_rows", "item_slot", "item_begin", "item_end", "n_items",
-                  "_first_item")
+                  "long_nchunks", "_scratch", "n_long", "long_rows", "item_slot", "item_begin", "item_end", "n_items")
 
     def _plan_state(self):
         return {k: getattr(self, k) for k in self._PLAN_KEYS}
@@ -110,7 +109,6 @@ class CsrGraph:
         self.col_block = None
         self.blocked_row_begin, self.blocked_min_deg, self.chunk_lanes = 0, 0, 0
         self.long_nchunks = None
-        self._first_item = None
         self._scratch = {}
         is_long = deg > LONG_ROW
         if spec is not None:
@@ -207,39 +205,22 @@ class CsrGraph:
         return d
 
     def subset_desc(self, dim, rows):
-        """(tagrec_csr_t, keep-alive tensors) for a launch that produces the listed rows only.  ``rows`` = int32 local row
-        ids, ascending, unique.  Short rows run from the row list; listed long rows run from their chunks of the PLAIN
-        plan (a long row's chunks are contiguous there), gathered into a per-call item list."""
-        plain_state = self._plain_plan if self._plain_plan is not None else None
+        """(tagrec_csr_t, undo) for a launch that produces the listed rows only.  ``rows`` = int32 local row ids, no
+        duplicates, negative entries = blanks (skipped).
+        Short rows run from the row list; the chunk list of the PLAIN plan is passed whole and the chunks of long rows
+        that are not listed exit on a byte map (``row_sel``), so nothing of data-dependent size is built per call.
+        ``undo()`` clears the byte map again (call it after the launch has been enqueued)."""
         d = self.desc(dim, plain=True)
-        st = self._plain_plan if plain_state is not None else self._plan_state()
-        keep = [rows]
+        sel = self.__dict__.get("_row_sel")
+        if sel is None:
+            sel = self._row_sel = torch.zeros(self.n_rows + 1, dtype=torch.uint8, device=self.device)
+        rows64 = rows.to(torch.int64)
+        rows64 = torch.where(rows64 < 0, torch.full_like(rows64, self.n_rows), rows64)    # blanked entries -> a dummy slot
+        sel.index_fill_(0, rows64, 1)
         d.row_list = ptr(rows)
         d.n_rows = int(rows.numel())
-        n_items = 0
-        if st["n_long"] and rows.numel():
-            first = st.get("_first_item")
-            if first is None:
-                nch = st["long_nchunks"].to(torch.int64)
-                first = torch.cumsum(nch, 0) - nch
-                st["_first_item"] = first
-                if plain_state is None:
-                    self._first_item = first
-            long_rows = st["long_rows"]
-            pos = torch.searchsorted(long_rows, rows).clamp_(max=st["n_long"] - 1)
-            slots = pos[long_rows[pos] == rows]
-            if slots.numel():
-                cnt = st["long_nchunks"][slots].to(torch.int64)
-                tot = int(cnt.sum())
-                start = torch.cumsum(cnt, 0) - cnt
-                rep = torch.repeat_interleave(torch.arange(slots.numel(), device=rows.device), cnt, output_size=tot)
-                idx = first[slots][rep] + (torch.arange(tot, device=rows.device) - start[rep])
-                i_slot, i_beg, i_end = st["item_slot"][idx], st["item_begin"][idx], st["item_end"][idx]
-                keep += [i_slot, i_beg, i_end]
-                d.item_slot, d.item_begin, d.item_end = ptr(i_slot), ptr(i_beg), ptr(i_end)
-                n_items = tot
-        d.n_items = n_items
-        return d, keep
+        d.row_sel = ptr(sel)
+        return d, (lambda: sel.index_fill_(0, rows64, 0))
 
     def halves(self):
         """(user-row block, item-row block) of an unsharded bipartite graph as CsrGraph views with their own launch

@@ -305,6 +305,7 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
         const int64_t item = per_sub ? unit * RPW + sub : unit;
         if (item >= a.n_items) return;
         const int slot = __ldg(a.item_slot + item);
+        if (a.row_sel && !__ldg(a.row_sel + __ldg(a.long_rows + slot))) return;      // row-subset launch: row not listed
         const int64_t b = __ldg(a.item_begin + item), e = __ldg(a.item_end + item);
         Slice<V> p;
         if (per_sub) {
@@ -356,9 +357,11 @@ spmm_kernel(tagrec_csr_t a, const float4* __restrict__ x4, Epi ep, int n_long_bl
     const int64_t w = ((int64_t)blockIdx.x - n_long_blocks) * kWarpsPerBlock + wib;
     if (w * RPW >= a.n_rows) return;
     const int64_t ridx = w * RPW + sub;
-    const bool valid = ridx < a.n_rows;
-    // row-subset launches: the n_rows listed rows instead of rows 0 .. n_rows-1
-    const int64_t r = (a.row_list && valid) ? (int64_t)__ldg(a.row_list + ridx) : ridx;
+    const bool in_range = ridx < a.n_rows;
+    // row-subset launches: the n_rows listed rows instead of rows 0 .. n_rows-1 (negative entries are skipped: the
+    // caller blanks duplicates and rows of other blocks instead of compacting the list)
+    const int64_t r = (a.row_list && in_range) ? (int64_t)__ldg(a.row_list + ridx) : ridx;
+    const bool valid = in_range && r >= 0;
     int64_t s = 0, e = 0;
     if (valid) {
         s = __ldg(a.rowptr + r);

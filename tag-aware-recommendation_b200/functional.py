@@ -72,18 +72,19 @@ def lightgcn_forward_layers(graph, e0, n_layer, raw, final, mirrors=None, last_r
         last = k == n_layer - 1
         my = mirrors.get(id(raw[k])) if (mirrors and not last) else None
         ma = mirrors.get(id(final)) if (mirrors and last) else None
-        dk, keep, label = d, None, "spmm_fwd"
+        dk, undo, label = d, None, "spmm_fwd"
         if last and last_rows is not None:
-            dk, keep = graph.subset_desc(dim, last_rows)
+            dk, undo = graph.subset_desc(dim, last_rows)
             label = "spmm_fwd_rows"
         if t:
             t.start(label)
         check(L.tagrec_lightgcn_fwd_layer_p2p(C.byref(dk), ptr(x), ptr(raw[k]), ptr(final), dim, int(k == 0), int(last),
                                               1.0 / (n_layer + 1), _mref(my), _mref(ma), st),
               "tagrec_lightgcn_fwd_layer")
+        if undo is not None:
+            undo()
         if t:
             t.stop(label)
-        del keep
         x = raw[k]
         if comm is not None:
             if mirrors:
@@ -290,13 +291,14 @@ class LightGCNLossFn(torch.autograd.Function):
         batch = batch.contiguous()
         nodes = torch.cat([batch[:, 0], batch[:, 1] + model.num_list[0], batch[:, 2] + model.num_list[0]])
         last_rows = None
-        if LAST_LAYER_ROWS and not torch.cuda.is_current_stream_capturing():
-            # the last layer on the batch's rows only (this rank's share of them); not under CUDA-graph capture: the
-            # row list has a data-dependent size
-            uniq = torch.unique(nodes)
-            if graph.comm is not None:
-                uniq = uniq[(uniq >= graph.comm.lo) & (uniq < graph.comm.hi)] - graph.comm.lo
-            last_rows = uniq.to(torch.int32)
+        if LAST_LAYER_ROWS:
+            # the last layer on the batch's rows only (this rank's share of them).  Fixed-size list, no host sync (also
+            # valid under CUDA-graph capture): sorted nodes, duplicates and other ranks' rows blanked with -1
+            srt = torch.sort(nodes).values
+            lo, hi = (graph.comm.lo, graph.comm.hi) if graph.comm is not None else (0, n)
+            bad = (srt < lo) | (srt >= hi)
+            bad[1:] |= srt[1:] == srt[:-1]
+            last_rows = torch.where(bad, torch.full_like(srt, -1), srt - lo).to(torch.int32)
         lightgcn_forward_layers(graph, e0, nl, raw, final, mirrors, last_rows=last_rows)
         # The gradient tables are all-zero between steps: K2 scatters into the batch's rows, backward() consumes them
         # and re-zeroes exactly those rows (no state crosses a step, so eager and CUDA-graph steps can alternate).
