@@ -284,6 +284,7 @@ def shard_graph(full: CsrGraph, rank, world, group=None, calibrate=True, weights
     g = CsrGraph(full.n, rp, col, val, val_t, None, full.norm_type, full.num_list, row_offset=lo, comm=comm)
     g.type_weight = tw
     g.type_bounds = tb
+    g.nnz_global = full._nnz()
     return g
 
 
@@ -322,7 +323,9 @@ def shard_with_bounds(full, bounds, rank, world, group=None, peer=None):
     if full.val_t is not full.val:
         a, b = int(full.rowptr[lo]), int(full.rowptr[hi])
         val_t = full.val_t[a:b].clone()
-    return CsrGraph(full.n, rp, col, val, val_t, None, full.norm_type, full.num_list, row_offset=lo, comm=comm)
+    g = CsrGraph(full.n, rp, col, val, val_t, None, full.norm_type, full.num_list, row_offset=lo, comm=comm)
+    g.nnz_global = full._nnz()
+    return g
 
 
 def measured_step_ms(model, batch, reps=2):

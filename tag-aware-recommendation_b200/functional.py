@@ -12,8 +12,21 @@ from ._lib import check, lib, ptr, stream_ptr
 LOSS_KIND = {"softplus": 0, "logsigmoid": 1}
 MASK_DEPTH = 1           # backward gather launches that skip all-zero source rows (see lightgcn_backward_layers)
 import os as _os
-PUSH_FIRST_BACKWARD = _os.environ.get("TAGREC_PUSH_BWD", "1") != "0"     # item-row half of the first backward launch: push
-LAST_LAYER_ROWS = _os.environ.get("TAGREC_LAST_LAYER_ROWS", "1") != "0"  # last forward layer of a training step: batch rows only
+
+
+def _structural_cut(env, graph):
+    """The two structural cuts of a LightGCN training step — last forward layer on the loss's rows only
+    (TAGREC_LAST_LAYER_ROWS), push form of the first backward launch's item-row half (TAGREC_PUSH_BWD) — save whole
+    launches on graphs where a launch is tens of milliseconds and cost a few small kernels per step, which is a loss on
+    the launch-bound small graphs (LastFM-shaped: 0.17 -> 0.35 ms per graphed step).  "0": off, "1" / "force": on,
+    unset: on from 2^25 stored entries up (counted over the whole graph of a sharded one)."""
+    v = _os.environ.get(env, "auto")
+    if v == "0":
+        return False
+    if v in ("1", "force"):
+        return True
+    total = getattr(graph, "nnz_global", None) or graph._nnz()
+    return total >= (1 << 25)
 
 
 class KernelTimer:
@@ -172,7 +185,7 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
     # gather (on the user-row block); the ITEM-row half sums over USER sources, of which only the batch's <= B users
     # count: instead of scanning every stored entry of the item rows for them (half of the launch), those users PUSH
     # their rows into an accumulation table (B x ~100 entries) and the item rows run the epilogue alone.
-    halves = graph.halves() if (sparse and mk is not None and comm is None and PUSH_FIRST_BACKWARD) else None
+    halves = graph.halves() if (sparse and mk is not None and comm is None and _structural_cut("TAGREC_PUSH_BWD", graph)) else None
     first_gather = True
     for k in range(n_layer - 1, 0, -1):
         out = bufs[k % 2]
@@ -291,7 +304,7 @@ class LightGCNLossFn(torch.autograd.Function):
         batch = batch.contiguous()
         nodes = torch.cat([batch[:, 0], batch[:, 1] + model.num_list[0], batch[:, 2] + model.num_list[0]])
         last_rows = None
-        if LAST_LAYER_ROWS:
+        if _structural_cut("TAGREC_LAST_LAYER_ROWS", graph):
             # the last layer on the batch's rows only (this rank's share of them).  Fixed-size list, no host sync (also
             # valid under CUDA-graph capture): sorted nodes, duplicates and other ranks' rows blanked with -1
             srt = torch.sort(nodes).values

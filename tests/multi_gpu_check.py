@@ -35,6 +35,9 @@ sys.path.insert(0, ROOT)
 
 STEPS = 3
 TOL = 1e-5
+# the check graph is small: switch the big-graph paths on (last forward layer on the loss's rows, each rank its share)
+os.environ.setdefault("TAGREC_LAST_LAYER_ROWS", "force")
+os.environ.setdefault("TAGREC_PUSH_BWD", "force")
 
 
 def main():

@@ -111,10 +111,15 @@ def test_k1_autograd_matches_transpose():
     assert relerr(x.grad.cpu().numpy(), OP.spmm_t(*csr, w.cpu().double()).numpy()) < TOL
 
 
+@pytest.mark.parametrize("cuts", ["auto", "force"])
 @pytest.mark.parametrize("tag,use_tag,kind", [("lgcn", False, "softplus"), ("lgcn_tag", True, "softplus"),
                                                ("lgcn_logsig", False, "logsigmoid")])
-def test_lightgcn_forward_loss_grad_vs_reference(tiny, tag, use_tag, kind):
-    """model.forward / model.loss + backward == the reference's outputs on identical inputs."""
+def test_lightgcn_forward_loss_grad_vs_reference(tiny, tag, use_tag, kind, cuts, monkeypatch):
+    """model.forward / model.loss + backward == the reference's outputs on identical inputs.  ``cuts`` = "force": with
+    the two structural cuts of the big-graph step (last forward layer on the loss's rows only, push form of the first
+    backward launch's item-row half) switched on for this small graph too."""
+    monkeypatch.setenv("TAGREC_LAST_LAYER_ROWS", cuts)
+    monkeypatch.setenv("TAGREC_PUSH_BWD", cuts)
     T.set_config("lightgcn", use_tag=use_tag, reg=1e-3, dim_layer_list=[64, 64, 64], device=dev(),
                  mul_loss_func=kind)
     model = T.LightGCN(make_data(tiny)).to(dev())
@@ -152,8 +157,12 @@ def test_lightgcn_forward_loss_grad_vs_reference(tiny, tag, use_tag, kind):
     assert relerr(r.cpu().numpy(), tiny[f"{tag}_pred"]) < TOL
 
 
-def test_lightgcn_long_rows_and_upstream_scale():
-    """Hub rows (chunked path) + non-unit upstream gradients, vs the fp64 oracle."""
+@pytest.mark.parametrize("cuts", ["auto", "force"])
+def test_lightgcn_long_rows_and_upstream_scale(cuts, monkeypatch):
+    """Hub rows (chunked path) + non-unit upstream gradients, vs the fp64 oracle ("force": the row-list launch of the last
+    layer then runs hub rows through the plan's chunk list behind the row_sel byte map)."""
+    monkeypatch.setenv("TAGREC_LAST_LAYER_ROWS", cuts)
+    monkeypatch.setenv("TAGREC_PUSH_BWD", cuts)
     U, I = 9000, 500
     ui = random_graph(U, I, 30000, 3, hub=8000)
     T.set_config("lightgcn", use_tag=False, reg=1e-2, dim_layer_list=[64, 64], device=dev())
@@ -231,9 +240,12 @@ def test_lightgcn_column_blocked_plan_vs_oracle(monkeypatch, window_mb, min_deg)
     assert relerr(fw.numpy(), final.numpy()) < TOL
 
 
-def test_training_trajectory_vs_reference(tiny):
-    """3+1 Adam steps through Basic_train's epoch_training on the reference's fixed triple file: same per-step
+@pytest.mark.parametrize("cuts", ["auto", "force"])
+def test_training_trajectory_vs_reference(tiny, cuts, monkeypatch):
+    """(``cuts``: see test_lightgcn_forward_loss_grad_vs_reference.)  3+1 Adam steps through Basic_train's epoch_training on the reference's fixed triple file: same per-step
     losses and same parameters afterwards (incl. the tail batch being trained twice)."""
+    monkeypatch.setenv("TAGREC_LAST_LAYER_ROWS", cuts)
+    monkeypatch.setenv("TAGREC_PUSH_BWD", cuts)
     T.set_config("lightgcn", use_tag=False, reg=1e-3, dim_layer_list=[64, 64, 64], device=dev(), train_batch=64, lr=0.01)
     model = T.LightGCN(make_data(tiny)).to(dev())
     with torch.no_grad():
@@ -1446,10 +1458,12 @@ def test_edge_dropout_and_message_dropout_path(tiny):
 
 # ------------------------------------------------------------------------------------------------ CUDA-graph step
 @pytest.mark.parametrize("model_name", ["lightgcn", "ngcf", "dgcf"])
-def test_graphed_step_matches_eager(tiny, model_name):
+def test_graphed_step_matches_eager(tiny, model_name, monkeypatch):
     """GraphedStep (loss + backward + capturable FusedAdam recorded into ONE CUDA graph, replayed) follows the same
     parameter trajectory as the eager step, including an odd-sized tail batch in the middle (eager fallback) and the
     device-side Adam step counter."""
+    monkeypatch.setenv("TAGREC_LAST_LAYER_ROWS", "force")      # both structural cuts are CUDA-graph capturable
+    monkeypatch.setenv("TAGREC_PUSH_BWD", "force")
     cls = {"lightgcn": T.LightGCN, "ngcf": T.NGCF, "dgcf": T.DGCF}[model_name]
     e = tiny["edge_index_train"]
     I = nums(tiny)[1]
