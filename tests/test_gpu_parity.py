@@ -1408,6 +1408,46 @@ def test_adam_in_the_last_backward_epilogue_equals_separate_passes(wd):
     assert not torch.equal(pa, p0)
 
 
+def test_single_gpu_adam_epilogue_optimizer_matches_fused_adam(tiny, monkeypatch):
+    """T.make_optimizer on one GPU with TAGREC_ADAM_EPILOGUE=force (the multi-GPU default; no gain on one GPU): the Adam update of the embedding
+    tables runs in the epilogue of the last backward launch — no gradient table, ``p.grad`` stays None — and follows
+    the same parameter trajectory as FusedAdam on the materialised gradients; a second backward() before step() raises."""
+    monkeypatch.setenv("TAGREC_ADAM_EPILOGUE", "force")
+    e = tiny["edge_index_train"]
+    I = nums(tiny)[1]
+    r = np.random.RandomState(9)
+    batches = []
+    for _ in range(4):
+        sel = r.randint(0, len(e), 64)
+        batches.append(torch.tensor(np.stack([e[sel, 0], e[sel, 1], r.randint(0, I, 64)], 1), device=dev()))
+    finals = []
+    for kind in ("fused", "epilogue"):
+        T.set_config("lightgcn", use_tag=False, reg=1e-3, dim_layer_list=[64, 64, 64], device=dev(), lr=0.01)
+        torch.manual_seed(3)
+        model = T.LightGCN(make_data(tiny)).to(dev())
+        model.train()
+        opt = T.make_optimizer(model, lr=0.01) if kind == "epilogue" else T.FusedAdam(model.parameters(), lr=0.01)
+        assert type(opt).__name__ == ("ShardedFusedAdam" if kind == "epilogue" else "FusedAdam")
+        losses = []
+        for b in batches:
+            lossx = model.loss(b)
+            opt.zero_grad()
+            sum(lossx).backward()
+            if kind == "epilogue":
+                assert all(p.grad is None for p in model.embed)
+            opt.step()
+            losses.append(float(lossx[0]))
+        finals.append((losses, torch.cat([p.detach() for p in model.embed]).clone()))
+        if kind == "epilogue":
+            lossx = model.loss(batches[0])
+            sum(lossx).backward()
+            with pytest.raises(RuntimeError):
+                lossx = model.loss(batches[1])
+                sum(lossx).backward()
+    assert np.allclose(finals[0][0], finals[1][0], rtol=1e-6, atol=0)
+    assert relerr(finals[1][1].cpu().numpy(), finals[0][1].cpu().numpy()) < 1e-6
+
+
 # ----------------------------------------------------------------------------------------------------- multi-GPU
 def test_multi_gpu_sharded_step_matches_single():
     """Only on boxes with >= 2 GPUs (gpurun --gpus N): torchrun tests/multi_gpu_check.py — NCCL all-gather, fused
