@@ -129,7 +129,8 @@ def workload_text(name):
     if name in SCALE_WORKLOADS:
         s = SCALE_WORKLOADS[name]
         return (f"LightGCN {LAYERS}-layer dim-{DIM} BPR batch {BATCH}, synthetic {s['n_user']} users x {s['n_item']} items, "
-                f"~{s['n_edge']} interactions ({name}); full-graph propagation fwd+bwd + Adam every step (reference semantics)")
+                f"~{s['n_edge']} interactions ({name}); one reference training step per batch (model.loss: propagation over the whole "
+                f"graph, BPR loss; backward; Adam over all parameters) with the reference's loss, gradients and parameters")
     model, shape, use_tag, _, over = NAMED_WORKLOADS[name]
     from importlib import import_module  # noqa: F401
     return (f"{model.upper()} dim-{DIM} BPR batch {BATCH} on the {shape}-shaped synthetic graph ({name}"
