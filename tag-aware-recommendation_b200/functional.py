@@ -195,13 +195,15 @@ def lightgcn_backward_layers(graph, raw, g_final, n_layer, bufs, g_out, reg_grad
         use_mask = first_gather and mk is not None
         if use_mask and halves is not None:
             ub, ib = halves
-            nb = batch_nodes.numel() // 3
-            users_sorted = torch.sort(batch_nodes[:nb]).values
-            keep = torch.ones(nb, dtype=torch.uint8, device=users_sorted.device)
-            keep[1:] = users_sorted[1:] != users_sorted[:-1]                  # a user that occurs twice pushes once
+            # the pushing rows = the batch's USER nodes, each once: sorted node list with a keep flag (fixed size, no
+            # host sync: the step stays CUDA-graph capturable)
+            srt = torch.sort(batch_nodes).values
+            keep = srt < int(graph.num_list[0])
+            keep[1:] &= srt[1:] != srt[:-1]
+            keep = keep.to(torch.uint8)
             acc_tab = _zero_buf(ws, "push_acc", (n, dim), g_final.device)
-            check(L.tagrec_spmm_push_rows(ptr(graph.rowptr), ptr(graph.col), ptr(graph.val), ptr(users_sorted), ptr(keep),
-                                          nb, ptr(g_next), ptr(acc_tab), dim, st), "tagrec_spmm_push_rows")
+            check(L.tagrec_spmm_push_rows(ptr(graph.rowptr), ptr(graph.col), ptr(graph.val), ptr(srt), ptr(keep),
+                                          srt.numel(), ptr(g_next), ptr(acc_tab), dim, st), "tagrec_spmm_push_rows")
             du = ub.desc(dim, transposed=True, plain=True)
             check(L.tagrec_lightgcn_bwd_layer_ex(C.byref(du), ptr(g_next), ptr(mk), ptr(raw[k - 1]), ptr(g_final), None,
                                                  ptr(upstream), inv, ptr(out), dim, None, st), "tagrec_lightgcn_bwd_layer")
