@@ -1,7 +1,7 @@
 #!/bin/sh
 # One GPU call, several jobs (the pod's queue is the bottleneck): full GPU test suite, the column-block sweep, and the
 # 8-lane K1 variants.  Everything lands in gpurun_out/.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/ra_tests.log
 grep -E "passed|failed" gpurun_out/ra_tests.log

@@ -1,7 +1,7 @@
 #!/bin/sh
 # Round B: the GPU tests that failed in round A (after their fixes), then the second column-block sweep (larger windows,
 # longer shortest blocked row, and the unblocked plan as the baseline).
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 > gpurun_out/rb_tests.log
 grep -E "passed|failed" gpurun_out/rb_tests.log

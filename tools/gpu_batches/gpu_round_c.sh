@@ -1,6 +1,6 @@
 #!/bin/sh
 # Round C: c2 TGCN test detail; then the shipped K1 configuration on lightgcn_1b: plain run, ncu launch list, ncu --set full.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for i in 1 2 3; do
 python -m pytest tests/test_gpu_shapes.py -m gpu -q -k c2_tgcn 2>&1 | grep -E "^E  |passed|failed" | cut -c1-400 | head -8

@@ -1,7 +1,7 @@
 #!/bin/sh
 # Round D: the CTA-pair evaluation kernel — parity tests first, then A/B timing against the single-CTA kernel, then the
 # cycle accounting of the instrumented variant (tools/probes/eval_tc2_experiments.py 5) if it was built.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "k3_tensor_core" 2>&1 | grep -v Warning | tail -25 > gpurun_out/rd_tests.log
 tail -3 gpurun_out/rd_tests.log

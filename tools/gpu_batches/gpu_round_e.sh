@@ -1,6 +1,6 @@
 #!/bin/sh
 # Round E: stage isolation of the CTA-pair evaluation kernel (tools/probes/eval_tc2_experiments.py variants).
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for v in 1 2 3 4; do
   echo "== variant t2x$v"

@@ -1,6 +1,6 @@
 #!/bin/sh
 # Round F: cycle accounting variants of the CTA-pair evaluation kernel (tools/probes/eval_tc2_experiments.py 5 6 7).
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for v in "$@"; do
   echo "== variant t2x$v"

@@ -1,7 +1,7 @@
 #!/bin/sh
 # Final 1-GPU round: the GPU suite, smoke(), the default bench line of both arms exactly as the driver runs it, and the four
 # named BASELINE workloads (both arms on the full configuration).
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/rfinal_tests.log
 grep -E "passed|failed|error" gpurun_out/rfinal_tests.log

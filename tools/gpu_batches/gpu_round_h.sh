@@ -1,6 +1,6 @@
 #!/bin/sh
 # Round H: K1 rolling-gather variants on lightgcn_1b (default plan), against the shipped library in the same call.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for v in base "$@"; do
   lib=""; [ "$v" != base ] && lib=$PWD/build/variants/lib_$v.so

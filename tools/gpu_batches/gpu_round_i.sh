@@ -1,7 +1,7 @@
 #!/bin/sh
 # Round I (2 GPUs): the whole GPU suite (incl. multi-GPU parity with the Adam epilogue), then the N = 2 bench with and
 # without the epilogue form.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 > gpurun_out/ri_tests.log
 grep -E "passed|failed|error" gpurun_out/ri_tests.log

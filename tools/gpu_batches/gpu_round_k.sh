@@ -1,7 +1,7 @@
 #!/bin/sh
 # Round K (1 GPU): the default bench line exactly as the driver runs it (both arms), then ncu of the CTA-pair evaluation
 # kernel (launch list + --set full) on the evaluation micro-benchmark.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 python bench.py --impl reference > gpurun_out/rk_bench_ref.json 2> gpurun_out/rk_bench_ref.err; echo "reference arm rc=$?"
 python bench.py > gpurun_out/rk_bench.json 2> gpurun_out/rk_bench.err; echo "our arm rc=$?"

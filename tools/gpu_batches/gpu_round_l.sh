@@ -1,6 +1,6 @@
 #!/bin/sh
 # Round L: pair-kernel item splits (wave-aware plan) — parity tests, then timing for several split counts.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "k3_tensor_core" 2>&1 | tail -3
 for sp in auto 1 2 4 8 15; do

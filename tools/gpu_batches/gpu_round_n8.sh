@@ -1,6 +1,6 @@
 #!/bin/sh
 # 8-GPU box: multi-GPU parity (every exchange path vs the single-GPU step), then the scaling bench at N = 8 and N = 4.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \

@@ -1,7 +1,7 @@
 #!/bin/sh
 # Round O (2 GPUs): parity of every multi-GPU mode (incl. split forward / backward partitions), then the N = 2 bench with
 # and without the split partitions.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
     tests/multi_gpu_check.py --out gpurun_out/r2_multi_gpu_parity_n2.jsonl > gpurun_out/n2_parity.log 2>&1

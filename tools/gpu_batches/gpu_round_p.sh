@@ -1,6 +1,6 @@
 #!/bin/sh
 # Round P (1 GPU): the push form of the first backward launch — full GPU suite, then the bench with and without it.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x 2>&1 | tail -6 > gpurun_out/rp_tests.log
 grep -E "passed|failed|error" gpurun_out/rp_tests.log

@@ -1,6 +1,6 @@
 #!/bin/sh
 # Round Q (1 GPU): last forward layer on the batch rows only — full GPU suite, then the bench with and without it.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x 2>&1 | tail -6 > gpurun_out/rq_tests.log
 grep -E "passed|failed|error" gpurun_out/rq_tests.log

@@ -1,6 +1,6 @@
 #!/bin/sh
 # Round W: K1 with the cp.async ring gather (SPMM_ASYNC variants) — parity of the K1 / LightGCN tests, then the bench.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for v in "$@"; do
   lib=$PWD/build/variants/lib_$v.so
