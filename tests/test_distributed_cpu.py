@@ -242,3 +242,31 @@ def test_sharded_ngcf_world2_gloo(tmp_path):
         if k.startswith("g_"):
             assert np.abs(a[k] - b[k]).max() <= 1e-10 * max(np.abs(a[k]).max(), 1e-300), k
     assert any(k.startswith("g_mat.W1") for k in a) and np.abs(a["g_mat.W1_0"]).max() > 0
+
+
+def test_cut_by_cost_and_feedback_scaling():
+    """Host logic of the measured partition (distributed.row_costs / cut_by_cost): contiguous ranges of equal modelled
+    cost; scaling one range's cost (a rank measured slower than the mean) moves its cuts inward; degenerate inputs stay
+    monotone."""
+    from tagrec_b200.distributed import cut_by_cost, row_costs
+
+    class G:
+        pass
+    rng = np.random.RandomState(1)
+    deg = np.r_[rng.randint(1, 200, 4000), rng.randint(200, 4000, 400)]
+    g = G()
+    g.rowptr = torch.tensor(np.r_[0, np.cumsum(deg)])
+    tb, tw = [0, 4000, 4400], [3e-11, 1e-11]                      # user rows cost 3x per entry
+    cost = row_costs(g, tb, tw)
+    assert cost.shape[0] == 4400 and float(cost.min()) > 0
+    for world in (2, 4, 8):
+        b = cut_by_cost(cost, world)
+        assert b[0] == 0 and b[-1] == 4400 and all(x <= y for x, y in zip(b, b[1:]))
+        per = [float(cost[b[i]:b[i + 1]].sum()) for i in range(world)]
+        assert max(per) - min(per) <= 2 * float(cost.max())          # within one (largest) row of each other
+    b4 = cut_by_cost(cost, 4)
+    slow = cost.clone()
+    slow[b4[1]:b4[2]] *= 1.3                                         # rank 1 measured 30 % over the mean
+    n4 = cut_by_cost(slow, 4)
+    assert n4[2] - n4[1] < b4[2] - b4[1]                             # it gets fewer rows
+    assert cut_by_cost(torch.ones(3, dtype=torch.float64), 8)[-1] == 3      # more ranks than rows: still monotone
