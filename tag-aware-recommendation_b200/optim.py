@@ -139,6 +139,25 @@ class ShardedFusedAdam(torch.optim.Optimizer):
         if comm is not None:
             comm.peer.barrier("e0")
 
+    def load_state_dict(self, state_dict):
+        """Resume: torch's loader replaces the state tensors by copies — move their contents into the flat exp_avg /
+        exp_avg_sq tables the kernels use (the state entries are views of those again afterwards) and restart the step
+        counter (bias corrections) from the loaded one."""
+        super().load_state_dict(state_dict)
+        off, step = 0, 0
+        with torch.no_grad():
+            for p in self.model.embed:
+                st = self.state.get(p, {})
+                rows = slice(off, off + p.shape[0])
+                if "exp_avg" in st and st["exp_avg"].data_ptr() != self._m[rows].data_ptr():
+                    self._m[rows].copy_(st["exp_avg"])
+                    self._v[rows].copy_(st["exp_avg_sq"])
+                step = max(step, int(st.get("step", 0)))
+                self.state[p] = {"step": step, "exp_avg": self._m[rows], "exp_avg_sq": self._v[rows]}
+                off += p.shape[0]
+        self._step = step
+        self._applied = False
+
     def begin_fused_step(self):
         """Called by LightGCNLossFn.backward: the tagrec_adam_t of step t + 1 for the epilogue of its last launch."""
         from ._lib import AdamDesc

@@ -1446,6 +1446,26 @@ def test_single_gpu_adam_epilogue_optimizer_matches_fused_adam(tiny, monkeypatch
                 sum(lossx).backward()
     assert np.allclose(finals[0][0], finals[1][0], rtol=1e-6, atol=0)
     assert relerr(finals[1][1].cpu().numpy(), finals[0][1].cpu().numpy()) < 1e-6
+    # resume: a state_dict round trip keeps the moments and the step counter (bias corrections) alive
+    T.set_config("lightgcn", use_tag=False, reg=1e-3, dim_layer_list=[64, 64, 64], device=dev(), lr=0.01)
+    outs = []
+    for resume in (False, True):
+        torch.manual_seed(3)
+        model = T.LightGCN(make_data(tiny)).to(dev())
+        model.train()
+        opt = T.make_optimizer(model, lr=0.01)
+        for i, b in enumerate(batches):
+            if resume and i == 2:
+                sd = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in opt.state_dict().items()}
+                opt = T.make_optimizer(model, lr=0.01)
+                opt.load_state_dict(sd)
+                assert opt._step == 2
+            lossx = model.loss(b)
+            opt.zero_grad()
+            sum(lossx).backward()
+            opt.step()
+        outs.append(torch.cat([p.detach() for p in model.embed]).clone())
+    assert relerr(outs[1].cpu().numpy(), outs[0].cpu().numpy()) < 1e-6
 
 
 # ----------------------------------------------------------------------------------------------------- multi-GPU
